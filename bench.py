@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the particle-filter step (predict + weight + resample).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4] [--impl b200|reference]
+
+One "step" is one full pass of the hot path over one filter: systematic resampling (forced every
+step: scan + gather) -> motion prediction -> landmark likelihood -> normaliser / ESS / arg-max /
+mean+covariance.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+L2_BYTES = 126 * 1024 * 1024
+BYTES_STEP_CANONICAL = 64  # fp32 SoA state, predict+weight 32 B + scan 4 B + gather 28 B
+BYTES_K_STEP = 32          # k_step as built: ancestor 4 B + gathered pose 12 B in, pose + log-weight 16 B out
+BYTES_K_SCAN = 8           # k_scan_ancestors: log-weight 4 B in, ancestor 4 B out
+
+WORKLOADS = {
+    # name: (particles per filter, landmarks, trials per GPU, description)
+    "c1": dict(n=1 << 20, L=16, T=1, desc="C1 single filter 2^20 particles x 16 landmarks"),
+    "c2": dict(n=16384, L=16, T=4096, desc="C2 4096 independent trials x 16384 particles x 16 landmarks"),
+    "c3": dict(n=125_000_000, L=64, T=1, desc="C3 one 125M-particle shard x 64 landmarks (1B over 8 GPUs)"),
+    "c4": dict(n=16 << 20, L=1024, T=1, desc="C4 16M particles x 1024 landmarks (FP-bound likelihood)"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def landmarks_for(L):
+    """the built-in 5 landmarks for L == 5, else uniform in [-20, 20]^2, default_rng(1234)."""
+    if L == 5:
+        return np.array([[5.0, 5.0], [2.0, -3.0], [-3.0, 4.0], [-5.0, -1.0], [0.0, 0.0]])
+    return np.random.default_rng(1234).uniform(-20.0, 20.0, (L, 2))
+
+
+class Truth:
+    """The reference's ground-truth circle (particle_filter.py:46-48, :74-79, :121-142) and its
+    observation model (:144-154), host side, one pose per step exactly as in the reference."""
+
+    def __init__(self, lm, seed, dt=0.1, phase=0.0):
+        self.lm = lm
+        self.rng = np.random.RandomState(seed)
+        self.dt = dt
+        self.w = np.deg2rad(10.0)
+        self.v = 10.0 * self.w
+        self.x = np.array([10.0 * math.cos(phase), 10.0 * math.sin(phase), math.pi / 2 + phase])
+        self.x[2] = (self.x[2] + math.pi) % (2 * math.pi) - math.pi
+
+    def pose(self):
+        return self.x.copy()
+
+    def advance(self):
+        x, y, th = self.x
+        th2 = th + self.w * self.dt
+        if abs(th2) > math.pi:
+            th2 = (abs(th2) - 2 * math.pi) * (1 if th2 > 0 else -1)
+        self.x = np.array([x + self.v * self.dt * math.cos(th), y + self.v * self.dt * math.sin(th), th2])
+
+    def observe(self):
+        x, y, th = self.x
+        s, c = math.sin(th), math.cos(th)
+        dx, dy = self.lm[:, 0] - x, self.lm[:, 1] - y
+        z = np.stack([s * dx - c * dy, c * dx + s * dy], axis=1)
+        return z + self.rng.normal(0.0, 0.3, z.shape)
+
+
+class ClockSampler(threading.Thread):
+    """NVML SM clock + throttle reasons sampled while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.active = threading.Event()
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            if self.active.is_set():
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self):
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ======================================================================================================
+# reference arm / CPU baseline: the numpy oracle (a port of the reference's step; the reference itself is
+# a per-particle Python loop that cannot finish these shapes) on the host cores
+# ======================================================================================================
+def _cpu_chunk(args):
+    from oracle import pf_oracle as O
+
+    px, v, z, lm, dt = args
+    P = O.PFParams(dt * 1000.0, n_particles=px.shape[1], landmarks=lm)
+    px2 = O.predict(px, v, P)
+    ll = O.loglik_cartesian(px2, z, lm, 0.3, 0.3)
+    return px2, ll
+
+
+def cpu_step_runner(n, L, procs):
+    """Returns step() -> seconds for ONE oracle step over n particles x L landmarks, `procs` processes.
+
+    Order as particle_filter.py:86-119: resample (cumsum + comb search + gather) -> predict (numpy
+    noise draw + motion) -> weight (log-domain likelihood, normalise) -> arg-max."""
+    from oracle import pf_oracle as O
+
+    lm = landmarks_for(L)
+    truth = Truth(lm, seed=5)
+    rng = np.random.RandomState(11)
+    P = O.PFParams(100.0, n_particles=n, landmarks=lm)
+    state = dict(px=np.tile(P.x0, (1, n)) + rng.normal(0, 0.05, (3, n)), pw=np.full(n, 1.0 / n))
+    pool = None
+    if procs > 1:
+        import multiprocessing as mp
+
+        pool = mp.get_context("fork").Pool(procs)
+
+    def step():
+        t0 = time.perf_counter()
+        truth.advance()
+        ofs = rng.rand() / n
+        anc = O.resample_indices(state["pw"], ofs)
+        px = state["px"][:, anc]
+        v = rng.multivariate_normal([0.0, 0.0, 0.0], P.Q, n).T
+        z = truth.observe()
+        if pool is None:
+            px2, ll = _cpu_chunk((px, v, z, lm, 0.1))
+        else:
+            cuts = np.linspace(0, n, procs + 1).astype(int)
+            parts = pool.map(_cpu_chunk, [(px[:, a:b], v[:, a:b], z, lm, 0.1) for a, b in zip(cuts[:-1], cuts[1:])])
+            px2 = np.concatenate([p[0] for p in parts], axis=1)
+            ll = np.concatenate([p[1] for p in parts])
+        w, _ = O.update_weights_log(np.full(n, -math.log(n)), ll)
+        state["px"], state["pw"] = px2, w
+        O.map_estimate(px2, w)
+        return time.perf_counter() - t0
+
+    def close():
+        if pool is not None:
+            pool.terminate()
+
+    return step, close
+
+
+def cpu_baseline(wl, budget_s=12.0, procs=1):
+    """Bounded sample: the same shape with fewer particles when one full step exceeds the budget."""
+    n = wl["n"] * wl["T"]
+    n_sample = min(n, 1 << 20)
+    step, close = cpu_step_runner(n_sample, wl["L"], procs)
+    step()  # warm-up (page faults, pool start)
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while time.perf_counter() < t_end and len(times) < 50:
+        times.append(step())
+    close()
+    t = float(np.median(times))
+    return {"value": n_sample / t, "unit": "particle-steps/s", "cores": procs, "kind": "port",
+            "sample": f"{len(times)} steps of {n_sample} particles x {wl['L']} landmarks (numpy fp64 oracle, "
+                      f"{procs} process{'es' if procs > 1 else ''}), median {t * 1e3:.1f} ms/step"}
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    procs = max(1, (os.cpu_count() or 1))
+    procs = min(procs, 32)
+    n = wl["n"] * wl["T"]
+    n_sample = min(n, 1 << 20)
+    step, close = cpu_step_runner(n_sample, wl["L"], procs)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    k = max(1, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        step()
+    dt = time.perf_counter() - t0
+    close()
+    value = n_sample * k / dt
+    sample = (f"{k} steps of {n_sample} particles x {wl['L']} landmarks per step (bounded sample of {wl['desc']}), "
+              f"numpy fp64 oracle port over {procs} processes")
+    line = {"impl": "reference", "metric": "particle-steps/s (predict+weight+resample)", "value": value,
+            "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": k, "warmup": args.warmup,
+            "ms_per_step": dt / k * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "landmarks": wl["L"], "particles_per_step": n_sample},
+            "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ======================================================================================================
+# the B200 arm
+# ======================================================================================================
+def run_b200(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    import slam_robot_simu_b200 as mcl
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, L, T = wl["n"], wl["L"], wl["T"]
+    lm = landmarks_for(L)
+    state_bytes = 2 * 16 * n * T + 4 * n * T
+    replicas = max(1, min(64, math.ceil(2.2 * L2_BYTES / state_bytes)))  # rotate filters so every step is L2-cold
+    K, W = args.steps, max(args.warmup, 3)
+
+    filters, truths = [], []
+    for r in range(replicas):
+        f = mcl.Filter(n_particles=n, n_trials=T, landmarks=lm, likelihood=args.likelihood, device=local,
+                       seed=42 + 1000 * rank + r, max_landmarks=L)
+        tr = [Truth(lm, seed=7 + 100 * rank + r * 17 + t, phase=0.05 * t) for t in range(T)]
+        f.init_particles(np.stack([t_.pose() for t_ in tr]))
+        filters.append(f)
+        truths.append(tr)
+
+    def make_z(r):
+        for t_ in truths[r]:
+            t_.advance()
+        return np.stack([t_.observe() for t_ in truths[r]])
+
+    # 20 spreading steps per replica -- untimed
+    for r in range(replicas):
+        for _ in range(20):
+            filters[r].step(make_z(r), force_resample=True)
+    torch.cuda.synchronize()
+
+    # device-resident observations for the kernel-throughput run
+    total_steps = W + K
+    z_host = [make_z(i % replicas) for i in range(total_steps)]
+    z_dev = [torch.from_numpy(z).to(dev) for z in z_host]
+    torch.cuda.synchronize()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # extra untimed spin-up so the clocks are at their loaded state (W is a minimum, not a maximum)
+    t_spin = time.perf_counter()
+    i = 0
+    while time.perf_counter() - t_spin < 0.3:
+        filters[i % replicas].step_dev(z_dev[i % total_steps], force_resample=True)
+        i += 1
+        if i % 64 == 0:
+            torch.cuda.synchronize()
+    for i in range(W):
+        filters[i % replicas].step_dev(z_dev[i], force_resample=True)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = sum(f.launch_count() for f in filters)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    sampler.active.set()
+    e0.record()
+    for i in range(K):
+        filters[(W + i) % replicas].step_dev(z_dev[W + i], force_resample=True)
+    e1.record()
+    sync_all()
+    sampler.active.clear()
+    ms = e0.elapsed_time(e1)
+    launches = sum(f.launch_count() for f in filters) - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = float(n) * T * K * world / (ms * 1e-3)
+
+    # ---- per-kernel durations, measured live with CUDA events inside the library (same steps, L2-cold) ----
+    kt = np.zeros(3)
+    kn = min(K, 200)
+    for f in filters:
+        f.profile(True)
+    for i in range(kn):
+        f = filters[(W + i) % replicas]
+        f.step_dev(z_dev[(W + i) % total_steps], force_resample=True)
+        kt += np.array(f.profile_read())
+    for f in filters:
+        f.profile(False)
+    kt /= kn
+    peak, peak_src = peaks()
+    ach = BYTES_K_STEP * n * T / (kt[2] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_step<0> (gather + predict + weight + reductions)", "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_particle": BYTES_K_STEP,
+                "kernel_ms": {"k_prep": kt[0], "k_scan_ancestors": kt[1], "k_step": kt[2]},
+                "scan_achieved_GBps": BYTES_K_SCAN * n * T / (kt[1] * 1e-3) / 1e9,
+                "step_canonical_bytes": BYTES_STEP_CANONICAL,
+                "step_canonical_frac": BYTES_STEP_CANONICAL * value / world / 1e9 / peak}
+
+    # ---- end to end through the reference-facing API: host observation in, host estimate out, every step ----
+    e2e = None
+    if T == 1:
+        sync_all()
+        pf = mcl.ParticleFilter(100, n_particles=n, landmarks=lm, noise="philox", likelihood=args.likelihood,
+                                lazy_px=True, force_resample=True, device=local, seed=4242 + rank)
+        for _ in range(max(W, 20)):
+            pf.main_pf()
+        ke = min(K, 500)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            out = pf.main_pf()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        import ctypes as C
+
+        e2e = {"value": float(n) * ke * world / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": 16 * L,
+               "d2h_bytes_per_step": C.sizeof(mcl.mcl_stats), "steps": ke,
+               "api": "ParticleFilter(period_ms, noise='philox', lazy_px=True, force_resample=True).main_pf()",
+               "note": "host truth motion + observation draw, H2D of z_l, 3 kernels, D2H of the mcl_stats block; px stays "
+                       "on the device until read (LazyParticles)"}
+        del pf
+    else:
+        sync_all()
+        f = filters[0]
+        ke = min(K, 200)
+        zs = [make_z(0) for _ in range(ke)]
+        t0 = time.perf_counter()
+        for i in range(ke):
+            f.step(zs[i], force_resample=True)
+            st = f.stats()
+        dt = time.perf_counter() - t0
+        import ctypes as C
+
+        e2e = {"value": float(n) * T * ke * world / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": 16 * L * T,
+               "d2h_bytes_per_step": C.sizeof(mcl.mcl_stats) * T, "steps": ke, "api": "Filter.step(z_host) + Filter.stats()"}
+    sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = cpu_baseline(wl) if world == 1 and not args.no_cpu else None
+    line = {"metric": "particle-steps/s (predict+weight+resample)", "value": value, "unit": "particle-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 state / f64 likelihood / u64 scan", "data": "synthetic",
+            "config": {"workload": wl["desc"], "particles": n, "landmarks": L, "trials": T, "likelihood": args.likelihood,
+                       "noise": "philox4x32-10 on device", "resampling": "forced every step",
+                       "l2": f"rotating {replicas} independent filter replicas ({replicas * state_bytes >> 20} MiB > 126 MiB L2)",
+                       "parallelism": "single GPU" if world == 1 else f"{world} ranks, independent filters"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": sampler.summary()}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
+    ap.add_argument("--likelihood", default="moment", choices=["pair", "moment"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_b200(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,201 @@
+/*
+ * mcl.h -- C ABI of the B200 Monte-Carlo-localisation engine (libmcl_b200.so).
+ *
+ * The reference (takuyani/SLAM-Robot_Simu) has no FFI: its boundary for this path is the Python
+ * class ParticleFilter(period_ms) / main_pf() (particle_filter.py:21, :86-119).  Each entry point
+ * below names the reference method it replaces; the Python mirror that binds them with ctypes is
+ * slam-robot_simu_b200/particle_filter.py, and INTEGRATION.md shows the stub a maintainer adds.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no C++/torch types cross this boundary.
+ *   - every call returns MCL_OK (0) or a negative mcl_status; nothing throws across the ABI;
+ *     mcl_last_error(h) gives the text of the last failure on that handle.
+ *   - "dev" pointers are CUDA device pointers owned by the caller (e.g. torch tensor data_ptr());
+ *     "host" pointers are ordinary process memory.  `stream` is a cudaStream_t passed as void*.
+ *   - all work is enqueued on `stream` and is asynchronous unless the call says "synchronises".
+ *   - one handle per (device, stream) user; calls on one handle are not thread-safe, different
+ *     handles are independent.
+ *   - there is no CPU fallback: creating a filter without a usable sm_100 device fails.
+ *
+ * Particle state is SoA fp32 (x, y, yaw, log-weight), `n_trials` independent filters of
+ * `n_particles` each, trial t at offset t * mcl_stride(h).  Likelihood arithmetic is fp64 in
+ * registers; resampling thresholds are fp64 and the cumulative weights are exact 64-bit integers
+ * on a 2^-52 grid (bit-exact against the reference walk, particle_filter.py:212-221).
+ */
+#ifndef MCL_B200_H
+#define MCL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCL_ABI_VERSION 1
+
+typedef struct mcl_filter mcl_filter; /* opaque */
+
+typedef enum mcl_status {
+    MCL_OK = 0,
+    MCL_ERR_ARG = -1,      /* bad argument / NULL pointer / size out of range          */
+    MCL_ERR_CUDA = -2,     /* a CUDA runtime call or kernel launch failed                */
+    MCL_ERR_STATE = -3,    /* call sequence error (e.g. no landmarks set)               */
+    MCL_ERR_NOMEM = -4,    /* workspace too small / allocation failed                    */
+    MCL_ERR_NODEVICE = -5  /* no CUDA device, or not compute capability 10.x             */
+} mcl_status;
+
+/* likelihood kernels (particle_filter.py:170-198 is the Cartesian model) */
+typedef enum mcl_likelihood {
+    MCL_LIK_PAIR = 0,   /* every particle x every landmark, fp64, landmarks staged in shared memory */
+    MCL_LIK_MOMENT = 1, /* same result from 13 per-step landmark moments (exact identity), O(1)/particle */
+    MCL_LIK_RB = 2      /* range/bearing residuals with limit_angle wrap (extension; sensor model
+                           graph_based_slam.py:150-167) */
+} mcl_likelihood;
+
+typedef enum mcl_motion {
+    MCL_MOTION_A = 0, /* particle_filter.py:121-142 (__f) + additive N(0,Q) noise (:165-166)  */
+    MCL_MOTION_B = 1  /* motion_model.py:31-62 (MotionModel.moveWithNoise), batched            */
+} mcl_motion;
+
+/* flags for mcl_step / mcl_resample */
+#define MCL_FORCE_RESAMPLE 1u /* resample regardless of the ESS gate (benchmark mode)           */
+#define MCL_NO_RESAMPLE 2u    /* skip the resampling stage                                      */
+#define MCL_PHILOX_NOISE 4u   /* draw motion noise (and the comb offset when ofs==NULL) on device */
+
+/* Constants of ParticleFilter.__init__ (particle_filter.py:30-84). mcl_config_default fills the
+ * reference literals; every field can then be overridden. */
+typedef struct mcl_config {
+    uint32_t struct_size;   /* = sizeof(mcl_config), checked                               */
+    int32_t device;         /* CUDA device ordinal                                         */
+    int64_t n_particles;    /* NP, particles per trial held by THIS handle (:31)           */
+    int32_t n_trials;       /* independent filters batched in one handle (>=1)             */
+    int32_t max_landmarks;  /* capacity of the landmark table (<= 4096)                    */
+    double dt;              /* DT_s = period_ms / 1000 (:30)                               */
+    double vel;             /* VEL_mps (:48)                                               */
+    double yaw_rate;        /* YAW_RATE_rps (:47)                                          */
+    double q_std[3];        /* sqrt(diag(Q)): x [m], y [m], yaw [rad] (:62-65)             */
+    double sigma_obs[2];    /* sqrt(R[0][0]), sqrt(R[1][1]) (:68-70, :179-180); in MCL_LIK_RB
+                               these are (sigma_range, sigma_bearing)                      */
+    double ess_threshold;   /* ESS_TH = NP / 100 (:33)                                     */
+    double motion_b_alpha[6]; /* a1..a6 of MotionModel (motion_model.py:20-29)            */
+    int32_t likelihood;     /* mcl_likelihood                                              */
+    int32_t motion;         /* mcl_motion                                                  */
+    uint64_t seed;          /* Philox key                                                  */
+    /* particle sharding of ONE filter over several handles/GPUs (n_trials must be 1):     */
+    int64_t n_global;       /* particles in the whole filter (== n_particles if unsharded) */
+    int64_t slot_base;      /* global index of this handle's first particle                */
+} mcl_config;
+
+/* Per-trial scalars of one step; the reference returns max_idx/max_val/x_est from main_pf
+ * (particle_filter.py:115-119); mean/cov are the extension that feeds
+ * mylib/error_ellipse.py:39-55 (ErrorEllipse.calc_error_ellipse(cov[0:2,0:2])). */
+typedef struct mcl_stats {
+    double log_norm;   /* log sum_i exp(logw_i): normalised weight = exp(logw_i - log_norm) */
+    double ess;        /* 1 / sum w_i^2 (:210)                                              */
+    double max_weight; /* max_val (:115)                                                    */
+    int64_t max_idx;   /* max_idx, first occurrence (:116); local index when sharded        */
+    double est[3];     /* x_est = px[:, max_idx] (:117)                                     */
+    double mean[3];    /* weighted mean, circular for yaw                                   */
+    double cov[9];     /* weighted 3x3 covariance, row-major, yaw residual wrapped           */
+    double sum_w;      /* s1: sum exp(logw - max_logw)  (partials for sharded merge)        */
+    double sum_w2;     /* s2: sum exp(2 (logw - max_logw))                                  */
+    double max_logw;   /* max_i logw_i                                                      */
+    double raw[12];    /* un-normalised moment sums about `ref` (for sharded merge)         */
+    double ref[3];     /* reference pose the moment sums are taken about                    */
+    int32_t resampled; /* 1 if this step's resampling stage fired                           */
+    int32_t step;      /* number of mcl_step/mcl_predict_weight calls so far                */
+} mcl_stats;
+
+int mcl_abi_version(void);
+const char *mcl_status_string(int status);
+const char *mcl_last_error(const mcl_filter *h);
+
+/* ParticleFilter.__init__ literals (particle_filter.py:30-84) for `period_ms`. */
+int mcl_config_default(mcl_config *cfg, double period_ms);
+
+/* Bytes of device workspace a filter of this config needs (state double-buffers, ancestors,
+ * scan tile descriptors, reduction partials). */
+int mcl_workspace_bytes(const mcl_config *cfg, size_t *bytes);
+
+/* Create a filter.  `workspace_dev` is caller-owned device memory of at least
+ * mcl_workspace_bytes (256-byte aligned), e.g. a torch uint8 tensor; pass NULL to let the library
+ * cudaMalloc it.  Replaces ParticleFilter.__init__ (:21-84) minus the state fill. */
+int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_bytes, mcl_filter **out);
+int mcl_destroy(mcl_filter *h);
+
+int64_t mcl_stride(const mcl_filter *h); /* elements between consecutive trials in the state arrays */
+
+/* self.__LM (:39-43): host array [L][2] fp64, shared by all trials. */
+int mcl_set_landmarks(mcl_filter *h, const double *lm_xy_host, int32_t n_landmarks, void *stream);
+
+/* px = repmat(x_true, 1, NP); pw = 1/NP (:81-84).  pose_host is [n_trials][3]. */
+int mcl_init_particles(mcl_filter *h, const double *pose_host, void *stream);
+
+/* Overwrite / read the particle state.  Arrays are [n_trials][n_particles] fp32 (dense, no
+ * stride); logw may be NULL (set: uniform; get: skipped).  `on_device` != 0 means the pointers
+ * are device pointers.  set recomputes the statistics; get synchronises when on_device == 0. */
+int mcl_set_particles(mcl_filter *h, const float *x, const float *y, const float *yaw, const float *logw,
+                      int on_device, void *stream);
+int mcl_get_particles(mcl_filter *h, float *x, float *y, float *yaw, float *logw, int on_device, void *stream);
+
+/* ---- stage calls (one per reference method) --------------------------------------------------
+ * __resampling (:200-224).  ofs_host: [n_trials] comb offsets = rand() * NP_RECIP (:214), or NULL
+ * with MCL_PHILOX_NOISE.  Fires per trial when ess < ess_threshold (:211) or MCL_FORCE_RESAMPLE. */
+int mcl_resample(mcl_filter *h, const double *ofs_host, uint32_t flags, void *stream);
+
+/* __predict (:156-168) + __likelihood/__normalize (:170-198, :226-237) + MAP estimate (:115-117).
+ * z_host: [n_trials][L][2] fp64 observations z_l (:151-153) -- (range, bearing) in MCL_LIK_RB.
+ * noise_dev: device fp32 [3][n_trials][n_particles] = the draw v of :165 (rows x, y, yaw), or NULL
+ * with MCL_PHILOX_NOISE.  For MCL_MOTION_B the three rows are standard normals (vel, omg, gam). */
+int mcl_predict_weight(mcl_filter *h, const double *z_host, const float *noise_dev, uint32_t flags, void *stream);
+
+/* main_pf (:86-119) without the ground-truth line: resample -> predict -> weight -> estimate. */
+int mcl_step(mcl_filter *h, const double *z_host, const double *ofs_host, const float *noise_dev, uint32_t flags,
+             void *stream);
+/* Same, with z and ofs already resident on the device (no host traffic, CUDA-graph friendly). */
+int mcl_step_dev(mcl_filter *h, const double *z_dev, const double *ofs_dev, const float *noise_dev, uint32_t flags,
+                 void *stream);
+
+/* Recompute mean/cov with the exact two-pass definition (wrap about the circular mean). */
+int mcl_pose_moments(mcl_filter *h, void *stream);
+
+/* ---- results ---------------------------------------------------------------------------------
+ * Copies [n_trials] mcl_stats to host memory and synchronises the stream. */
+int mcl_get_stats(mcl_filter *h, mcl_stats *out_host, void *stream);
+/* Device address of the [n_trials] mcl_stats block (for callers that poll asynchronously). */
+int mcl_stats_dev(mcl_filter *h, const mcl_stats **out_dev);
+/* Normalised weights exp(logw - log_norm) as fp64 [n_trials][n_particles] (pw of :194-196). */
+int mcl_get_weights(mcl_filter *h, double *w_host, void *stream);
+/* The integers the resampler scans: rint(w * 2^52) as uint64 [n_trials][n_particles]. */
+int mcl_get_qweights(mcl_filter *h, uint64_t *q_host, void *stream);
+/* Ancestor of every slot from the last resampling stage, [n_trials][n_particles] uint32. */
+int mcl_get_ancestors(mcl_filter *h, uint32_t *anc_host, void *stream);
+
+/* ---- measurement hooks (bench.py) -----------------------------------------------------------------
+ * mcl_profile(h, 1): every following mcl_step* call brackets its three kernels (k_prep, k_scan_ancestors,
+ * k_step) with CUDA events on the caller's stream.  mcl_profile_read synchronises on the last step and
+ * returns that step's kernel durations in milliseconds: ms[0] prep, ms[1] scan, ms[2] step.
+ * mcl_launch_count: kernels launched through this handle since creation. */
+int mcl_profile(mcl_filter *h, int enable);
+int mcl_profile_read(mcl_filter *h, double *ms3_host);
+uint64_t mcl_launch_count(const mcl_filter *h);
+
+/* ---- particle-sharded single filter (n_trials == 1, one handle per GPU) -----------------------
+ * The host exchanges the small records; see slam-robot_simu_b200/sharded.py.
+ * mcl_shard_total: sum of this shard's quantised weights given the GLOBAL log-normaliser.      */
+int mcl_shard_total(mcl_filter *h, double global_log_norm, uint64_t *total_dev, void *stream);
+/* mcl_shard_expand: with k_offset = sum of totals of lower ranks, write for every global slot this
+ * shard's particles fill the resampled pose into out_{x,y,yaw}_dev[slot - *first_slot]; capacity
+ * `cap` slots.  first_slot/n_slots (host, written after a stream sync) describe the filled range. */
+int mcl_shard_expand(mcl_filter *h, double global_log_norm, uint64_t k_offset, double ofs, float *out_x_dev,
+                     float *out_y_dev, float *out_yaw_dev, int64_t cap, int64_t *first_slot, int64_t *n_slots,
+                     void *stream);
+/* Override the statistics the next step uses (global log-normaliser, MAP estimate, resample
+ * decision) after merging the per-shard mcl_stats on the host. */
+int mcl_shard_set_global(mcl_filter *h, const mcl_stats *merged_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCL_B200_H */

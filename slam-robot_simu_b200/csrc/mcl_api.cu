@@ -1,0 +1,816 @@
+// libmcl_b200.so -- host side of the C ABI declared in include/mcl.h.
+//
+// Everything here is plumbing: argument checks, the workspace layout, kernel launches on the
+// caller's stream.  No arithmetic of the filter happens on the host; there is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "mcl_kernels.cuh"
+
+using namespace mcl;
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Layout {
+    long long n, ld;
+    int T, Lmax, tpt, bpt, cov_bpt;
+    size_t off_state[2], off_anc, off_desc, off_tickets, off_partials, off_cov, off_stats, off_prep, off_tab, off_lm,
+        off_z, off_ofs, off_pose, off_total, total;
+};
+
+int make_layout(const mcl_config &c, int sm_count, Layout &L) {
+    if (c.n_particles < 1 || c.n_particles > 0xFFFFFFF0ll) return MCL_ERR_ARG;
+    if (c.n_trials < 1 || c.n_trials > 65535) return MCL_ERR_ARG;
+    if (c.max_landmarks < 1 || c.max_landmarks > 4096) return MCL_ERR_ARG;
+    L.n = c.n_particles;
+    L.ld = static_cast<long long>(align_up(static_cast<size_t>(c.n_particles), 128));
+    L.T = c.n_trials;
+    L.Lmax = c.max_landmarks;
+    L.tpt = static_cast<int>((L.n + kScanTile - 1) / kScanTile);
+    const long long need = (L.n + kStepTile - 1) / kStepTile;
+    long long cap = static_cast<long long>(sm_count) * 2 * 4;  // 4 grid-stride waves of 2 resident CTAs per SM
+    if (L.T > 1) cap = cap / L.T > 16 ? cap / L.T : 16;
+    L.bpt = static_cast<int>(need < cap ? need : cap);
+    L.cov_bpt = L.bpt;
+    size_t o = 0;
+    const size_t state_bytes = static_cast<size_t>(4) * L.T * L.ld * sizeof(float);
+    for (int b = 0; b < 2; ++b) {
+        L.off_state[b] = o;
+        o = align_up(o + state_bytes, kAlign);
+    }
+    L.off_anc = o;      o = align_up(o + static_cast<size_t>(L.T) * L.ld * sizeof(uint32_t), kAlign);
+    L.off_desc = o;     o = align_up(o + static_cast<size_t>(L.T) * L.tpt * sizeof(unsigned long long), kAlign);
+    L.off_tickets = o;  o = align_up(o + static_cast<size_t>(L.T) * 4 * sizeof(unsigned int), kAlign);
+    L.off_partials = o; o = align_up(o + static_cast<size_t>(L.T) * L.bpt * kPart * sizeof(double), kAlign);
+    L.off_cov = o;      o = align_up(o + static_cast<size_t>(L.T) * L.cov_bpt * 8 * sizeof(double), kAlign);
+    L.off_stats = o;    o = align_up(o + static_cast<size_t>(L.T) * sizeof(mcl_stats), kAlign);
+    L.off_prep = o;     o = align_up(o + static_cast<size_t>(L.T) * sizeof(PrepOut), kAlign);
+    L.off_tab = o;      o = align_up(o + static_cast<size_t>(L.T) * L.Lmax * sizeof(double4), kAlign);
+    L.off_lm = o;       o = align_up(o + static_cast<size_t>(L.Lmax) * 2 * sizeof(double), kAlign);
+    L.off_z = o;        o = align_up(o + static_cast<size_t>(L.T) * L.Lmax * 2 * sizeof(double), kAlign);
+    L.off_ofs = o;      o = align_up(o + static_cast<size_t>(L.T) * sizeof(double), kAlign);
+    L.off_pose = o;     o = align_up(o + static_cast<size_t>(L.T) * 3 * sizeof(double), kAlign);
+    L.off_total = o;    o = align_up(o + static_cast<size_t>(L.T) * sizeof(unsigned long long), kAlign);
+    L.total = o;
+    return MCL_OK;
+}
+
+int validate(const mcl_config *c) {
+    if (c == nullptr || c->struct_size != sizeof(mcl_config)) return MCL_ERR_ARG;
+    if (!(c->dt > 0.0) || !(c->sigma_obs[0] > 0.0) || !(c->sigma_obs[1] > 0.0)) return MCL_ERR_ARG;
+    if (c->likelihood < MCL_LIK_PAIR || c->likelihood > MCL_LIK_RB) return MCL_ERR_ARG;
+    if (c->motion < MCL_MOTION_A || c->motion > MCL_MOTION_B) return MCL_ERR_ARG;
+    if (c->n_global < c->n_particles || c->slot_base < 0 || c->slot_base + c->n_particles > c->n_global)
+        return MCL_ERR_ARG;
+    if (c->n_global != c->n_particles && c->n_trials != 1) return MCL_ERR_ARG;
+    if (c->n_global > 0xFFFFFFF0ll * 64) return MCL_ERR_ARG;
+    return MCL_OK;
+}
+
+}  // namespace
+
+struct mcl_filter {
+    mcl_config cfg;
+    Layout lay;
+    int sm_count = 0;
+    bool owns_ws = false;
+    unsigned char *ws = nullptr;
+    StateView state[2];
+    uint32_t *anc = nullptr;
+    unsigned long long *desc = nullptr;
+    unsigned int *tickets = nullptr;
+    double *partials = nullptr, *cov_partials = nullptr;
+    mcl_stats *stats = nullptr;
+    PrepOut *prep = nullptr;
+    double4 *tab = nullptr;
+    double *lm = nullptr, *z = nullptr, *ofs = nullptr, *pose = nullptr;
+    unsigned long long *total = nullptr;
+    int cur = 0;
+    int L = 0;
+    uint32_t step = 0;
+    bool have_particles = false;
+    bool stats_from_particle0 = false;  // next reduce-only pass takes its reference pose from particle 0
+    double delta = 0.0;                 // fl(1 / n_global), NP_RECIP (particle_filter.py:32)
+    std::string err;
+    uint64_t launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+thread_local std::string g_err;  // errors raised before a handle exists
+
+int fail(mcl_filter *h, int code, const char *what) {
+    if (h) h->err = what;
+    else g_err = what;
+    return code;
+}
+
+#define MCL_CUDA(h, call)                                                                         \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            char buf__[512];                                                                      \
+            snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                     __FILE__, __LINE__);                                                         \
+            return fail(h, MCL_ERR_CUDA, buf__);                                                  \
+        }                                                                                         \
+    } while (0)
+
+#define MCL_LAUNCH_CHECK(h, name)                                                          \
+    do {                                                                                   \
+        (h)->launches += 1;                                                                \
+        cudaError_t e__ = cudaGetLastError();                                              \
+        if (e__ != cudaSuccess) {                                                          \
+            char buf__[512];                                                               \
+            snprintf(buf__, sizeof buf__, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+            return fail(h, MCL_ERR_CUDA, buf__);                                           \
+        }                                                                                  \
+    } while (0)
+
+inline cudaStream_t S(void *stream) { return static_cast<cudaStream_t>(stream); }
+
+int use_device(mcl_filter *h) {
+    int d = -1;
+    MCL_CUDA(h, cudaGetDevice(&d));
+    if (d != h->cfg.device) MCL_CUDA(h, cudaSetDevice(h->cfg.device));
+    return MCL_OK;
+}
+
+// host twin of mcl::count_le (same rounding: no FMA contraction on the host build)
+long long host_count_le(unsigned long long K, double delta, double ofs, long long n) {
+    const double nd = static_cast<double>(n);
+    const double c = static_cast<double>(K) * kInvTwo52;
+    double g = std::floor((c - ofs) * nd);
+    g = std::fmin(std::fmax(g, -1.0), nd - 1.0);
+    long long i = static_cast<long long>(g);
+    auto comb = [&](long long k) {
+        volatile double m = static_cast<double>(k) * delta;  // force the intermediate rounding
+        return m + ofs;
+    };
+    while (i + 1 < n && comb(i + 1) <= c) ++i;
+    while (i >= 0 && comb(i) > c) --i;
+    return i + 1;
+}
+
+// ---- launch helpers ------------------------------------------------------------------------------
+int launch_prep(mcl_filter *h, const double *z_dev, const double *ofs_dev, uint32_t flags, bool reduce_only,
+                cudaStream_t st) {
+    const mcl_config &c = h->cfg;
+    PrepParams p{};
+    p.lm = h->lm;
+    p.z = reduce_only ? nullptr : z_dev;
+    p.ofs = ofs_dev;
+    p.stats = h->stats;
+    p.prep = h->prep;
+    p.tab = h->tab;
+    p.desc = h->desc;
+    p.tickets = h->tickets;
+    p.cur = h->state[h->cur];
+    p.ld = h->lay.ld;
+    p.L = h->L;
+    p.Lmax = h->lay.Lmax;
+    p.tpt = h->lay.tpt;
+    p.flags = flags;
+    p.likelihood = c.likelihood;
+    p.ref_from_particle0 = (reduce_only && h->stats_from_particle0) ? 1 : 0;
+    p.ess_threshold = c.ess_threshold;
+    p.vdt = c.vel * c.dt;
+    p.wdt = c.yaw_rate * c.dt;
+    p.inv_s0sq = 1.0 / (c.sigma_obs[0] * c.sigma_obs[0]);
+    p.inv_s1sq = 1.0 / (c.sigma_obs[1] * c.sigma_obs[1]);
+    p.lik_const = -static_cast<double>(h->L) * std::log(2.0 * kPi * c.sigma_obs[0] * c.sigma_obs[1]);
+    p.base_lw = -std::log(static_cast<double>(c.n_global));
+    p.inv_n = h->delta;
+    p.seed = c.seed;
+    p.step = h->step;
+    p.reduce_only = reduce_only ? 1 : 0;
+    k_prep<<<h->lay.T, 128, 0, st>>>(p);
+    MCL_LAUNCH_CHECK(h, "k_prep");
+    return MCL_OK;
+}
+
+void fill_scan(mcl_filter *h, ScanParams &p) {
+    p = ScanParams{};
+    p.lw = h->state[h->cur].lw;
+    p.prep = h->prep;
+    p.desc = h->desc;
+    p.tickets = h->tickets;
+    p.anc = h->anc;
+    p.total = nullptr;
+    p.n = h->lay.n;
+    p.ld = h->lay.ld;
+    p.n_global = h->cfg.n_global;
+    p.j_global_base = h->cfg.slot_base;
+    p.slot_first = 0;
+    p.anc_cap = h->lay.ld;
+    p.k_offset = 0;
+    p.delta = h->delta;
+    p.tpt = h->lay.tpt;
+}
+
+int launch_scan(mcl_filter *h, const ScanParams &p, cudaStream_t st) {
+    dim3 grid(h->lay.tpt, h->lay.T);
+    if (p.mode == kScanExpand) k_scan_ancestors<kScanExpand><<<grid, kScanThreads, 0, st>>>(p);
+    else if (p.mode == kScanTotals) k_scan_ancestors<kScanTotals><<<grid, kScanThreads, 0, st>>>(p);
+    else k_scan_ancestors<kScanAncestors><<<grid, kScanThreads, 0, st>>>(p);
+    MCL_LAUNCH_CHECK(h, "k_scan_ancestors");
+    return MCL_OK;
+}
+
+int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool reduce_only, cudaStream_t st) {
+    const mcl_config &c = h->cfg;
+    StepParams p{};
+    p.in = h->state[h->cur];
+    p.out = h->state[h->cur ^ 1];
+    p.anc = h->anc;
+    p.noise = noise_dev;
+    p.prep = h->prep;
+    p.tab = h->tab;
+    p.partials = h->partials;
+    p.tickets = h->tickets;
+    p.stats = h->stats;
+    p.n = h->lay.n;
+    p.ld = h->lay.ld;
+    p.slot_base = c.slot_base;
+    p.T = h->lay.T;
+    p.bpt = h->lay.bpt;
+    p.Lmax = h->lay.Lmax;
+    p.likelihood = c.likelihood;
+    p.motion = c.motion;
+    p.flags = flags;
+    p.step = h->step;
+    p.seed = c.seed;
+    p.vdt = c.vel * c.dt;
+    p.wdt = c.yaw_rate * c.dt;
+    p.vel = c.vel;
+    p.yaw_rate = c.yaw_rate;
+    p.dt = c.dt;
+    for (int k = 0; k < 3; ++k) p.q_std[k] = c.q_std[k];
+    p.inv_s0sq = 1.0 / (c.sigma_obs[0] * c.sigma_obs[0]);
+    p.inv_s1sq = 1.0 / (c.sigma_obs[1] * c.sigma_obs[1]);
+    {
+        // motion_model.py:43-48: sigma = a_i v^2 + a_j w^2 and np.random.normal(0, sigma ** 2)
+        const double v2 = c.vel * c.vel, w2 = c.yaw_rate * c.yaw_rate;
+        const double *a = c.motion_b_alpha;
+        const double s0 = a[0] * v2 + a[1] * w2, s1 = a[2] * v2 + a[3] * w2, s2 = a[4] * v2 + a[5] * w2;
+        p.mb_sig[0] = s0 * s0;
+        p.mb_sig[1] = s1 * s1;
+        p.mb_sig[2] = s2 * s2;
+    }
+    dim3 grid(h->lay.bpt, h->lay.T);
+    if (reduce_only) {
+        k_step<1><<<grid, kStepThreads, 0, st>>>(p);
+    } else {
+        const size_t smem = (c.likelihood == MCL_LIK_MOMENT) ? 0 : static_cast<size_t>(h->L) * sizeof(double4);
+        k_step<0><<<grid, kStepThreads, smem, st>>>(p);
+    }
+    MCL_LAUNCH_CHECK(h, "k_step");
+    return MCL_OK;
+}
+
+int reduce_only_pass(mcl_filter *h, cudaStream_t st) {
+    int rc = launch_prep(h, nullptr, nullptr, MCL_NO_RESAMPLE, true, st);
+    if (rc != MCL_OK) return rc;
+    rc = launch_step(h, nullptr, MCL_NO_RESAMPLE, true, st);
+    h->stats_from_particle0 = false;
+    return rc;
+}
+
+int copy2d(mcl_filter *h, void *dst, size_t dpitch_el, const void *src, size_t spitch_el, size_t el_bytes, size_t width_el,
+           size_t rows, cudaMemcpyKind kind, cudaStream_t st) {
+    MCL_CUDA(h, cudaMemcpy2DAsync(dst, dpitch_el * el_bytes, src, spitch_el * el_bytes, width_el * el_bytes, rows, kind, st));
+    return MCL_OK;
+}
+
+int step_impl(mcl_filter *h, const double *z_dev, const double *ofs_dev, const float *noise_dev, uint32_t flags,
+              cudaStream_t st) {
+    if (h->L <= 0) return fail(h, MCL_ERR_STATE, "mcl_set_landmarks has not been called");
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "particles are not initialised");
+    if (noise_dev == nullptr && !(flags & MCL_PHILOX_NOISE))
+        return fail(h, MCL_ERR_ARG, "noise_dev is NULL and MCL_PHILOX_NOISE is not set");
+    if (h->cfg.n_global != h->cfg.n_particles && !(flags & MCL_NO_RESAMPLE))
+        return fail(h, MCL_ERR_STATE, "a particle-sharded filter resamples through mcl_shard_total/mcl_shard_expand");
+    const bool prof = h->profiling;
+    if (prof) MCL_CUDA(h, cudaEventRecord(h->ev[0], st));
+    int rc = launch_prep(h, z_dev, ofs_dev, flags, false, st);
+    if (rc != MCL_OK) return rc;
+    if (prof) MCL_CUDA(h, cudaEventRecord(h->ev[1], st));
+    if (!(flags & MCL_NO_RESAMPLE)) {
+        ScanParams sp;
+        fill_scan(h, sp);
+        sp.mode = kScanAncestors;
+        rc = launch_scan(h, sp, st);
+        if (rc != MCL_OK) return rc;
+    }
+    if (prof) MCL_CUDA(h, cudaEventRecord(h->ev[2], st));
+    rc = launch_step(h, noise_dev, flags, false, st);
+    if (rc != MCL_OK) return rc;
+    if (prof) MCL_CUDA(h, cudaEventRecord(h->ev[3], st));
+    h->cur ^= 1;
+    h->step += 1;
+    return MCL_OK;
+}
+
+int stage_inputs(mcl_filter *h, const double *z_host, const double *ofs_host, cudaStream_t st) {
+    if (z_host != nullptr) {
+        const size_t bytes = static_cast<size_t>(h->lay.T) * h->L * 2 * sizeof(double);
+        MCL_CUDA(h, cudaMemcpyAsync(h->z, z_host, bytes, cudaMemcpyHostToDevice, st));
+    }
+    if (ofs_host != nullptr)
+        MCL_CUDA(h, cudaMemcpyAsync(h->ofs, ofs_host, static_cast<size_t>(h->lay.T) * sizeof(double), cudaMemcpyHostToDevice, st));
+    return MCL_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int mcl_abi_version(void) { return MCL_ABI_VERSION; }
+
+const char *mcl_status_string(int status) {
+    switch (status) {
+        case MCL_OK: return "ok";
+        case MCL_ERR_ARG: return "bad argument";
+        case MCL_ERR_CUDA: return "CUDA error";
+        case MCL_ERR_STATE: return "call sequence error";
+        case MCL_ERR_NOMEM: return "out of memory / workspace too small";
+        case MCL_ERR_NODEVICE: return "no sm_100 CUDA device";
+        default: return "unknown status";
+    }
+}
+
+const char *mcl_last_error(const mcl_filter *h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int mcl_config_default(mcl_config *cfg, double period_ms) {
+    if (cfg == nullptr) return MCL_ERR_ARG;
+    std::memset(cfg, 0, sizeof *cfg);
+    const double deg = kPi / 180.0;
+    cfg->struct_size = sizeof(mcl_config);
+    cfg->device = 0;
+    cfg->n_particles = 1000;             // particle_filter.py:31
+    cfg->n_trials = 1;
+    cfg->max_landmarks = 64;
+    cfg->dt = period_ms / 1000.0;        // :30
+    cfg->yaw_rate = 10.0 * deg;          // :47
+    cfg->vel = 10.0 * cfg->yaw_rate;     // :46,:48
+    cfg->q_std[0] = 0.03;                // :62-65
+    cfg->q_std[1] = 0.03;
+    cfg->q_std[2] = 2.0 * deg;
+    cfg->sigma_obs[0] = 0.3;             // :68-70
+    cfg->sigma_obs[1] = 0.3;
+    cfg->ess_threshold = 1000.0 / 100.0; // :33
+    for (int k = 0; k < 6; ++k) cfg->motion_b_alpha[k] = 0.1;  // graph_based_slam.py:605
+    cfg->likelihood = MCL_LIK_PAIR;
+    cfg->motion = MCL_MOTION_A;
+    cfg->seed = 42;
+    cfg->n_global = cfg->n_particles;
+    cfg->slot_base = 0;
+    return MCL_OK;
+}
+
+int mcl_workspace_bytes(const mcl_config *cfg, size_t *bytes) {
+    if (bytes == nullptr) return MCL_ERR_ARG;
+    int rc = validate(cfg);
+    if (rc != MCL_OK) return fail(nullptr, rc, "invalid mcl_config");
+    Layout L;
+    rc = make_layout(*cfg, 148, L);  // layout caps assume the B200's 148 SMs; mcl_create re-checks
+    if (rc != MCL_OK) return fail(nullptr, rc, "invalid sizes in mcl_config");
+    *bytes = L.total;
+    return MCL_OK;
+}
+
+int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_bytes, mcl_filter **out) {
+    if (out == nullptr) return MCL_ERR_ARG;
+    *out = nullptr;
+    int rc = validate(cfg);
+    if (rc != MCL_OK) return fail(nullptr, rc, "invalid mcl_config");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return fail(nullptr, MCL_ERR_NODEVICE, "no CUDA device is visible (this engine has no CPU fallback)");
+    }
+    if (cfg->device < 0 || cfg->device >= count) return fail(nullptr, MCL_ERR_ARG, "device ordinal out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, MCL_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return fail(nullptr, MCL_ERR_NODEVICE, "device is not compute capability 10.x (kernels are built for sm_100a only)");
+    mcl_filter *h = new (std::nothrow) mcl_filter();
+    if (h == nullptr) return fail(nullptr, MCL_ERR_NOMEM, "host allocation failed");
+    h->cfg = *cfg;
+    h->sm_count = prop.multiProcessorCount;
+    rc = make_layout(*cfg, 148, h->lay);
+    if (rc != MCL_OK) {
+        delete h;
+        return fail(nullptr, rc, "invalid sizes in mcl_config");
+    }
+    if (cudaSetDevice(cfg->device) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, MCL_ERR_CUDA, "cudaSetDevice failed");
+    }
+    if (workspace_dev != nullptr) {
+        if (workspace_bytes < h->lay.total || (reinterpret_cast<uintptr_t>(workspace_dev) % kAlign) != 0) {
+            delete h;
+            return fail(nullptr, MCL_ERR_NOMEM, "workspace too small or not 256-byte aligned");
+        }
+        h->ws = static_cast<unsigned char *>(workspace_dev);
+    } else {
+        void *p = nullptr;
+        if (cudaMalloc(&p, h->lay.total) != cudaSuccess) {
+            cudaGetLastError();
+            delete h;
+            return fail(nullptr, MCL_ERR_NOMEM, "cudaMalloc of the workspace failed");
+        }
+        h->ws = static_cast<unsigned char *>(p);
+        h->owns_ws = true;
+    }
+    const Layout &L = h->lay;
+    const size_t plane = static_cast<size_t>(L.T) * L.ld;
+    for (int b = 0; b < 2; ++b) {
+        float *base = reinterpret_cast<float *>(h->ws + L.off_state[b]);
+        h->state[b].x = base;
+        h->state[b].y = base + plane;
+        h->state[b].th = base + 2 * plane;
+        h->state[b].lw = base + 3 * plane;
+    }
+    h->anc = reinterpret_cast<uint32_t *>(h->ws + L.off_anc);
+    h->desc = reinterpret_cast<unsigned long long *>(h->ws + L.off_desc);
+    h->tickets = reinterpret_cast<unsigned int *>(h->ws + L.off_tickets);
+    h->partials = reinterpret_cast<double *>(h->ws + L.off_partials);
+    h->cov_partials = reinterpret_cast<double *>(h->ws + L.off_cov);
+    h->stats = reinterpret_cast<mcl_stats *>(h->ws + L.off_stats);
+    h->prep = reinterpret_cast<PrepOut *>(h->ws + L.off_prep);
+    h->tab = reinterpret_cast<double4 *>(h->ws + L.off_tab);
+    h->lm = reinterpret_cast<double *>(h->ws + L.off_lm);
+    h->z = reinterpret_cast<double *>(h->ws + L.off_z);
+    h->ofs = reinterpret_cast<double *>(h->ws + L.off_ofs);
+    h->pose = reinterpret_cast<double *>(h->ws + L.off_pose);
+    h->total = reinterpret_cast<unsigned long long *>(h->ws + L.off_total);
+    h->delta = 1.0 / static_cast<double>(cfg->n_global);
+    // the pair kernels stage up to 4096 landmarks (128 KiB) in dynamic shared memory
+    cudaFuncSetAttribute(k_step<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * static_cast<int>(sizeof(double4)));
+    cudaError_t e = cudaMemset(h->ws + L.off_tickets, 0, static_cast<size_t>(L.T) * 4 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_stats, 0, static_cast<size_t>(L.T) * sizeof(mcl_stats));
+    if (e != cudaSuccess) {
+        if (h->owns_ws) cudaFree(h->ws);
+        delete h;
+        return fail(nullptr, MCL_ERR_CUDA, "initialising the workspace failed");
+    }
+    *out = h;
+    return MCL_OK;
+}
+
+int mcl_destroy(mcl_filter *h) {
+    if (h == nullptr) return MCL_OK;
+    cudaSetDevice(h->cfg.device);
+    for (cudaEvent_t &e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->owns_ws && h->ws) cudaFree(h->ws);
+    delete h;
+    return MCL_OK;
+}
+
+int64_t mcl_stride(const mcl_filter *h) { return h ? h->lay.ld : 0; }
+
+int mcl_set_landmarks(mcl_filter *h, const double *lm_xy_host, int32_t n_landmarks, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (lm_xy_host == nullptr || n_landmarks < 1 || n_landmarks > h->lay.Lmax)
+        return fail(h, MCL_ERR_ARG, "landmark table is NULL or larger than max_landmarks");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    MCL_CUDA(h, cudaMemcpyAsync(h->lm, lm_xy_host, static_cast<size_t>(n_landmarks) * 2 * sizeof(double),
+                                cudaMemcpyHostToDevice, S(stream)));
+    MCL_CUDA(h, cudaStreamSynchronize(S(stream)));  // the host array may be a temporary
+    h->L = n_landmarks;
+    return MCL_OK;
+}
+
+int mcl_init_particles(mcl_filter *h, const double *pose_host, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (pose_host == nullptr) return fail(h, MCL_ERR_ARG, "pose_host is NULL");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    cudaStream_t st = S(stream);
+    const Layout &L = h->lay;
+    MCL_CUDA(h, cudaMemcpyAsync(h->pose, pose_host, static_cast<size_t>(L.T) * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    MCL_CUDA(h, cudaStreamSynchronize(st));
+    const float lw0 = static_cast<float>(-std::log(static_cast<double>(h->cfg.n_global)));
+    const int bx = static_cast<int>(std::min<long long>((L.ld + 255) / 256, 2048));
+    h->cur = 0;
+    k_init<<<dim3(bx, L.T), 256, 0, st>>>(h->state[0], h->pose, L.n, L.ld, lw0);
+    MCL_LAUNCH_CHECK(h, "k_init");
+    k_init<<<dim3(bx, L.T), 256, 0, st>>>(h->state[1], h->pose, L.n, L.ld, lw0);
+    MCL_LAUNCH_CHECK(h, "k_init");
+    k_init_stats<<<(L.T + 127) / 128, 128, 0, st>>>(h->stats, h->pose, static_cast<double>(h->cfg.n_global), L.T);
+    MCL_LAUNCH_CHECK(h, "k_init_stats");
+    h->have_particles = true;
+    h->step = 0;
+    return MCL_OK;
+}
+
+int mcl_set_particles(mcl_filter *h, const float *x, const float *y, const float *yaw, const float *logw, int on_device,
+                      void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (x == nullptr || y == nullptr || yaw == nullptr) return fail(h, MCL_ERR_ARG, "x, y and yaw must not be NULL");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    cudaStream_t st = S(stream);
+    const Layout &L = h->lay;
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    StateView &s = h->state[h->cur];
+    const float *src[4] = {x, y, yaw, logw};
+    float *dst[4] = {s.x, s.y, s.th, s.lw};
+    for (int a = 0; a < 4; ++a) {
+        if (src[a] == nullptr) continue;
+        rc = copy2d(h, dst[a], L.ld, src[a], L.n, sizeof(float), L.n, L.T, kind, st);
+        if (rc != MCL_OK) return rc;
+    }
+    if (logw == nullptr) {
+        const float lw0 = static_cast<float>(-std::log(static_cast<double>(h->cfg.n_global)));
+        const int bx = static_cast<int>(std::min<long long>((L.ld + 255) / 256, 2048));
+        k_fill<<<dim3(bx, L.T), 256, 0, st>>>(s.lw, L.ld, lw0);
+        MCL_LAUNCH_CHECK(h, "k_fill");
+    }
+    if (!on_device) MCL_CUDA(h, cudaStreamSynchronize(st));  // pageable host sources may go away
+    h->have_particles = true;
+    h->stats_from_particle0 = true;
+    return reduce_only_pass(h, st);
+}
+
+int mcl_get_particles(mcl_filter *h, float *x, float *y, float *yaw, float *logw, int on_device, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "particles are not initialised");
+    cudaStream_t st = S(stream);
+    const Layout &L = h->lay;
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const StateView &s = h->state[h->cur];
+    float *dst[4] = {x, y, yaw, logw};
+    const float *src[4] = {s.x, s.y, s.th, s.lw};
+    for (int a = 0; a < 4; ++a) {
+        if (dst[a] == nullptr) continue;
+        rc = copy2d(h, dst[a], L.n, src[a], L.ld, sizeof(float), L.n, L.T, kind, st);
+        if (rc != MCL_OK) return rc;
+    }
+    if (!on_device) MCL_CUDA(h, cudaStreamSynchronize(st));
+    return MCL_OK;
+}
+
+int mcl_resample(mcl_filter *h, const double *ofs_host, uint32_t flags, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "particles are not initialised");
+    if (h->cfg.n_global != h->cfg.n_particles)
+        return fail(h, MCL_ERR_STATE, "a particle-sharded filter resamples through mcl_shard_total/mcl_shard_expand");
+    if (ofs_host == nullptr && !(flags & MCL_PHILOX_NOISE))
+        return fail(h, MCL_ERR_ARG, "ofs_host is NULL and MCL_PHILOX_NOISE is not set");
+    cudaStream_t st = S(stream);
+    rc = stage_inputs(h, nullptr, ofs_host, st);
+    if (rc != MCL_OK) return rc;
+    rc = launch_prep(h, nullptr, ofs_host ? h->ofs : nullptr, flags & ~MCL_NO_RESAMPLE, true, st);
+    if (rc != MCL_OK) return rc;
+    ScanParams sp;
+    fill_scan(h, sp);
+    sp.mode = kScanAncestors;
+    rc = launch_scan(h, sp, st);
+    if (rc != MCL_OK) return rc;
+    GatherParams g{};
+    g.in = h->state[h->cur];
+    g.out = h->state[h->cur ^ 1];
+    g.anc = h->anc;
+    g.prep = h->prep;
+    g.stats = h->stats;
+    g.n = h->lay.n;
+    g.ld = h->lay.ld;
+    g.n_global = static_cast<double>(h->cfg.n_global);
+    const int bx = static_cast<int>(std::min<long long>((h->lay.n + 255) / 256, 148 * 16));
+    k_gather<<<dim3(bx, h->lay.T), 256, 0, st>>>(g);
+    MCL_LAUNCH_CHECK(h, "k_gather");
+    h->cur ^= 1;
+    return MCL_OK;
+}
+
+int mcl_predict_weight(mcl_filter *h, const double *z_host, const float *noise_dev, uint32_t flags, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (z_host == nullptr) return fail(h, MCL_ERR_ARG, "z_host is NULL");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    cudaStream_t st = S(stream);
+    rc = stage_inputs(h, z_host, nullptr, st);
+    if (rc != MCL_OK) return rc;
+    return step_impl(h, h->z, nullptr, noise_dev, (flags | MCL_NO_RESAMPLE) & ~MCL_FORCE_RESAMPLE, st);
+}
+
+int mcl_step(mcl_filter *h, const double *z_host, const double *ofs_host, const float *noise_dev, uint32_t flags,
+             void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (z_host == nullptr) return fail(h, MCL_ERR_ARG, "z_host is NULL");
+    if (ofs_host == nullptr && !(flags & (MCL_PHILOX_NOISE | MCL_NO_RESAMPLE)))
+        return fail(h, MCL_ERR_ARG, "ofs_host is NULL and neither MCL_PHILOX_NOISE nor MCL_NO_RESAMPLE is set");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    cudaStream_t st = S(stream);
+    rc = stage_inputs(h, z_host, ofs_host, st);
+    if (rc != MCL_OK) return rc;
+    return step_impl(h, h->z, ofs_host ? h->ofs : nullptr, noise_dev, flags, st);
+}
+
+int mcl_step_dev(mcl_filter *h, const double *z_dev, const double *ofs_dev, const float *noise_dev, uint32_t flags,
+                 void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (z_dev == nullptr) return fail(h, MCL_ERR_ARG, "z_dev is NULL");
+    if (ofs_dev == nullptr && !(flags & (MCL_PHILOX_NOISE | MCL_NO_RESAMPLE)))
+        return fail(h, MCL_ERR_ARG, "ofs_dev is NULL and neither MCL_PHILOX_NOISE nor MCL_NO_RESAMPLE is set");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    return step_impl(h, z_dev, ofs_dev, noise_dev, flags, S(stream));
+}
+
+int mcl_pose_moments(mcl_filter *h, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "particles are not initialised");
+    CovParams p{};
+    p.in = h->state[h->cur];
+    p.stats = h->stats;
+    p.partials = h->cov_partials;
+    p.tickets = h->tickets;
+    p.n = h->lay.n;
+    p.ld = h->lay.ld;
+    p.bpt = h->lay.cov_bpt;
+    k_cov<<<dim3(h->lay.cov_bpt, h->lay.T), 256, 0, S(stream)>>>(p);
+    MCL_LAUNCH_CHECK(h, "k_cov");
+    return MCL_OK;
+}
+
+int mcl_get_stats(mcl_filter *h, mcl_stats *out_host, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (out_host == nullptr) return fail(h, MCL_ERR_ARG, "out_host is NULL");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    MCL_CUDA(h, cudaMemcpyAsync(out_host, h->stats, static_cast<size_t>(h->lay.T) * sizeof(mcl_stats), cudaMemcpyDeviceToHost,
+                                S(stream)));
+    MCL_CUDA(h, cudaStreamSynchronize(S(stream)));
+    return MCL_OK;
+}
+
+int mcl_stats_dev(mcl_filter *h, const mcl_stats **out_dev) {
+    if (h == nullptr || out_dev == nullptr) return MCL_ERR_ARG;
+    *out_dev = h->stats;
+    return MCL_OK;
+}
+
+static int export_weights(mcl_filter *h, double *w_host, uint64_t *q_host, void *stream) {
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "particles are not initialised");
+    cudaStream_t st = S(stream);
+    const Layout &L = h->lay;
+    // the idle state buffer (16 B per particle) is the staging area for the 8 B per particle export
+    void *stage = h->state[h->cur ^ 1].x;
+    const int bx = static_cast<int>(std::min<long long>((L.n + 255) / 256, 148 * 16));
+    k_export_weights<<<dim3(bx, L.T), 256, 0, st>>>(h->state[h->cur].lw, h->stats, w_host ? static_cast<double *>(stage) : nullptr,
+                                                     q_host ? static_cast<unsigned long long *>(stage) : nullptr, L.n, L.ld, 0, 0.0);
+    MCL_LAUNCH_CHECK(h, "k_export_weights");
+    void *dst = w_host ? static_cast<void *>(w_host) : static_cast<void *>(q_host);
+    MCL_CUDA(h, cudaMemcpyAsync(dst, stage, static_cast<size_t>(L.T) * L.n * 8, cudaMemcpyDeviceToHost, st));
+    MCL_CUDA(h, cudaStreamSynchronize(st));
+    return MCL_OK;
+}
+
+int mcl_get_weights(mcl_filter *h, double *w_host, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (w_host == nullptr) return fail(h, MCL_ERR_ARG, "w_host is NULL");
+    return export_weights(h, w_host, nullptr, stream);
+}
+
+int mcl_get_qweights(mcl_filter *h, uint64_t *q_host, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (q_host == nullptr) return fail(h, MCL_ERR_ARG, "q_host is NULL");
+    return export_weights(h, nullptr, q_host, stream);
+}
+
+int mcl_get_ancestors(mcl_filter *h, uint32_t *anc_host, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (anc_host == nullptr) return fail(h, MCL_ERR_ARG, "anc_host is NULL");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    const Layout &L = h->lay;
+    rc = copy2d(h, anc_host, L.n, h->anc, L.ld, sizeof(uint32_t), L.n, L.T, cudaMemcpyDeviceToHost, S(stream));
+    if (rc != MCL_OK) return rc;
+    MCL_CUDA(h, cudaStreamSynchronize(S(stream)));
+    return MCL_OK;
+}
+
+int mcl_profile(mcl_filter *h, int enable) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    if (enable && h->ev[0] == nullptr)
+        for (cudaEvent_t &e : h->ev) MCL_CUDA(h, cudaEventCreate(&e));
+    h->profiling = enable != 0;
+    return MCL_OK;
+}
+
+int mcl_profile_read(mcl_filter *h, double *ms3_host) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (ms3_host == nullptr) return fail(h, MCL_ERR_ARG, "ms3_host is NULL");
+    if (!h->profiling || h->ev[0] == nullptr) return fail(h, MCL_ERR_STATE, "mcl_profile(h, 1) has not been called");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    MCL_CUDA(h, cudaEventSynchronize(h->ev[3]));
+    for (int k = 0; k < 3; ++k) {
+        float ms = 0.f;
+        MCL_CUDA(h, cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1]));
+        ms3_host[k] = ms;
+    }
+    return MCL_OK;
+}
+
+uint64_t mcl_launch_count(const mcl_filter *h) { return h ? h->launches : 0; }
+
+// ---- particle-sharded single filter -----------------------------------------------------------
+int mcl_shard_total(mcl_filter *h, double global_log_norm, uint64_t *total_dev, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (total_dev == nullptr) return fail(h, MCL_ERR_ARG, "total_dev is NULL");
+    if (h->lay.T != 1) return fail(h, MCL_ERR_STATE, "sharding needs n_trials == 1");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    cudaStream_t st = S(stream);
+    k_reset_scan<<<(h->lay.tpt + 255) / 256, 256, 0, st>>>(h->desc, h->tickets, h->lay.tpt);
+    MCL_LAUNCH_CHECK(h, "k_reset_scan");
+    ScanParams sp;
+    fill_scan(h, sp);
+    sp.mode = kScanTotals;
+    sp.total = reinterpret_cast<unsigned long long *>(total_dev);
+    sp.use_override = 1;
+    sp.log_norm_override = global_log_norm;
+    sp.ofs_override = 0.0;
+    return launch_scan(h, sp, st);
+}
+
+int mcl_shard_expand(mcl_filter *h, double global_log_norm, uint64_t k_offset, double ofs, float *out_x_dev, float *out_y_dev,
+                     float *out_yaw_dev, int64_t cap, int64_t *first_slot, int64_t *n_slots, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (out_x_dev == nullptr || out_y_dev == nullptr || out_yaw_dev == nullptr || first_slot == nullptr || n_slots == nullptr || cap < 0)
+        return fail(h, MCL_ERR_ARG, "NULL output or negative capacity");
+    if (h->lay.T != 1) return fail(h, MCL_ERR_STATE, "sharding needs n_trials == 1");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    cudaStream_t st = S(stream);
+    const long long NG = h->cfg.n_global;
+    const long long s0 = host_count_le(k_offset, h->delta, ofs, NG);
+    k_reset_scan<<<(h->lay.tpt + 255) / 256, 256, 0, st>>>(h->desc, h->tickets, h->lay.tpt);
+    MCL_LAUNCH_CHECK(h, "k_reset_scan");
+    ScanParams sp;
+    fill_scan(h, sp);
+    sp.mode = kScanExpand;
+    sp.total = h->total;
+    sp.use_override = 1;
+    sp.log_norm_override = global_log_norm;
+    sp.ofs_override = ofs;
+    sp.k_offset = k_offset;
+    sp.slot_first = s0;
+    sp.anc_cap = cap;
+    sp.src = h->state[h->cur];
+    sp.ox = out_x_dev;
+    sp.oy = out_y_dev;
+    sp.oth = out_yaw_dev;
+    rc = launch_scan(h, sp, st);
+    if (rc != MCL_OK) return rc;
+    unsigned long long total = 0;
+    MCL_CUDA(h, cudaMemcpyAsync(&total, h->total, sizeof total, cudaMemcpyDeviceToHost, st));
+    MCL_CUDA(h, cudaStreamSynchronize(st));
+    const bool last = (h->cfg.slot_base + h->cfg.n_particles == NG);
+    const long long s1 = last ? NG : host_count_le(k_offset + total, h->delta, ofs, NG);
+    *first_slot = s0;
+    *n_slots = s1 - s0;
+    if (s1 - s0 > cap) return fail(h, MCL_ERR_NOMEM, "mcl_shard_expand: this shard fills more slots than `cap`");
+    return MCL_OK;
+}
+
+int mcl_shard_set_global(mcl_filter *h, const mcl_stats *merged_host, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (merged_host == nullptr) return fail(h, MCL_ERR_ARG, "merged_host is NULL");
+    if (h->lay.T != 1) return fail(h, MCL_ERR_STATE, "sharding needs n_trials == 1");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    MCL_CUDA(h, cudaMemcpyAsync(h->stats, merged_host, sizeof(mcl_stats), cudaMemcpyHostToDevice, S(stream)));
+    MCL_CUDA(h, cudaStreamSynchronize(S(stream)));
+    h->stats_from_particle0 = false;
+    return MCL_OK;
+}
+
+}  // extern "C"

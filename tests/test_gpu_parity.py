@@ -1,0 +1,427 @@
+"""GPU parity tests: the CUDA path (through the ctypes C ABI) against the CPU oracle.
+
+Everything here needs a B200 (``-m gpu``).  The oracle (oracle/pf_oracle.py) is only the checker.
+Tolerances: resampling indices bit-exact; poses / weights / covariances 1e-5 relative (fp32 state
+against the fp64 oracle, BASELINE.json north_star).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def mcl():
+    import slam_robot_simu_b200 as m
+
+    return m
+
+
+def _golden(golden_dir, seed=0):
+    return np.load(os.path.join(golden_dir, f"pf_seed{seed}.npz"))
+
+
+def _logw32(pw):
+    with np.errstate(divide="ignore"):
+        return np.log(np.asarray(pw, dtype=np.float64).reshape(-1)).astype(np.float32)
+
+
+def _weights_from_logw32(lw32):
+    w = np.exp(lw32.astype(np.float64))
+    return w / w.sum()
+
+
+def _assert_weights_close(got, want, rtol=RTOL):
+    """1e-5 relative on every weight that carries mass; an absolute floor for the e^-100 tails
+    (their fp32 log-weight has an ulp of ~1e-5, their mass is below 1e-40 of the total)."""
+    got, want = np.asarray(got).reshape(-1), np.asarray(want).reshape(-1)
+    big = want > want.max() * 1e-12
+    np.testing.assert_allclose(got[big], want[big], rtol=rtol)
+    np.testing.assert_allclose(got[~big], want[~big], rtol=1e-3, atol=want.max() * 1e-40)
+
+
+def _oracle_predict_weight(px32, w_prev, v32, z_l, P, sx=0.3, sy=0.3):
+    """fp64 oracle on the fp32 inputs the GPU saw; likelihood evaluated at the GPU's stored pose."""
+    px_pred = O.predict(px32.astype(np.float64), v32.astype(np.float64), P)
+    return px_pred
+
+
+@pytest.mark.parametrize("likelihood", ["pair", "moment"])
+@pytest.mark.parametrize("seed,k", [(0, 0), (0, 1), (0, 5), (0, 7), (0, 100), (0, 359), (1, 39), (2, 39)])
+def test_predict_weight_stage_parity(mcl, golden_dir, likelihood, seed, k):
+    """__predict + __likelihood + __normalize + MAP (particle_filter.py:156-198, :115-117) on the
+    reference's own arrays at the stored steps (no resampling at these steps)."""
+    g = _golden(golden_dir, seed)
+    if g["resampled"][k]:
+        pytest.skip("resampling step: covered by test_full_step_parity")
+    P = O.PFParams(100)
+    px0 = g[f"s{k}_px_before"].astype(np.float32)
+    lw0 = _logw32(g[f"s{k}_pw_before"])
+    v32 = g[f"s{k}_v"].astype(np.float32)
+    z_l = g["z_l"][k]
+    f = mcl.Filter(n_particles=1000, landmarks=P.LM, likelihood=likelihood)
+    f.set_particles(px0[0], px0[1], px0[2], lw0)
+    f.predict_weight(z_l[None], noise=v32[:, None, :])
+    x, y, th, lw = f.get_particles()
+    got_px = np.stack([x[0], y[0], th[0]]).astype(np.float64)
+    # poses: fp64 oracle on the same fp32 inputs
+    want_px = O.predict(px0.astype(np.float64), v32.astype(np.float64), P)
+    np.testing.assert_allclose(got_px, want_px, rtol=RTOL, atol=1e-6)
+    # and against the reference's own fp64 arrays (inputs rounded to fp32: ~1e-6 absolute)
+    np.testing.assert_allclose(got_px, g[f"s{k}_px"], rtol=RTOL, atol=5e-6)
+    # weights: oracle likelihood at the stored fp32 poses times the stored previous weights
+    w_prev = _weights_from_logw32(lw0)
+    ll = O.loglik_cartesian(got_px, z_l, P.LM, 0.3, 0.3)
+    with np.errstate(divide="ignore"):
+        want_w, _ = O.update_weights_log(np.log(w_prev), ll)
+    got_w = f.weights()[0]
+    _assert_weights_close(got_w, want_w)
+    assert abs(got_w.sum() - 1.0) < 1e-6
+    st = f.stats()[0]
+    assert st.ess == pytest.approx(O.ess(want_w), rel=RTOL)
+    # the reference's own weights (fp64 poses): looser, fp32 pose rounding moves log-weights by ~1e-4
+    _assert_weights_close(got_w, g[f"s{k}_pw"], rtol=2e-3)
+    # MAP estimate: arg-max of the oracle weights unless the top two are closer than the tolerance
+    mi = int(np.argmax(want_w))
+    assert st.max_idx == mi or want_w[st.max_idx] >= want_w[mi] * (1 - RTOL)
+    assert st.max_idx == int(g["max_idx"][k])
+    assert st.max_weight == pytest.approx(want_w[st.max_idx], rel=RTOL)
+    np.testing.assert_allclose(np.array(st.est[:]), got_px[:, st.max_idx], rtol=0, atol=0)
+    assert st.resampled == 0
+
+
+@pytest.mark.parametrize("seed,k", [(0, 6), (0, 10), (1, 6)])
+def test_full_step_parity_with_resampling(mcl, golden_dir, seed, k):
+    """main_pf (:86-119) at steps where the reference resampled: indices bit-exact on the GPU's own
+    quantised weights, and identical to the reference's fp64 walk except at razor-edge thresholds."""
+    g = _golden(golden_dir, seed)
+    assert g["resampled"][k]
+    P = O.PFParams(100)
+    px0 = g[f"s{k}_px_before"].astype(np.float32)
+    lw0 = _logw32(g[f"s{k}_pw_before"])
+    v32 = g[f"s{k}_v"].astype(np.float32)
+    ofs = float(g["ofs"][k])
+    z_l = g["z_l"][k]
+    f = mcl.Filter(n_particles=1000, landmarks=P.LM)
+    f.set_particles(px0[0], px0[1], px0[2], lw0)
+    st0 = f.stats()[0]
+    assert st0.ess < P.ESS_TH  # the gate of :211 fires on the device too
+    q = f.qweights()[0]
+    f.step(z_l[None], ofs=ofs, noise=v32[:, None, :])  # ESS-gated, not forced
+    anc = f.ancestors()[0].astype(np.int64)
+    st = f.stats()[0]
+    assert st.resampled == 1
+    # bit-exact against the literal reference walk fed the same (quantised) weights
+    wq = O.dequantize_weights(q)
+    np.testing.assert_array_equal(anc, O.resample_indices_literal(wq, ofs))
+    # against the reference's walk on its un-quantised fp64 weights
+    a_ref = O.resample_indices(g[f"s{k}_pw_before"], ofs, clamp=False)
+    assert (anc != a_ref).mean() <= 0.003
+    # poses after gather + predict
+    x, y, th, _ = f.get_particles()
+    got_px = np.stack([x[0], y[0], th[0]]).astype(np.float64)
+    want_px = O.predict(px0.astype(np.float64)[:, anc], v32.astype(np.float64), P)
+    np.testing.assert_allclose(got_px, want_px, rtol=RTOL, atol=1e-6)
+    same = anc == a_ref
+    np.testing.assert_allclose(got_px[:, same], g[f"s{k}_px"][:, same], rtol=RTOL, atol=5e-6)
+    # weights restart from 1/NP (:222)
+    ll = O.loglik_cartesian(got_px, z_l, P.LM, 0.3, 0.3)
+    want_w, _ = O.update_weights_log(np.full(1000, -np.log(1000.0)), ll)
+    _assert_weights_close(f.weights()[0], want_w)
+    assert st.max_idx == int(np.argmax(want_w))
+
+
+@pytest.mark.parametrize("n", [1000, 4097, 16384, 1 << 20, 1000003])
+@pytest.mark.parametrize("kind", ["random", "peaked", "degenerate"])
+def test_resampling_indices_bit_exact(mcl, n, kind):
+    """__resampling (:200-224): ancestors equal the reference walk on the same weights, bit for bit."""
+    rng = np.random.RandomState(n % 9973 + len(kind))
+    if kind == "random":
+        lw = rng.normal(0, 1.5, n)
+    elif kind == "peaked":
+        lw = -0.5 * ((np.arange(n) - 0.37 * n) / (0.001 * n + 3)) ** 2 + rng.normal(0, 0.1, n)
+    else:
+        lw = np.full(n, -60.0)
+        lw[rng.randint(0, n, 7)] = rng.normal(0, 1, 7)
+    lw = (lw - lw.max()).astype(np.float32)
+    pos = rng.normal(0, 1, (3, n)).astype(np.float32)
+    f = mcl.Filter(n_particles=n, landmarks=[[0.0, 0.0]])
+    f.set_particles(pos[0], pos[1], pos[2], lw)
+    q = f.qweights()[0]
+    w = f.weights()[0]
+    want_w = _weights_from_logw32(lw)
+    _assert_weights_close(w, want_w)
+    assert np.array_equal(q, O.quantize_weights(w))  # the scan sees exactly rint(w * 2^52)
+    ofs = rng.rand() * (1 / n)
+    f.resample(ofs=ofs, force=True)
+    anc = f.ancestors()[0].astype(np.int64)
+    want = O.resample_indices(O.dequantize_weights(q), ofs, clamp=True)
+    np.testing.assert_array_equal(anc, want)
+    if n <= 4097:
+        wq = O.dequantize_weights(q)
+        try:
+            lit = O.resample_indices_literal(wq, ofs)
+            np.testing.assert_array_equal(anc, lit)
+        except IndexError:
+            pass  # the reference walk ran off the end of pw_cum; ours clamps
+    # size-independent properties: monotone ancestors, offspring counts within 1 of N w
+    assert np.all(np.diff(anc) >= 0)
+    counts = np.bincount(anc, minlength=n)
+    assert np.all(np.abs(counts - n * w) < 1.0 + 1e-6 * n * w + 1e-3)
+    # the gather moved the poses and reset the weights to 1/NP (:216-222)
+    x, y, th, lw1 = f.get_particles()
+    np.testing.assert_array_equal(x[0], pos[0][anc])
+    np.testing.assert_array_equal(th[0], pos[2][anc])
+    np.testing.assert_allclose(lw1[0], -np.log(float(n)), rtol=1e-6)
+    assert f.stats()[0].ess == pytest.approx(n)
+
+
+def test_ess_gate_skips_resampling(mcl):
+    n = 2048
+    rng = np.random.RandomState(5)
+    pos = rng.normal(0, 1, (3, n)).astype(np.float32)
+    lw = rng.normal(0, 0.1, n).astype(np.float32)  # ESS ~ n: far above n/100
+    f = mcl.Filter(n_particles=n, landmarks=[[0.0, 0.0]])
+    f.set_particles(pos[0], pos[1], pos[2], lw)
+    f.resample(ofs=0.3 / n)
+    x, y, th, lw1 = f.get_particles()
+    np.testing.assert_array_equal(x[0], pos[0])
+    np.testing.assert_array_equal(lw1[0], lw)
+
+
+def test_weighted_mean_and_covariance(mcl, golden_dir):
+    """Extension a-14: moments that feed ErrorEllipse.calc_error_ellipse (mylib/error_ellipse.py:39-55)."""
+    g = _golden(golden_dir, 0)
+    P = O.PFParams(100)
+    for k in (5, 100, 359):
+        px = g[f"s{k}_px"].astype(np.float32)
+        lw = _logw32(g[f"s{k}_pw"])
+        f = mcl.Filter(n_particles=1000, landmarks=P.LM)
+        f.set_particles(px[0], px[1], px[2], lw)
+        w = _weights_from_logw32(lw)
+        mean, cov = O.weighted_moments(px.astype(np.float64), w)
+        st = f.stats()[0]
+        np.testing.assert_allclose(np.array(st.mean[:]), mean, rtol=RTOL, atol=1e-7)
+        got = np.array(st.cov[:]).reshape(3, 3)
+        scale = np.sqrt(np.outer(np.diag(cov), np.diag(cov)))
+        np.testing.assert_allclose(got, cov, rtol=RTOL, atol=RTOL * scale.min())
+        f.pose_moments()  # exact two-pass variant
+        got2 = np.array(f.stats()[0].cov[:]).reshape(3, 3)
+        np.testing.assert_allclose(got2, cov, rtol=RTOL, atol=1e-6 * scale.min())
+
+
+def test_yaw_seam_mean(mcl):
+    """Particles straddling +-pi: circular mean and wrapped residuals (mylib/limit.py:11-26)."""
+    n = 4096
+    rng = np.random.RandomState(11)
+    th = O.limit_angle_vec(np.pi + rng.normal(0, 0.05, n)).astype(np.float32)
+    x = rng.normal(2, 0.1, n).astype(np.float32)
+    y = rng.normal(-3, 0.2, n).astype(np.float32)
+    lw = rng.normal(0, 0.5, n).astype(np.float32)
+    f = mcl.Filter(n_particles=n, landmarks=[[0.0, 0.0]])
+    f.set_particles(x, y, th, lw)
+    mean, cov = O.weighted_moments(np.stack([x, y, th]).astype(np.float64), _weights_from_logw32(lw))
+    st = f.stats()[0]
+    assert abs(O.limit_angle(st.mean[2] - mean[2])) < 1e-6
+    np.testing.assert_allclose(np.array(st.cov[:]).reshape(3, 3), cov, rtol=1e-4, atol=1e-7)
+
+
+def test_dropin_seeded_trajectory(mcl, golden_dir):
+    """ParticleFilter(100).main_pf() under np.random.seed(0): same RNG consumption as the reference
+    (x_true and the resampling schedule depend on it), estimates tracking the reference run."""
+    g = _golden(golden_dir, 0)
+    np.random.seed(0)
+    pf = mcl.ParticleFilter(100)
+    n_steps = 120
+    resampled, err_gpu, err_ref = [], [], []
+    for k in range(n_steps):
+        LM, x_true, x_est, px, Q, max_idx, max_val = pf.main_pf()
+        assert LM.shape == (5, 2) and x_true.shape == (3, 1) and x_est.shape == (3, 1)
+        assert px.shape == (3, 1000) and px.dtype == np.float64 and Q.shape == (3, 3)
+        np.testing.assert_allclose(x_true[:, 0], g["x_true"][k], atol=1e-12)
+        resampled.append(pf.last_stats.resampled)
+        if k < 6:  # before the first resampling fp32 rounding has not yet changed any decision
+            assert max_idx == g["max_idx"][k]
+            assert max_val == pytest.approx(g["max_val"][k], rel=2e-3)
+            np.testing.assert_allclose(x_est[:, 0], g["x_est"][k], atol=1e-5)
+            np.testing.assert_allclose(px.mean(axis=1), g["px_mean"][k], atol=1e-5)
+            assert pf.last_stats.ess == pytest.approx(g["ess_after"][k], rel=2e-3)
+        err_gpu.append(np.hypot(*(x_est[:2, 0] - x_true[:2, 0])))
+        err_ref.append(np.hypot(*(g["x_est"][k][:2] - g["x_true"][k][:2])))
+    # identical schedule: every draw of np.random was consumed in the reference's order
+    assert resampled == [int(b) for b in g["resampled"][:n_steps]]
+    assert np.mean(err_gpu) < 1.5 * np.mean(err_ref) + 0.05
+
+
+def test_trials_batch_equals_single_filters(mcl):
+    """n_trials independent filters in one handle == the same filters one by one (bit-exact)."""
+    T, n, Lm = 5, 3000, 7
+    rng = np.random.RandomState(2)
+    lm = rng.uniform(-10, 10, (Lm, 2))
+    pos = rng.normal(0, 0.3, (3, T, n)).astype(np.float32) + np.array([3.0, 1.0, 0.5], dtype=np.float32)[:, None, None]
+    lw = rng.normal(0, 1.0, (T, n)).astype(np.float32)
+    noise = (rng.normal(0, 1, (3, T, n)) * np.array([0.03, 0.03, 0.035])[:, None, None]).astype(np.float32)
+    z = rng.normal(0, 3, (T, Lm, 2))
+    ofs = rng.rand(T) / n
+    fb = mcl.Filter(n_particles=n, n_trials=T, landmarks=lm)
+    fb.set_particles(pos[0], pos[1], pos[2], lw)
+    fb.step(z, ofs=ofs, noise=noise, force_resample=True)
+    xb, yb, tb, lb = fb.get_particles()
+    ancb = fb.ancestors()
+    sb = fb.stats()
+    for t in range(T):
+        f1 = mcl.Filter(n_particles=n, landmarks=lm)
+        f1.set_particles(pos[0, t], pos[1, t], pos[2, t], lw[t])
+        f1.step(z[t][None], ofs=ofs[t], noise=noise[:, t:t + 1], force_resample=True)
+        x1, y1, t1, l1 = f1.get_particles()
+        np.testing.assert_array_equal(ancb[t], f1.ancestors()[0])
+        np.testing.assert_array_equal(xb[t], x1[0])
+        np.testing.assert_array_equal(tb[t], t1[0])
+        np.testing.assert_array_equal(lb[t], l1[0])
+        s1 = f1.stats()[0]
+        assert sb[t].max_idx == s1.max_idx and sb[t].ess == s1.ess and sb[t].log_norm == s1.log_norm
+
+
+@pytest.mark.parametrize("likelihood", ["pair", "moment"])
+def test_c1_size_step_parity(mcl, likelihood):
+    """C1 shape (2^20 particles x 16 landmarks), forced resampling, injected noise: full step vs oracle."""
+    n, Lm = 1 << 20, 16
+    rng = np.random.RandomState(1234)
+    lm = np.random.default_rng(1234).uniform(-20, 20, (Lm, 2))
+    P = O.PFParams(100, n_particles=n, landmarks=lm)
+    truth = np.array([[10.0], [0.0], [np.pi / 2]])
+    pos = (truth + rng.normal(0, 1, (3, n)) * np.array([[0.08], [0.08], [0.03]])).astype(np.float32)
+    z = O.world2robot(truth, lm) + rng.normal(0, 0.3, (Lm, 2))
+    # weights of a previous step
+    ll0 = O.loglik_cartesian(pos.astype(np.float64), z, lm, 0.3, 0.3)
+    lw = (ll0 - ll0.max()).astype(np.float32)
+    noise = (rng.normal(0, 1, (3, n)) * np.sqrt(np.diag(P.Q))[:, None]).astype(np.float32)
+    truth1 = O.f_motion(truth, P)
+    z1 = O.world2robot(truth1, lm) + rng.normal(0, 0.3, (Lm, 2))
+    ofs = rng.rand() / n
+    f = mcl.Filter(n_particles=n, landmarks=lm, likelihood=likelihood)
+    f.set_particles(pos[0], pos[1], pos[2], lw)
+    q = f.qweights()[0]
+    f.step(z1[None], ofs=ofs, noise=noise[:, None, :], force_resample=True)
+    anc = f.ancestors()[0].astype(np.int64)
+    np.testing.assert_array_equal(anc, O.resample_indices(O.dequantize_weights(q), ofs))
+    x, y, th, _ = f.get_particles()
+    got_px = np.stack([x[0], y[0], th[0]]).astype(np.float64)
+    want_px = O.predict(pos.astype(np.float64)[:, anc], noise.astype(np.float64), P)
+    np.testing.assert_allclose(got_px, want_px, rtol=RTOL, atol=1e-6)
+    ll = O.loglik_cartesian(got_px, z1, lm, 0.3, 0.3)
+    want_w, logz = O.update_weights_log(np.full(n, -np.log(float(n))), ll)
+    got_w = f.weights()[0]
+    _assert_weights_close(got_w, want_w)
+    st = f.stats()[0]
+    assert st.ess == pytest.approx(O.ess(want_w), rel=RTOL)
+    mi = int(np.argmax(want_w))
+    assert st.max_idx == mi or want_w[st.max_idx] >= want_w[mi] * (1 - RTOL)
+    mean, cov = O.weighted_moments(got_px, want_w)
+    np.testing.assert_allclose(np.array(st.mean[:]), mean, rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(np.array(st.cov[:]).reshape(3, 3), cov, rtol=1e-4, atol=1e-9)
+
+
+def test_likelihood_64_and_1024_landmarks(mcl):
+    """L = 64 (C3) and L = 1024 (C4): pair kernel == moment kernel == log-domain oracle."""
+    rng = np.random.RandomState(99)
+    for Lm, n in ((64, 1 << 16), (1024, 1 << 13)):
+        lm = rng.uniform(-20, 20, (Lm, 2))
+        truth = np.array([[3.0], [-2.0], [0.7]])
+        spread = 0.3 / np.sqrt(Lm)
+        pos = (truth + rng.normal(0, 1, (3, n)) * np.array([[spread], [spread], [spread / 8]])).astype(np.float32)
+        z = O.world2robot(truth, lm) + rng.normal(0, 0.3, (Lm, 2))
+        P = O.PFParams(100, n_particles=n, landmarks=lm)
+        noise = np.zeros((3, 1, n), dtype=np.float32)
+        res = {}
+        for lik in ("pair", "moment"):
+            f = mcl.Filter(n_particles=n, landmarks=lm, likelihood=lik, max_landmarks=Lm)
+            f.set_particles(pos[0], pos[1], pos[2], None)
+            f.predict_weight(z[None], noise=noise)
+            x, y, th, _ = f.get_particles()
+            got_px = np.stack([x[0], y[0], th[0]]).astype(np.float64)
+            res[lik] = f.weights()[0]
+        ll = O.loglik_cartesian(got_px, z, lm, 0.3, 0.3)
+        want_w, _ = O.update_weights_log(np.full(n, -np.log(float(n))), ll)
+        _assert_weights_close(res["pair"], want_w)
+        _assert_weights_close(res["moment"], want_w)
+
+
+def test_motion_b_and_rb_likelihood(mcl, golden_dir):
+    """Extensions a-15 (MotionModel.moveWithNoise, motion_model.py:31-62) and a-16 (range/bearing)."""
+    n, Lm = 8192, 9
+    rng = np.random.RandomState(17)
+    lm = rng.uniform(-8, 8, (Lm, 2))
+    truth = np.array([[1.0], [2.0], [0.4]])
+    pos = (truth + rng.normal(0, 1, (3, n)) * np.array([[0.1], [0.1], [0.03]])).astype(np.float32)
+    normals = rng.normal(0, 1, (3, n)).astype(np.float32)
+    v, w, dt = 10 * np.deg2rad(10.0), np.deg2rad(10.0), 2.0
+    z_rb = O.rb_observation(truth, lm) + rng.normal(0, 1, (Lm, 2)) * np.array([0.1, 0.03])
+    f = mcl.Filter(n_particles=n, landmarks=lm, likelihood="rb", motion="b", sigma_obs=[0.1, 0.03], dt=dt, vel=v,
+                   yaw_rate=w, motion_b_alpha=[0.1] * 6, max_landmarks=16)
+    f.set_particles(pos[0], pos[1], pos[2], None)
+    f.predict_weight(z_rb[None], noise=normals[:, None, :])
+    x, y, th, _ = f.get_particles()
+    got_px = np.stack([x[0], y[0], th[0]]).astype(np.float64)
+    want_px = O.motion_b(pos.astype(np.float64), v, w, dt, [0.1] * 6, normals.astype(np.float64))
+    np.testing.assert_allclose(got_px, want_px, rtol=RTOL, atol=2e-6)
+    ll = O.loglik_rb(got_px, z_rb, lm, 0.1, 0.03)
+    want_w, _ = O.update_weights_log(np.full(n, -np.log(float(n))), ll)
+    _assert_weights_close(f.weights()[0], want_w)
+
+
+def test_philox_noise_statistics_and_determinism(mcl):
+    """Device noise cannot be bit-compared with MT19937: check moments, independence of launch
+    geometry (trial batching / particle offset) and run-to-run determinism."""
+    n = 1 << 18
+    lm = [[5.0, 5.0], [2.0, -3.0], [-3.0, 4.0]]
+    z = np.zeros((1, 3, 2))
+
+    def run(seed, **kw):
+        f = mcl.Filter(n_particles=n, landmarks=lm, seed=seed, **kw)
+        f.init_particles([0.0, 0.0, 0.0])
+        f.step(z, no_resample=True)
+        x, y, th, _ = f.get_particles()
+        return x[0].astype(np.float64), y[0].astype(np.float64), th[0].astype(np.float64)
+
+    x, y, th = run(7)
+    x2, y2, th2 = run(7)
+    assert np.array_equal(x, x2) and np.array_equal(th, th2)
+    x3, _, _ = run(8)
+    assert not np.array_equal(x, x3)
+    P = O.PFParams(100)
+    det = O.f_motion(np.zeros((3, 1)), P)[:, 0]
+    for arr, mu, sd in ((x, det[0], 0.03), (y, det[1], 0.03), (th, det[2], np.deg2rad(2.0))):
+        r = (arr - mu) / sd
+        assert abs(r.mean()) < 5 / np.sqrt(n)
+        assert abs(r.std() - 1) < 5 / np.sqrt(2 * n)
+        assert abs((r ** 3).mean()) < 0.03 and abs((r ** 4).mean() - 3) < 0.08
+    assert abs(np.corrcoef(x - det[0], y - det[1])[0, 1]) < 0.01
+    assert abs(np.corrcoef(x - det[0], th - det[2])[0, 1]) < 0.01
+    # a shard holding the second half of a 2n filter draws the noise of global slots [n, 2n)
+    ff = mcl.Filter(n_particles=2 * n, landmarks=lm, seed=7)
+    ff.init_particles([0.0, 0.0, 0.0])
+    ff.step(z, no_resample=True)
+    x_full = ff.get_particles()[0][0]
+    fs = mcl.Filter(n_particles=n, landmarks=lm, seed=7, n_global=2 * n, slot_base=n)
+    fs.init_particles([0.0, 0.0, 0.0])
+    fs.step(z, no_resample=True)
+    assert np.array_equal(fs.get_particles()[0][0], x_full[n:])
+    assert np.array_equal(x_full[:n].astype(np.float64), x)
+
+
+def test_error_paths(mcl):
+    f = mcl.Filter(n_particles=1000, max_landmarks=4)
+    with pytest.raises(mcl.MclError):
+        f.step(np.zeros((1, 0, 2)))  # no landmarks set
+    with pytest.raises(mcl.MclError):
+        f.set_landmarks(np.zeros((9, 2)))  # more than max_landmarks
+    f.set_landmarks(np.zeros((2, 2)))
+    with pytest.raises(mcl.MclError):
+        f.step(np.zeros((1, 2, 2)))  # particles not initialised
