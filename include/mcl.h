@@ -182,18 +182,20 @@ int mcl_profile_read(mcl_filter *h, double *ms3_host);
 uint64_t mcl_launch_count(const mcl_filter *h);
 
 /* ---- particle-sharded single filter (n_trials == 1, one handle per GPU) -----------------------
- * The host exchanges the small records; see slam-robot_simu_b200/sharded.py.
- * mcl_shard_total: sum of this shard's quantised weights given the GLOBAL log-normaliser.      */
-int mcl_shard_total(mcl_filter *h, double global_log_norm, uint64_t *total_dev, void *stream);
+ * The host exchanges the small records; see slam-robot_simu_b200/sharded.py.  Order per step:
+ *   mcl_predict_weight on every shard -> allgather + merge of mcl_stats -> mcl_shard_set_global;
+ *   when resampling: mcl_shard_total -> allgather of the totals -> mcl_shard_expand -> all-to-all
+ *   of the expanded poses -> mcl_set_particles.
+ * mcl_shard_set_global: install the merged statistics (global max_logw / sum_w define the weight
+ * map, est the reference pose, ess the resampling gate). */
+int mcl_shard_set_global(mcl_filter *h, const mcl_stats *merged_host, void *stream);
+/* mcl_shard_total: sum of this shard's quantised weights under the global weight map -> *total_dev. */
+int mcl_shard_total(mcl_filter *h, uint64_t *total_dev, void *stream);
 /* mcl_shard_expand: with k_offset = sum of totals of lower ranks, write for every global slot this
  * shard's particles fill the resampled pose into out_{x,y,yaw}_dev[slot - *first_slot]; capacity
  * `cap` slots.  first_slot/n_slots (host, written after a stream sync) describe the filled range. */
-int mcl_shard_expand(mcl_filter *h, double global_log_norm, uint64_t k_offset, double ofs, float *out_x_dev,
-                     float *out_y_dev, float *out_yaw_dev, int64_t cap, int64_t *first_slot, int64_t *n_slots,
-                     void *stream);
-/* Override the statistics the next step uses (global log-normaliser, MAP estimate, resample
- * decision) after merging the per-shard mcl_stats on the host. */
-int mcl_shard_set_global(mcl_filter *h, const mcl_stats *merged_host, void *stream);
+int mcl_shard_expand(mcl_filter *h, uint64_t k_offset, double ofs, float *out_x_dev, float *out_y_dev,
+                     float *out_yaw_dev, int64_t cap, int64_t *first_slot, int64_t *n_slots, void *stream);
 
 #ifdef __cplusplus
 }

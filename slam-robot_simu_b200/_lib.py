@@ -108,8 +108,8 @@ PROTOTYPES = {
     "mcl_profile": (C.c_int, [_vp, C.c_int]),
     "mcl_profile_read": (C.c_int, [_vp, _P(C.c_double)]),
     "mcl_launch_count": (C.c_uint64, [_vp]),
-    "mcl_shard_total": (C.c_int, [_vp, C.c_double, _vp, _vp]),
-    "mcl_shard_expand": (C.c_int, [_vp, C.c_double, C.c_uint64, C.c_double, _vp, _vp, _vp, C.c_int64,
+    "mcl_shard_total": (C.c_int, [_vp, _vp, _vp]),
+    "mcl_shard_expand": (C.c_int, [_vp, C.c_uint64, C.c_double, _vp, _vp, _vp, C.c_int64,
                                    _P(C.c_int64), _P(C.c_int64), _vp]),
     "mcl_shard_set_global": (C.c_int, [_vp, _P(mcl_stats), _vp]),
 }

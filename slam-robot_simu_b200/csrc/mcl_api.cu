@@ -22,12 +22,13 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct Layout {
     long long n, ld;
     int T, Lmax, tpt, bpt, cov_bpt;
+    uint32_t per;
     size_t off_state[2], off_anc, off_desc, off_tickets, off_partials, off_cov, off_stats, off_prep, off_tab, off_lm,
-        off_z, off_ofs, off_pose, off_total, total;
+        off_z, off_ofs, off_pose, off_total, off_trig, total;
 };
 
 int make_layout(const mcl_config &c, int sm_count, Layout &L) {
-    if (c.n_particles < 1 || c.n_particles > 0xFFFFFFF0ll) return MCL_ERR_ARG;
+    if (c.n_particles < 1 || c.n_particles > 0x7FFFFF00ll) return MCL_ERR_ARG;  // 32-bit particle indices
     if (c.n_trials < 1 || c.n_trials > 65535) return MCL_ERR_ARG;
     if (c.max_landmarks < 1 || c.max_landmarks > 4096) return MCL_ERR_ARG;
     L.n = c.n_particles;
@@ -35,10 +36,16 @@ int make_layout(const mcl_config &c, int sm_count, Layout &L) {
     L.T = c.n_trials;
     L.Lmax = c.max_landmarks;
     L.tpt = static_cast<int>((L.n + kScanTile - 1) / kScanTile);
-    const long long need = (L.n + kStepTile - 1) / kStepTile;
-    long long cap = static_cast<long long>(sm_count) * 2 * 4;  // 4 grid-stride waves of 2 resident CTAs per SM
-    if (L.T > 1) cap = cap / L.T > 16 ? cap / L.T : 16;
-    L.bpt = static_cast<int>(need < cap ? need : cap);
+    // k_step is persistent: 2 resident CTAs per SM share a trial's particles in contiguous ranges that are
+    // multiples of 128 particles; with many trials every trial still gets at least one CTA per 8192 particles
+    const long long units = (L.n + kStepUnit - 1) / kStepUnit;
+    long long blocks = static_cast<long long>(sm_count) * 2 / L.T;
+    const long long min_blocks = (L.n + 8191) / 8192;
+    if (blocks < min_blocks) blocks = min_blocks;
+    if (blocks > units) blocks = units;
+    if (blocks < 1) blocks = 1;
+    L.per = static_cast<uint32_t>(((units + blocks - 1) / blocks) * kStepUnit);
+    L.bpt = static_cast<int>((L.n + L.per - 1) / L.per);
     L.cov_bpt = L.bpt;
     size_t o = 0;
     const size_t state_bytes = static_cast<size_t>(4) * L.T * L.ld * sizeof(float);
@@ -47,7 +54,7 @@ int make_layout(const mcl_config &c, int sm_count, Layout &L) {
         o = align_up(o + state_bytes, kAlign);
     }
     L.off_anc = o;      o = align_up(o + static_cast<size_t>(L.T) * L.ld * sizeof(uint32_t), kAlign);
-    L.off_desc = o;     o = align_up(o + static_cast<size_t>(L.T) * L.tpt * sizeof(unsigned long long), kAlign);
+    L.off_desc = o;     o = align_up(o + static_cast<size_t>(2) * L.T * L.tpt * sizeof(unsigned long long), kAlign);
     L.off_tickets = o;  o = align_up(o + static_cast<size_t>(L.T) * 4 * sizeof(unsigned int), kAlign);
     L.off_partials = o; o = align_up(o + static_cast<size_t>(L.T) * L.bpt * kPart * sizeof(double), kAlign);
     L.off_cov = o;      o = align_up(o + static_cast<size_t>(L.T) * L.cov_bpt * 8 * sizeof(double), kAlign);
@@ -59,6 +66,7 @@ int make_layout(const mcl_config &c, int sm_count, Layout &L) {
     L.off_ofs = o;      o = align_up(o + static_cast<size_t>(L.T) * sizeof(double), kAlign);
     L.off_pose = o;     o = align_up(o + static_cast<size_t>(L.T) * 3 * sizeof(double), kAlign);
     L.off_total = o;    o = align_up(o + static_cast<size_t>(L.T) * sizeof(unsigned long long), kAlign);
+    L.off_trig = o;     o = align_up(o + static_cast<size_t>(kTrigEntries) * sizeof(TrigEntry), kAlign);
     L.total = o;
     return MCL_OK;
 }
@@ -71,7 +79,7 @@ int validate(const mcl_config *c) {
     if (c->n_global < c->n_particles || c->slot_base < 0 || c->slot_base + c->n_particles > c->n_global)
         return MCL_ERR_ARG;
     if (c->n_global != c->n_particles && c->n_trials != 1) return MCL_ERR_ARG;
-    if (c->n_global > 0xFFFFFFF0ll * 64) return MCL_ERR_ARG;
+    if (c->n_global > 0xFFFFFFF0ll) return MCL_ERR_ARG;  // slots and ancestors are 32-bit
     return MCL_OK;
 }
 
@@ -85,7 +93,8 @@ struct mcl_filter {
     unsigned char *ws = nullptr;
     StateView state[2];
     uint32_t *anc = nullptr;
-    unsigned long long *desc = nullptr;
+    unsigned long long *desc[2] = {nullptr, nullptr};
+    int desc_cur = 0;  // descriptor buffer the next scan launch uses (all zero)
     unsigned int *tickets = nullptr;
     double *partials = nullptr, *cov_partials = nullptr;
     mcl_stats *stats = nullptr;
@@ -93,6 +102,7 @@ struct mcl_filter {
     double4 *tab = nullptr;
     double *lm = nullptr, *z = nullptr, *ofs = nullptr, *pose = nullptr;
     unsigned long long *total = nullptr;
+    TrigEntry *trig = nullptr;
     int cur = 0;
     int L = 0;
     uint32_t step = 0;
@@ -146,64 +156,53 @@ int use_device(mcl_filter *h) {
     return MCL_OK;
 }
 
-// host twin of mcl::count_le (same rounding: no FMA contraction on the host build)
+// host twin of mcl::count_le (same formula; no FMA contraction on the host build, and the comb's two
+// roundings are forced through volatiles)
 long long host_count_le(unsigned long long K, double delta, double ofs, long long n) {
     const double nd = static_cast<double>(n);
     const double c = static_cast<double>(K) * kInvTwo52;
-    double g = std::floor((c - ofs) * nd);
-    g = std::fmin(std::fmax(g, -1.0), nd - 1.0);
-    long long i = static_cast<long long>(g);
-    auto comb = [&](long long k) {
-        volatile double m = static_cast<double>(k) * delta;  // force the intermediate rounding
-        return m + ofs;
+    const double g = std::floor((c - ofs) * nd);
+    auto comb = [&](double k) {
+        volatile double m = k * delta;
+        volatile double u = m + ofs;
+        return static_cast<double>(u);
     };
-    while (i + 1 < n && comb(i + 1) <= c) ++i;
-    while (i >= 0 && comb(i) > c) --i;
-    return i + 1;
+    double r = g;
+    if (comb(g + 1.0) <= c) r = g + 1.0;
+    else if (comb(g) > c) r = g - 1.0;
+    return static_cast<long long>(std::fmin(std::fmax(r + 1.0, 0.0), nd));
 }
 
 // ---- launch helpers ------------------------------------------------------------------------------
-int launch_prep(mcl_filter *h, const double *z_dev, const double *ofs_dev, uint32_t flags, bool reduce_only,
-                cudaStream_t st) {
+void fill_prep(mcl_filter *h, PrepParams &p, const double *z_dev, const double *ofs_dev, uint32_t flags) {
     const mcl_config &c = h->cfg;
-    PrepParams p{};
+    p = PrepParams{};
     p.lm = h->lm;
-    p.z = reduce_only ? nullptr : z_dev;
+    p.z = z_dev;
     p.ofs = ofs_dev;
-    p.stats = h->stats;
     p.prep = h->prep;
     p.tab = h->tab;
-    p.desc = h->desc;
-    p.tickets = h->tickets;
-    p.cur = h->state[h->cur];
-    p.ld = h->lay.ld;
     p.L = h->L;
     p.Lmax = h->lay.Lmax;
-    p.tpt = h->lay.tpt;
     p.flags = flags;
     p.likelihood = c.likelihood;
-    p.ref_from_particle0 = (reduce_only && h->stats_from_particle0) ? 1 : 0;
     p.ess_threshold = c.ess_threshold;
     p.vdt = c.vel * c.dt;
     p.wdt = c.yaw_rate * c.dt;
     p.inv_s0sq = 1.0 / (c.sigma_obs[0] * c.sigma_obs[0]);
     p.inv_s1sq = 1.0 / (c.sigma_obs[1] * c.sigma_obs[1]);
     p.lik_const = -static_cast<double>(h->L) * std::log(2.0 * kPi * c.sigma_obs[0] * c.sigma_obs[1]);
-    p.base_lw = -std::log(static_cast<double>(c.n_global));
     p.inv_n = h->delta;
     p.seed = c.seed;
     p.step = h->step;
-    p.reduce_only = reduce_only ? 1 : 0;
-    k_prep<<<h->lay.T, 128, 0, st>>>(p);
-    MCL_LAUNCH_CHECK(h, "k_prep");
-    return MCL_OK;
 }
 
 void fill_scan(mcl_filter *h, ScanParams &p) {
     p = ScanParams{};
     p.lw = h->state[h->cur].lw;
-    p.prep = h->prep;
-    p.desc = h->desc;
+    p.stats = h->stats;
+    p.desc = h->desc[h->desc_cur];
+    p.desc_next = nullptr;
     p.tickets = h->tickets;
     p.anc = h->anc;
     p.total = nullptr;
@@ -218,13 +217,47 @@ void fill_scan(mcl_filter *h, ScanParams &p) {
     p.tpt = h->lay.tpt;
 }
 
-int launch_scan(mcl_filter *h, const ScanParams &p, cudaStream_t st) {
-    dim3 grid(h->lay.tpt, h->lay.T);
-    if (p.mode == kScanExpand) k_scan_ancestors<kScanExpand><<<grid, kScanThreads, 0, st>>>(p);
-    else if (p.mode == kScanTotals) k_scan_ancestors<kScanTotals><<<grid, kScanThreads, 0, st>>>(p);
-    else k_scan_ancestors<kScanAncestors><<<grid, kScanThreads, 0, st>>>(p);
-    MCL_LAUNCH_CHECK(h, "k_scan_ancestors");
+// In-step (or stage) scan: per-step scalars by block 0 of each trial, then the scan of the trials that
+// resample.  `full` = false launches the scalars only (MCL_NO_RESAMPLE).
+int launch_step_scan(mcl_filter *h, const double *z_dev, const double *ofs_dev, uint32_t flags, bool full,
+                     cudaStream_t st) {
+    ScanParams sp;
+    fill_scan(h, sp);
+    fill_prep(h, sp.prep, z_dev, ofs_dev, flags);
+    sp.do_prep = 1;
+    if (full) {
+        sp.desc_next = h->desc[h->desc_cur ^ 1];
+        h->desc_cur ^= 1;
+    }
+    dim3 grid(full ? h->lay.tpt : 1, h->lay.T);
+    k_scan<kScanAncestors><<<grid, kScanThreads, 0, st>>>(sp);
+    MCL_LAUNCH_CHECK(h, "k_scan");
     return MCL_OK;
+}
+
+// Sharded resampling: the scan runs outside a step, with the weight map of the (global) statistics.
+int launch_shard_scan(mcl_filter *h, ScanParams &sp, int mode, cudaStream_t st) {
+    k_reset_scan<<<(h->lay.tpt + 255) / 256, 256, 0, st>>>(sp.desc, h->tickets, h->lay.tpt);
+    MCL_LAUNCH_CHECK(h, "k_reset_scan");
+    dim3 grid(h->lay.tpt, 1);
+    if (mode == kScanTotals) k_scan<kScanTotals><<<grid, kScanThreads, 0, st>>>(sp);
+    else k_scan<kScanExpand><<<grid, kScanThreads, 0, st>>>(sp);
+    MCL_LAUNCH_CHECK(h, "k_scan");
+    k_reset_scan<<<(h->lay.tpt + 255) / 256, 256, 0, st>>>(sp.desc, h->tickets, h->lay.tpt);
+    MCL_LAUNCH_CHECK(h, "k_reset_scan");
+    return MCL_OK;
+}
+
+template <int LIK>
+void launch_step_lik(const StepParams &p, dim3 grid, size_t smem, bool philox, cudaStream_t st) {
+    if (philox) k_step<LIK, true><<<grid, kStepThreads, smem, st>>>(p);
+    else k_step<LIK, false><<<grid, kStepThreads, smem, st>>>(p);
+}
+
+int step_variant(const mcl_config &c) {
+    if (c.likelihood == MCL_LIK_PAIR) return kLikPair;
+    if (c.likelihood == MCL_LIK_RB) return kLikRB;
+    return (c.sigma_obs[0] == c.sigma_obs[1]) ? kLikMomentIso : kLikMomentGen;
 }
 
 int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool reduce_only, cudaStream_t st) {
@@ -236,26 +269,27 @@ int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool redu
     p.noise = noise_dev;
     p.prep = h->prep;
     p.tab = h->tab;
+    p.trig = h->trig;
     p.partials = h->partials;
     p.tickets = h->tickets;
     p.stats = h->stats;
-    p.n = h->lay.n;
+    p.n = static_cast<uint32_t>(h->lay.n);
+    p.per = h->lay.per;
     p.ld = h->lay.ld;
     p.slot_base = c.slot_base;
     p.T = h->lay.T;
     p.bpt = h->lay.bpt;
     p.Lmax = h->lay.Lmax;
-    p.likelihood = c.likelihood;
     p.motion = c.motion;
-    p.flags = flags;
     p.step = h->step;
     p.seed = c.seed;
-    p.vdt = c.vel * c.dt;
+    p.vdt_f = static_cast<float>(c.vel * c.dt);
+    p.wdt_f = static_cast<float>(c.yaw_rate * c.dt);
     p.wdt = c.yaw_rate * c.dt;
     p.vel = c.vel;
     p.yaw_rate = c.yaw_rate;
     p.dt = c.dt;
-    for (int k = 0; k < 3; ++k) p.q_std[k] = c.q_std[k];
+    for (int k = 0; k < 3; ++k) p.q_std[k] = static_cast<float>(c.q_std[k]);
     p.inv_s0sq = 1.0 / (c.sigma_obs[0] * c.sigma_obs[0]);
     p.inv_s1sq = 1.0 / (c.sigma_obs[1] * c.sigma_obs[1]);
     {
@@ -269,19 +303,24 @@ int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool redu
     }
     dim3 grid(h->lay.bpt, h->lay.T);
     if (reduce_only) {
-        k_step<1><<<grid, kStepThreads, 0, st>>>(p);
-    } else {
-        const size_t smem = (c.likelihood == MCL_LIK_MOMENT) ? 0 : static_cast<size_t>(h->L) * sizeof(double4);
-        k_step<0><<<grid, kStepThreads, smem, st>>>(p);
+        k_reduce<<<grid, kStepThreads, 0, st>>>(p, h->stats_from_particle0 ? 1 : 0);
+        MCL_LAUNCH_CHECK(h, "k_reduce");
+        return MCL_OK;
+    }
+    const bool philox = (noise_dev == nullptr);
+    const size_t smem = static_cast<size_t>(h->L) * sizeof(double4);
+    switch (step_variant(c)) {
+        case kLikPair: launch_step_lik<kLikPair>(p, grid, smem, philox, st); break;
+        case kLikRB: launch_step_lik<kLikRB>(p, grid, smem, philox, st); break;
+        case kLikMomentIso: launch_step_lik<kLikMomentIso>(p, grid, 0, philox, st); break;
+        default: launch_step_lik<kLikMomentGen>(p, grid, 0, philox, st); break;
     }
     MCL_LAUNCH_CHECK(h, "k_step");
     return MCL_OK;
 }
 
 int reduce_only_pass(mcl_filter *h, cudaStream_t st) {
-    int rc = launch_prep(h, nullptr, nullptr, MCL_NO_RESAMPLE, true, st);
-    if (rc != MCL_OK) return rc;
-    rc = launch_step(h, nullptr, MCL_NO_RESAMPLE, true, st);
+    int rc = launch_step(h, nullptr, MCL_NO_RESAMPLE, true, st);
     h->stats_from_particle0 = false;
     return rc;
 }
@@ -302,16 +341,9 @@ int step_impl(mcl_filter *h, const double *z_dev, const double *ofs_dev, const f
         return fail(h, MCL_ERR_STATE, "a particle-sharded filter resamples through mcl_shard_total/mcl_shard_expand");
     const bool prof = h->profiling;
     if (prof) MCL_CUDA(h, cudaEventRecord(h->ev[0], st));
-    int rc = launch_prep(h, z_dev, ofs_dev, flags, false, st);
-    if (rc != MCL_OK) return rc;
     if (prof) MCL_CUDA(h, cudaEventRecord(h->ev[1], st));
-    if (!(flags & MCL_NO_RESAMPLE)) {
-        ScanParams sp;
-        fill_scan(h, sp);
-        sp.mode = kScanAncestors;
-        rc = launch_scan(h, sp, st);
-        if (rc != MCL_OK) return rc;
-    }
+    int rc = launch_step_scan(h, z_dev, ofs_dev, flags, !(flags & MCL_NO_RESAMPLE), st);
+    if (rc != MCL_OK) return rc;
     if (prof) MCL_CUDA(h, cudaEventRecord(h->ev[2], st));
     rc = launch_step(h, noise_dev, flags, false, st);
     if (rc != MCL_OK) return rc;
@@ -443,7 +475,8 @@ int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_byte
         h->state[b].lw = base + 3 * plane;
     }
     h->anc = reinterpret_cast<uint32_t *>(h->ws + L.off_anc);
-    h->desc = reinterpret_cast<unsigned long long *>(h->ws + L.off_desc);
+    h->desc[0] = reinterpret_cast<unsigned long long *>(h->ws + L.off_desc);
+    h->desc[1] = h->desc[0] + static_cast<size_t>(L.T) * L.tpt;
     h->tickets = reinterpret_cast<unsigned int *>(h->ws + L.off_tickets);
     h->partials = reinterpret_cast<double *>(h->ws + L.off_partials);
     h->cov_partials = reinterpret_cast<double *>(h->ws + L.off_cov);
@@ -455,10 +488,32 @@ int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_byte
     h->ofs = reinterpret_cast<double *>(h->ws + L.off_ofs);
     h->pose = reinterpret_cast<double *>(h->ws + L.off_pose);
     h->total = reinterpret_cast<unsigned long long *>(h->ws + L.off_total);
+    h->trig = reinterpret_cast<TrigEntry *>(h->ws + L.off_trig);
     h->delta = 1.0 / static_cast<double>(cfg->n_global);
     // the pair kernels stage up to 4096 landmarks (128 KiB) in dynamic shared memory
-    cudaFuncSetAttribute(k_step<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * static_cast<int>(sizeof(double4)));
+    const int max_dyn = 4096 * static_cast<int>(sizeof(double4));
+    cudaFuncSetAttribute(k_step<kLikPair, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    cudaFuncSetAttribute(k_step<kLikPair, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    cudaFuncSetAttribute(k_step<kLikRB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    cudaFuncSetAttribute(k_step<kLikRB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    // sin/cos table of sincos_tab: entry k-128 holds sin, cos of k*pi/32 and the correction -k*(pi/32 - HI)
+    {
+        static TrigEntry tab[kTrigEntries];
+        for (int i = 0; i < kTrigEntries; ++i) {
+            const double k = static_cast<double>(i - 128);
+            tab[i].s = std::sin(k * (kPi / 32.0));
+            tab[i].c = std::cos(k * (kPi / 32.0));
+            tab[i].corr = -k * (kPi / 32.0 - static_cast<double>(kTrigStepHi));
+            tab[i].pad = 0.0;
+        }
+        if (cudaMemcpy(h->trig, tab, sizeof tab, cudaMemcpyHostToDevice) != cudaSuccess) {
+            if (h->owns_ws) cudaFree(h->ws);
+            delete h;
+            return fail(nullptr, MCL_ERR_CUDA, "uploading the trig table failed");
+        }
+    }
     cudaError_t e = cudaMemset(h->ws + L.off_tickets, 0, static_cast<size_t>(L.T) * 4 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_desc, 0, static_cast<size_t>(2) * L.T * L.tpt * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_stats, 0, static_cast<size_t>(L.T) * sizeof(mcl_stats));
     if (e != cudaSuccess) {
         if (h->owns_ws) cudaFree(h->ws);
@@ -503,7 +558,7 @@ int mcl_init_particles(mcl_filter *h, const double *pose_host, void *stream) {
     const Layout &L = h->lay;
     MCL_CUDA(h, cudaMemcpyAsync(h->pose, pose_host, static_cast<size_t>(L.T) * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     MCL_CUDA(h, cudaStreamSynchronize(st));
-    const float lw0 = static_cast<float>(-std::log(static_cast<double>(h->cfg.n_global)));
+    const float lw0 = 0.0f;  // stored log-weights are relative: uniform = all equal
     const int bx = static_cast<int>(std::min<long long>((L.ld + 255) / 256, 2048));
     h->cur = 0;
     k_init<<<dim3(bx, L.T), 256, 0, st>>>(h->state[0], h->pose, L.n, L.ld, lw0);
@@ -535,7 +590,7 @@ int mcl_set_particles(mcl_filter *h, const float *x, const float *y, const float
         if (rc != MCL_OK) return rc;
     }
     if (logw == nullptr) {
-        const float lw0 = static_cast<float>(-std::log(static_cast<double>(h->cfg.n_global)));
+        const float lw0 = 0.0f;
         const int bx = static_cast<int>(std::min<long long>((L.ld + 255) / 256, 2048));
         k_fill<<<dim3(bx, L.T), 256, 0, st>>>(s.lw, L.ld, lw0);
         MCL_LAUNCH_CHECK(h, "k_fill");
@@ -578,12 +633,7 @@ int mcl_resample(mcl_filter *h, const double *ofs_host, uint32_t flags, void *st
     cudaStream_t st = S(stream);
     rc = stage_inputs(h, nullptr, ofs_host, st);
     if (rc != MCL_OK) return rc;
-    rc = launch_prep(h, nullptr, ofs_host ? h->ofs : nullptr, flags & ~MCL_NO_RESAMPLE, true, st);
-    if (rc != MCL_OK) return rc;
-    ScanParams sp;
-    fill_scan(h, sp);
-    sp.mode = kScanAncestors;
-    rc = launch_scan(h, sp, st);
+    rc = launch_step_scan(h, nullptr, ofs_host ? h->ofs : nullptr, flags & ~MCL_NO_RESAMPLE, true, st);
     if (rc != MCL_OK) return rc;
     GatherParams g{};
     g.in = h->state[h->cur];
@@ -591,6 +641,7 @@ int mcl_resample(mcl_filter *h, const double *ofs_host, uint32_t flags, void *st
     g.anc = h->anc;
     g.prep = h->prep;
     g.stats = h->stats;
+    g.tickets = h->tickets;
     g.n = h->lay.n;
     g.ld = h->lay.ld;
     g.n_global = static_cast<double>(h->cfg.n_global);
@@ -682,7 +733,7 @@ static int export_weights(mcl_filter *h, double *w_host, uint64_t *q_host, void 
     void *stage = h->state[h->cur ^ 1].x;
     const int bx = static_cast<int>(std::min<long long>((L.n + 255) / 256, 148 * 16));
     k_export_weights<<<dim3(bx, L.T), 256, 0, st>>>(h->state[h->cur].lw, h->stats, w_host ? static_cast<double *>(stage) : nullptr,
-                                                     q_host ? static_cast<unsigned long long *>(stage) : nullptr, L.n, L.ld, 0, 0.0);
+                                                     q_host ? static_cast<unsigned long long *>(stage) : nullptr, L.n, L.ld);
     MCL_LAUNCH_CHECK(h, "k_export_weights");
     void *dst = w_host ? static_cast<void *>(w_host) : static_cast<void *>(q_host);
     MCL_CUDA(h, cudaMemcpyAsync(dst, stage, static_cast<size_t>(L.T) * L.n * 8, cudaMemcpyDeviceToHost, st));
@@ -742,26 +793,22 @@ int mcl_profile_read(mcl_filter *h, double *ms3_host) {
 uint64_t mcl_launch_count(const mcl_filter *h) { return h ? h->launches : 0; }
 
 // ---- particle-sharded single filter -----------------------------------------------------------
-int mcl_shard_total(mcl_filter *h, double global_log_norm, uint64_t *total_dev, void *stream) {
+int mcl_shard_total(mcl_filter *h, uint64_t *total_dev, void *stream) {
     if (h == nullptr) return MCL_ERR_ARG;
     if (total_dev == nullptr) return fail(h, MCL_ERR_ARG, "total_dev is NULL");
     if (h->lay.T != 1) return fail(h, MCL_ERR_STATE, "sharding needs n_trials == 1");
     int rc = use_device(h);
     if (rc != MCL_OK) return rc;
     cudaStream_t st = S(stream);
-    k_reset_scan<<<(h->lay.tpt + 255) / 256, 256, 0, st>>>(h->desc, h->tickets, h->lay.tpt);
-    MCL_LAUNCH_CHECK(h, "k_reset_scan");
     ScanParams sp;
     fill_scan(h, sp);
-    sp.mode = kScanTotals;
     sp.total = reinterpret_cast<unsigned long long *>(total_dev);
     sp.use_override = 1;
-    sp.log_norm_override = global_log_norm;
     sp.ofs_override = 0.0;
-    return launch_scan(h, sp, st);
+    return launch_shard_scan(h, sp, kScanTotals, st);
 }
 
-int mcl_shard_expand(mcl_filter *h, double global_log_norm, uint64_t k_offset, double ofs, float *out_x_dev, float *out_y_dev,
+int mcl_shard_expand(mcl_filter *h, uint64_t k_offset, double ofs, float *out_x_dev, float *out_y_dev,
                      float *out_yaw_dev, int64_t cap, int64_t *first_slot, int64_t *n_slots, void *stream) {
     if (h == nullptr) return MCL_ERR_ARG;
     if (out_x_dev == nullptr || out_y_dev == nullptr || out_yaw_dev == nullptr || first_slot == nullptr || n_slots == nullptr || cap < 0)
@@ -772,14 +819,10 @@ int mcl_shard_expand(mcl_filter *h, double global_log_norm, uint64_t k_offset, d
     cudaStream_t st = S(stream);
     const long long NG = h->cfg.n_global;
     const long long s0 = host_count_le(k_offset, h->delta, ofs, NG);
-    k_reset_scan<<<(h->lay.tpt + 255) / 256, 256, 0, st>>>(h->desc, h->tickets, h->lay.tpt);
-    MCL_LAUNCH_CHECK(h, "k_reset_scan");
     ScanParams sp;
     fill_scan(h, sp);
-    sp.mode = kScanExpand;
     sp.total = h->total;
     sp.use_override = 1;
-    sp.log_norm_override = global_log_norm;
     sp.ofs_override = ofs;
     sp.k_offset = k_offset;
     sp.slot_first = s0;
@@ -788,7 +831,7 @@ int mcl_shard_expand(mcl_filter *h, double global_log_norm, uint64_t k_offset, d
     sp.ox = out_x_dev;
     sp.oy = out_y_dev;
     sp.oth = out_yaw_dev;
-    rc = launch_scan(h, sp, st);
+    rc = launch_shard_scan(h, sp, kScanExpand, st);
     if (rc != MCL_OK) return rc;
     unsigned long long total = 0;
     MCL_CUDA(h, cudaMemcpyAsync(&total, h->total, sizeof total, cudaMemcpyDeviceToHost, st));

@@ -11,10 +11,13 @@ constexpr double kPi = 3.141592653589793238462643383279502884;
 constexpr double kTwoPi = 6.283185307179586476925286766559005768;
 constexpr double kTwo52 = 4503599627370496.0;
 constexpr double kInvTwo52 = 1.0 / 4503599627370496.0;
+constexpr float kLog2e = 1.4426950408889634f;
 
 constexpr int kStepThreads = 256;  // predict+weight block
 constexpr int kPPT = 4;            // particles per thread per iteration (one float4 per array)
 constexpr int kStepTile = kStepThreads * kPPT;
+constexpr int kStepUnit = 128;     // granularity of the static particle partition over blocks
+constexpr int kFlushEvery = 8;     // fp32 group sums are folded into the fp64 sums every 8 iterations
 
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
@@ -28,13 +31,14 @@ constexpr int kPart = 16;
 
 // Per-trial, per-step scalars written by k_prep and read by every other kernel of the step.
 struct PrepOut {
-    double mom[13];        // landmark/observation moments for MCL_LIK_MOMENT
+    double mom[13];        // landmark/observation moments for the moment likelihood
     double c_shift;        // log-likelihood of the reference pose, subtracted from every particle
     double ref[3];         // reference pose: moment sums are accumulated about it
-    double log_norm_prev;  // normaliser of the stored log-weights
+    double max_prev;       // max of the stored log-weights (they are kept relative to it)
     double ofs;            // comb offset (already multiplied by 1/N)
     double lik_const;      // -L log(2 pi s0 s1)
-    double base_lw;        // -log(n_global): normalised log-weight right after resampling
+    float wq_m;            // weight map of the stored log-weights: w * 2^52 = ex2((lw - wq_m) log2e) * wq_scale
+    float wq_scale;
     int32_t do_resample;
     int32_t L;
 };
@@ -52,6 +56,29 @@ __device__ __forceinline__ double limit_angle(double a) {
     return (a < 0.0) ? -r : r;
 }
 
+// fp32 wrap of a residual into [-pi, pi] (statistics only; one turn is enough for |d| < 3 pi)
+__device__ __forceinline__ float wrap_residual(float d) {
+    if (d > 3.14159265f) d -= 6.28318531f;
+    if (d < -3.14159265f) d += 6.28318531f;
+    return d;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11), counter-based: the noise of particle i at step k does not
 // depend on launch geometry or on how the filter is sharded.
@@ -59,8 +86,10 @@ __device__ __forceinline__ double limit_angle(double a) {
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        const unsigned long long p0 = static_cast<unsigned long long>(0xD2511F53u) * c.x;
+        const unsigned long long p1 = static_cast<unsigned long long>(0xCD9E8D57u) * c.z;
+        const uint32_t hi0 = static_cast<uint32_t>(p0 >> 32), lo0 = static_cast<uint32_t>(p0);
+        const uint32_t hi1 = static_cast<uint32_t>(p1 >> 32), lo1 = static_cast<uint32_t>(p1);
         c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
         k.x += 0x9E3779B9u;
         k.y += 0xBB67AE85u;
@@ -68,11 +97,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
-// two standard normals from two 32-bit words (Box-Muller, fp32; |n| <= 5.9)
+// Two standard normals from two 32-bit words: Box-Muller in fp32 on the MUFU pipe.  The top 23 bits
+// of each word become a float in [1,2) without touching the conversion unit; |n| <= 5.65.
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
-    const float u1 = (static_cast<float>(a >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
-    const float u2 = (static_cast<float>(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float r = sqrtf(-2.0f * __logf(u1));
+    const float u1 = 2.0f - __uint_as_float(0x3f800000u | (a >> 9));  // (0, 1]
+    const float u2 = __uint_as_float(0x3f800000u | (b >> 9)) - 1.0f;  // [0, 1)
+    const float r = sqrt_approx(-1.3862943611198906f * lg2_approx(u1));  // sqrt(-2 ln u1)
     float s, c;
     __sincosf(6.28318530717958647692f * u2, &s, &c);
     return make_float2(r * c, r * s);
@@ -83,37 +113,97 @@ __device__ __forceinline__ double philox_uniform01(uint4 r) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fixed-point weight: rint(exp(logw - log_norm) * 2^52).  One definition shared by the scan, the
-// shard-total and the export kernel so that all three see identical integers.
+// The weight of a stored log-weight, on the 2^-52 grid.  ONE definition shared by the resampling
+// scan, the shard totals and the export kernels, so all of them see identical integers:
+//     q = rn_u64( ex2((lw - m) * log2e) * scale ),  scale = fl32(2^52 / sum_i exp(lw_i - m)),
+//     w = q * 2^-52.
+// fp32 + MUFU.EX2: relative error ~3e-7 against exp() in fp64, far inside the 1e-5 parity band;
+// what must be exact -- the cumulative sums and the comparison with the comb -- is integer.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long quantize_weight(float logw, double log_norm) {
-    const double w = exp(__dsub_rn(static_cast<double>(logw), log_norm));
-    return __double2ull_rn(__dmul_rn(w, kTwo52));
+struct WeightMap {
+    float m, scale;
+};
+__device__ __forceinline__ float weight_scaled(float lw, WeightMap wm) {
+    return __fmul_rn(ex2_approx(__fmul_rn(__fsub_rn(lw, wm.m), kLog2e)), wm.scale);
+}
+__device__ __forceinline__ unsigned long long quantize_weight(float lw, WeightMap wm) {
+    return __float2ull_rn(weight_scaled(lw, wm));
+}
+// the same integer as a double (exact: rint of an fp32 value below 2^53)
+__device__ __forceinline__ double quantize_weight_d(float lw, WeightMap wm) {
+    return static_cast<double>(rintf(weight_scaled(lw, wm)));
+}
+__device__ __forceinline__ WeightMap make_weight_map(double max_logw, double sum_w) {
+    WeightMap wm;
+    wm.m = static_cast<float>(max_logw);
+    wm.scale = static_cast<float>(kTwo52 / sum_w);
+    return wm;
 }
 
 // u_i = fl(fl(i * (1/N)) + ofs): numpy rounds twice (np.arange then "+ ofs",
 // particle_filter.py:213-215); the explicit _rn intrinsics stop nvcc contracting them into one FMA.
-__device__ __forceinline__ double comb_value(long long i, double delta, double ofs) {
-    return __dadd_rn(__dmul_rn(static_cast<double>(i), delta), ofs);
+__device__ __forceinline__ double comb_value(double i, double delta, double ofs) {
+    return __dadd_rn(__dmul_rn(i, delta), ofs);
 }
 
-// Number of comb teeth u_i (0 <= i < n) with u_i <= K * 2^-52.  The walk of particle_filter.py:219
-// advances while u_i > pw_cum[idx]; with integer cumulative weights K_j the ancestor of slot i is
-// the first j with K_j * 2^-52 >= u_i, so source j owns slots [count_le(K_{j-1}), count_le(K_j)).
-__device__ __forceinline__ long long count_le(unsigned long long K, double delta, double ofs, long long n,
-                                              double n_as_double) {
-    const double c = __dmul_rn(static_cast<double>(K), kInvTwo52);  // exact for K < 2^53
-    double g = floor((c - ofs) * n_as_double);
-    g = fmin(fmax(g, -1.0), n_as_double - 1.0);
-    long long i = static_cast<long long>(g);
-    while (i + 1 < n && comb_value(i + 1, delta, ofs) <= c) ++i;
-    while (i >= 0 && comb_value(i, delta, ofs) > c) --i;
-    return i + 1;
+// Number of comb teeth u_i (0 <= i < n) with u_i <= K * 2^-52, all in fp64 on integer-valued doubles
+// (K < 2^53 and i < 2^32 are exact).  The walk of particle_filter.py:219 advances while
+// u_i > pw_cum[idx]; with integer cumulative weights K_j the ancestor of slot i is the first j with
+// K_j * 2^-52 >= u_i, so source j owns slots [count_le(K_{j-1}), count_le(K_j)).
+// Branch-free: the real-arithmetic guess floor((c - ofs) N) is within one of the answer (its error is
+// ~1e-15 N teeth), and the two neighbouring teeth are checked against the comb exactly as numpy rounds it.
+__device__ __forceinline__ double count_le(double Kd, double delta, double ofs, double nd) {
+    const double c = Kd * kInvTwo52;  // exact
+    const double g = floor((c - ofs) * nd);
+    const double g1 = g + 1.0;
+    const double u1 = comb_value(g1, delta, ofs);
+    const double u0 = comb_value(g, delta, ofs);
+    double r = g;
+    if (u1 <= c) r = g1;
+    else if (u0 > c) r = g - 1.0;
+    return fmin(fmax(r + 1.0, 0.0), nd);
 }
 
 // ---------------------------------------------------------------------------------------------
-// block-wide sum of NV doubles (256 threads); result valid in thread 0 .. (all threads after sync
-// read smem[0..NV)).  smem must hold (blockDim/32) * NV doubles.
+// sin/cos of an fp32 angle to ~1e-13 with 12 fp64 operations and ONE conversion:
+//   k = rint(th * 32/pi) by the magic-number trick (no F2I), r_hi = th - k * HI exactly in fp32
+//   (HI = pi/32 rounded to 17 bits), r = r_hi + corr[k] with corr[k] = -k (pi/32 - HI) tabulated,
+//   sin r / cos r by short Taylor polynomials (|r| <= pi/64), rotated by the tabulated sin/cos(k pi/32).
+// The table (256 entries of 32 B, k in [-128, 127]) is built on the host and read through L1.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTrigEntries = 256;
+constexpr float kTrigInvStep = 10.185916357881302f;  // 32 / pi
+constexpr float kTrigStepHi = 0x1.921fp-4f;          // pi/32 to 17 significant bits
+constexpr double kTrigStepLo = 6.752708724411249e-07;  // pi/32 - kTrigStepHi
+
+struct __align__(32) TrigEntry {
+    double s, c, corr, pad;
+};
+
+__device__ __forceinline__ void sincos_tab(float th, const TrigEntry *__restrict__ tab, double &s, double &c) {
+    const float t = fmaf(th, kTrigInvStep, 12582912.0f);
+    const int k = __float_as_int(t) - 0x4B400000;
+    if (abs(k) > 127 || !(fabsf(th) < 16.0f)) {  // outside the table (or NaN): the libm path
+        sincos(static_cast<double>(th), &s, &c);
+        return;
+    }
+    const float kf = t - 12582912.0f;
+    const float rh = fmaf(-kf, kTrigStepHi, th);  // exact: k has 7 bits, HI 17, and the result is small
+    const double2 sc = __ldg(reinterpret_cast<const double2 *>(tab + (k + 128)));  // L1-resident 8 KB table
+    const double r = static_cast<double>(rh) + __ldg(&tab[k + 128].corr);
+    const double r2 = r * r;
+    const double ps = fma(r2, 1.0 / 120.0, -1.0 / 6.0) * r2;
+    const double sr = fma(r, ps, r);
+    double pc = fma(r2, -1.0 / 720.0, 1.0 / 24.0);
+    pc = fma(r2, pc, -0.5);
+    const double cr = fma(r2, pc, 1.0);
+    s = fma(sc.x, cr, sc.y * sr);
+    c = fma(sc.y, cr, -(sc.x * sr));
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-wide sum of NV doubles (256 threads); result valid in all threads.
+// smem must hold (blockDim/32) * NV doubles.
 // ---------------------------------------------------------------------------------------------
 template <int NV>
 __device__ __forceinline__ void block_sum(double (&v)[NV], double *smem) {

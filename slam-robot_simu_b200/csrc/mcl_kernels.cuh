@@ -1,12 +1,14 @@
 // Kernels of the MCL step (sm_100a).  One translation unit: included by mcl_api.cu.
 //
-//   k_prep            1 block / trial : per-step scalars (resample gate, comb offset, reference pose,
-//                                       landmark table + moments, likelihood shift), resets tickets
-//   k_scan_ancestors  decoupled look-back scan of 64-bit fixed-point weights -> ancestor of every slot
-//   k_step            [gather] + predict + weight + block partials + last-block finalise (stats)
-//   k_gather          stand-alone resampling gather (stage API)
-//   k_cov             exact two-pass weighted covariance
-//   k_export_*        weights / quantised weights for the host
+// A filter step is TWO launches:
+//   k_scan   block 0 of every trial first derives the per-step scalars (resample gate, comb offset,
+//            reference pose, landmark table + moments, likelihood shift); then all blocks run the
+//            decoupled look-back scan of the 64-bit fixed-point weights and write the ancestor of
+//            every slot.  Trials that do not resample leave after the scalars.
+//   k_step   [gather through the ancestors] + predict + weight + statistics partials; the last
+//            block of a trial merges the partials into mcl_stats.
+// Stage / utility kernels: k_reduce (statistics only), k_gather (stand-alone resampling gather),
+// k_cov (exact two-pass covariance), k_export_weights, k_init*, k_fill, k_reset_scan.
 #pragma once
 #include "mcl_device.cuh"
 
@@ -16,29 +18,11 @@ struct StateView {
     float *x, *y, *th, *lw;
 };
 
-// -------------------------------------------------------------------------------------------------
-// k_prep
-// -------------------------------------------------------------------------------------------------
-struct PrepParams {
-    const double *lm;       // [L][2]
-    const double *z;        // [T][L][2]  (may be null in reduce-only mode)
-    const double *ofs;      // [T] or null
-    const mcl_stats *stats; // [T] previous step
-    PrepOut *prep;          // [T]
-    double4 *tab;           // [T][Lmax]
-    unsigned long long *desc;  // [T][tpt] scan tile descriptors
-    unsigned int *tickets;  // [T][4]
-    StateView cur;          // for ref-from-first-particle mode
-    long long ld;
-    int L, Lmax, tpt;
-    uint32_t flags;
-    int likelihood;
-    int ref_from_particle0; // reduce-only after set_particles
-    int reduce_only;        // no motion this pass: the reference pose is the stored estimate itself
-    double ess_threshold, vdt, wdt, inv_s0sq, inv_s1sq, lik_const, base_lw, inv_n;
-    uint64_t seed;
-    uint32_t step;
-};
+// likelihood variants of k_step (template parameter)
+constexpr int kLikPair = 0;       // per (particle, landmark) pair, landmarks staged in shared memory
+constexpr int kLikMomentIso = 1;  // 8 per-step moments, sigma_x == sigma_y (the reference's R)
+constexpr int kLikMomentGen = 2;  // 13 per-step moments, sigma_x != sigma_y
+constexpr int kLikRB = 3;         // range / bearing residuals with limit_angle wrap
 
 __device__ __forceinline__ void pair_residual_c(double s, double c, double tx, double ty, double4 t, double &ex,
                                                 double &ey) {
@@ -56,29 +40,51 @@ __device__ __forceinline__ void pair_residual_rb(double s, double c, double tx, 
     ephi = limit_angle(t.w - atan2(ry, rx));
 }
 
-__global__ void __launch_bounds__(128) k_prep(const PrepParams p) {
-    const int t = blockIdx.x, tid = threadIdx.x;
-    __shared__ double red[4 * 16];
-    const mcl_stats st = p.stats[t];
-    PrepOut *po = p.prep + t;
+// -------------------------------------------------------------------------------------------------
+// per-step scalars ("prep"), executed by block 0 of each trial inside k_scan
+// -------------------------------------------------------------------------------------------------
+struct PrepParams {
+    const double *lm;       // [L][2]
+    const double *z;        // [T][L][2]  (null: decision fields only, stage API)
+    const double *ofs;      // [T] or null
+    PrepOut *prep;          // [T]
+    double4 *tab;           // [T][Lmax]
+    int L, Lmax;
+    uint32_t flags;
+    int likelihood;
+    double ess_threshold, vdt, wdt, inv_s0sq, inv_s1sq, lik_const, inv_n;
+    uint64_t seed;
+    uint32_t step;
+};
 
-    // ---- reference pose: previous MAP estimate pushed through the noise-free motion (__f) ----
-    double rx, ry, rth;
-    if (p.ref_from_particle0) {
-        rx = p.cur.x[t * p.ld];
-        ry = p.cur.y[t * p.ld];
-        rth = p.cur.th[t * p.ld];
-    } else if (p.reduce_only) {
-        rx = st.est[0];
-        ry = st.est[1];
-        rth = st.est[2];
-    } else {
-        double s0, c0;
-        sincos(st.est[2], &s0, &c0);
-        rx = st.est[0] + p.vdt * c0;
-        ry = st.est[1] + p.vdt * s0;
-        rth = limit_angle(st.est[2] + p.wdt);
+// resample gate and comb offset of trial t: every block of the trial evaluates the same expression
+__device__ __forceinline__ int decide_resample(uint32_t flags, double ess, double ess_threshold) {
+    if (flags & MCL_NO_RESAMPLE) return 0;
+    if (flags & MCL_FORCE_RESAMPLE) return 1;
+    return (ess < ess_threshold) ? 1 : 0;  // particle_filter.py:211
+}
+__device__ __forceinline__ double comb_offset(const PrepParams &p, int t) {
+    if (p.ofs != nullptr) return p.ofs[t];
+    if (p.flags & MCL_PHILOX_NOISE) {
+        const uint4 r = philox4x32_10(make_uint4(0xFFFFFFFFu, 0u, p.step, static_cast<uint32_t>(t)),
+                                      make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32)));
+        return __dmul_rn(philox_uniform01(r), p.inv_n);  // rand() * NP_RECIP, particle_filter.py:214
     }
+    return 0.0;
+}
+
+// all kScanThreads threads of one block; red: >= 8 * 15 doubles of shared memory
+__device__ __noinline__ void prep_block(const PrepParams &p, const mcl_stats *stp, int t, int do_resample, double ofs,
+                                           double *red) {
+    const int tid = threadIdx.x;
+    PrepOut *po = p.prep + t;
+    // ---- reference pose: previous MAP estimate pushed through the noise-free motion (__f) ----
+    double s0, c0;
+    sincos(stp->est[2], &s0, &c0);
+    // the kernels subtract the reference in fp32: make it exactly representable
+    const double rx = static_cast<double>(static_cast<float>(stp->est[0] + p.vdt * c0));
+    const double ry = static_cast<double>(static_cast<float>(stp->est[1] + p.vdt * s0));
+    const double rth = static_cast<double>(static_cast<float>(limit_angle(stp->est[2] + p.wdt)));
 
     // ---- landmark table, moments, likelihood of the reference pose ----
     double acc[15];
@@ -104,13 +110,8 @@ __global__ void __launch_bounds__(128) k_prep(const PrepParams p) {
             acc[13] = fma(e0, e0, acc[13]);
             acc[14] = fma(e1, e1, acc[14]);
         }
+        block_sum<15>(acc, red);
     }
-    block_sum<15>(acc, red);
-
-    // ---- reset the scan tile descriptors and tickets of this trial ----
-    for (int i = tid; i < p.tpt; i += blockDim.x) p.desc[static_cast<long long>(t) * p.tpt + i] = 0ull;
-    if (tid < 4) p.tickets[t * 4 + tid] = 0u;
-
     if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < 13; ++k) po->mom[k] = acc[k];
@@ -118,35 +119,37 @@ __global__ void __launch_bounds__(128) k_prep(const PrepParams p) {
         po->ref[0] = rx;
         po->ref[1] = ry;
         po->ref[2] = rth;
-        po->log_norm_prev = st.log_norm;
+        po->max_prev = stp->max_logw;
         po->lik_const = p.lik_const;
-        po->base_lw = p.base_lw;
+        const WeightMap wm = make_weight_map(stp->max_logw, stp->sum_w);
+        po->wq_m = wm.m;
+        po->wq_scale = wm.scale;
         po->L = p.L;
-        int rs;
-        if (p.flags & MCL_NO_RESAMPLE) rs = 0;
-        else if (p.flags & MCL_FORCE_RESAMPLE) rs = 1;
-        else rs = (st.ess < p.ess_threshold) ? 1 : 0;  // particle_filter.py:211
-        po->do_resample = rs;
-        double ofs = 0.0;
-        if (p.ofs != nullptr) ofs = p.ofs[t];
-        else if (p.flags & MCL_PHILOX_NOISE) {
-            const uint4 r = philox4x32_10(make_uint4(0xFFFFFFFFu, 0u, p.step, static_cast<uint32_t>(t)),
-                                          make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32)));
-            ofs = __dmul_rn(philox_uniform01(r), p.inv_n);  // rand() * NP_RECIP, particle_filter.py:214
-        }
+        po->do_resample = do_resample;
         po->ofs = ofs;
     }
 }
 
 // -------------------------------------------------------------------------------------------------
-// k_scan_ancestors : single-pass chained scan (decoupled look-back) over uint64 fixed-point weights.
+// k_scan : per-step scalars + single-pass chained scan (decoupled look-back) over the fixed-point
+// weights + ancestors.
 // Tile descriptor = status (2 bits) << 62 | value, one 64-bit word, so status and value are read
 // atomically.  Tiles are handed out by an atomic ticket so a tile's predecessors are always running.
+// The look-back is block-wide (256 predecessors per round): when every tile of a 2^20-particle
+// filter starts in the same wave, the prefix reaches the last tile in two rounds instead of sixteen.
+// Descriptors are double-buffered: this launch clears the buffer the NEXT scan will use.
+//
+// Ancestors: every source's slot range [count_le(K_{j-1}), count_le(K_j)) comes from a branch-free
+// fp64 evaluation; the block then fills ancestors by slot -- owners mark their first slot in a
+// shared-memory window, an inclusive max-scan spreads the marks, stores are coalesced.
 // -------------------------------------------------------------------------------------------------
 struct ScanParams {
+    PrepParams prep;
+    int do_prep;                // 1: block 0 of each trial writes PrepOut
     const float *lw;            // [T][ld]
-    const PrepOut *prep;        // [T]
-    unsigned long long *desc;   // [T][tpt]
+    const mcl_stats *stats;     // [T] statistics of the stored weights (weight map, ESS, estimate)
+    unsigned long long *desc;   // [T][tpt] tile descriptors of this launch (all zero on entry)
+    unsigned long long *desc_next;  // [T][tpt] cleared for the next launch (may be null)
     unsigned int *tickets;      // [T][4]  (slot 0 = scan ticket)
     uint32_t *anc;              // [T][ld] (slot - slot_first)
     unsigned long long *total;  // optional [T] : inclusive total of the local weights
@@ -157,9 +160,8 @@ struct ScanParams {
     unsigned long long k_offset;  // sum of the quantised weights of all lower-ranked shards
     double delta;               // fl(1 / n_global)
     int tpt;
-    int mode;                   // kScanAncestors / kScanTotals / kScanExpand
-    int use_override;           // 1: take log_norm / ofs from the two fields below, always resample
-    double log_norm_override, ofs_override;
+    int use_override;           // 1: always resample, ofs from ofs_override (sharded resampling)
+    double ofs_override;
     StateView src;              // kScanExpand: poses of the local sources ...
     float *ox, *oy, *oth;       // ... copied to out[slot - slot_first] for every slot they fill
 };
@@ -167,8 +169,6 @@ struct ScanParams {
 constexpr int kScanAncestors = 0;  // write the ancestor of every slot
 constexpr int kScanTotals = 1;     // only the inclusive total of the quantised weights
 constexpr int kScanExpand = 2;     // write the resampled pose of every slot (sender side of the sharded filter)
-constexpr int kShortRun = 16;      // offspring runs up to this length are written by the owning thread
-constexpr int kRunQueue = 128;     // longer runs are queued and written by the whole block
 
 enum : unsigned long long {
     kDescAggregate = 1ull << 62,
@@ -177,41 +177,51 @@ enum : unsigned long long {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kScanThreads) k_scan_ancestors(const ScanParams p) {
+__global__ void __launch_bounds__(kScanThreads, 4) k_scan(const ScanParams p) {
     const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const PrepOut *po = p.prep + t;
-    if (!p.use_override && !po->do_resample) return;
-    const double log_norm = p.use_override ? p.log_norm_override : po->log_norm_prev;
-    const double ofs = p.use_override ? p.ofs_override : po->ofs;
-
+    constexpr int NW = kScanThreads / 32;
     __shared__ unsigned int s_tile;
-    __shared__ unsigned long long s_warp[kScanThreads / 32];
-    __shared__ unsigned long long s_excl;
+    __shared__ unsigned long long s_warp[NW];
+    __shared__ int s_first[NW];
+    __shared__ double s_slot[2];
+    __shared__ __align__(16) uint32_t s_mark[kScanTile];  // also the reduction scratch of prep_block
+    __shared__ uint32_t s_wmax[NW];
+
+    if (p.desc_next != nullptr && tid == 0) p.desc_next[static_cast<long long>(t) * p.tpt + blockIdx.x] = 0ull;
+    const mcl_stats *stp = p.stats + t;
+    const int resample = p.use_override ? 1 : decide_resample(p.prep.flags, stp->ess, p.prep.ess_threshold);
+    const double ofs = p.use_override ? p.ofs_override : (resample ? comb_offset(p.prep, t) : 0.0);
+    if (p.do_prep && blockIdx.x == 0) {
+        prep_block(p.prep, stp, t, resample, ofs, reinterpret_cast<double *>(s_mark));
+        __syncthreads();
+    }
+    if (!resample) return;
+    const WeightMap wm = make_weight_map(stp->max_logw, stp->sum_w);
+
     if (tid == 0) s_tile = atomicAdd(&p.tickets[t * 4 + 0], 1u);
     __syncthreads();
     const long long tile = s_tile;
+    if (tile >= p.tpt) return;  // prep-only launches use a one-block grid; never taken otherwise
     const long long j0 = tile * kScanTile + static_cast<long long>(tid) * kScanItems;
     const float *lw = p.lw + static_cast<long long>(t) * p.ld;
 
     // ---- load + quantise (8 consecutive items per thread, two 16-byte loads) ----
-    unsigned long long q[kScanItems];
-    {
-        float v[kScanItems];
-        if (j0 + kScanItems <= p.n) {
-            const float4 a = *reinterpret_cast<const float4 *>(lw + j0);
-            const float4 b = *reinterpret_cast<const float4 *>(lw + j0 + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    double qd[kScanItems];  // integer-valued: rint(w * 2^52)
+    if (j0 < p.n) {
+        // the state arrays are padded to a multiple of 128 elements, so the vector loads stay in bounds
+        const float4 a = *reinterpret_cast<const float4 *>(lw + j0);
+        const float4 b = *reinterpret_cast<const float4 *>(lw + j0 + 4);
+        const float v[kScanItems] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int k = 0; k < kScanItems; ++k) q[k] = quantize_weight(v[k], log_norm);
-        } else {
+        for (int k = 0; k < kScanItems; ++k) qd[k] = (j0 + k < p.n) ? quantize_weight_d(v[k], wm) : 0.0;
+    } else {
 #pragma unroll
-            for (int k = 0; k < kScanItems; ++k) q[k] = (j0 + k < p.n) ? quantize_weight(lw[j0 + k], log_norm) : 0ull;
-        }
+        for (int k = 0; k < kScanItems; ++k) qd[k] = 0.0;
     }
-    unsigned long long tsum = 0;
+    double tsum_d = 0.0;  // sums of integers below 2^53 are exact in fp64
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) tsum += q[k];
+    for (int k = 0; k < kScanItems; ++k) tsum_d += qd[k];
+    const unsigned long long tsum = static_cast<unsigned long long>(tsum_d);
 
     // ---- block exclusive scan of the thread sums ----
     unsigned long long incl = tsum;
@@ -224,118 +234,404 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_ancestors(const ScanParam
     __syncthreads();
     unsigned long long warp_off = 0, tile_total = 0;
 #pragma unroll
-    for (int w = 0; w < kScanThreads / 32; ++w) {
+    for (int w = 0; w < NW; ++w) {
         const unsigned long long v = s_warp[w];
         if (w < warp) warp_off += v;
         tile_total += v;
     }
     const unsigned long long thread_excl = warp_off + incl - tsum;
+    __syncthreads();  // s_warp is reused by the look-back
 
-    // ---- decoupled look-back (warp 0) ----
+    // ---- decoupled look-back, block-wide ----
     unsigned long long *desc = p.desc + static_cast<long long>(t) * p.tpt;
-    if (warp == 0) {
-        unsigned long long excl = 0;
-        if (tile == 0) {
-            if (lane == 0) atomicExch(&desc[0], kDescPrefix | tile_total);
-        } else {
-            if (lane == 0) atomicExch(&desc[tile], kDescAggregate | tile_total);
-            long long look = tile - 1;  // window covers tiles [look-31, look]
-            while (true) {
-                const long long idx = look - lane;
-                unsigned long long d;
-                do {
-                    d = (idx >= 0) ? *reinterpret_cast<volatile unsigned long long *>(&desc[idx]) : kDescPrefix;
-                } while (__any_sync(0xffffffffu, (d >> 62) == 0ull));
-                const unsigned int is_prefix = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
-                const int first = is_prefix ? (__ffs(is_prefix) - 1) : 32;  // nearest predecessor holding a prefix
-                unsigned long long contrib = (lane <= first) ? (d & kDescValueMask) : 0ull;
-                if (idx < 0) contrib = 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-                excl += contrib;
-                if (is_prefix) break;
-                look -= 32;
+    unsigned long long excl = 0;
+    if (tile == 0) {
+        if (tid == 0) atomicExch(&desc[0], kDescPrefix | tile_total);
+    } else {
+        if (tid == 0) atomicExch(&desc[tile], kDescAggregate | tile_total);
+        long long look = tile - 1;  // window covers tiles [look-255, look]
+        while (true) {
+            const long long idx = look - tid;
+            unsigned long long d = kDescPrefix;  // tiles before the first one: an empty prefix
+            if (idx >= 0) d = *reinterpret_cast<volatile unsigned long long *>(&desc[idx]);
+            while (!__syncthreads_and((d >> 62) != 0ull)) {
+                if ((d >> 62) == 0ull) d = *reinterpret_cast<volatile unsigned long long *>(&desc[idx]);
             }
-            if (lane == 0) atomicExch(&desc[tile], kDescPrefix | (excl + tile_total));
+            const unsigned int is_prefix = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
+            if (lane == 0) s_first[warp] = is_prefix ? (warp * 32 + __ffs(is_prefix) - 1) : 0x7fffffff;
+            __syncthreads();
+            int first = 0x7fffffff;  // nearest predecessor (smallest tid) that already holds a prefix
+#pragma unroll
+            for (int w = 0; w < NW; ++w) first = min(first, s_first[w]);
+            unsigned long long contrib = (tid <= first && idx >= 0) ? (d & kDescValueMask) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+            if (lane == 0) s_warp[warp] = contrib;
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < NW; ++w) excl += s_warp[w];
+            __syncthreads();
+            if (first != 0x7fffffff) break;
+            look -= kScanThreads;
         }
-        if (lane == 0) {
-            s_excl = excl;
-            if (p.total != nullptr && tile == p.tpt - 1) p.total[t] = excl + tile_total;
-        }
+        if (tid == 0) atomicExch(&desc[tile], kDescPrefix | (excl + tile_total));
     }
-    __syncthreads();
+    if (tid == 0 && p.total != nullptr && tile == p.tpt - 1) p.total[t] = excl + tile_total;
     if (MODE == kScanTotals) return;
 
-    // ---- ancestors: source j owns slots [count_le(K_{j-1}), count_le(K_j)) ----
-    __shared__ long long s_run_lo[kRunQueue], s_run_hi[kRunQueue];
-    __shared__ unsigned int s_run_src[kRunQueue];
-    __shared__ unsigned int s_nrun;
-    if (tid == 0) s_nrun = 0u;
-    __syncthreads();
-    unsigned long long K = p.k_offset + s_excl + thread_excl;
+    // ---- slot range of every source ----
     const double nd = static_cast<double>(p.n_global);
-    uint32_t *anc = p.anc + static_cast<long long>(t) * p.anc_cap;
-    auto emit = [&](long long o, uint32_t j, float px, float py, float pth) {
-        if (o >= 0 && o < p.anc_cap) {
-            if (MODE == kScanExpand) {
-                p.ox[o] = px;
-                p.oy[o] = py;
-                p.oth[o] = pth;
-            } else {
-                anc[o] = j;
-            }
-        }
-    };
-    if (j0 < p.n) {
-        long long start = count_le(K, p.delta, ofs, p.n_global, nd);
+    double Kd = static_cast<double>(p.k_offset + excl + thread_excl);
+    const double first_slot = count_le(Kd, p.delta, ofs, nd);
+    double cur = first_slot;
+    uint32_t rel[kScanItems];  // first slot of source k relative to the thread's first slot
+    uint32_t owners = 0;       // bit k: source k owns at least one slot
 #pragma unroll
-        for (int k = 0; k < kScanItems; ++k) {
-            const long long j = j0 + k;
-            if (j < p.n) {
-                K += q[k];
-                // the last particle of the whole filter also takes every slot past the final cumulative
-                // weight (the reference would raise IndexError there)
-                const long long end =
-                    (p.j_global_base + j == p.n_global - 1) ? p.n_global : count_le(K, p.delta, ofs, p.n_global, nd);
-                if (end > start) {
-                    unsigned int slot = kRunQueue;
-                    if (end - start > kShortRun) slot = atomicAdd(&s_nrun, 1u);
-                    if (slot < kRunQueue) {
-                        s_run_lo[slot] = start;
-                        s_run_hi[slot] = end;
-                        s_run_src[slot] = static_cast<uint32_t>(j);
-                    } else {
-                        float px = 0.f, py = 0.f, pth = 0.f;
-                        if (MODE == kScanExpand) {
-                            px = p.src.x[j];
-                            py = p.src.y[j];
-                            pth = p.src.th[j];
-                        }
-                        for (long long s = start; s < end; ++s) emit(s - p.slot_first, static_cast<uint32_t>(j), px, py, pth);
-                    }
-                }
-                start = end;
-            }
+    for (int k = 0; k < kScanItems; ++k) {
+        rel[k] = static_cast<uint32_t>(cur - first_slot);
+        Kd += qd[k];
+        double end = count_le(Kd, p.delta, ofs, nd);
+        // the last particle of the whole filter also takes every slot past the final cumulative weight
+        // (the reference would raise IndexError there)
+        if (p.j_global_base + j0 + k == p.n_global - 1) end = nd;
+        if (j0 + k < p.n && end > cur) {
+            owners |= 1u << k;
+            cur = end;
         }
     }
+    // tile slot range [S0, S1): S0 from the first thread, S1 from the last thread holding sources
+    const long long n_in_tile = min(static_cast<long long>(kScanTile), p.n - tile * kScanTile);
+    const int last_tid = static_cast<int>((n_in_tile - 1) / kScanItems);
+    if (tid == 0) s_slot[0] = first_slot;
+    if (tid == last_tid) s_slot[1] = cur;
     __syncthreads();
-    const unsigned int nrun = min(s_nrun, static_cast<unsigned int>(kRunQueue));
-    for (unsigned int r = 0; r < nrun; ++r) {
-        const long long lo = s_run_lo[r], hi = s_run_hi[r];
-        const uint32_t j = s_run_src[r];
-        float px = 0.f, py = 0.f, pth = 0.f;
-        if (MODE == kScanExpand) {
-            px = p.src.x[j];
-            py = p.src.y[j];
-            pth = p.src.th[j];
+    const double S0d = s_slot[0];
+    const long long S0 = static_cast<long long>(S0d), span = static_cast<long long>(s_slot[1] - S0d);
+    const long long my_off = static_cast<long long>(first_slot - S0d);  // >= 0 for threads that hold sources
+
+    uint32_t *anc = p.anc + static_cast<long long>(t) * p.anc_cap;
+    uint32_t carry = 0;  // source (local index + 1) that owns the slot just before the window
+    for (long long cb = 0; cb < span; cb += kScanTile) {
+        // window of kScanTile slots starting at S0 + cb
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) s_mark[k * kScanThreads + tid] = 0u;
+        __syncthreads();
+        if (owners) {
+#pragma unroll
+            for (int k = 0; k < kScanItems; ++k) {
+                const long long pos = my_off + rel[k] - cb;
+                if (((owners >> k) & 1u) && pos >= 0 && pos < kScanTile)
+                    s_mark[pos] = static_cast<uint32_t>(tid * kScanItems + k + 1);
+            }
         }
-        for (long long s = lo + tid; s < hi; s += kScanThreads) emit(s - p.slot_first, j, px, py, pth);
+        __syncthreads();
+        // inclusive max-scan over the window, 8 consecutive entries per thread
+        uint32_t v[kScanItems];
+        {
+            const uint4 a = *reinterpret_cast<const uint4 *>(&s_mark[tid * kScanItems]);
+            const uint4 b = *reinterpret_cast<const uint4 *>(&s_mark[tid * kScanItems + 4]);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
+#pragma unroll
+        for (int k = 1; k < kScanItems; ++k) v[k] = max(v[k], v[k - 1]);
+        uint32_t run = v[kScanItems - 1];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, run, o);
+            if (lane >= o) run = max(run, n);
+        }
+        if (lane == 31) s_wmax[warp] = run;
+        uint32_t before = __shfl_up_sync(0xffffffffu, run, 1);
+        if (lane == 0) before = 0u;
+        __syncthreads();
+        uint32_t wbefore = carry, wall = carry;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t m = s_wmax[w];
+            if (w < warp) wbefore = max(wbefore, m);
+            wall = max(wall, m);
+        }
+        before = max(before, wbefore);
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) v[k] = max(v[k], before);
+        *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(v[4], v[5], v[6], v[7]);
+        carry = wall;
+        __syncthreads();
+        // coalesced stores
+        const int lim = static_cast<int>(min(static_cast<long long>(kScanTile), span - cb));
+        const uint32_t jbase = static_cast<uint32_t>(tile * kScanTile) - 1u;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const int pos = k * kScanThreads + tid;
+            if (pos < lim) {
+                const long long o = S0 + cb + pos - p.slot_first;
+                const uint32_t j = jbase + s_mark[pos];
+                if (MODE == kScanExpand) {
+                    if (o >= 0 && o < p.anc_cap) {
+                        p.ox[o] = p.src.x[j];
+                        p.oy[o] = p.src.y[j];
+                        p.oth[o] = p.src.th[j];
+                    }
+                } else {
+                    anc[o] = j;  // slot_first == 0 and anc_cap >= n_global here
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
 // -------------------------------------------------------------------------------------------------
-// k_step : [gather] + predict + weight + reductions.
-// MODE 0 = full step; MODE 1 = reduce only (statistics of the current state, nothing written back)
+// Running statistics.  Every warp keeps ONE running maximum (warp-uniform, so rescaling is a
+// uniform branch) and fp32 sums relative to it; every kFlushEvery iterations the sums are reduced
+// across the warp and folded into fp64 sums held one-per-lane (lane k owns sum k).
+//   sums: 0 s1  1 s2  2 dx 3 dy 4 dth 5 sin 6 cos 7 xx 8 xy 9 yy 10 xth 11 yth 12 thth
+// sin/cos (5, 6) use the fp64 sin/cos of the likelihood and are kept per thread in fp64.
+// -------------------------------------------------------------------------------------------------
+struct WarpStats {
+    float m;            // warp-uniform running max of the stored log-weights (finite sentinel)
+    float g[11];        // fp32 group sums: s1 s2 dx dy dth xx xy yy xth yth thth
+    double asin_, acos_;  // per-thread fp64 sums of e sin(th), e cos(th)
+    double wacc;        // lane k < 11: fp64 sum k (order as g[])
+    float best_v;
+    uint32_t best_i;
+
+    __device__ __forceinline__ void init() {
+        m = -3.4028234e38f;
+        best_v = -INFINITY;
+        best_i = 0xffffffffu;
+        asin_ = acos_ = wacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 11; ++k) g[k] = 0.f;
+    }
+    // called by ALL lanes of the warp with the largest log-weight of their current group (-inf if none)
+    __device__ __forceinline__ void raise_max(float gm) {
+        if (__any_sync(0xffffffffu, gm > m)) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+            const float r = ex2_approx((m - gm) * kLog2e);  // 0 the first time
+            const float r2 = r * r;
+            const int lane = threadIdx.x & 31;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) g[k] *= (k == 1) ? r2 : r;  // s2 carries exp(2 (lw - m))
+            const double rd = r;
+            asin_ *= rd;
+            acos_ *= rd;
+            wacc *= (lane == 1) ? static_cast<double>(r2) : rd;
+            m = gm;
+        }
+    }
+    __device__ __forceinline__ void add(float lw, float x, float y, float th, double s, double c, float rx, float ry,
+                                        float rth, uint32_t idx) {
+        if (lw > best_v) {  // strict: first occurrence wins (np.argmax, particle_filter.py:116)
+            best_v = lw;
+            best_i = idx;
+        }
+        const float e = ex2_approx((lw - m) * kLog2e);  // lw = -inf gives 0 (m is finite)
+        const float dx = x - rx, dy = y - ry, dth = wrap_residual(th - rth);
+        const float ex = e * dx, ey = e * dy, et = e * dth;
+        g[0] += e;
+        g[1] = fmaf(e, e, g[1]);
+        g[2] += ex;
+        g[3] += ey;
+        g[4] += et;
+        g[5] = fmaf(ex, dx, g[5]);
+        g[6] = fmaf(ex, dy, g[6]);
+        g[7] = fmaf(ey, dy, g[7]);
+        g[8] = fmaf(ex, dth, g[8]);
+        g[9] = fmaf(ey, dth, g[9]);
+        g[10] = fmaf(et, dth, g[10]);
+        const double ed = e;
+        asin_ = fma(ed, s, asin_);
+        acos_ = fma(ed, c, acos_);
+    }
+    // warp-wide: all lanes
+    __device__ __forceinline__ void flush() {
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+            float v = g[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == k) wacc += static_cast<double>(v);
+            g[k] = 0.f;
+        }
+    }
+};
+
+__device__ __forceinline__ uint32_t float_order_key(float v) {
+    const uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_key(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Block partial -> partials[]; the last block of the trial merges all partials into mcl_stats and
+// re-arms the tickets.  Must be called by all threads of the block (kStepThreads).
+struct FinishParams {
+    double *partials;       // [T][bpt][kPart]
+    unsigned int *tickets;  // [T][4]  (slot 0 = scan ticket, slot 1 = reduce ticket)
+    mcl_stats *stats;       // [T]
+    int bpt;
+    const float *ex, *ey, *eth;  // trial-offset arrays of the state the statistics describe
+    double ref_x, ref_y, ref_th;
+    int set_step;           // 1: also write resampled / step
+    int resampled;
+    int step;
+};
+
+__device__ __forceinline__ void stats_finish(WarpStats &ws, const FinishParams &f, int t) {
+    constexpr int NW = kStepThreads / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double s_sum[NW][kNumSums];
+    __shared__ float s_m[NW];
+    __shared__ uint32_t s_bk[NW], s_bi[NW];
+    __shared__ int s_last;
+    __shared__ double s_fin[kNumSums + 1];
+
+    ws.flush();
+    double as = ws.asin_, ac = ws.acos_;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        as += __shfl_xor_sync(0xffffffffu, as, o);
+        ac += __shfl_xor_sync(0xffffffffu, ac, o);
+    }
+    // arg-max of the warp: largest value, then smallest index
+    const uint32_t key = float_order_key(ws.best_v);
+    const uint32_t wkey = __reduce_max_sync(0xffffffffu, key);
+    const uint32_t widx = __reduce_min_sync(0xffffffffu, (key == wkey) ? ws.best_i : 0xffffffffu);
+    // sums in the order of the partial record: s1 s2 dx dy dth sin cos xx xy yy xth yth thth
+    if (lane < 5) s_sum[warp][lane] = ws.wacc;
+    if (lane >= 5 && lane < 11) s_sum[warp][lane + 2] = ws.wacc;
+    if (lane == 0) {
+        s_sum[warp][5] = as;
+        s_sum[warp][6] = ac;
+        s_m[warp] = ws.m;
+        s_bk[warp] = wkey;
+        s_bi[warp] = widx;
+    }
+    __syncthreads();
+    if (tid < kNumSums + 1) {
+        float M = s_m[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) M = fmaxf(M, s_m[w]);
+        double *pp = f.partials + (static_cast<long long>(t) * f.bpt + blockIdx.x) * kPart;
+        if (tid < kNumSums) {
+            double acc = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const float r = ex2_approx((s_m[w] - M) * kLog2e);
+                acc = fma(s_sum[w][tid], static_cast<double>((tid == 1) ? r * r : r), acc);
+            }
+            pp[1 + tid] = acc;
+        } else {
+            uint32_t bk = s_bk[0], bi = s_bi[0];
+#pragma unroll
+            for (int w = 1; w < NW; ++w)
+                if (s_bk[w] > bk || (s_bk[w] == bk && s_bi[w] < bi)) { bk = s_bk[w]; bi = s_bi[w]; }
+            pp[0] = static_cast<double>(M);
+            pp[14] = static_cast<double>(float_from_order_key(bk));
+            pp[15] = static_cast<double>(bi);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&f.tickets[t * 4 + 1], 1u) == static_cast<unsigned int>(gridDim.x) - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+
+    // ---------------- last block of the trial: merge partials (fixed order) -> stats ----------------
+    const double *pp = f.partials + static_cast<long long>(t) * f.bpt * kPart;
+    const int nb = static_cast<int>(gridDim.x);
+    // warp w < 13 merges quantity w over the blocks (lane-strided, then a shuffle tree); all warps need MM first
+    double mm = -INFINITY;
+    for (int b = tid; b < nb; b += kStepThreads) mm = fmax(mm, __ldcg(pp + b * kPart));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mm = fmax(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+    __shared__ double s_mm[NW];
+    if (lane == 0) s_mm[warp] = mm;
+    __syncthreads();
+    double MM = s_mm[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) MM = fmax(MM, s_mm[w]);
+    for (int q = warp; q < kNumSums + 1; q += NW) {
+        if (q < kNumSums) {
+            double acc = 0.0;
+            for (int b = lane; b < nb; b += 32) {
+                const double r = exp(__ldcg(pp + b * kPart) - MM);  // partial maxima are finite (sentinel -> 0)
+                acc = fma(__ldcg(pp + b * kPart + 1 + q), (q == 1) ? r * r : r, acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) s_fin[q] = acc;
+        } else {
+            float bv = -INFINITY;
+            uint32_t bi = 0xffffffffu;
+            for (int b = lane; b < nb; b += 32) {
+                const float v = static_cast<float>(__ldcg(pp + b * kPart + 14));
+                const uint32_t i = static_cast<uint32_t>(__ldcg(pp + b * kPart + 15));
+                if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+            }
+            const uint32_t k = float_order_key(bv);
+            const uint32_t wk = __reduce_max_sync(0xffffffffu, k);
+            const uint32_t wi = __reduce_min_sync(0xffffffffu, (k == wk) ? bi : 0xffffffffu);
+            if (lane == 0) {
+                s_bk[0] = wk;
+                s_bi[0] = wi;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double *tot = s_fin;
+        const float bv = float_from_order_key(s_bk[0]);
+        const long long bi = s_bi[0];
+        mcl_stats *st = f.stats + t;
+        const double s1 = tot[0], s2 = tot[1];
+        st->max_logw = MM;
+        st->sum_w = s1;
+        st->sum_w2 = s2;
+        st->log_norm = MM + log(s1);
+        st->ess = s1 * s1 / s2;  // 1 / sum (w/s1)^2, particle_filter.py:210
+        st->max_weight = exp(static_cast<double>(bv) - MM) / s1;
+        st->max_idx = bi;
+        st->est[0] = __ldcg(f.ex + bi);
+        st->est[1] = __ldcg(f.ey + bi);
+        st->est[2] = __ldcg(f.eth + bi);
+#pragma unroll
+        for (int k = 0; k < 11; ++k) st->raw[k] = tot[2 + k];
+        st->raw[11] = 0.0;
+        st->ref[0] = f.ref_x; st->ref[1] = f.ref_y; st->ref[2] = f.ref_th;
+        // mean / covariance about the reference pose (single pass)
+        const double inv = 1.0 / s1;
+        const double mdx = tot[2] * inv, mdy = tot[3] * inv, mdt = tot[4] * inv;
+        const double mth = atan2(tot[5], tot[6]);         // circular mean of the yaw
+        const double del = limit_angle(mth - f.ref_th);    // its offset from the reference
+        st->mean[0] = f.ref_x + mdx;
+        st->mean[1] = f.ref_y + mdy;
+        st->mean[2] = mth;
+        const double cxx = tot[7] * inv - mdx * mdx, cxy = tot[8] * inv - mdx * mdy, cyy = tot[9] * inv - mdy * mdy;
+        const double cxt = tot[10] * inv - mdx * mdt, cyt = tot[11] * inv - mdy * mdt;
+        const double ctt = tot[12] * inv - 2.0 * del * mdt + del * del;
+        st->cov[0] = cxx; st->cov[1] = cxy; st->cov[2] = cxt;
+        st->cov[3] = cxy; st->cov[4] = cyy; st->cov[5] = cyt;
+        st->cov[6] = cxt; st->cov[7] = cyt; st->cov[8] = ctt;
+        if (f.set_step) {
+            st->resampled = f.resampled;
+            st->step = f.step;
+        }
+        // re-arm the tickets: every block of this trial has passed both
+        f.tickets[t * 4 + 0] = 0u;
+        f.tickets[t * 4 + 1] = 0u;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_step : [gather] + predict + weight + reductions, one launch per filter step.
 // -------------------------------------------------------------------------------------------------
 struct StepParams {
     StateView in, out;
@@ -343,47 +639,54 @@ struct StepParams {
     const float *noise;    // [3][T][n] dense, or null
     const PrepOut *prep;   // [T]
     const double4 *tab;    // [T][Lmax]
+    const TrigEntry *trig; // [kTrigEntries]
     double *partials;      // [T][bpt][kPart]
-    unsigned int *tickets; // [T][4] (slot 1 = reduce ticket)
+    unsigned int *tickets; // [T][4]
     mcl_stats *stats;      // [T]
-    long long n, ld;
+    uint32_t n;            // particles per trial
+    uint32_t per;          // particles per block (multiple of kStepUnit)
+    long long ld;
     long long slot_base;   // global index of local particle 0 (Philox counters)
     int T, bpt, Lmax;
-    int likelihood, motion;
-    uint32_t flags, step;
+    int motion;
+    uint32_t step;
     uint64_t seed;
-    double vdt, wdt;       // VEL*dt, YAW_RATE*dt
+    float vdt_f, wdt_f;    // VEL*dt, YAW_RATE*dt
+    double wdt;
     double vel, yaw_rate, dt;
-    double q_std[3];
+    float q_std[3];
     double inv_s0sq, inv_s1sq;
     double mb_sig[3];      // motion B: the three "sigma ** 2" scales (motion_model.py:43-48)
 };
 
-template <int MODE>
+template <int LIK, bool PHILOX>
 __global__ void __launch_bounds__(kStepThreads, 2) k_step(const StepParams p) {
-    const int t = blockIdx.y, tid = threadIdx.x;
+    const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double4 *s_tab = reinterpret_cast<double4 *>(smem_raw);                    // [L]
-    __shared__ double s_red[(kStepThreads / 32) * kPart];
-    __shared__ double s_prep[24];
-    __shared__ int s_last;
+    double4 *s_tab = reinterpret_cast<double4 *>(smem_raw);  // [L] (pair / RB only)
+    __shared__ PrepOut s_prep;
 
-    const PrepOut *po = p.prep + t;
-    const int L = po->L;
-    if (MODE == 0 && p.likelihood != MCL_LIK_MOMENT) {
-        const double4 *g = p.tab + static_cast<long long>(t) * p.Lmax;
-        for (int l = tid; l < L; l += blockDim.x) s_tab[l] = g[l];
-    }
-    if (tid < 13) s_prep[tid] = po->mom[tid];
-    if (tid == 13) s_prep[13] = po->c_shift;
-    if (tid >= 14 && tid < 17) s_prep[tid] = po->ref[tid - 14];
-    if (tid == 17) s_prep[17] = po->log_norm_prev;
-    if (tid == 18) s_prep[18] = po->lik_const;
-    if (tid == 19) s_prep[19] = po->base_lw;
-    const int resample = (MODE == 0) ? po->do_resample : 0;
+    if (tid < static_cast<int>(sizeof(PrepOut) / sizeof(double)))
+        reinterpret_cast<double *>(&s_prep)[tid] = reinterpret_cast<const double *>(p.prep + t)[tid];
     __syncthreads();
-    const double c_shift = s_prep[13], ref_x = s_prep[14], ref_y = s_prep[15], ref_th = s_prep[16];
-    const double log_norm_prev = s_prep[17], lik_const = s_prep[18], base_lw = s_prep[19];
+    const int L = s_prep.L;
+    if (LIK == kLikPair || LIK == kLikRB) {
+        const double4 *g = p.tab + static_cast<long long>(t) * p.Lmax;
+        for (int l = tid; l < L; l += kStepThreads) s_tab[l] = g[l];
+        __syncthreads();
+    }
+    const int resample = s_prep.do_resample;
+    const float ref_x = static_cast<float>(s_prep.ref[0]), ref_y = static_cast<float>(s_prep.ref[1]),
+                ref_th = static_cast<float>(s_prep.ref[2]);
+    const float max_prev = static_cast<float>(s_prep.max_prev);
+    const double shift = s_prep.lik_const - s_prep.c_shift;  // per-step constant added to every log-likelihood
+    // moment constants
+    const double Ld = static_cast<double>(L);
+    const double Slx = s_prep.mom[0], Sly = s_prep.mom[1], Szx = s_prep.mom[2], Szy = s_prep.mom[3];
+    const double isoK0 = s_prep.mom[4] + s_prep.mom[5] + s_prep.mom[7] + s_prep.mom[8];  // S_ll + S_zz
+    const double isoA = s_prep.mom[9] + s_prep.mom[12];                                  // sum zx lx + zy ly
+    const double isoB = s_prep.mom[11] - s_prep.mom[10];                                 // sum zy lx - zx ly
+    const double half0 = -0.5 * p.inv_s0sq, half1 = -0.5 * p.inv_s1sq;
 
     const long long off = static_cast<long long>(t) * p.ld;
     const float *ix = p.in.x + off, *iy = p.in.y + off, *ith = p.in.th + off, *ilw = p.in.lw + off;
@@ -391,44 +694,49 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const StepParams p) {
     const uint32_t *anc = p.anc + off;
     const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
 
-    // running (max, sums) of this thread
-    double m = -INFINITY;
-    double acc[kNumSums];
-#pragma unroll
-    for (int k = 0; k < kNumSums; ++k) acc[k] = 0.0;
-    float best_v = -INFINITY;
-    long long best_i = 0x7fffffffffffffffll;
+    WarpStats ws;
+    ws.init();
 
-    for (long long base = (static_cast<long long>(blockIdx.x) * kStepThreads + tid) * kPPT; base < p.n;
-         base += static_cast<long long>(gridDim.x) * kStepTile) {
+    // static contiguous partition of the trial's particles over the blocks (p.per is a multiple of 128,
+    // so a warp's 128 particles are either all inside the block's range or all outside)
+    const unsigned long long first64 = static_cast<unsigned long long>(blockIdx.x) * p.per;
+    const uint32_t first = static_cast<uint32_t>(min(first64, static_cast<unsigned long long>(p.n)));
+    const uint32_t last = static_cast<uint32_t>(min(first64 + p.per, static_cast<unsigned long long>(p.n)));
+
+    int since_flush = 0;
+    for (uint32_t wbase = first + (tid - lane) * kPPT; wbase < last; wbase += kStepTile) {
+        const uint32_t base = wbase + lane * kPPT;
+        const bool active = base < last;  // false only in the last, partial unit of the trial
         float x[kPPT], y[kPPT], th[kPPT], lwp[kPPT] = {0.f, 0.f, 0.f, 0.f};
-        // ---------------- load (gather through the ancestors when this step resamples) ----------------
-        if (resample) {
-            const uint4 a4 = *reinterpret_cast<const uint4 *>(anc + base);
-            const uint32_t a[kPPT] = {a4.x, a4.y, a4.z, a4.w};
+        float lwf[kPPT] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        double s[kPPT], c[kPPT];
+        if (active) {
+            // ---------------- load (gather through the ancestors when this step resamples) ----------------
+            if (resample) {
+                const uint4 a4 = *reinterpret_cast<const uint4 *>(anc + base);
+                const uint32_t a[kPPT] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-            for (int k = 0; k < kPPT; ++k) {
-                const uint32_t j = (base + k < p.n) ? a[k] : 0u;
-                x[k] = ix[j];
-                y[k] = iy[j];
-                th[k] = ith[j];
+                for (int k = 0; k < kPPT; ++k) {
+                    const uint32_t j = (base + k < p.n) ? a[k] : 0u;
+                    x[k] = ix[j];
+                    y[k] = iy[j];
+                    th[k] = ith[j];
+                }
+            } else {
+                const float4 vx = *reinterpret_cast<const float4 *>(ix + base);
+                const float4 vy = *reinterpret_cast<const float4 *>(iy + base);
+                const float4 vt = *reinterpret_cast<const float4 *>(ith + base);
+                const float4 vw = *reinterpret_cast<const float4 *>(ilw + base);
+                x[0] = vx.x; x[1] = vx.y; x[2] = vx.z; x[3] = vx.w;
+                y[0] = vy.x; y[1] = vy.y; y[2] = vy.z; y[3] = vy.w;
+                th[0] = vt.x; th[1] = vt.y; th[2] = vt.z; th[3] = vt.w;
+                // weights stay relative to their maximum: pw * bn (:194) in logs, minus a per-step constant
+                lwp[0] = vw.x - max_prev; lwp[1] = vw.y - max_prev; lwp[2] = vw.z - max_prev; lwp[3] = vw.w - max_prev;
             }
-        } else {
-            const float4 vx = *reinterpret_cast<const float4 *>(ix + base);
-            const float4 vy = *reinterpret_cast<const float4 *>(iy + base);
-            const float4 vt = *reinterpret_cast<const float4 *>(ith + base);
-            const float4 vw = *reinterpret_cast<const float4 *>(ilw + base);
-            x[0] = vx.x; x[1] = vx.y; x[2] = vx.z; x[3] = vx.w;
-            y[0] = vy.x; y[1] = vy.y; y[2] = vy.z; y[3] = vy.w;
-            th[0] = vt.x; th[1] = vt.y; th[2] = vt.z; th[3] = vt.w;
-            lwp[0] = vw.x; lwp[1] = vw.y; lwp[2] = vw.z; lwp[3] = vw.w;
-        }
 
-        double lw_new[kPPT];
-        if (MODE == 0) {
             // ---------------- motion noise ----------------
             float nz[kPPT][3];
-            if (p.noise != nullptr) {
+            if (!PHILOX) {
                 const long long plane = static_cast<long long>(p.T) * p.n;
                 const float *nb = p.noise + static_cast<long long>(t) * p.n;
 #pragma unroll
@@ -442,36 +750,40 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const StepParams p) {
                 const unsigned long long grp = static_cast<unsigned long long>(p.slot_base + base) >> 2;
                 float nrm[12];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(grp), static_cast<uint32_t>(grp >> 32) * 4u + c,
-                                                             p.step, static_cast<uint32_t>(t)), key);
+                for (int cc = 0; cc < 3; ++cc) {
+                    const uint4 r = philox4x32_10(
+                        make_uint4(static_cast<uint32_t>(grp), static_cast<uint32_t>(grp >> 32) * 4u + cc, p.step,
+                                   static_cast<uint32_t>(t)), key);
                     const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
-                    nrm[4 * c + 0] = a.x; nrm[4 * c + 1] = a.y; nrm[4 * c + 2] = b.x; nrm[4 * c + 3] = b.y;
+                    nrm[4 * cc + 0] = a.x; nrm[4 * cc + 1] = a.y; nrm[4 * cc + 2] = b.x; nrm[4 * cc + 3] = b.y;
                 }
 #pragma unroll
                 for (int k = 0; k < kPPT; ++k)
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        const float sc = (p.motion == MCL_MOTION_A) ? static_cast<float>(p.q_std[d]) : 1.0f;
-                        nz[k][d] = nrm[3 * k + d] * sc;
-                    }
+                    for (int d = 0; d < 3; ++d)
+                        nz[k][d] = nrm[3 * k + d] * ((p.motion == MCL_MOTION_A) ? p.q_std[d] : 1.0f);
             }
 
             // ---------------- predict ----------------
+            if (p.motion == MCL_MOTION_A) {
 #pragma unroll
-            for (int k = 0; k < kPPT; ++k) {
-                const double thd = static_cast<double>(th[k]);
-                double xn, yn, thn;
-                if (p.motion == MCL_MOTION_A) {
-                    // particle_filter.py:129-142 then "+ v" (:166): cos/sin of the PRE-update yaw; the wrap is
-                    // applied before the noise, so the stored yaw may leave [-pi, pi]
+                for (int k = 0; k < kPPT; ++k) {
+                    // particle_filter.py:129-142 then "+ v" (:166): cos/sin of the PRE-update yaw; the wrap
+                    // is applied before the noise, so the stored yaw may leave [-pi, pi]
                     float s0, c0;
-                    sincosf(th[k], &s0, &c0);
-                    xn = static_cast<double>(x[k]) + p.vdt * static_cast<double>(c0) + static_cast<double>(nz[k][0]);
-                    yn = static_cast<double>(y[k]) + p.vdt * static_cast<double>(s0) + static_cast<double>(nz[k][1]);
-                    thn = limit_angle(thd + p.wdt) + static_cast<double>(nz[k][2]);
-                } else {
+                    __sincosf(th[k], &s0, &c0);
+                    x[k] = fmaf(p.vdt_f, c0, x[k]) + nz[k][0];
+                    y[k] = fmaf(p.vdt_f, s0, y[k]) + nz[k][1];
+                    float tn = th[k] + p.wdt_f;
+                    if (!(fabsf(tn) < 3.1415f))  // at or past the seam: wrap exactly like mylib/limit.py, in fp64
+                        tn = static_cast<float>(limit_angle(static_cast<double>(th[k]) + p.wdt));
+                    th[k] = tn + nz[k][2];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kPPT; ++k) {
                     // motion_model.py:46-56; sigma**2 used as the standard deviation (reference quirk)
+                    const double thd = static_cast<double>(th[k]);
                     const double vh = p.vel + static_cast<double>(nz[k][0]) * p.mb_sig[0];
                     const double wh = p.yaw_rate + static_cast<double>(nz[k][1]) * p.mb_sig[1];
                     const double gh = static_cast<double>(nz[k][2]) * p.mb_sig[2];
@@ -479,242 +791,163 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const StepParams p) {
                     double s0, c0, s1, c1;
                     sincos(thd, &s0, &c0);
                     sincos(thd + b, &s1, &c1);
-                    xn = static_cast<double>(x[k]) - a * s0 + a * s1;
-                    yn = static_cast<double>(y[k]) + a * c0 - a * c1;
-                    thn = limit_angle(thd + (wh + gh) * p.dt);
+                    x[k] = static_cast<float>(static_cast<double>(x[k]) - a * s0 + a * s1);
+                    y[k] = static_cast<float>(static_cast<double>(y[k]) + a * c0 - a * c1);
+                    th[k] = static_cast<float>(limit_angle(thd + (wh + gh) * p.dt));
                 }
-                x[k] = static_cast<float>(xn);
-                y[k] = static_cast<float>(yn);
-                th[k] = static_cast<float>(thn);
             }
 
             // ---------------- weight: log-likelihood of the STORED (fp32) pose, fp64 arithmetic ----------------
-            double s[kPPT], c[kPPT], tx[kPPT], ty[kPPT];
 #pragma unroll
             for (int k = 0; k < kPPT; ++k) {
-                sincos(static_cast<double>(th[k]), &s[k], &c[k]);
+                sincos_tab(th[k], p.trig, s[k], c[k]);
                 const double xd = x[k], yd = y[k];
-                tx[k] = -(s[k] * xd - c[k] * yd);
-                ty[k] = -(c[k] * xd + s[k] * yd);
-            }
-            double q0[kPPT], q1[kPPT];
-            if (p.likelihood == MCL_LIK_MOMENT) {
-                // sum_l ex^2 = S(aa) - 2 P1 S(a) + L P1^2 with a_l = s lx - c ly - zx, P1 = s x - c y (= -tx)
-                const double Slx = s_prep[0], Sly = s_prep[1], Szx = s_prep[2], Szy = s_prep[3];
-                const double Sxx = s_prep[4], Syy = s_prep[5], Sxy = s_prep[6], Szxzx = s_prep[7], Szyzy = s_prep[8];
-                const double Slxzx = s_prep[9], Slyzx = s_prep[10], Slxzy = s_prep[11], Slyzy = s_prep[12];
-                const double Ld = static_cast<double>(L);
-#pragma unroll
-                for (int k = 0; k < kPPT; ++k) {
+                double ll;
+                if (LIK == kLikMomentIso) {
+                    // sum_l |M(l - p) - z_l|^2 = S_ll + S_zz - 2 p.S_l + L |p|^2 - 2 (s A + c B) + 2 S_z.(M p),
+                    // M = [[s, -c], [c, s]]  (rotations preserve the norm; exact identity, evaluated in fp64)
+                    const double mpx = fma(s[k], xd, -(c[k] * yd)), mpy = fma(c[k], xd, s[k] * yd);
+                    double Q = fma(Ld, fma(xd, xd, yd * yd), isoK0);
+                    Q = fma(-2.0, fma(xd, Slx, yd * Sly), Q);
+                    Q = fma(-2.0, fma(s[k], isoA, c[k] * isoB), Q);
+                    Q = fma(2.0, fma(Szx, mpx, Szy * mpy), Q);
+                    ll = half0 * Q;
+                } else if (LIK == kLikMomentGen) {
+                    // sum_l ex^2 = S(aa) + 2 tx S(a) + L tx^2 with a_l = s lx - c ly - zx, tx = -(s x - c y)
+                    const double tx = -(s[k] * xd - c[k] * yd), ty = -(c[k] * xd + s[k] * yd);
                     const double ss = s[k] * s[k], cc = c[k] * c[k], sc = s[k] * c[k];
+                    const double Sxx = s_prep.mom[4], Syy = s_prep.mom[5], Sxy = s_prep.mom[6];
                     const double Sa = s[k] * Slx - c[k] * Sly - Szx;
-                    const double Saa = ss * Sxx + cc * Syy - 2.0 * sc * Sxy + Szxzx - 2.0 * s[k] * Slxzx + 2.0 * c[k] * Slyzx;
+                    const double Saa = ss * Sxx + cc * Syy - 2.0 * sc * Sxy + s_prep.mom[7] -
+                                       2.0 * s[k] * s_prep.mom[9] + 2.0 * c[k] * s_prep.mom[10];
                     const double Sb = c[k] * Slx + s[k] * Sly - Szy;
-                    const double Sbb = cc * Sxx + ss * Syy + 2.0 * sc * Sxy + Szyzy - 2.0 * c[k] * Slxzy - 2.0 * s[k] * Slyzy;
-                    q0[k] = Saa + 2.0 * tx[k] * Sa + Ld * tx[k] * tx[k];
-                    q1[k] = Sbb + 2.0 * ty[k] * Sb + Ld * ty[k] * ty[k];
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < kPPT; ++k) q0[k] = q1[k] = 0.0;
-                if (p.likelihood == MCL_LIK_PAIR) {
-#pragma unroll 4
-                    for (int l = 0; l < L; ++l) {
-                        const double4 tb = s_tab[l];
-#pragma unroll
-                        for (int k = 0; k < kPPT; ++k) {
-                            double ex, ey;
-                            pair_residual_c(s[k], c[k], tx[k], ty[k], tb, ex, ey);
-                            q0[k] = fma(ex, ex, q0[k]);
-                            q1[k] = fma(ey, ey, q1[k]);
-                        }
-                    }
+                    const double Sbb = cc * Sxx + ss * Syy + 2.0 * sc * Sxy + s_prep.mom[8] -
+                                       2.0 * c[k] * s_prep.mom[11] - 2.0 * s[k] * s_prep.mom[12];
+                    const double q0 = Saa + 2.0 * tx * Sa + Ld * tx * tx;
+                    const double q1 = Sbb + 2.0 * ty * Sb + Ld * ty * ty;
+                    ll = fma(half0, q0, half1 * q1);
                 } else {
-                    for (int l = 0; l < L; ++l) {
-                        const double4 tb = s_tab[l];
-#pragma unroll
-                        for (int k = 0; k < kPPT; ++k) {
-                            double ed, ephi;
-                            pair_residual_rb(s[k], c[k], tx[k], ty[k], tb, ed, ephi);
-                            q0[k] = fma(ed, ed, q0[k]);
-                            q1[k] = fma(ephi, ephi, q1[k]);
+                    const double tx = -(s[k] * xd - c[k] * yd), ty = -(c[k] * xd + s[k] * yd);
+                    double q0 = 0.0, q1 = 0.0;
+                    if (LIK == kLikPair) {
+#pragma unroll 4
+                        for (int l = 0; l < L; ++l) {
+                            double e0, e1;
+                            pair_residual_c(s[k], c[k], tx, ty, s_tab[l], e0, e1);
+                            q0 = fma(e0, e0, q0);
+                            q1 = fma(e1, e1, q1);
+                        }
+                    } else {
+                        for (int l = 0; l < L; ++l) {
+                            double e0, e1;
+                            pair_residual_rb(s[k], c[k], tx, ty, s_tab[l], e0, e1);
+                            q0 = fma(e0, e0, q0);
+                            q1 = fma(e1, e1, q1);
                         }
                     }
+                    ll = fma(half0, q0, half1 * q1);
                 }
-            }
-#pragma unroll
-            for (int k = 0; k < kPPT; ++k) {
-                const double ll = -0.5 * (q0[k] * p.inv_s0sq + q1[k] * p.inv_s1sq) + lik_const;
-                const double prev = resample ? base_lw : (static_cast<double>(lwp[k]) - log_norm_prev);
-                lw_new[k] = prev + (ll - c_shift);  // pw * bn (:194), in logs, shifted by a per-step constant
+                lwf[k] = static_cast<float>(static_cast<double>(lwp[k]) + (ll + shift));
             }
             // ---------------- store ----------------
-            float lwf[kPPT];
-#pragma unroll
-            for (int k = 0; k < kPPT; ++k) lwf[k] = static_cast<float>(lw_new[k]);
             *reinterpret_cast<float4 *>(ox + base) = make_float4(x[0], x[1], x[2], x[3]);
             *reinterpret_cast<float4 *>(oy + base) = make_float4(y[0], y[1], y[2], y[3]);
             *reinterpret_cast<float4 *>(oth + base) = make_float4(th[0], th[1], th[2], th[3]);
             *reinterpret_cast<float4 *>(olw + base) = make_float4(lwf[0], lwf[1], lwf[2], lwf[3]);
 #pragma unroll
-            for (int k = 0; k < kPPT; ++k) lw_new[k] = static_cast<double>(lwf[k]);  // statistics of what is stored
-        } else {
-#pragma unroll
-            for (int k = 0; k < kPPT; ++k) lw_new[k] = static_cast<double>(lwp[k]);
+            for (int k = 0; k < kPPT; ++k)
+                if (base + k >= p.n) lwf[k] = -INFINITY;  // padding of the last unit: no statistics
         }
 
-        // ---------------- running statistics (online max + rescaled sums) ----------------
+        // ---------------- running statistics of what was stored (all lanes take part in the votes) ----------------
+        ws.raise_max(fmaxf(fmaxf(lwf[0], lwf[1]), fmaxf(lwf[2], lwf[3])));
+        if (active) {
 #pragma unroll
-        for (int k = 0; k < kPPT; ++k) {
-            if (base + k >= p.n) continue;
-            const double lw = lw_new[k];
-            const float lwf = static_cast<float>(lw);
-            if (lwf > best_v) {  // strict: first occurrence wins (np.argmax, particle_filter.py:116)
-                best_v = lwf;
-                best_i = base + k;
-            }
-            double e;
-            if (lw > m) {
-                const double r = exp(m - lw);  // exp(-inf) = 0 on the first particle
-#pragma unroll
-                for (int a = 0; a < kNumSums; ++a) acc[a] *= (a == 1) ? r * r : r;  // s2 carries exp(2 (lw - m))
-                m = lw;
-                e = 1.0;
-            } else {
-                e = exp(lw - m);
-            }
-            const double dx = static_cast<double>(x[k]) - ref_x, dy = static_cast<double>(y[k]) - ref_y;
-            const double thd = static_cast<double>(th[k]);
-            const double dth = limit_angle(thd - ref_th);
-            double sn, cs;
-            sincos(thd, &sn, &cs);
-            acc[0] += e;
-            acc[1] = fma(e, e, acc[1]);
-            const double ex = e * dx, ey = e * dy, et = e * dth;
-            acc[2] += ex;  acc[3] += ey;  acc[4] += et;
-            acc[5] = fma(e, sn, acc[5]);
-            acc[6] = fma(e, cs, acc[6]);
-            acc[7] = fma(ex, dx, acc[7]);
-            acc[8] = fma(ex, dy, acc[8]);
-            acc[9] = fma(ey, dy, acc[9]);
-            acc[10] = fma(ex, dth, acc[10]);
-            acc[11] = fma(ey, dth, acc[11]);
-            acc[12] = fma(et, dth, acc[12]);
+            for (int k = 0; k < kPPT; ++k)
+                if (base + k < p.n) ws.add(lwf[k], x[k], y[k], th[k], s[k], c[k], ref_x, ref_y, ref_th, base + k);
+        }
+        if (++since_flush == kFlushEvery) {
+            ws.flush();
+            since_flush = 0;
         }
     }
 
-    // ---------------- block partial ----------------
-    const double M = block_max(m, s_red);
-    {
-        const double r = (m == -INFINITY) ? 0.0 : exp(m - M);
-        // s2 carries exp(2 (lw - m)): rescale with r^2
-#pragma unroll
-        for (int a = 0; a < kNumSums; ++a) acc[a] *= (a == 1) ? r * r : r;
-    }
-    block_sum<kNumSums>(acc, s_red);
-    // argmax across the block
-    {
-        float bv = best_v;
-        long long bi = best_i;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        __shared__ float s_bv[kStepThreads / 32];
-        __shared__ long long s_bi[kStepThreads / 32];
-        if ((tid & 31) == 0) { s_bv[tid >> 5] = bv; s_bi[tid >> 5] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < kStepThreads / 32; ++w)
-                if (s_bv[w] > bv || (s_bv[w] == bv && s_bi[w] < bi)) { bv = s_bv[w]; bi = s_bi[w]; }
-            double *pp = p.partials + (static_cast<long long>(t) * p.bpt + blockIdx.x) * kPart;
-            pp[0] = M;
-#pragma unroll
-            for (int a = 0; a < kNumSums; ++a) pp[1 + a] = acc[a];
-            pp[14] = static_cast<double>(bv);
-            pp[15] = static_cast<double>(bi);
-            __threadfence();
-            s_last = (atomicAdd(&p.tickets[t * 4 + 1], 1u) == static_cast<unsigned int>(gridDim.x) - 1u);
-        }
-        __syncthreads();
-    }
-    if (!s_last) return;
-    __threadfence();
+    FinishParams f;
+    f.partials = p.partials;
+    f.tickets = p.tickets;
+    f.stats = p.stats;
+    f.bpt = p.bpt;
+    f.ex = ox;
+    f.ey = oy;
+    f.eth = oth;
+    f.ref_x = s_prep.ref[0];
+    f.ref_y = s_prep.ref[1];
+    f.ref_th = s_prep.ref[2];
+    f.set_step = 1;
+    f.resampled = resample;
+    f.step = static_cast<int>(p.step + 1u);
+    stats_finish(ws, f, t);
+}
 
-    // ---------------- last block of the trial: merge partials -> stats ----------------
-    const double *pp = p.partials + static_cast<long long>(t) * p.bpt * kPart;
-    double mm = -INFINITY;
-    for (int b = tid; b < static_cast<int>(gridDim.x); b += blockDim.x) mm = fmax(mm, __ldcg(pp + b * kPart));
-    const double MM = block_max(mm, s_red);
-    double tot[kNumSums];
-#pragma unroll
-    for (int a = 0; a < kNumSums; ++a) tot[a] = 0.0;
-    float bv = -INFINITY;
-    long long bi = 0x7fffffffffffffffll;
-    for (int b = tid; b < static_cast<int>(gridDim.x); b += blockDim.x) {
-        const double *q = pp + b * kPart;
-        const double mb = __ldcg(q);
-        const double r = (mb == -INFINITY) ? 0.0 : exp(mb - MM);
-#pragma unroll
-        for (int a = 0; a < kNumSums; ++a) tot[a] += __ldcg(q + 1 + a) * ((a == 1) ? r * r : r);
-        const float v = static_cast<float>(__ldcg(q + 14));
-        const long long i = static_cast<long long>(__ldcg(q + 15));
-        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+// -------------------------------------------------------------------------------------------------
+// k_reduce : statistics of the stored state (after mcl_set_particles); nothing is written back.
+// The reference pose of the moment sums is particle 0 (from_particle0) or the stored estimate.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kStepThreads, 2) k_reduce(const StepParams p, int from_particle0) {
+    const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const long long off = static_cast<long long>(t) * p.ld;
+    const float *ix = p.in.x + off, *iy = p.in.y + off, *ith = p.in.th + off, *ilw = p.in.lw + off;
+    float ref_x, ref_y, ref_th;
+    if (from_particle0) {
+        ref_x = ix[0];
+        ref_y = iy[0];
+        ref_th = ith[0];
+    } else {
+        ref_x = static_cast<float>(p.stats[t].est[0]);
+        ref_y = static_cast<float>(p.stats[t].est[1]);
+        ref_th = static_cast<float>(p.stats[t].est[2]);
     }
-    block_sum<kNumSums>(tot, s_red);
-    {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    WarpStats ws;
+    ws.init();
+    int since_flush = 0;
+    const uint32_t stride = gridDim.x * kStepThreads;
+    for (uint32_t wb = blockIdx.x * kStepThreads + (tid - lane); wb < p.n; wb += stride) {
+        const uint32_t i = wb + lane;
+        const bool active = i < p.n;
+        float lw = -INFINITY, x = 0.f, y = 0.f, th = 0.f;
+        if (active) {
+            lw = ilw[i];
+            x = ix[i];
+            y = iy[i];
+            th = ith[i];
         }
-        __shared__ float s_bv2[kStepThreads / 32];
-        __shared__ long long s_bi2[kStepThreads / 32];
-        if ((tid & 31) == 0) { s_bv2[tid >> 5] = bv; s_bi2[tid >> 5] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < kStepThreads / 32; ++w)
-                if (s_bv2[w] > bv || (s_bv2[w] == bv && s_bi2[w] < bi)) { bv = s_bv2[w]; bi = s_bi2[w]; }
-            mcl_stats *st = p.stats + t;
-            const double s1 = tot[0], s2 = tot[1];
-            st->max_logw = MM;
-            st->sum_w = s1;
-            st->sum_w2 = s2;
-            st->log_norm = MM + log(s1);
-            st->ess = s1 * s1 / s2;  // 1 / sum (w/s1)^2, particle_filter.py:210
-            st->max_weight = exp(static_cast<double>(bv) - MM) / s1;
-            st->max_idx = bi;
-            const float *ex = (MODE == 0) ? ox : ix, *ey = (MODE == 0) ? oy : iy, *eth = (MODE == 0) ? oth : ith;
-            st->est[0] = __ldcg(ex + bi);
-            st->est[1] = __ldcg(ey + bi);
-            st->est[2] = __ldcg(eth + bi);
-#pragma unroll
-            for (int a = 0; a < 11; ++a) st->raw[a] = tot[2 + a];
-            st->raw[11] = 0.0;
-            st->ref[0] = ref_x; st->ref[1] = ref_y; st->ref[2] = ref_th;
-            // mean / covariance about the reference pose (single pass)
-            const double inv = 1.0 / s1;
-            const double mdx = tot[2] * inv, mdy = tot[3] * inv, mdt = tot[4] * inv;
-            const double mth = atan2(tot[5], tot[6]);            // circular mean of the yaw
-            const double del = limit_angle(mth - ref_th);         // its offset from the reference
-            st->mean[0] = ref_x + mdx;
-            st->mean[1] = ref_y + mdy;
-            st->mean[2] = mth;
-            const double cxx = tot[7] * inv - mdx * mdx, cxy = tot[8] * inv - mdx * mdy, cyy = tot[9] * inv - mdy * mdy;
-            const double cxt = tot[10] * inv - mdx * mdt, cyt = tot[11] * inv - mdy * mdt;
-            const double ctt = tot[12] * inv - 2.0 * del * mdt + del * del;
-            st->cov[0] = cxx; st->cov[1] = cxy; st->cov[2] = cxt;
-            st->cov[3] = cxy; st->cov[4] = cyy; st->cov[5] = cyt;
-            st->cov[6] = cxt; st->cov[7] = cyt; st->cov[8] = ctt;
-            if (MODE == 0) {
-                st->resampled = resample;
-                st->step = static_cast<int32_t>(p.step + 1u);
-            }
+        ws.raise_max(lw);
+        if (active) {
+            double s, c;
+            sincos(static_cast<double>(th), &s, &c);
+            ws.add(lw, x, y, th, s, c, ref_x, ref_y, ref_th, i);
         }
+        if (++since_flush == 32) {
+            ws.flush();
+            since_flush = 0;
+        }
+        if (wb + stride < wb) break;  // 32-bit wrap guard for n close to 2^32
     }
+    FinishParams f;
+    f.partials = p.partials;
+    f.tickets = p.tickets;
+    f.stats = p.stats;
+    f.bpt = p.bpt;
+    f.ex = ix;
+    f.ey = iy;
+    f.eth = ith;
+    f.ref_x = ref_x;
+    f.ref_y = ref_y;
+    f.ref_th = ref_th;
+    f.set_step = 0;
+    f.resampled = 0;
+    f.step = 0;
+    stats_finish(ws, f, t);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -725,6 +958,7 @@ struct GatherParams {
     const uint32_t *anc;
     const PrepOut *prep;
     mcl_stats *stats;
+    unsigned int *tickets;
     long long n, ld;
     double n_global;
 };
@@ -734,7 +968,6 @@ __global__ void __launch_bounds__(256) k_gather(const GatherParams p) {
     const PrepOut *po = p.prep + t;
     const int rs = po->do_resample;
     const long long off = static_cast<long long>(t) * p.ld;
-    const float base_lw = static_cast<float>(po->base_lw);
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         if (rs) {
@@ -742,7 +975,7 @@ __global__ void __launch_bounds__(256) k_gather(const GatherParams p) {
             p.out.x[off + i] = p.in.x[off + j];
             p.out.y[off + i] = p.in.y[off + j];
             p.out.th[off + i] = p.in.th[off + j];
-            p.out.lw[off + i] = base_lw;
+            p.out.lw[off + i] = 0.0f;
         } else {
             p.out.x[off + i] = p.in.x[off + i];
             p.out.y[off + i] = p.in.y[off + i];
@@ -751,35 +984,17 @@ __global__ void __launch_bounds__(256) k_gather(const GatherParams p) {
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+        p.tickets[t * 4 + 0] = 0u;  // re-arm the scan ticket (no k_step follows in the stage API)
         mcl_stats *st = p.stats + t;
         st->resampled = rs;
-        if (rs) {  // weights reset to 1/NP (:222)
-            st->log_norm = 0.0;
+        if (rs) {  // weights reset to 1/NP (:222): stored log-weights 0, normaliser log NP
+            st->log_norm = log(p.n_global);
             st->ess = p.n_global;
             st->max_weight = 1.0 / p.n_global;
-            st->max_logw = po->base_lw;
+            st->max_logw = 0.0;
+            st->sum_w = p.n_global;
+            st->sum_w2 = p.n_global;
         }
-    }
-}
-
-// -------------------------------------------------------------------------------------------------
-// k_shard_expand : sender side of the sharded resampling: resampled poses of every global slot this
-// shard's particles fill, written at (slot - slot_first).
-// -------------------------------------------------------------------------------------------------
-struct ExpandParams {
-    StateView in;
-    const uint32_t *anc;  // indexed by slot - slot_first
-    float *ox, *oy, *oth;
-    long long n_slots;
-};
-
-__global__ void __launch_bounds__(256) k_shard_expand(const ExpandParams p) {
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n_slots;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const uint32_t j = p.anc[i];
-        p.ox[i] = p.in.x[j];
-        p.oy[i] = p.in.y[j];
-        p.oth[i] = p.in.th[j];
     }
 }
 
@@ -854,11 +1069,11 @@ __global__ void k_init_stats(mcl_stats *stats, const double *pose, double n_glob
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     mcl_stats z = {};
-    z.log_norm = 0.0;
+    z.log_norm = log(n_global);  // stored log-weights are 0: w = exp(0 - log NP) = 1/NP (particle_filter.py:83-84)
     z.ess = n_global;
     z.max_weight = 1.0 / n_global;
     z.max_idx = 0;
-    z.sum_w = 1.0; z.sum_w2 = 1.0 / n_global; z.max_logw = -log(n_global);
+    z.sum_w = n_global; z.sum_w2 = n_global; z.max_logw = 0.0;
     for (int k = 0; k < 3; ++k) { z.est[k] = pose[3 * t + k]; z.mean[k] = pose[3 * t + k]; z.ref[k] = pose[3 * t + k]; }
     stats[t] = z;
 }
@@ -877,22 +1092,17 @@ __global__ void k_reset_scan(unsigned long long *desc, unsigned int *tickets, in
     if (i == 0) tickets[0] = 0u;
 }
 
+// normalised weights w = q 2^-52 (fp64) and the integers q the resampler scans
 __global__ void k_export_weights(const float *lw, const mcl_stats *stats, double *w, unsigned long long *q, long long n,
-                                 long long ld, int use_override, double log_norm_override) {
+                                 long long ld) {
     const int t = blockIdx.y;
-    const double ln = use_override ? log_norm_override : stats[t].log_norm;
+    const WeightMap wm = make_weight_map(stats[t].max_logw, stats[t].sum_w);
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const float v = lw[t * ld + i];
-        if (w) w[t * n + i] = exp(__dsub_rn(static_cast<double>(v), ln));
-        if (q) q[t * n + i] = quantize_weight(v, ln);
+        if (w) w[t * n + i] = static_cast<double>(weight_scaled(v, wm)) * kInvTwo52;
+        if (q) q[t * n + i] = quantize_weight(v, wm);
     }
-}
-
-__global__ void k_philox_selftest(uint4 ctr, uint2 key, uint4 *out, float2 *bm) {
-    const uint4 r = philox4x32_10(ctr, key);
-    out[0] = r;
-    bm[0] = box_muller(r.x, r.y);
 }
 
 }  // namespace mcl

@@ -238,14 +238,13 @@ class Filter:
         return int(self.lib.mcl_launch_count(self._h))
 
     # ------------------------------------------------------------------ particle-sharded filter
-    def shard_total(self, global_log_norm, total_dev):
-        self._check(self.lib.mcl_shard_total(self._h, float(global_log_norm), C.c_void_p(total_dev.data_ptr()), self._stream()),
-                    "mcl_shard_total")
+    def shard_total(self, total_dev):
+        self._check(self.lib.mcl_shard_total(self._h, C.c_void_p(total_dev.data_ptr()), self._stream()), "mcl_shard_total")
 
-    def shard_expand(self, global_log_norm, k_offset, ofs, out_x, out_y, out_yaw):
+    def shard_expand(self, k_offset, ofs, out_x, out_y, out_yaw):
         first, count = C.c_int64(0), C.c_int64(0)
         cap = min(out_x.numel(), out_y.numel(), out_yaw.numel())
-        self._check(self.lib.mcl_shard_expand(self._h, float(global_log_norm), int(k_offset), float(ofs),
+        self._check(self.lib.mcl_shard_expand(self._h, int(k_offset), float(ofs),
                                               C.c_void_p(out_x.data_ptr()), C.c_void_p(out_y.data_ptr()),
                                               C.c_void_p(out_yaw.data_ptr()), cap, C.byref(first), C.byref(count),
                                               self._stream()), "mcl_shard_expand")

@@ -34,7 +34,7 @@ from mylib import limit as ref_limit  # noqa: E402
 from mylib import transform as ref_tf  # noqa: E402
 from mylib import error_ellipse as ref_ee  # noqa: E402
 
-FULL_STEPS = {0: [0, 1, 5, 6, 7, 10, 100, 359], 1: [0, 6, 39], 2: [0, 39]}
+FULL_STEPS = {0: [0, 1, 5, 6, 7, 10, 100, 359], 1: [0, 5, 6, 39], 2: [0, 4, 39]}
 N_STEPS = {0: 360, 1: 40, 2: 40}
 
 

@@ -31,12 +31,11 @@ def main():
         wl["n"] = a.n
     lm = bench.landmarks_for(wl["L"])
     f = mcl.Filter(n_particles=wl["n"], n_trials=wl["T"], landmarks=lm, likelihood=a.likelihood, max_landmarks=wl["L"])
-    tr = [bench.Truth(lm, seed=7 + t, phase=0.05 * t) for t in range(wl["T"])]
-    f.init_particles(np.stack([t.pose() for t in tr]))
+    tr = bench.Truth(lm, seed=7, T=wl["T"])
+    f.init_particles(tr.pose())
     for _ in range(a.steps):
-        for t in tr:
-            t.advance()
-        f.step(np.stack([t.observe() for t in tr]), force_resample=True)
+        tr.advance()
+        f.step(tr.observe(), force_resample=True)
     torch.cuda.synchronize()
     st = f.stats()[0]
     print(f"ok ess={st.ess:.1f} max_idx={st.max_idx} launches={f.launch_count()}")
