@@ -36,11 +36,11 @@ int make_layout(const mcl_config &c, int sm_count, Layout &L) {
     L.T = c.n_trials;
     L.Lmax = c.max_landmarks;
     L.tpt = static_cast<int>((L.n + kScanTile - 1) / kScanTile);
-    // k_step is persistent: 2 resident CTAs per SM share a trial's particles in contiguous ranges that are
+    // k_step is persistent: the resident CTAs of every SM share a trial's particles in contiguous ranges that are
     // multiples of 128 particles; with many trials every trial still gets at least one CTA per 8192 particles
     const long long units = (L.n + kStepUnit - 1) / kStepUnit;
-    long long blocks = static_cast<long long>(sm_count) * 2 / L.T;
-    const long long min_blocks = (L.n + 8191) / 8192;
+    long long blocks = static_cast<long long>(sm_count) * kStepCtasPerSm / L.T;
+    const long long min_blocks = (L.T > 1) ? (L.n + 8191) / 8192 : 1;
     if (blocks < min_blocks) blocks = min_blocks;
     if (blocks > units) blocks = units;
     if (blocks < 1) blocks = 1;
@@ -79,7 +79,7 @@ int validate(const mcl_config *c) {
     if (c->n_global < c->n_particles || c->slot_base < 0 || c->slot_base + c->n_particles > c->n_global)
         return MCL_ERR_ARG;
     if (c->n_global != c->n_particles && c->n_trials != 1) return MCL_ERR_ARG;
-    if (c->n_global > 0xFFFFFFF0ll) return MCL_ERR_ARG;  // slots and ancestors are 32-bit
+    if (c->n_global > 0x7FFFFF00ll) return MCL_ERR_ARG;  // slots and ancestors are 32-bit
     return MCL_OK;
 }
 

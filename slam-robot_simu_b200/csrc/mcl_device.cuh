@@ -14,6 +14,10 @@ constexpr double kInvTwo52 = 1.0 / 4503599627370496.0;
 constexpr float kLog2e = 1.4426950408889634f;
 
 constexpr int kStepThreads = 256;  // predict+weight block
+#ifndef MCL_STEP_CTAS_PER_SM
+#define MCL_STEP_CTAS_PER_SM 3
+#endif
+constexpr int kStepCtasPerSm = MCL_STEP_CTAS_PER_SM;  // resident CTAs per SM k_step is compiled for
 constexpr int kPPT = 4;            // particles per thread per iteration (one float4 per array)
 constexpr int kStepTile = kStepThreads * kPPT;
 constexpr int kStepUnit = 128;     // granularity of the static particle partition over blocks
@@ -108,6 +112,16 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
     return make_float2(r * c, r * s);
 }
 
+// the same from two 21-bit fields (k_step slices 256 Philox bits into twelve of them); |n| <= 5.4
+__device__ __forceinline__ float2 box_muller21(uint32_t a, uint32_t b) {
+    const float u1 = 2.0f - __uint_as_float(0x3f800000u | (a << 2));  // (0, 1]
+    const float u2 = __uint_as_float(0x3f800000u | (b << 2)) - 1.0f;  // [0, 1)
+    const float r = sqrt_approx(-1.3862943611198906f * lg2_approx(u1));
+    float s, c;
+    __sincosf(6.28318530717958647692f * u2, &s, &c);
+    return make_float2(r * c, r * s);
+}
+
 __device__ __forceinline__ double philox_uniform01(uint4 r) {
     return (static_cast<double>(r.x) * 4294967296.0 + static_cast<double>(r.y)) * (1.0 / 18446744073709551616.0);
 }
@@ -158,10 +172,33 @@ __device__ __forceinline__ double count_le(double Kd, double delta, double ofs, 
     const double g1 = g + 1.0;
     const double u1 = comb_value(g1, delta, ofs);
     const double u0 = comb_value(g, delta, ofs);
-    double r = g;
-    if (u1 <= c) r = g1;
-    else if (u0 > c) r = g - 1.0;
-    return fmin(fmax(r + 1.0, 0.0), nd);
+    double r = g1;                 // count if tooth g is the last one at or below c
+    if (u1 <= c) r = g1 + 1.0;
+    else if (u0 > c) r = g;
+    return (r > nd) ? nd : r;      // r >= 0 always: c >= 0 and ofs < 1/N give g >= -1
+}
+
+// The same count when the real-arithmetic position a = (K 2^-52 - ofs) N is safely inside a tooth
+// interval: one FMA, one floor.  The rounding of a (<= 1.2e-16 N) plus the deviation of numpy's doubly
+// rounded comb from i/N + ofs (<= 2.3e-16 N) is below 8e-7 teeth for N < 2^31, so a fractional part in
+// [2^-16, 1 - 2^-16] decides exactly; anything closer to an integer takes the exact path above.
+struct CombFast {
+    double a1, a0, nd;  // a = fma(K, a1, a0): a1 = N 2^-52 (exact), a0 = -fl(ofs N)
+};
+__device__ __forceinline__ CombFast make_comb_fast(double ofs, double nd) {
+    CombFast f;
+    f.a1 = nd * kInvTwo52;
+    f.a0 = -(ofs * nd);
+    f.nd = nd;
+    return f;
+}
+__device__ __forceinline__ double count_le_fast(double Kd, const CombFast &f, double delta, double ofs) {
+    const double a = fma(Kd, f.a1, f.a0);
+    const double g = floor(a);
+    const double fr = a - g;
+    if (fr < 0x1p-16 || fr > 1.0 - 0x1p-16) return count_le(Kd, delta, ofs, f.nd);
+    const double r = g + 1.0;
+    return (r > f.nd) ? f.nd : r;
 }
 
 // ---------------------------------------------------------------------------------------------

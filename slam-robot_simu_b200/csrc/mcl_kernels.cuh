@@ -176,11 +176,18 @@ enum : unsigned long long {
     kDescValueMask = (1ull << 62) - 1ull
 };
 
+struct ScanShared {
+    double ofs;
+    float wq_m, wq_scale;
+    int resample;
+    unsigned int tile;
+};
+
 template <int MODE>
-__global__ void __launch_bounds__(kScanThreads, 4) k_scan(const ScanParams p) {
+__global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant__ ScanParams p) {
     const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kScanThreads / 32;
-    __shared__ unsigned int s_tile;
+    __shared__ ScanShared s_sc;
     __shared__ unsigned long long s_warp[NW];
     __shared__ int s_first[NW];
     __shared__ double s_slot[2];
@@ -189,18 +196,27 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const ScanParams p) {
 
     if (p.desc_next != nullptr && tid == 0) p.desc_next[static_cast<long long>(t) * p.tpt + blockIdx.x] = 0ull;
     const mcl_stats *stp = p.stats + t;
-    const int resample = p.use_override ? 1 : decide_resample(p.prep.flags, stp->ess, p.prep.ess_threshold);
-    const double ofs = p.use_override ? p.ofs_override : (resample ? comb_offset(p.prep, t) : 0.0);
+    if (tid == 0) {
+        const int rs = p.use_override ? 1 : decide_resample(p.prep.flags, stp->ess, p.prep.ess_threshold);
+        s_sc.resample = rs;
+        s_sc.ofs = p.use_override ? p.ofs_override : (rs ? comb_offset(p.prep, t) : 0.0);
+        const WeightMap w0 = make_weight_map(stp->max_logw, stp->sum_w);
+        s_sc.wq_m = w0.m;
+        s_sc.wq_scale = w0.scale;
+        s_sc.tile = rs ? atomicAdd(&p.tickets[t * 4 + 0], 1u) : 0u;
+    }
+    __syncthreads();
+    const int resample = s_sc.resample;
+    const double ofs = s_sc.ofs;
+    WeightMap wm;
+    wm.m = s_sc.wq_m;
+    wm.scale = s_sc.wq_scale;
+    const long long tile = s_sc.tile;
     if (p.do_prep && blockIdx.x == 0) {
         prep_block(p.prep, stp, t, resample, ofs, reinterpret_cast<double *>(s_mark));
         __syncthreads();
     }
     if (!resample) return;
-    const WeightMap wm = make_weight_map(stp->max_logw, stp->sum_w);
-
-    if (tid == 0) s_tile = atomicAdd(&p.tickets[t * 4 + 0], 1u);
-    __syncthreads();
-    const long long tile = s_tile;
     if (tile >= p.tpt) return;  // prep-only launches use a one-block grid; never taken otherwise
     const long long j0 = tile * kScanTile + static_cast<long long>(tid) * kScanItems;
     const float *lw = p.lw + static_cast<long long>(t) * p.ld;
@@ -281,20 +297,24 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const ScanParams p) {
 
     // ---- slot range of every source ----
     const double nd = static_cast<double>(p.n_global);
+    const CombFast cf = make_comb_fast(ofs, nd);
     double Kd = static_cast<double>(p.k_offset + excl + thread_excl);
-    const double first_slot = count_le(Kd, p.delta, ofs, nd);
+    const double first_slot = count_le_fast(Kd, cf, p.delta, ofs);
     double cur = first_slot;
     uint32_t rel[kScanItems];  // first slot of source k relative to the thread's first slot
     uint32_t owners = 0;       // bit k: source k owns at least one slot
+    // the last particle of the whole filter also takes every slot past the final cumulative weight
+    // (the reference would raise IndexError there)
+    const long long k_last64 = p.n_global - 1 - p.j_global_base - j0;
+    const int k_last = (k_last64 >= 0 && k_last64 < kScanItems) ? static_cast<int>(k_last64) : -1;
+    const int n_valid = static_cast<int>(min(static_cast<long long>(kScanItems), max(0ll, p.n - j0)));
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        rel[k] = static_cast<uint32_t>(cur - first_slot);
+        rel[k] = static_cast<uint32_t>(static_cast<int>(cur - first_slot));
         Kd += qd[k];
-        double end = count_le(Kd, p.delta, ofs, nd);
-        // the last particle of the whole filter also takes every slot past the final cumulative weight
-        // (the reference would raise IndexError there)
-        if (p.j_global_base + j0 + k == p.n_global - 1) end = nd;
-        if (j0 + k < p.n && end > cur) {
+        double end = count_le_fast(Kd, cf, p.delta, ofs);
+        if (k == k_last) end = nd;
+        if (k < n_valid && end > cur) {
             owners |= 1u << k;
             cur = end;
         }
@@ -307,7 +327,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const ScanParams p) {
     __syncthreads();
     const double S0d = s_slot[0];
     const long long S0 = static_cast<long long>(S0d), span = static_cast<long long>(s_slot[1] - S0d);
-    const long long my_off = static_cast<long long>(first_slot - S0d);  // >= 0 for threads that hold sources
+    const uint32_t my_off = static_cast<uint32_t>(static_cast<long long>(first_slot - S0d));  // threads with sources: >= 0
 
     uint32_t *anc = p.anc + static_cast<long long>(t) * p.anc_cap;
     uint32_t carry = 0;  // source (local index + 1) that owns the slot just before the window
@@ -317,10 +337,12 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const ScanParams p) {
         for (int k = 0; k < kScanItems; ++k) s_mark[k * kScanThreads + tid] = 0u;
         __syncthreads();
         if (owners) {
+            // slot positions relative to the window, modulo 2^32 (n_global < 2^31: no aliasing)
+            const uint32_t wofs = my_off - static_cast<uint32_t>(cb);
 #pragma unroll
             for (int k = 0; k < kScanItems; ++k) {
-                const long long pos = my_off + rel[k] - cb;
-                if (((owners >> k) & 1u) && pos >= 0 && pos < kScanTile)
+                const uint32_t pos = wofs + rel[k];
+                if (((owners >> k) & 1u) && pos < static_cast<uint32_t>(kScanTile))
                     s_mark[pos] = static_cast<uint32_t>(tid * kScanItems + k + 1);
             }
         }
@@ -660,7 +682,7 @@ struct StepParams {
 };
 
 template <int LIK, bool PHILOX>
-__global__ void __launch_bounds__(kStepThreads, 2) k_step(const StepParams p) {
+__global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const StepParams p) {
     const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double4 *s_tab = reinterpret_cast<double4 *>(smem_raw);  // [L] (pair / RB only)
@@ -693,6 +715,9 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const StepParams p) {
     float *ox = p.out.x + off, *oy = p.out.y + off, *oth = p.out.th + off, *olw = p.out.lw + off;
     const uint32_t *anc = p.anc + off;
     const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
+
+    // injected noise is the final draw v of particle_filter.py:165; Philox normals are unit and get sqrt(diag Q)
+    const float nscale[3] = {PHILOX ? p.q_std[0] : 1.0f, PHILOX ? p.q_std[1] : 1.0f, PHILOX ? p.q_std[2] : 1.0f};
 
     WarpStats ws;
     ws.init();
@@ -734,7 +759,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const StepParams p) {
                 lwp[0] = vw.x - max_prev; lwp[1] = vw.y - max_prev; lwp[2] = vw.z - max_prev; lwp[3] = vw.w - max_prev;
             }
 
-            // ---------------- motion noise ----------------
+            // ---------------- motion noise (unit normals; Motion A scales them by sqrt(diag Q)) ----------------
             float nz[kPPT][3];
             if (!PHILOX) {
                 const long long plane = static_cast<long long>(p.T) * p.n;
@@ -746,22 +771,35 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const StepParams p) {
                     for (int d = 0; d < 3; ++d) nz[k][d] = ok ? nb[d * plane + base + k] : 0.0f;
                 }
             } else {
-                // 3 Philox calls give the 12 normals of this thread's 4 particles
+                // 2 Philox calls = 256 bits = twelve 21-bit uniforms = the 12 normals of this thread's 4 particles
                 const unsigned long long grp = static_cast<unsigned long long>(p.slot_base + base) >> 2;
+                const uint4 r0 = philox4x32_10(make_uint4(static_cast<uint32_t>(grp), static_cast<uint32_t>(grp >> 32) * 2u,
+                                                          p.step, static_cast<uint32_t>(t)), key);
+                const uint4 r1 = philox4x32_10(make_uint4(static_cast<uint32_t>(grp), static_cast<uint32_t>(grp >> 32) * 2u + 1u,
+                                                          p.step, static_cast<uint32_t>(t)), key);
+                const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
                 float nrm[12];
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc) {
-                    const uint4 r = philox4x32_10(
-                        make_uint4(static_cast<uint32_t>(grp), static_cast<uint32_t>(grp >> 32) * 4u + cc, p.step,
-                                   static_cast<uint32_t>(t)), key);
-                    const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
-                    nrm[4 * cc + 0] = a.x; nrm[4 * cc + 1] = a.y; nrm[4 * cc + 2] = b.x; nrm[4 * cc + 3] = b.y;
+                for (int q = 0; q < 4; ++q) {
+                    // words 2q, 2q+1 -> three 21-bit fields: top 21 of each word, and 11 + 10 of their low bits
+                    const uint32_t f0 = w[2 * q] >> 11, f1 = w[2 * q + 1] >> 11;
+                    const uint32_t f2 = ((w[2 * q] & 0x7ffu) << 10) | (w[2 * q + 1] & 0x3ffu);
+                    // fields pair up across the two halves: (q, q+2) share one Box-Muller for their third normal
+                    const float2 a = box_muller21(f0, f1);
+                    nrm[3 * q + 0] = a.x;
+                    nrm[3 * q + 1] = a.y;
+                    nrm[3 * q + 2] = __uint_as_float(f2);  // third field, paired below
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float2 a = box_muller21(__float_as_uint(nrm[3 * q + 2]), __float_as_uint(nrm[3 * (q + 2) + 2]));
+                    nrm[3 * q + 2] = a.x;
+                    nrm[3 * (q + 2) + 2] = a.y;
                 }
 #pragma unroll
                 for (int k = 0; k < kPPT; ++k)
 #pragma unroll
-                    for (int d = 0; d < 3; ++d)
-                        nz[k][d] = nrm[3 * k + d] * ((p.motion == MCL_MOTION_A) ? p.q_std[d] : 1.0f);
+                    for (int d = 0; d < 3; ++d) nz[k][d] = nrm[3 * k + d];
             }
 
             // ---------------- predict ----------------
@@ -772,12 +810,12 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_step(const StepParams p) {
                     // is applied before the noise, so the stored yaw may leave [-pi, pi]
                     float s0, c0;
                     __sincosf(th[k], &s0, &c0);
-                    x[k] = fmaf(p.vdt_f, c0, x[k]) + nz[k][0];
-                    y[k] = fmaf(p.vdt_f, s0, y[k]) + nz[k][1];
+                    x[k] = fmaf(nz[k][0], nscale[0], fmaf(p.vdt_f, c0, x[k]));
+                    y[k] = fmaf(nz[k][1], nscale[1], fmaf(p.vdt_f, s0, y[k]));
                     float tn = th[k] + p.wdt_f;
                     if (!(fabsf(tn) < 3.1415f))  // at or past the seam: wrap exactly like mylib/limit.py, in fp64
                         tn = static_cast<float>(limit_angle(static_cast<double>(th[k]) + p.wdt));
-                    th[k] = tn + nz[k][2];
+                    th[k] = fmaf(nz[k][2], nscale[2], tn);
                 }
             } else {
 #pragma unroll
