@@ -261,6 +261,48 @@ def run_reference(args, wl):
 # ======================================================================================================
 # the B200 arm
 # ======================================================================================================
+def measure_sharded(mcl, torch, dist, dev, n_per_gpu, L, likelihood, steps, warmup):
+    """One filter of world * n_per_gpu particles sharded over the ranks: allgather of statistics and
+    weight totals + variable-count all-to-all of the resampled poses (NCCL), forced resampling."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n_global = n_per_gpu * world
+    lm = landmarks_for(L)
+    truth = Truth(lm, seed=77)  # the same observations on every rank
+    cyc = truth.cycle()
+    sf = mcl.ShardedParticleFilter(n_global, lm, likelihood=likelihood, seed=4711, max_landmarks=L)
+    sf.init_particles(truth.pose()[0])
+    k = 0
+    for _ in range(max(warmup, 3)):
+        sf.step(cyc[k % Truth.PERIOD], force_resample=True)
+        k += 1
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    moved = 0
+    for _ in range(steps):
+        g = sf.step(cyc[k % Truth.PERIOD], force_resample=True)
+        k += 1
+        first, count = sf.last_ranges[rank]
+        lo, hi = rank * sf.m, (rank + 1) * sf.m
+        moved += count - max(0, min(first + count, hi) - max(first, lo))
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt, float(moved)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t[0].item())
+    out = {"workload": f"one filter of {n_global} particles x {L} landmarks over {world} GPUs, global systematic resampling",
+           "value": n_global * steps / dt, "unit": "particle-steps/s", "ms_per_step": dt / steps * 1e3, "steps": steps,
+           "ess_over_n": g["ess"] / n_global,
+           "max_slots_sent_off_rank_per_step": float(t[1].item()) / steps,
+           "collectives": "allgather(mcl_stats 304 B) + allgather(u64 total) + allgather(range) + 3 x all_to_all_single(fp32 poses)"}
+    del sf
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args, wl):
     import torch
     import torch.distributed as dist
@@ -278,6 +320,28 @@ def run_b200(args, wl):
 
     n, L, T = wl["n"], wl["L"], wl["T"]
     lm = landmarks_for(L)
+    if world > 1 and args.workload == "c3":
+        sh = measure_sharded(mcl, torch, dist, dev, n, L, args.likelihood, args.steps, args.warmup)
+        if rank == 0:
+            peak, peak_src = peaks()
+            line = {"metric": "particle-steps/s (predict+weight+resample)", "value": sh["value"], "unit": "particle-steps/s",
+                    "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": sh["ms_per_step"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "f32 state / f64 likelihood / u64 scan", "data": "synthetic",
+                    "config": {"workload": sh["workload"], "likelihood": args.likelihood, "noise": "philox4x32-10 on device",
+                               "resampling": "forced every step, global", "ess_over_n": sh["ess_over_n"],
+                               "l2": f"{36 * n >> 20} MiB of state per GPU > 126 MiB L2", "parallelism": f"particle-sharded x{world}"},
+                    "roofline": {"bound": "hbm", "achieved": BYTES_STEP_CANONICAL * sh["value"] / world / 1e9, "peak": peak,
+                                 "unit": "GB/s", "frac": BYTES_STEP_CANONICAL * sh["value"] / world / 1e9 / peak, "traffic": None,
+                                 "peak_source": peak_src, "note": "whole step per GPU at the canonical 64 B per particle-step"},
+                    "cpu_baseline": None, "e2e": {"value": sh["value"], "unit": "particle-steps/s",
+                                                  "h2d_bytes_per_step": 16 * L + 304, "d2h_bytes_per_step": 304 + 8 + 16,
+                                                  "note": "the sharded step is host-mediated: its timing already includes the "
+                                                          "observation upload and the statistics read-back of every step"},
+                    "sharded_filter": sh, "gpu_launches": None}
+            print(json.dumps(line), flush=True)
+        dist.destroy_process_group()
+        return
     state_bytes = 2 * 16 * n * T + 4 * n * T
     replicas = max(1, min(64, math.ceil(2.2 * L2_BYTES / state_bytes)))  # rotate filters so every step is L2-cold
     K, W = args.steps, max(args.warmup, 3)
@@ -406,6 +470,12 @@ def run_b200(args, wl):
                "d2h_bytes_per_step": C.sizeof(mcl.mcl_stats) * T, "steps": ke, "api": "Filter.step(z_host) + Filter.stats()"}
     sampler.stop()
 
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        del filters, zcyc
+        torch.cuda.empty_cache()
+        c3 = WORKLOADS["c3"]
+        sharded = measure_sharded(mcl, torch, dist, dev, c3["n"], c3["L"], args.likelihood, 8, 3)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -418,8 +488,8 @@ def run_b200(args, wl):
                        "noise": "philox4x32-10 on device", "resampling": "forced every step",
                        "ess_over_n": ess_frac,
                        "l2": f"rotating {replicas} independent filter replicas ({replicas * state_bytes >> 20} MiB > 126 MiB L2)",
-                       "parallelism": "single GPU" if world == 1 else f"{world} ranks, independent filters"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                       "parallelism": "single GPU" if world == 1 else f"{world} ranks, one independent filter each (no data-path collective)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sharded_filter": sharded, "gpu_launches": int(launches),
             "clocks": sampler.summary()}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -435,6 +505,7 @@ def main():
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
     ap.add_argument("--likelihood", default="moment", choices=["pair", "moment"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the particle-sharded C3 measurement")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

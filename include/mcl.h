@@ -133,8 +133,12 @@ int mcl_set_landmarks(mcl_filter *h, const double *lm_xy_host, int32_t n_landmar
 int mcl_init_particles(mcl_filter *h, const double *pose_host, void *stream);
 
 /* Overwrite / read the particle state.  Arrays are [n_trials][n_particles] fp32 (dense, no
- * stride); logw may be NULL (set: uniform; get: skipped).  `on_device` != 0 means the pointers
- * are device pointers.  set recomputes the statistics; get synchronises when on_device == 0. */
+ * stride); logw may be NULL (set: uniform; get: skipped).  `on_device` is a bit set: MCL_SET_ON_DEVICE
+ * = the pointers are device pointers; MCL_SET_SKIP_STATS (set only) = do not recompute the statistics
+ * (the sharded filter installs global ones with mcl_shard_set_global).  get synchronises when the
+ * pointers are host pointers. */
+#define MCL_SET_ON_DEVICE 1
+#define MCL_SET_SKIP_STATS 2
 int mcl_set_particles(mcl_filter *h, const float *x, const float *y, const float *yaw, const float *logw,
                       int on_device, void *stream);
 int mcl_get_particles(mcl_filter *h, float *x, float *y, float *yaw, float *logw, int on_device, void *stream);

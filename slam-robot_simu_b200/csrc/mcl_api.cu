@@ -580,6 +580,8 @@ int mcl_set_particles(mcl_filter *h, const float *x, const float *y, const float
     if (rc != MCL_OK) return rc;
     cudaStream_t st = S(stream);
     const Layout &L = h->lay;
+    const bool skip_stats = (on_device & MCL_SET_SKIP_STATS) != 0;
+    on_device &= MCL_SET_ON_DEVICE;
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     StateView &s = h->state[h->cur];
     const float *src[4] = {x, y, yaw, logw};
@@ -597,6 +599,7 @@ int mcl_set_particles(mcl_filter *h, const float *x, const float *y, const float
     }
     if (!on_device) MCL_CUDA(h, cudaStreamSynchronize(st));  // pageable host sources may go away
     h->have_particles = true;
+    if (skip_stats) return MCL_OK;  // the caller installs statistics itself (mcl_shard_set_global)
     h->stats_from_particle0 = true;
     return reduce_only_pass(h, st);
 }

@@ -115,7 +115,7 @@ class Filter:
         p = np.ascontiguousarray(np.broadcast_to(np.asarray(pose, dtype=np.float64).reshape(-1, 3), (self.T, 3)))
         self._check(self.lib.mcl_init_particles(self._h, p.ctypes.data, self._stream()), "mcl_init_particles")
 
-    def set_particles(self, x, y, yaw, logw=None):
+    def set_particles(self, x, y, yaw, logw=None, skip_stats=False):
         """Arrays (T,n)/(n,) -- numpy (host) or torch CUDA tensors (device), fp32."""
         torch = _torch()
         on_dev = isinstance(x, torch.Tensor)
@@ -128,7 +128,8 @@ class Filter:
         for a in arrs:
             if a is not None and (a.numel() if on_dev else a.size) != self.T * self.n:
                 raise ValueError("particle arrays must hold n_trials * n_particles elements")
-        self._check(self.lib.mcl_set_particles(self._h, *ptrs, 1 if on_dev else 0, self._stream()), "mcl_set_particles")
+        mode = (1 if on_dev else 0) | (2 if skip_stats else 0)
+        self._check(self.lib.mcl_set_particles(self._h, *ptrs, mode, self._stream()), "mcl_set_particles")
         self._keep = arrs  # device sources must outlive the async copies
 
     def get_particles(self, want_logw=True, device=False):

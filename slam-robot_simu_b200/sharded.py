@@ -1,0 +1,297 @@
+"""One particle filter sharded over the ranks of a torch.distributed group (one process per GPU).
+
+Rank g owns the contiguous global particles / output slots [g * m, (g + 1) * m), m = n_global / G.
+Predict + weight is local.  Two exchanges couple the shards:
+
+  * statistics -- every rank allgathers its 304-byte mcl_stats record and merges them on the host
+    (`merge_stats`): global max, normaliser, ESS, arg-max, weighted mean / covariance.  The merged
+    record goes back into every shard (mcl_shard_set_global), so all shards quantise their weights
+    with the same map and take the same resampling decision;
+  * resampling -- allgather of the per-shard integer weight totals gives every shard the cumulative
+    offset of its first particle; because the weights are integers on a 2^-52 grid the global scan is
+    exact, and each shard computes, with GLOBAL slot numbers, the resampled pose of every slot its own
+    particles fill (mcl_shard_expand).  Ancestors are monotone, so that is one contiguous slot range
+    per shard; `plan_exchange` cuts it at the owners' boundaries and one variable-count all-to-all
+    (NCCL over NVLink on GPUs) delivers every slot to its owner.  The result is bit-identical to the
+    unsharded filter, and to the reference walk of particle_filter.py:212-221.
+
+The pure-host pieces (`merge_stats`, `plan_exchange`, `exchange`, `philox_ofs`) import neither CUDA
+nor the C library and are what the world_size-2 gloo tests exercise on CPU.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+_TWO_PI = 2.0 * math.pi
+
+
+# ---------------------------------------------------------------------------------------------
+# host logic
+# ---------------------------------------------------------------------------------------------
+def limit_angle(a):
+    """mylib/limit.py:11-26."""
+    r = abs(a)
+    while r > math.pi:
+        r -= _TWO_PI
+    return -r if a < 0 else r
+
+
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon et al. 2011) on Python ints; the device twin is mcl::philox4x32_10."""
+    c = [int(v) & 0xFFFFFFFF for v in counter]
+    k = [int(v) & 0xFFFFFFFF for v in key]
+    for _ in range(10):
+        p0 = 0xD2511F53 * c[0]
+        p1 = 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c[3] ^ k[1]) & 0xFFFFFFFF, p0 & 0xFFFFFFFF]
+        k = [(k[0] + 0x9E3779B9) & 0xFFFFFFFF, (k[1] + 0xBB67AE85) & 0xFFFFFFFF]
+    return c
+
+
+def philox_ofs(seed, step, n_global, trial=0):
+    """The comb offset rand() * NP_RECIP (particle_filter.py:214) the device draws when no offset is
+    injected (mcl::comb_offset): every rank computes the same value, and it equals the unsharded one."""
+    r = philox4x32_10((0xFFFFFFFF, 0, step, trial), (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
+    u = (float(r[0]) * 4294967296.0 + float(r[1])) * (1.0 / 18446744073709551616.0)
+    return u * (1.0 / n_global)
+
+
+def merge_stats(records, slot_bases):
+    """Merge per-shard statistics (dicts as returned by engine.stats_to_dict) into the global record.
+
+    Shards share the reference pose of the moment sums (it derives from the previous GLOBAL estimate),
+    so their un-normalised sums add after rescaling to the global maximum."""
+    M = max(r["max_logw"] for r in records)
+    scale = [math.exp(r["max_logw"] - M) if r["sum_w"] > 0 else 0.0 for r in records]
+    s1 = sum(r["sum_w"] * s for r, s in zip(records, scale))
+    s2 = sum(r["sum_w2"] * s * s for r, s in zip(records, scale))
+    ref = np.asarray(records[0]["ref"], dtype=np.float64)
+    raw = np.zeros(12)
+    for r, s in zip(records, scale):
+        a = np.asarray(r["raw"], dtype=np.float64) * s
+        # re-centre the sums of a shard that used another reference pose (only right after
+        # set_local_particles; in a running filter all shards derive it from the global estimate)
+        d = np.asarray(r["ref"], dtype=np.float64) - ref
+        d[2] = limit_angle(d[2])
+        if np.any(d != 0.0):
+            e = r["sum_w"] * s
+            fx, fy, ft = a[0], a[1], a[2]
+            a[5] += 2 * d[0] * fx + d[0] * d[0] * e
+            a[6] += d[0] * fy + d[1] * fx + d[0] * d[1] * e
+            a[7] += 2 * d[1] * fy + d[1] * d[1] * e
+            a[8] += d[0] * ft + d[2] * fx + d[0] * d[2] * e
+            a[9] += d[1] * ft + d[2] * fy + d[1] * d[2] * e
+            a[10] += 2 * d[2] * ft + d[2] * d[2] * e
+            a[0] += d[0] * e
+            a[1] += d[1] * e
+            a[2] += d[2] * e
+        raw += a
+    # arg-max: largest stored log-weight; ties go to the lowest global index (np.argmax, :116)
+    best = None
+    for g, r in enumerate(records):
+        v = r["best_logw"]
+        if best is None or v > best[0]:
+            best = (v, g)
+    bv, bg = best
+    inv = 1.0 / s1
+    mdx, mdy, mdt = raw[0] * inv, raw[1] * inv, raw[2] * inv
+    mth = math.atan2(raw[3], raw[4])
+    dl = limit_angle(mth - ref[2])
+    cov = np.empty((3, 3))
+    cov[0, 0] = raw[5] * inv - mdx * mdx
+    cov[0, 1] = cov[1, 0] = raw[6] * inv - mdx * mdy
+    cov[1, 1] = raw[7] * inv - mdy * mdy
+    cov[0, 2] = cov[2, 0] = raw[8] * inv - mdx * mdt
+    cov[1, 2] = cov[2, 1] = raw[9] * inv - mdy * mdt
+    cov[2, 2] = raw[10] * inv - 2.0 * dl * mdt + dl * dl
+    return dict(max_logw=M, sum_w=s1, sum_w2=s2, log_norm=M + math.log(s1), ess=s1 * s1 / s2,
+                max_weight=math.exp(bv - M) / s1, max_idx=int(slot_bases[bg] + records[bg]["max_idx"]),
+                est=np.asarray(records[bg]["est"], dtype=np.float64), mean=np.array([ref[0] + mdx, ref[1] + mdy, mth]),
+                cov=cov, raw=raw, ref=ref, owner=bg)
+
+
+def plan_exchange(ranges, n_global, world, rank):
+    """Split sizes of the all-to-all.  ranges[s] = (first_slot, n_slots) of the slots shard s fills.
+
+    Returns (send_counts, recv_counts): send_counts[g] slots of MY expanded range go to owner g, in slot
+    order; recv_counts[s] slots arrive from shard s -- concatenated in rank order they are exactly my
+    m = n_global / world output slots, because the shards' ranges tile [0, n_global) in rank order."""
+    m = n_global // world
+    first, count = ranges[rank]
+    send = [max(0, min(first + count, (g + 1) * m) - max(first, g * m)) for g in range(world)]
+    lo, hi = rank * m, (rank + 1) * m
+    recv = [max(0, min(f + c, hi) - max(f, lo)) for f, c in ranges]
+    if sum(recv) != m:
+        raise RuntimeError(f"rank {rank}: shards fill {sum(recv)} of my {m} slots -- ranges {ranges} do not tile the comb")
+    return send, recv
+
+
+def exchange(arrays, first, count, n_global, group=None):
+    """Variable-count all-to-all of the expanded poses.  `arrays`: tensors whose first `count` elements
+    are the resampled values of global slots [first, first + count).  Returns my m output slots of each."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = arrays[0].device
+    mine = torch.tensor([first, count], dtype=torch.int64, device=dev)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    ranges = [tuple(int(v) for v in t.tolist()) for t in gathered]
+    send, recv = plan_exchange(ranges, n_global, world, rank)
+    m = n_global // world
+    out = []
+    for a in arrays:
+        o = torch.empty(m, dtype=a.dtype, device=dev)
+        dist.all_to_all_single(o, a[:count].contiguous(), recv, send, group=group)
+        out.append(o)
+    return out, ranges
+
+
+# ---------------------------------------------------------------------------------------------
+# the sharded filter (needs CUDA + libmcl_b200.so)
+# ---------------------------------------------------------------------------------------------
+class ShardedParticleFilter:
+    """n_global particles, contiguous shards of n_global / world_size per rank."""
+
+    def __init__(self, n_global, landmarks, period_ms=100.0, likelihood="moment", seed=42, group=None, device=None,
+                 ess_div=100.0, expand_factor=2.0, **cfg):
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib as L
+        from .engine import Filter, stats_to_dict
+
+        self._L, self._stats_to_dict = L, stats_to_dict
+        self.dist, self.torch, self.group = dist, torch, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if n_global % self.world or (n_global // self.world) % 4:
+            raise ValueError("n_global must be a multiple of 4 * world_size")
+        self.n_global, self.m = int(n_global), int(n_global) // self.world
+        self.seed = int(seed)
+        self.ess_threshold = self.n_global / ess_div  # ESS_TH = NP / 100 (particle_filter.py:33)
+        dev_index = torch.cuda.current_device() if device is None else int(device)
+        self.flt = Filter(n_particles=self.m, n_trials=1, period_ms=period_ms, landmarks=landmarks, likelihood=likelihood,
+                          device=dev_index, seed=seed, n_global=self.n_global, slot_base=self.rank * self.m,
+                          ess_threshold=self.ess_threshold, **cfg)
+        self.dev = self.flt.device
+        self.slot_bases = [g * self.m for g in range(self.world)]
+        # a shard's heavy particles can fill more slots than it owns: the expand buffers hold `cap` slots,
+        # and grow (up to n_global) when a step needs more
+        self.cap = min(self.n_global, int(self.m * expand_factor) + 1024)
+        self._alloc_expand()
+        self.total_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.step_count = 0
+        self.global_stats = None
+        self.last_ranges = None
+
+    def _alloc_expand(self):
+        t = self.torch
+        self.ex = [t.empty(self.cap, dtype=t.float32, device=self.dev) for _ in range(3)]
+
+    # -- statistics ---------------------------------------------------------------------------
+    def _uniform_stats(self, est):
+        s = self._L.mcl_stats()
+        s.log_norm = math.log(self.n_global)
+        s.ess = float(self.n_global)
+        s.max_weight = 1.0 / self.n_global
+        s.max_logw = 0.0
+        s.sum_w = float(self.n_global)
+        s.sum_w2 = float(self.n_global)
+        for k in range(3):
+            s.est[k] = float(est[k])
+            s.mean[k] = float(est[k])
+            s.ref[k] = float(est[k])
+        return s
+
+    def _install(self, merged):
+        s = self._L.mcl_stats()
+        s.log_norm, s.ess, s.max_weight = merged["log_norm"], merged["ess"], merged["max_weight"]
+        s.max_idx = merged["max_idx"]
+        s.max_logw, s.sum_w, s.sum_w2 = merged["max_logw"], merged["sum_w"], merged["sum_w2"]
+        for k in range(3):
+            s.est[k], s.mean[k], s.ref[k] = merged["est"][k], merged["mean"][k], merged["ref"][k]
+        for k in range(9):
+            s.cov[k] = merged["cov"].reshape(-1)[k]
+        for k in range(12):
+            s.raw[k] = merged["raw"][k]
+        s.step = self.step_count
+        self.flt.shard_set_global(s)
+
+    def _merge(self):
+        import ctypes as C
+
+        t = self.torch
+        st = self.flt.stats()[0]
+        buf = t.frombuffer(bytearray(bytes(st)), dtype=t.uint8).to(self.dev)
+        gathered = [t.empty_like(buf) for _ in range(self.world)]
+        self.dist.all_gather(gathered, buf, group=self.group)
+        recs = []
+        for g in gathered:
+            s = self._L.mcl_stats.from_buffer_copy(bytes(g.cpu().numpy()))
+            d = self._stats_to_dict(s)
+            # the stored log-weight of the shard's best particle IS its max_logw
+            d["best_logw"] = d["max_logw"]
+            recs.append(d)
+        assert C.sizeof(self._L.mcl_stats) == buf.numel()
+        merged = merge_stats(recs, self.slot_bases)
+        self.global_stats = merged
+        self._install(merged)
+        return merged
+
+    # -- API ------------------------------------------------------------------------------------
+    def init_particles(self, pose):
+        pose = np.asarray(pose, dtype=np.float64).reshape(3)
+        self.flt.init_particles(pose)
+        self.flt.shard_set_global(self._uniform_stats(pose))
+        self.global_stats = dict(ess=float(self.n_global), est=pose.copy(), log_norm=math.log(self.n_global))
+
+    def set_local_particles(self, x, y, yaw, logw=None):
+        """This rank's m particles (numpy or CUDA tensors); all ranks then merge their statistics."""
+        self.flt.set_particles(x, y, yaw, logw)
+        return self._merge()
+
+    def resample(self, ofs=None):
+        """Global systematic resampling (particle_filter.py:212-222) across the shards."""
+        t = self.torch
+        if ofs is None:
+            ofs = philox_ofs(self.seed, self.step_count, self.n_global)
+        self.flt.shard_total(self.total_dev)
+        totals = [t.empty_like(self.total_dev) for _ in range(self.world)]
+        self.dist.all_gather(totals, self.total_dev, group=self.group)
+        totals = [int(v.item()) for v in totals]
+        k_offset = sum(totals[:self.rank])
+        while True:
+            try:
+                first, count = self.flt.shard_expand(k_offset, ofs, *self.ex)
+                break
+            except self._L.MclError as e:
+                if e.status != self._L.MCL_ERR_NOMEM or self.cap >= self.n_global:
+                    raise
+                self.cap = min(self.n_global, 2 * self.cap)
+                self._alloc_expand()
+        (rx, ry, rth), ranges = exchange(self.ex, first, count, self.n_global, self.group)
+        self.last_ranges = ranges
+        self.flt.set_particles(rx, ry, rth, None, skip_stats=True)
+        est = self.global_stats["est"]
+        self.flt.shard_set_global(self._uniform_stats(est))  # weights reset to 1/NP (:222)
+        self.global_stats = dict(self.global_stats, ess=float(self.n_global), log_norm=math.log(self.n_global))
+        return ofs
+
+    def step(self, z, ofs=None, noise=None, force_resample=False):
+        """main_pf minus the ground-truth line: resample (gated on the global ESS) -> predict -> weight ->
+        merged statistics.  `noise`: this rank's (3, 1, m) slice of the draw, or None for Philox."""
+        resampled = force_resample or (self.global_stats["ess"] < self.ess_threshold)
+        if resampled:
+            self.resample(ofs)
+        self.flt.predict_weight(np.asarray(z, dtype=np.float64).reshape(1, -1, 2), noise=noise)
+        self.step_count += 1
+        merged = self._merge()
+        merged["resampled"] = int(resampled)
+        return merged
+
+    def local_particles(self, device=False):
+        x, y, th, lw = self.flt.get_particles(device=device)
+        return x[0], y[0], th[0], lw[0]

@@ -438,3 +438,98 @@ def test_error_paths(mcl):
     f.set_landmarks(np.zeros((2, 2)))
     with pytest.raises(mcl.MclError):
         f.step(np.zeros((1, 2, 2)))  # particles not initialised
+
+
+@pytest.mark.parametrize("G", [2, 4, 8])
+def test_sharded_resampling_matches_unsharded(mcl, G):
+    """G shards (G handles on this one GPU, exchange done by hand) resample to exactly the
+    particles of the unsharded filter, and the merged statistics equal the unsharded ones."""
+    import importlib
+
+    import torch
+
+    sh = importlib.import_module("slam-robot_simu_b200.sharded")
+    n = 1 << 16
+    m = n // G
+    rng = np.random.RandomState(G)
+    lm = rng.uniform(-10, 10, (6, 2))
+    pos = (rng.normal(0, 1, (3, n)) * np.array([[0.2], [0.2], [0.05]]) + np.array([[2.0], [1.0], [0.4]])).astype(np.float32)
+    lw = (-0.5 * ((np.arange(n) - 0.3 * n) / (0.05 * n)) ** 2 + rng.normal(0, 1.0, n)).astype(np.float32)
+    ofs = rng.rand() / n
+    # unsharded
+    f1 = mcl.Filter(n_particles=n, landmarks=lm)
+    f1.set_particles(pos[0], pos[1], pos[2], lw)
+    s1 = f1.stats()[0]
+    q1 = f1.qweights()[0]
+    f1.resample(ofs=ofs, force=True)
+    x1, y1, t1, _ = f1.get_particles()
+    anc1 = f1.ancestors()[0]
+    # sharded
+    fs = []
+    for g in range(G):
+        f = mcl.Filter(n_particles=m, landmarks=lm, n_global=n, slot_base=g * m)
+        sl = slice(g * m, (g + 1) * m)
+        f.set_particles(pos[0, sl], pos[1, sl], pos[2, sl], lw[sl])
+        fs.append(f)
+    recs = []
+    for f in fs:
+        d = mcl.stats_to_dict(f.stats()[0])
+        d["best_logw"] = d["max_logw"]
+        recs.append(d)
+    merged = sh.merge_stats(recs, [g * m for g in range(G)])
+    assert merged["max_idx"] == s1.max_idx
+    assert merged["ess"] == pytest.approx(s1.ess, rel=1e-12)
+    assert merged["log_norm"] == pytest.approx(s1.log_norm, rel=1e-13)
+    np.testing.assert_allclose(merged["mean"], np.array(s1.mean[:]), rtol=1e-9)
+    np.testing.assert_allclose(merged["cov"], np.array(s1.cov[:]).reshape(3, 3), rtol=1e-6, atol=1e-12)
+    g_stats = mcl.mcl_stats()
+    g_stats.max_logw, g_stats.sum_w, g_stats.sum_w2 = merged["max_logw"], merged["sum_w"], merged["sum_w2"]
+    g_stats.log_norm, g_stats.ess = merged["log_norm"], merged["ess"]
+    for k in range(3):
+        g_stats.est[k] = merged["est"][k]
+    totals, ranges, chunks = [], [], []
+    tot = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for f in fs:
+        f.shard_set_global(g_stats)
+        # identical weight map on every shard -> identical integers to the unsharded filter
+        f.shard_total(tot)
+        totals.append(int(tot.item()))
+    for g, f in enumerate(fs):
+        assert np.array_equal(f.qweights()[0], q1[g * m:(g + 1) * m])
+    assert sum(totals) == int(q1.sum())
+    for g, f in enumerate(fs):
+        ex = [torch.full((n,), np.nan, dtype=torch.float32, device="cuda") for _ in range(3)]
+        first, count = f.shard_expand(sum(totals[:g]), ofs, *ex)
+        ranges.append((first, count))
+        chunks.append([e[:count].cpu().numpy() for e in ex])
+        # the shard fills exactly the slots whose ancestor it holds
+        mine = np.nonzero((anc1 >= g * m) & (anc1 < (g + 1) * m))[0]
+        assert count == mine.size and (count == 0 or first == mine[0])
+    for r in range(G):
+        send, recv = sh.plan_exchange(ranges, n, G, r)
+        assert sum(recv) == m
+    got = [np.concatenate([c[d] for c in chunks]) for d in range(3)]
+    np.testing.assert_array_equal(got[0], x1[0])
+    np.testing.assert_array_equal(got[1], y1[0])
+    np.testing.assert_array_equal(got[2], t1[0])
+    # capacity too small is reported, not overrun
+    ex = [torch.empty(8, dtype=torch.float32, device="cuda") for _ in range(3)]
+    heavy = int(np.argmax([c for _, c in ranges]))
+    with pytest.raises(mcl.MclError):
+        fs[heavy].shard_expand(sum(totals[:heavy]), ofs, *ex)
+
+
+def test_sharded_filter_two_gpus_nccl():
+    """The real thing: ShardedParticleFilter over NCCL on 2 GPUs == the unsharded filter (Philox noise)."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", os.path.join(root, "tests", "_nccl_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    assert r.returncode == 0 and "nccl worker ok" in r.stdout, r.stdout[-3000:] + r.stderr[-4000:]

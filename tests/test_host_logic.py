@@ -1,0 +1,150 @@
+"""CPU tests (no GPU): the C ABI loads and exports everything include/mcl.h declares, fails loudly
+without a device, the host-side mirror of the reference interface, and the sharded filter's host logic
+(including a world_size-2 gloo run)."""
+import ctypes as C
+import importlib
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import pf_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    sys.path.insert(0, ROOT)
+    bld = importlib.util.spec_from_file_location("mcl_build", os.path.join(ROOT, "slam-robot_simu_b200", "build.py"))
+    mod = importlib.util.module_from_spec(bld)
+    bld.loader.exec_module(mod)
+    mod.build()  # no-op when libmcl_b200.so is up to date; nvcc cross-compiles without a GPU
+    return importlib.import_module("slam-robot_simu_b200")
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "mcl.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mcl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg._lib.load()
+    names = _declared_functions()
+    assert len(names) >= 28
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/mcl.h but not exported by libmcl_b200.so"
+        assert n in pkg._lib.PROTOTYPES, f"{n} has no ctypes prototype"
+    assert set(pkg._lib.PROTOTYPES) == set(names)
+    assert lib.mcl_abi_version() == pkg._lib.MCL_ABI_VERSION
+    assert lib.mcl_status_string(0) == b"ok" and lib.mcl_status_string(-5) == b"no sm_100 CUDA device"
+
+
+def test_struct_layout_matches_the_header(pkg, tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include "mcl.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu\\n",'
+                   'sizeof(mcl_config),sizeof(mcl_stats),offsetof(mcl_stats,raw),offsetof(mcl_config,seed));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    L = pkg._lib
+    assert got == [C.sizeof(L.mcl_config), C.sizeof(L.mcl_stats), L.mcl_stats.raw.offset, L.mcl_config.seed.offset]
+
+
+def test_config_defaults_are_the_reference_literals(pkg):
+    cfg = pkg.default_config(100.0)
+    P = O.PFParams(100)
+    assert cfg.struct_size == C.sizeof(pkg.mcl_config)
+    assert cfg.n_particles == P.NP and cfg.dt == P.DT_s
+    assert cfg.vel == pytest.approx(P.VEL_mps, rel=1e-15) and cfg.yaw_rate == pytest.approx(P.YAW_RATE_rps, rel=1e-15)
+    np.testing.assert_allclose(np.array(cfg.q_std[:]) ** 2, np.diag(P.Q), rtol=1e-15)
+    np.testing.assert_allclose(np.array(cfg.sigma_obs[:]) ** 2, np.diag(P.R), rtol=1e-15)
+    assert cfg.ess_threshold == P.ESS_TH
+
+
+def test_no_device_fails_loudly_and_never_falls_back(pkg):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = pkg._lib.load()
+    cfg = pkg.default_config(100.0)
+    need = C.c_size_t(0)
+    assert lib.mcl_workspace_bytes(C.byref(cfg), C.byref(need)) == 0 and need.value > 1000 * 36
+    h = C.c_void_p()
+    assert lib.mcl_create(C.byref(cfg), None, 0, C.byref(h)) == pkg._lib.MCL_ERR_NODEVICE
+    assert not h.value and b"no CPU fallback" in lib.mcl_last_error(None)
+    with pytest.raises(pkg.MclError):
+        pkg.Filter(n_particles=1000)
+    with pytest.raises(pkg.MclError):
+        pkg.ParticleFilter(100)
+    # argument validation happens before any device work
+    cfg.struct_size = 8
+    assert lib.mcl_workspace_bytes(C.byref(cfg), C.byref(need)) == pkg._lib.MCL_ERR_ARG
+    cfg = pkg.default_config(100.0)
+    cfg.n_trials = 2
+    cfg.n_global = 4000  # sharding and trial batching are exclusive
+    assert lib.mcl_workspace_bytes(C.byref(cfg), C.byref(need)) == pkg._lib.MCL_ERR_ARG
+    for fn in ("mcl_destroy", ):
+        assert getattr(lib, fn)(None) == 0
+    assert lib.mcl_step(None, None, None, None, 0, None) == pkg._lib.MCL_ERR_ARG
+
+
+def test_workspace_scales_with_the_configs(pkg):
+    lib = pkg._lib.load()
+    for n, T, per_particle in ((1 << 20, 1, 36), (16384, 4096, 36), (125_000_000, 1, 36)):
+        cfg = pkg.default_config(100.0)
+        cfg.n_particles, cfg.n_trials, cfg.n_global = n, T, n
+        need = C.c_size_t(0)
+        assert lib.mcl_workspace_bytes(C.byref(cfg), C.byref(need)) == 0
+        assert per_particle * n * T <= need.value <= per_particle * n * T * 1.02 + (8 << 20)
+
+
+def test_host_mirror_of_the_reference_helpers(pkg, golden_dir):
+    pf = importlib.import_module("slam-robot_simu_b200.particle_filter")
+    h = np.load(os.path.join(golden_dir, "helpers.npz"))
+    got = np.array([float(pf.limit_angle(a)) for a in h["lim_in"]])
+    assert np.array_equal(got, h["lim_out"])
+    for p, want in zip(h["w2r_pose"], h["w2r_out"]):
+        np.testing.assert_allclose(pf.world2robot(p, h["w2r_lm"]), want, rtol=0, atol=1e-12)
+
+
+def test_philox_known_answers(pkg):
+    sh = importlib.import_module("slam-robot_simu_b200.sharded")
+    # Random123 known-answer vectors for philox4x32-10
+    assert sh.philox4x32_10((0, 0, 0, 0), (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert sh.philox4x32_10((0xffffffff,) * 4, (0xffffffff,) * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert sh.philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    u = [sh.philox_ofs(42, k, 1000) for k in range(2000)]
+    assert 0.0 <= min(u) and max(u) < 1e-3 and abs(np.mean(u) * 1000 - 0.5) < 0.03
+
+
+def test_plan_exchange_properties(pkg):
+    sh = importlib.import_module("slam-robot_simu_b200.sharded")
+    rng = np.random.RandomState(0)
+    for world in (2, 4, 8):
+        n = 1024 * world
+        m = n // world
+        for _ in range(50):
+            cuts = np.sort(rng.randint(0, n + 1, world - 1))
+            bounds = np.concatenate([[0], cuts, [n]])
+            ranges = [(int(a), int(b - a)) for a, b in zip(bounds[:-1], bounds[1:])]
+            sends, recvs = zip(*(sh.plan_exchange(ranges, n, world, r) for r in range(world)))
+            S, R = np.array(sends), np.array(recvs)
+            assert np.array_equal(S, R.T)  # what s sends to g is what g expects from s
+            assert np.all(R.sum(axis=1) == m) and np.array_equal(S.sum(axis=1), [c for _, c in ranges])
+        with pytest.raises(RuntimeError):
+            sh.plan_exchange([(0, 10)] + [(10, 0)] * (world - 1), n, world, 0)
+
+
+def test_sharded_host_logic_under_gloo_world_size_2():
+    env = dict(os.environ, OMP_NUM_THREADS="1", MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29617", os.path.join(ROOT, "tests", "_gloo_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "gloo worker ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
