@@ -189,17 +189,28 @@ uint64_t mcl_launch_count(const mcl_filter *h);
  * The host exchanges the small records; see slam-robot_simu_b200/sharded.py.  Order per step:
  *   mcl_predict_weight on every shard -> allgather + merge of mcl_stats -> mcl_shard_set_global;
  *   when resampling: mcl_shard_total -> allgather of the totals -> mcl_shard_expand -> all-to-all
- *   of the expanded poses -> mcl_set_particles.
+ *   of the off-rank poses -> mcl_shard_step (instead of mcl_predict_weight).
  * mcl_shard_set_global: install the merged statistics (global max_logw / sum_w define the weight
  * map, est the reference pose, ess the resampling gate). */
 int mcl_shard_set_global(mcl_filter *h, const mcl_stats *merged_host, void *stream);
 /* mcl_shard_total: sum of this shard's quantised weights under the global weight map -> *total_dev. */
 int mcl_shard_total(mcl_filter *h, uint64_t *total_dev, void *stream);
-/* mcl_shard_expand: with k_offset = sum of totals of lower ranks, write for every global slot this
- * shard's particles fill the resampled pose into out_{x,y,yaw}_dev[slot - *first_slot]; capacity
- * `cap` slots.  first_slot/n_slots (host, written after a stream sync) describe the filled range. */
-int mcl_shard_expand(mcl_filter *h, uint64_t k_offset, double ofs, float *out_x_dev, float *out_y_dev,
-                     float *out_yaw_dev, int64_t cap, int64_t *first_slot, int64_t *n_slots, void *stream);
+/* mcl_shard_expand: with k_offset = sum of the totals of lower ranks, resample this shard's particles
+ * with GLOBAL slot numbers.  Slots inside the shard's own range [slot_base, slot_base + n_particles) keep
+ * the ancestor path (an index into the local state, consumed by mcl_shard_step); slots owned by other
+ * ranks get their resampled pose written to send_{x,y,yaw}_dev, packed in slot order: first the slots
+ * below the own range, then the slots above it -- exactly the layout a rank-ordered all-to-all sends.
+ * `cap` = capacity of the send buffers in slots.  first_slot/n_slots (host; may both be NULL, then the
+ * call does not synchronise) return the filled range [first, first + n). */
+int mcl_shard_expand(mcl_filter *h, uint64_t k_offset, double ofs, float *send_x_dev, float *send_y_dev,
+                     float *send_yaw_dev, int64_t cap, int64_t *first_slot, int64_t *n_slots, void *stream);
+/* mcl_shard_step: predict + weight of the resampled shard.  Output slots [0, n_prefix) and
+ * [n_particles - n_suffix, n_particles) were filled by other ranks: their poses are recv_*[0 .. n_prefix +
+ * n_suffix) ([prefix | suffix], what the all-to-all delivers in rank order); the slots between gather
+ * through the ancestors of mcl_shard_expand.  Weights restart from 1/NP (particle_filter.py:222). */
+int mcl_shard_step(mcl_filter *h, const double *z_host, const float *noise_dev, const float *recv_x_dev,
+                   const float *recv_y_dev, const float *recv_yaw_dev, int64_t n_prefix, int64_t n_suffix, uint32_t flags,
+                   void *stream);
 
 #ifdef __cplusplus
 }

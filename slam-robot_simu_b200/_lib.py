@@ -111,6 +111,7 @@ PROTOTYPES = {
     "mcl_shard_total": (C.c_int, [_vp, _vp, _vp]),
     "mcl_shard_expand": (C.c_int, [_vp, C.c_uint64, C.c_double, _vp, _vp, _vp, C.c_int64,
                                    _P(C.c_int64), _P(C.c_int64), _vp]),
+    "mcl_shard_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_uint32, _vp]),
     "mcl_shard_set_global": (C.c_int, [_vp, _P(mcl_stats), _vp]),
 }
 

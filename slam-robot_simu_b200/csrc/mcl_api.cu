@@ -4,6 +4,7 @@
 // caller's stream.  No arithmetic of the filter happens on the host; there is no CPU fallback.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -212,6 +213,8 @@ void fill_scan(mcl_filter *h, ScanParams &p) {
     p.j_global_base = h->cfg.slot_base;
     p.slot_first = 0;
     p.anc_cap = h->lay.ld;
+    p.own_lo = 0;
+    p.own_hi = h->cfg.n_global;
     p.k_offset = 0;
     p.delta = h->delta;
     p.tpt = h->lay.tpt;
@@ -225,6 +228,7 @@ int launch_step_scan(mcl_filter *h, const double *z_dev, const double *ofs_dev, 
     fill_scan(h, sp);
     fill_prep(h, sp.prep, z_dev, ofs_dev, flags);
     sp.do_prep = 1;
+    sp.prep_only = full ? 0 : 1;
     if (full) {
         sp.desc_next = h->desc[h->desc_cur ^ 1];
         h->desc_cur ^= 1;
@@ -260,12 +264,23 @@ int step_variant(const mcl_config &c) {
     return (c.sigma_obs[0] == c.sigma_obs[1]) ? kLikMomentIso : kLikMomentGen;
 }
 
-int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool reduce_only, cudaStream_t st) {
+struct StepWindow {
+    uint32_t lo, hi;
+    const float *x, *y, *th;
+};
+
+int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool reduce_only, cudaStream_t st,
+                const StepWindow *win = nullptr) {
     const mcl_config &c = h->cfg;
     StepParams p{};
     p.in = h->state[h->cur];
     p.out = h->state[h->cur ^ 1];
     p.anc = h->anc;
+    p.win_lo = win ? win->lo : 0u;
+    p.win_hi = win ? win->hi : static_cast<uint32_t>(h->lay.n);
+    p.recv_x = win ? win->x : nullptr;
+    p.recv_y = win ? win->y : nullptr;
+    p.recv_th = win ? win->th : nullptr;
     p.noise = noise_dev;
     p.prep = h->prep;
     p.tab = h->tab;
@@ -811,16 +826,18 @@ int mcl_shard_total(mcl_filter *h, uint64_t *total_dev, void *stream) {
     return launch_shard_scan(h, sp, kScanTotals, st);
 }
 
-int mcl_shard_expand(mcl_filter *h, uint64_t k_offset, double ofs, float *out_x_dev, float *out_y_dev,
-                     float *out_yaw_dev, int64_t cap, int64_t *first_slot, int64_t *n_slots, void *stream) {
+int mcl_shard_expand(mcl_filter *h, uint64_t k_offset, double ofs, float *send_x_dev, float *send_y_dev,
+                     float *send_yaw_dev, int64_t cap, int64_t *first_slot, int64_t *n_slots, void *stream) {
     if (h == nullptr) return MCL_ERR_ARG;
-    if (out_x_dev == nullptr || out_y_dev == nullptr || out_yaw_dev == nullptr || first_slot == nullptr || n_slots == nullptr || cap < 0)
-        return fail(h, MCL_ERR_ARG, "NULL output or negative capacity");
+    if (cap < 0 || (cap > 0 && (send_x_dev == nullptr || send_y_dev == nullptr || send_yaw_dev == nullptr)))
+        return fail(h, MCL_ERR_ARG, "NULL send buffer or negative capacity");
+    if ((first_slot == nullptr) != (n_slots == nullptr)) return fail(h, MCL_ERR_ARG, "first_slot and n_slots go together");
     if (h->lay.T != 1) return fail(h, MCL_ERR_STATE, "sharding needs n_trials == 1");
     int rc = use_device(h);
     if (rc != MCL_OK) return rc;
     cudaStream_t st = S(stream);
     const long long NG = h->cfg.n_global;
+    const long long lo = h->cfg.slot_base, hi = lo + h->cfg.n_particles;
     const long long s0 = host_count_le(k_offset, h->delta, ofs, NG);
     ScanParams sp;
     fill_scan(h, sp);
@@ -830,20 +847,60 @@ int mcl_shard_expand(mcl_filter *h, uint64_t k_offset, double ofs, float *out_x_
     sp.k_offset = k_offset;
     sp.slot_first = s0;
     sp.anc_cap = cap;
+    sp.own_lo = lo;
+    sp.own_hi = hi;
+    sp.send_hi_off = (lo > s0) ? lo - s0 : 0;   // size of the piece below own_lo when the range reaches own_lo
+    sp.send_hi_base = (hi > s0) ? hi : s0;
     sp.src = h->state[h->cur];
-    sp.ox = out_x_dev;
-    sp.oy = out_y_dev;
-    sp.oth = out_yaw_dev;
+    sp.ox = send_x_dev;
+    sp.oy = send_y_dev;
+    sp.oth = send_yaw_dev;
     rc = launch_shard_scan(h, sp, kScanExpand, st);
     if (rc != MCL_OK) return rc;
+    if (first_slot == nullptr) return MCL_OK;  // the caller derives the range from the allgathered totals
     unsigned long long total = 0;
     MCL_CUDA(h, cudaMemcpyAsync(&total, h->total, sizeof total, cudaMemcpyDeviceToHost, st));
     MCL_CUDA(h, cudaStreamSynchronize(st));
-    const bool last = (h->cfg.slot_base + h->cfg.n_particles == NG);
+    const bool last = (hi == NG);
     const long long s1 = last ? NG : host_count_le(k_offset + total, h->delta, ofs, NG);
     *first_slot = s0;
     *n_slots = s1 - s0;
-    if (s1 - s0 > cap) return fail(h, MCL_ERR_NOMEM, "mcl_shard_expand: this shard fills more slots than `cap`");
+    const long long off_rank = std::max(0ll, std::min(lo, s1) - s0) + std::max(0ll, s1 - std::max(hi, s0));
+    if (off_rank > cap) return fail(h, MCL_ERR_NOMEM, "mcl_shard_expand: more off-rank slots than `cap`");
+    return MCL_OK;
+}
+
+int mcl_shard_step(mcl_filter *h, const double *z_host, const float *noise_dev, const float *recv_x_dev,
+                   const float *recv_y_dev, const float *recv_yaw_dev, int64_t n_prefix, int64_t n_suffix, uint32_t flags,
+                   void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (z_host == nullptr) return fail(h, MCL_ERR_ARG, "z_host is NULL");
+    if (h->lay.T != 1) return fail(h, MCL_ERR_STATE, "sharding needs n_trials == 1");
+    if (n_prefix < 0 || n_suffix < 0 || n_prefix + n_suffix > h->lay.n) return fail(h, MCL_ERR_ARG, "bad prefix/suffix");
+    if ((n_prefix + n_suffix > 0) && (recv_x_dev == nullptr || recv_y_dev == nullptr || recv_yaw_dev == nullptr))
+        return fail(h, MCL_ERR_ARG, "received poses are NULL");
+    if (h->L <= 0) return fail(h, MCL_ERR_STATE, "mcl_set_landmarks has not been called");
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "particles are not initialised");
+    if (noise_dev == nullptr && !(flags & MCL_PHILOX_NOISE))
+        return fail(h, MCL_ERR_ARG, "noise_dev is NULL and MCL_PHILOX_NOISE is not set");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    cudaStream_t st = S(stream);
+    rc = stage_inputs(h, z_host, nullptr, st);
+    if (rc != MCL_OK) return rc;
+    // scalars only; the gate is forced: the resampling itself was done by mcl_shard_expand + the exchange
+    rc = launch_step_scan(h, h->z, nullptr, (flags | MCL_FORCE_RESAMPLE) & ~MCL_NO_RESAMPLE, false, st);
+    if (rc != MCL_OK) return rc;
+    StepWindow win;
+    win.lo = static_cast<uint32_t>(n_prefix);
+    win.hi = static_cast<uint32_t>(h->lay.n - n_suffix);
+    win.x = recv_x_dev;
+    win.y = recv_y_dev;
+    win.th = recv_yaw_dev;
+    rc = launch_step(h, noise_dev, flags, false, st, &win);
+    if (rc != MCL_OK) return rc;
+    h->cur ^= 1;
+    h->step += 1;
     return MCL_OK;
 }
 

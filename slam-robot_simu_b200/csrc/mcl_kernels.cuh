@@ -161,9 +161,15 @@ struct ScanParams {
     double delta;               // fl(1 / n_global)
     int tpt;
     int use_override;           // 1: always resample, ofs from ofs_override (sharded resampling)
+    int prep_only;              // 1: per-step scalars only (the sharded step resamples beforehand)
     double ofs_override;
-    StateView src;              // kScanExpand: poses of the local sources ...
-    float *ox, *oy, *oth;       // ... copied to out[slot - slot_first] for every slot they fill
+    // kScanExpand (sharded filter): slots inside this shard's own output range [own_lo, own_hi) keep the
+    // ancestor path (anc[slot - own_lo]); slots owned by other ranks get the resampled POSE written to
+    // the send buffers: slots below own_lo at (slot - slot_first), slots from own_hi on at
+    // send_hi_off + (slot - max(own_hi, slot_first)); anc_cap = capacity of the send buffers.
+    long long own_lo, own_hi, send_hi_off, send_hi_base;
+    StateView src;
+    float *ox, *oy, *oth;
 };
 
 constexpr int kScanAncestors = 0;  // write the ancestor of every slot
@@ -203,7 +209,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
         const WeightMap w0 = make_weight_map(stp->max_logw, stp->sum_w);
         s_sc.wq_m = w0.m;
         s_sc.wq_scale = w0.scale;
-        s_sc.tile = rs ? atomicAdd(&p.tickets[t * 4 + 0], 1u) : 0u;
+        s_sc.tile = (rs && !p.prep_only) ? atomicAdd(&p.tickets[t * 4 + 0], 1u) : 0u;
     }
     __syncthreads();
     const int resample = s_sc.resample;
@@ -216,8 +222,8 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
         prep_block(p.prep, stp, t, resample, ofs, reinterpret_cast<double *>(s_mark));
         __syncthreads();
     }
-    if (!resample) return;
-    if (tile >= p.tpt) return;  // prep-only launches use a one-block grid; never taken otherwise
+    if (!resample || p.prep_only) return;
+    if (tile >= p.tpt) return;  // never taken: scalars-only launches leave above
     const long long j0 = tile * kScanTile + static_cast<long long>(tid) * kScanItems;
     const float *lw = p.lw + static_cast<long long>(t) * p.ld;
 
@@ -329,7 +335,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     const long long S0 = static_cast<long long>(S0d), span = static_cast<long long>(s_slot[1] - S0d);
     const uint32_t my_off = static_cast<uint32_t>(static_cast<long long>(first_slot - S0d));  // threads with sources: >= 0
 
-    uint32_t *anc = p.anc + static_cast<long long>(t) * p.anc_cap;
+    uint32_t *anc = p.anc + static_cast<long long>(t) * p.ld;
     uint32_t carry = 0;  // source (local index + 1) that owns the slot just before the window
     for (long long cb = 0; cb < span; cb += kScanTile) {
         // window of kScanTile slots starting at S0 + cb
@@ -388,16 +394,21 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
         for (int k = 0; k < kScanItems; ++k) {
             const int pos = k * kScanThreads + tid;
             if (pos < lim) {
-                const long long o = S0 + cb + pos - p.slot_first;
+                const long long slot = S0 + cb + pos;
                 const uint32_t j = jbase + s_mark[pos];
                 if (MODE == kScanExpand) {
-                    if (o >= 0 && o < p.anc_cap) {
-                        p.ox[o] = p.src.x[j];
-                        p.oy[o] = p.src.y[j];
-                        p.oth[o] = p.src.th[j];
+                    if (slot >= p.own_lo && slot < p.own_hi) {
+                        anc[slot - p.own_lo] = j;
+                    } else {
+                        const long long o = (slot < p.own_lo) ? slot - p.slot_first : p.send_hi_off + (slot - p.send_hi_base);
+                        if (o >= 0 && o < p.anc_cap) {
+                            p.ox[o] = p.src.x[j];
+                            p.oy[o] = p.src.y[j];
+                            p.oth[o] = p.src.th[j];
+                        }
                     }
                 } else {
-                    anc[o] = j;  // slot_first == 0 and anc_cap >= n_global here
+                    anc[slot] = j;  // unsharded: slots are local indices, anc holds ld >= n of them
                 }
             }
         }
@@ -658,6 +669,10 @@ __device__ __forceinline__ void stats_finish(WarpStats &ws, const FinishParams &
 struct StepParams {
     StateView in, out;
     const uint32_t *anc;   // [T][ld]
+    // sharded filter: output slots [0, win_lo) and [win_hi, n) were filled by other ranks; their resampled
+    // poses arrive in recv_* ([prefix | suffix]).  Unsharded: win_lo = 0, win_hi = n.
+    uint32_t win_lo, win_hi;
+    const float *recv_x, *recv_y, *recv_th;
     const float *noise;    // [3][T][n] dense, or null
     const PrepOut *prep;   // [T]
     const double4 *tab;    // [T][Lmax]
@@ -740,12 +755,30 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const Ste
             if (resample) {
                 const uint4 a4 = *reinterpret_cast<const uint4 *>(anc + base);
                 const uint32_t a[kPPT] = {a4.x, a4.y, a4.z, a4.w};
+                if (base >= p.win_lo && base + kPPT <= p.win_hi) {
 #pragma unroll
-                for (int k = 0; k < kPPT; ++k) {
-                    const uint32_t j = (base + k < p.n) ? a[k] : 0u;
-                    x[k] = ix[j];
-                    y[k] = iy[j];
-                    th[k] = ith[j];
+                    for (int k = 0; k < kPPT; ++k) {
+                        const uint32_t j = (base + k < p.n) ? a[k] : 0u;
+                        x[k] = ix[j];
+                        y[k] = iy[j];
+                        th[k] = ith[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kPPT; ++k) {
+                        const uint32_t i = base + k;
+                        if (i >= p.win_lo && i < p.win_hi) {
+                            const uint32_t j = (i < p.n) ? a[k] : 0u;
+                            x[k] = ix[j];
+                            y[k] = iy[j];
+                            th[k] = ith[j];
+                        } else {
+                            const uint32_t r = (i < p.win_lo) ? i : min(i, p.n - 1u) - p.win_hi + p.win_lo;
+                            x[k] = p.recv_x[r];
+                            y[k] = p.recv_y[r];
+                            th[k] = p.recv_th[r];
+                        }
+                    }
                 }
             } else {
                 const float4 vx = *reinterpret_cast<const float4 *>(ix + base);

@@ -242,14 +242,22 @@ class Filter:
     def shard_total(self, total_dev):
         self._check(self.lib.mcl_shard_total(self._h, C.c_void_p(total_dev.data_ptr()), self._stream()), "mcl_shard_total")
 
-    def shard_expand(self, k_offset, ofs, out_x, out_y, out_yaw):
+    def shard_expand(self, k_offset, ofs, send_x, send_y, send_yaw, want_range=True):
+        """-> (first_slot, n_slots) of the slots this shard fills (None, None with want_range=False: no sync)."""
+        cap = min(send_x.numel(), send_y.numel(), send_yaw.numel())
         first, count = C.c_int64(0), C.c_int64(0)
-        cap = min(out_x.numel(), out_y.numel(), out_yaw.numel())
-        self._check(self.lib.mcl_shard_expand(self._h, int(k_offset), float(ofs),
-                                              C.c_void_p(out_x.data_ptr()), C.c_void_p(out_y.data_ptr()),
-                                              C.c_void_p(out_yaw.data_ptr()), cap, C.byref(first), C.byref(count),
+        self._check(self.lib.mcl_shard_expand(self._h, int(k_offset), float(ofs), C.c_void_p(send_x.data_ptr()),
+                                              C.c_void_p(send_y.data_ptr()), C.c_void_p(send_yaw.data_ptr()), cap,
+                                              C.byref(first) if want_range else None, C.byref(count) if want_range else None,
                                               self._stream()), "mcl_shard_expand")
-        return first.value, count.value
+        return (first.value, count.value) if want_range else (None, None)
+
+    def shard_step(self, z, recv_x, recv_y, recv_yaw, n_prefix, n_suffix, noise=None):
+        zz = self._f64(z, (1, self.n_landmarks, 2))
+        ptr = lambda a: None if a is None else C.c_void_p(a.data_ptr())  # noqa: E731
+        self._check(self.lib.mcl_shard_step(self._h, zz.ctypes.data, self._noise_ptr(noise), ptr(recv_x), ptr(recv_y),
+                                            ptr(recv_yaw), int(n_prefix), int(n_suffix), self._flags(noise, False, False),
+                                            self._stream()), "mcl_shard_step")
 
     def shard_set_global(self, merged: L.mcl_stats):
         self._check(self.lib.mcl_shard_set_global(self._h, C.byref(merged), self._stream()), "mcl_shard_set_global")

@@ -11,9 +11,11 @@ Predict + weight is local.  Two exchanges couple the shards:
     offset of its first particle; because the weights are integers on a 2^-52 grid the global scan is
     exact, and each shard computes, with GLOBAL slot numbers, the resampled pose of every slot its own
     particles fill (mcl_shard_expand).  Ancestors are monotone, so that is one contiguous slot range
-    per shard; `plan_exchange` cuts it at the owners' boundaries and one variable-count all-to-all
-    (NCCL over NVLink on GPUs) delivers every slot to its owner.  The result is bit-identical to the
-    unsharded filter, and to the reference walk of particle_filter.py:212-221.
+    per shard (`shard_ranges` derives all of them from the totals).  Slots inside a shard's own range
+    keep the local ancestor/gather path; only the slots owned by other ranks are materialised as poses
+    and travel in one variable-count all-to-all per pose array (`plan_offrank`, NCCL over NVLink).
+    mcl_shard_step then predicts + weights [received prefix | locally gathered middle | received suffix].
+    The result is bit-identical to the unsharded filter, and to the reference walk of :212-221.
 
 The pure-host pieces (`merge_stats`, `plan_exchange`, `exchange`, `philox_ofs`) import neither CUDA
 nor the C library and are what the world_size-2 gloo tests exercise on CPU.
@@ -112,6 +114,49 @@ def merge_stats(records, slot_bases):
                 cov=cov, raw=raw, ref=ref, owner=bg)
 
 
+def count_le(K, n_global, ofs):
+    """Number of comb teeth u_i = fl(fl(i * (1/N)) + ofs) <= K * 2^-52 (host twin of mcl::count_le; plain
+    Python floats are IEEE doubles and CPython never fuses the multiply and the add)."""
+    nd = float(n_global)
+    delta = 1.0 / nd
+    c = float(K) * 2.0 ** -52
+    g = float(math.floor((c - ofs) * nd))
+
+    def comb(i):
+        m = i * delta
+        return m + ofs
+
+    r = g
+    if comb(g + 1.0) <= c:
+        r = g + 1.0
+    elif comb(g) > c:
+        r = g - 1.0
+    return int(min(max(r + 1.0, 0.0), nd))
+
+
+def shard_ranges(totals, n_global, ofs):
+    """(first_slot, n_slots) of every shard from the allgathered integer weight totals: shard g fills the
+    slots whose tooth falls in (K_g, K_g + total_g]; the last shard also takes any slots past the final
+    cumulative weight.  Every rank computes the same list, so no second exchange is needed."""
+    out, k = [], 0
+    for g, t in enumerate(totals):
+        first = count_le(k, n_global, ofs)
+        k += int(t)
+        end = n_global if g == len(totals) - 1 else count_le(k, n_global, ofs)
+        out.append((first, end - first))
+    return out
+
+
+def plan_offrank(ranges, n_global, world, rank):
+    """Split sizes when a shard keeps the slots of its own range and only off-rank slots travel.
+    Returns (send, recv, n_prefix, n_suffix): send[g]/recv[s] as plan_exchange with the diagonal zeroed;
+    the received buffer is [prefix | suffix] of my output range."""
+    send, recv = plan_exchange(ranges, n_global, world, rank)
+    send[rank] = 0
+    recv[rank] = 0
+    return send, recv, sum(recv[:rank]), sum(recv[rank + 1:])
+
+
 def plan_exchange(ranges, n_global, world, rank):
     """Split sizes of the all-to-all.  ranges[s] = (first_slot, n_slots) of the slots shard s fills.
 
@@ -150,6 +195,23 @@ def exchange(arrays, first, count, n_global, group=None):
     return out, ranges
 
 
+def exchange_offrank(send_arrays, ranges, n_global, group=None):
+    """All-to-all of the off-rank slots only.  `send_arrays`: [slots below my range | slots above it] as
+    written by mcl_shard_expand.  Returns (recv_arrays, n_prefix, n_suffix)."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    send, recv, n_prefix, n_suffix = plan_offrank(ranges, n_global, world, rank)
+    n_send, n_recv = sum(send), sum(recv)
+    out = []
+    for a in send_arrays:
+        o = torch.empty(max(n_recv, 1), dtype=a.dtype, device=a.device)
+        dist.all_to_all_single(o[:n_recv], a[:n_send].contiguous(), recv, send, group=group)
+        out.append(o)
+    return out, n_prefix, n_suffix
+
+
 # ---------------------------------------------------------------------------------------------
 # the sharded filter (needs CUDA + libmcl_b200.so)
 # ---------------------------------------------------------------------------------------------
@@ -157,7 +219,7 @@ class ShardedParticleFilter:
     """n_global particles, contiguous shards of n_global / world_size per rank."""
 
     def __init__(self, n_global, landmarks, period_ms=100.0, likelihood="moment", seed=42, group=None, device=None,
-                 ess_div=100.0, expand_factor=2.0, **cfg):
+                 ess_div=100.0, expand_factor=0.125, **cfg):
         import torch
         import torch.distributed as dist
 
@@ -178,8 +240,8 @@ class ShardedParticleFilter:
                           ess_threshold=self.ess_threshold, **cfg)
         self.dev = self.flt.device
         self.slot_bases = [g * self.m for g in range(self.world)]
-        # a shard's heavy particles can fill more slots than it owns: the expand buffers hold `cap` slots,
-        # and grow (up to n_global) when a step needs more
+        # only slots owned by OTHER ranks are materialised as poses: the send buffers hold `cap` slots and
+        # grow when a step needs more (worst case n_global - m, when one shard holds all the weight)
         self.cap = min(self.n_global, int(self.m * expand_factor) + 1024)
         self._alloc_expand()
         self.total_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
@@ -253,40 +315,37 @@ class ShardedParticleFilter:
         self.flt.set_particles(x, y, yaw, logw)
         return self._merge()
 
-    def resample(self, ofs=None):
-        """Global systematic resampling (particle_filter.py:212-222) across the shards."""
+    def _expand(self, ofs):
+        """Global systematic resampling (particle_filter.py:212-222): local slots keep the ancestor path,
+        off-rank slots are exchanged as poses.  Returns (recv arrays, n_prefix, n_suffix, ranges)."""
         t = self.torch
-        if ofs is None:
-            ofs = philox_ofs(self.seed, self.step_count, self.n_global)
         self.flt.shard_total(self.total_dev)
         totals = [t.empty_like(self.total_dev) for _ in range(self.world)]
         self.dist.all_gather(totals, self.total_dev, group=self.group)
-        totals = [int(v.item()) for v in totals]
-        k_offset = sum(totals[:self.rank])
-        while True:
-            try:
-                first, count = self.flt.shard_expand(k_offset, ofs, *self.ex)
-                break
-            except self._L.MclError as e:
-                if e.status != self._L.MCL_ERR_NOMEM or self.cap >= self.n_global:
-                    raise
-                self.cap = min(self.n_global, 2 * self.cap)
-                self._alloc_expand()
-        (rx, ry, rth), ranges = exchange(self.ex, first, count, self.n_global, self.group)
+        totals = [int(v) for v in t.cat(totals).tolist()]
+        ranges = shard_ranges(totals, self.n_global, ofs)
+        send, _, _, _ = plan_offrank(ranges, self.n_global, self.world, self.rank)
+        if sum(send) > self.cap:
+            self.cap = min(self.n_global, max(2 * self.cap, sum(send) + 1024))
+            self._alloc_expand()
+        self.flt.shard_expand(sum(totals[:self.rank]), ofs, *self.ex, want_range=False)
+        recv, n_prefix, n_suffix = exchange_offrank(self.ex, ranges, self.n_global, self.group)
         self.last_ranges = ranges
-        self.flt.set_particles(rx, ry, rth, None, skip_stats=True)
-        est = self.global_stats["est"]
-        self.flt.shard_set_global(self._uniform_stats(est))  # weights reset to 1/NP (:222)
-        self.global_stats = dict(self.global_stats, ess=float(self.n_global), log_norm=math.log(self.n_global))
-        return ofs
+        return recv, n_prefix, n_suffix
 
     def step(self, z, ofs=None, noise=None, force_resample=False):
         """main_pf minus the ground-truth line: resample (gated on the global ESS) -> predict -> weight ->
         merged statistics.  `noise`: this rank's (3, 1, m) slice of the draw, or None for Philox."""
         resampled = force_resample or (self.global_stats["ess"] < self.ess_threshold)
+        z = np.asarray(z, dtype=np.float64).reshape(1, -1, 2)
         if resampled:
-            self.resample(ofs)
-        self.flt.predict_weight(np.asarray(z, dtype=np.float64).reshape(1, -1, 2), noise=noise)
+            if ofs is None:
+                ofs = philox_ofs(self.seed, self.step_count, self.n_global)
+            recv, n_prefix, n_suffix = self._expand(ofs)
+            self.flt.shard_step(z, recv[0], recv[1], recv[2], n_prefix, n_suffix, noise=noise)
+            self._keep = recv
+        else:
+            self.flt.predict_weight(z, noise=noise)
         self.step_count += 1
         merged = self._merge()
         merged["resampled"] = int(resampled)

@@ -76,6 +76,23 @@ def main():
             if not np.array_equal(out[d].numpy(), want[d]):
                 print(f"rank {rank} case {kind}: exchange mismatch in row {d}", flush=True)
                 sys.exit(1)
+        # the same ranges follow from the allgathered integer totals alone
+        totals = [int(q[g * m:(g + 1) * m].sum()) for g in range(world)]
+        derived = sh.shard_ranges(totals, n_global, ofs)
+        for (f_a, c_a), (f_b, c_b) in zip(ranges, derived):
+            assert c_a == c_b and (c_a == 0 or f_a == f_b), (ranges, derived)
+        # off-rank exchange: a shard keeps the slots of its own range and sends [below | above]
+        lo, hi = rank * m, (rank + 1) * m
+        sel = np.concatenate([np.arange(first, min(lo, first + count)), np.arange(max(hi, first), first + count)]).astype(np.int64)
+        send = [torch.from_numpy(np.concatenate([pose[d][anc[sel]].astype(np.float32), np.zeros(3, np.float32)])) for d in range(3)]
+        recv, n_pre, n_suf = sh.exchange_offrank(send, derived, n_global)
+        own = np.arange(max(lo, first), min(hi, first + count))
+        assert n_pre + own.size + n_suf == m
+        for d in range(3):
+            full = np.concatenate([recv[d].numpy()[:n_pre], pose[d][anc[own]].astype(np.float32), recv[d].numpy()[n_pre:n_pre + n_suf]])
+            if not np.array_equal(full, want[d]):
+                print(f"rank {rank} case {kind}: off-rank exchange mismatch in row {d}", flush=True)
+                sys.exit(1)
         # the ranges tile the comb in rank order
         assert ranges[0][0] == 0 and sum(c for _, c in ranges) == n_global
         for (f0, c0), (f1, _) in zip(ranges[:-1], ranges[1:]):
