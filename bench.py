@@ -504,10 +504,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
     ap.add_argument("--likelihood", default="moment", choices=["pair", "moment"])
+    ap.add_argument("--n", type=int, default=0, help="override the particle count of the workload (experiments)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the particle-sharded C3 measurement")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.n:
+        wl["n"] = args.n
+        wl["desc"] += f" [particle count overridden: {args.n}]"
     if args.impl == "reference":
         run_reference(args, wl)
     else:

@@ -101,10 +101,14 @@ typedef struct mcl_stats {
     double sum_w;      /* s1: sum exp(logw - max_logw)  (partials for sharded merge)        */
     double sum_w2;     /* s2: sum exp(2 (logw - max_logw))                                  */
     double max_logw;   /* max_i logw_i                                                      */
-    double raw[12];    /* un-normalised moment sums about `ref` (for sharded merge)         */
+    double raw[12];    /* un-normalised sums about `ref`: dx dy dth sin cos xx xy yy xth yth thth,
+                          then [11] = stored log-weight of the MAP particle                  */
     double ref[3];     /* reference pose the moment sums are taken about                    */
     int32_t resampled; /* 1 if this step's resampling stage fired                           */
     int32_t step;      /* number of mcl_step/mcl_predict_weight calls so far                */
+    int32_t derived;   /* 1 once log_norm, max_weight, mean and cov have been derived from the sums:
+                          the kernels write only the sums; mcl_get_stats derives the rest on the host */
+    int32_t reserved;
 } mcl_stats;
 
 int mcl_abi_version(void);
@@ -167,7 +171,8 @@ int mcl_pose_moments(mcl_filter *h, void *stream);
 /* ---- results ---------------------------------------------------------------------------------
  * Copies [n_trials] mcl_stats to host memory and synchronises the stream. */
 int mcl_get_stats(mcl_filter *h, mcl_stats *out_host, void *stream);
-/* Device address of the [n_trials] mcl_stats block (for callers that poll asynchronously). */
+/* Device address of the [n_trials] mcl_stats block (for callers that poll asynchronously).  On the device
+ * only the sums, ess, max_idx and est are current (see `derived`). */
 int mcl_stats_dev(mcl_filter *h, const mcl_stats **out_dev);
 /* Normalised weights exp(logw - log_norm) as fp64 [n_trials][n_particles] (pw of :194-196). */
 int mcl_get_weights(mcl_filter *h, double *w_host, void *stream);
@@ -184,6 +189,12 @@ int mcl_get_ancestors(mcl_filter *h, uint32_t *anc_host, void *stream);
 int mcl_profile(mcl_filter *h, int enable);
 int mcl_profile_read(mcl_filter *h, double *ms3_host);
 uint64_t mcl_launch_count(const mcl_filter *h);
+/* Debug aid: the first call (stamps_host may be NULL) arms a per-CTA phase timeline of k_step; later calls
+ * copy [n_ctas][12] global-timer nanosecond stamps of the most recent step (synchronises the device;
+ * n_ctas = k_step CTAs followed by k_scan CTAs):
+ * 0 start, 1 scalars loaded, 2 loop done, 3 warp sums flushed, 4 partial written, 5 ticket taken,
+ * 6 statistics written, 7..10 stages of the merge (last CTA only). */
+int mcl_debug_timeline(mcl_filter *h, uint64_t *stamps_host, int64_t capacity, int32_t *n_ctas);
 
 /* ---- particle-sharded single filter (n_trials == 1, one handle per GPU) -----------------------
  * The host exchanges the small records; see slam-robot_simu_b200/sharded.py.  Order per step:

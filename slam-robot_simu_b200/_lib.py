@@ -75,6 +75,8 @@ class mcl_stats(C.Structure):
         ("ref", C.c_double * 3),
         ("resampled", C.c_int32),
         ("step", C.c_int32),
+        ("derived", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -108,6 +110,7 @@ PROTOTYPES = {
     "mcl_profile": (C.c_int, [_vp, C.c_int]),
     "mcl_profile_read": (C.c_int, [_vp, _P(C.c_double)]),
     "mcl_launch_count": (C.c_uint64, [_vp]),
+    "mcl_debug_timeline": (C.c_int, [_vp, _vp, C.c_int64, _P(C.c_int32)]),
     "mcl_shard_total": (C.c_int, [_vp, _vp, _vp]),
     "mcl_shard_expand": (C.c_int, [_vp, C.c_uint64, C.c_double, _vp, _vp, _vp, C.c_int64,
                                    _P(C.c_int64), _P(C.c_int64), _vp]),

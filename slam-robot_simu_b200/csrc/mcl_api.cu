@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -25,7 +26,7 @@ struct Layout {
     int T, Lmax, tpt, bpt, cov_bpt;
     uint32_t per;
     size_t off_state[2], off_anc, off_desc, off_tickets, off_partials, off_cov, off_stats, off_prep, off_tab, off_lm,
-        off_z, off_ofs, off_pose, off_total, off_trig, total;
+        off_z, off_ofs, off_pose, off_total, off_trig, off_pub, total;
 };
 
 int make_layout(const mcl_config &c, int sm_count, Layout &L) {
@@ -67,6 +68,7 @@ int make_layout(const mcl_config &c, int sm_count, Layout &L) {
     L.off_ofs = o;      o = align_up(o + static_cast<size_t>(L.T) * sizeof(double), kAlign);
     L.off_pose = o;     o = align_up(o + static_cast<size_t>(L.T) * 3 * sizeof(double), kAlign);
     L.off_total = o;    o = align_up(o + static_cast<size_t>(L.T) * sizeof(unsigned long long), kAlign);
+    L.off_pub = o;      o = align_up(o + static_cast<size_t>(L.T) * 2 * sizeof(uint4), kAlign);
     L.off_trig = o;     o = align_up(o + static_cast<size_t>(kTrigEntries) * sizeof(TrigEntry), kAlign);
     L.total = o;
     return MCL_OK;
@@ -104,16 +106,20 @@ struct mcl_filter {
     double *lm = nullptr, *z = nullptr, *ofs = nullptr, *pose = nullptr;
     unsigned long long *total = nullptr;
     TrigEntry *trig = nullptr;
+    uint4 *wm_pub = nullptr;
+    unsigned int scan_epoch = 0;
     int cur = 0;
     int L = 0;
     uint32_t step = 0;
     bool have_particles = false;
     bool stats_from_particle0 = false;  // next reduce-only pass takes its reference pose from particle 0
+    bool stats_dirty = false;           // the CTA partials of the last k_step / k_reduce are newer than stats[]
     double delta = 0.0;                 // fl(1 / n_global), NP_RECIP (particle_filter.py:32)
     std::string err;
     uint64_t launches = 0;
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned long long *dbg = nullptr;  // optional k_step phase timeline (mcl_debug_timeline)
 };
 
 namespace {
@@ -175,6 +181,32 @@ long long host_count_le(unsigned long long K, double delta, double ofs, long lon
 }
 
 // ---- launch helpers ------------------------------------------------------------------------------
+// The two kernels of a step are launched with programmatic stream serialization (PDL): the dependent
+// grid is scheduled while the previous one drains, and waits in cudaGridDependencySynchronize().
+// MCL_PDL=0 in the environment turns it off.
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char *e = std::getenv("MCL_PDL");
+        return !(e != nullptr && e[0] == '0');
+    }();
+    return on;
+}
+
+template <typename P>
+void launch_pdl(void (*kernel)(P), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, const P &params) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, params);
+}
+
 void fill_prep(mcl_filter *h, PrepParams &p, const double *z_dev, const double *ofs_dev, uint32_t flags) {
     const mcl_config &c = h->cfg;
     p = PrepParams{};
@@ -218,9 +250,28 @@ void fill_scan(mcl_filter *h, ScanParams &p) {
     p.k_offset = 0;
     p.delta = h->delta;
     p.tpt = h->lay.tpt;
+    p.wm_pub = h->wm_pub;
+    p.epoch = ++h->scan_epoch;
+    if (p.epoch == 0u) p.epoch = ++h->scan_epoch;  // 0 is the initial value of the flags
 }
 
-// In-step (or stage) scan: per-step scalars by block 0 of each trial, then the scan of the trials that
+// mcl_stats on the device is merged lazily from the CTA partials: by the statistics CTA of the next k_scan,
+// or here when the host (or a stage call) needs it first.
+int ensure_stats(mcl_filter *h, cudaStream_t st) {
+    if (!h->stats_dirty) return MCL_OK;
+    MergeParams m{};
+    m.partials = h->partials;
+    m.bpt = h->lay.bpt;
+    m.stats = h->stats;
+    m.cur = h->state[h->cur];
+    m.ld = h->lay.ld;
+    k_merge<<<h->lay.T, kStepThreads, 0, st>>>(m);
+    MCL_LAUNCH_CHECK(h, "k_merge");
+    h->stats_dirty = false;
+    return MCL_OK;
+}
+
+// In-step (or stage) scan: per-step scalars by an extra CTA of each trial, then the scan of the trials that
 // resample.  `full` = false launches the scalars only (MCL_NO_RESAMPLE).
 int launch_step_scan(mcl_filter *h, const double *z_dev, const double *ofs_dev, uint32_t flags, bool full,
                      cudaStream_t st) {
@@ -228,13 +279,26 @@ int launch_step_scan(mcl_filter *h, const double *z_dev, const double *ofs_dev, 
     fill_scan(h, sp);
     fill_prep(h, sp.prep, z_dev, ofs_dev, flags);
     sp.do_prep = 1;
-    sp.prep_only = full ? 0 : 1;
+    sp.trig = h->trig;
+    sp.dbg = (h->dbg != nullptr && full) ? h->dbg + static_cast<size_t>(h->lay.T) * h->lay.bpt * kDbgSlots : nullptr;
     if (full) {
         sp.desc_next = h->desc[h->desc_cur ^ 1];
         h->desc_cur ^= 1;
     }
-    dim3 grid(full ? h->lay.tpt : 1, h->lay.T);
-    k_scan<kScanAncestors><<<grid, kScanThreads, 0, st>>>(sp);
+    if (h->stats_dirty) {  // statistics still live in the CTA partials of the previous k_step / k_reduce
+        sp.partials = h->partials;
+        sp.n_partials = h->lay.bpt;
+        sp.cur = h->state[h->cur];
+    }
+    // persistent tile CTAs (at most 4 per SM) + [the CTA that merges the partials into mcl_stats] + the CTA
+    // that derives the per-step scalars
+    // (one filter: one CTA per tile, the hardware scheduler keeps the look-back pipeline full; many trials:
+    // a trial's few tiles share persistent CTAs so the per-CTA prologue is paid once)
+    const int tile_ctas = !full ? 0 : (h->lay.T == 1 ? h->lay.tpt : std::min(h->lay.tpt, std::max(1, h->sm_count * 4 / h->lay.T)));
+    sp.persistent = (tile_ctas < h->lay.tpt) ? 1 : 0;
+    dim3 grid(tile_ctas + (h->stats_dirty ? 2 : 1), h->lay.T);
+    h->stats_dirty = false;
+    launch_pdl(k_scan<kScanAncestors>, grid, dim3(kScanThreads), 0, st, pdl_enabled() && !h->profiling, sp);
     MCL_LAUNCH_CHECK(h, "k_scan");
     return MCL_OK;
 }
@@ -253,9 +317,9 @@ int launch_shard_scan(mcl_filter *h, ScanParams &sp, int mode, cudaStream_t st) 
 }
 
 template <int LIK>
-void launch_step_lik(const StepParams &p, dim3 grid, size_t smem, bool philox, cudaStream_t st) {
-    if (philox) k_step<LIK, true><<<grid, kStepThreads, smem, st>>>(p);
-    else k_step<LIK, false><<<grid, kStepThreads, smem, st>>>(p);
+void launch_step_lik(const StepParams &p, dim3 grid, size_t smem, bool philox, cudaStream_t st, bool pdl) {
+    if (philox) launch_pdl(k_step<LIK, true>, grid, dim3(kStepThreads), smem, st, pdl, p);
+    else launch_pdl(k_step<LIK, false>, grid, dim3(kStepThreads), smem, st, pdl, p);
 }
 
 int step_variant(const mcl_config &c) {
@@ -288,6 +352,7 @@ int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool redu
     p.partials = h->partials;
     p.tickets = h->tickets;
     p.stats = h->stats;
+    p.dbg = h->dbg;
     p.n = static_cast<uint32_t>(h->lay.n);
     p.per = h->lay.per;
     p.ld = h->lay.ld;
@@ -320,22 +385,27 @@ int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool redu
     if (reduce_only) {
         k_reduce<<<grid, kStepThreads, 0, st>>>(p, h->stats_from_particle0 ? 1 : 0);
         MCL_LAUNCH_CHECK(h, "k_reduce");
+        h->stats_dirty = true;
         return MCL_OK;
     }
     const bool philox = (noise_dev == nullptr);
+    const bool pdl = pdl_enabled() && !h->profiling;
     const size_t smem = static_cast<size_t>(h->L) * sizeof(double4);
     switch (step_variant(c)) {
-        case kLikPair: launch_step_lik<kLikPair>(p, grid, smem, philox, st); break;
-        case kLikRB: launch_step_lik<kLikRB>(p, grid, smem, philox, st); break;
-        case kLikMomentIso: launch_step_lik<kLikMomentIso>(p, grid, 0, philox, st); break;
-        default: launch_step_lik<kLikMomentGen>(p, grid, 0, philox, st); break;
+        case kLikPair: launch_step_lik<kLikPair>(p, grid, smem, philox, st, pdl); break;
+        case kLikRB: launch_step_lik<kLikRB>(p, grid, smem, philox, st, pdl); break;
+        case kLikMomentIso: launch_step_lik<kLikMomentIso>(p, grid, 0, philox, st, pdl); break;
+        default: launch_step_lik<kLikMomentGen>(p, grid, 0, philox, st, pdl); break;
     }
     MCL_LAUNCH_CHECK(h, "k_step");
+    h->stats_dirty = true;
     return MCL_OK;
 }
 
 int reduce_only_pass(mcl_filter *h, cudaStream_t st) {
-    int rc = launch_step(h, nullptr, MCL_NO_RESAMPLE, true, st);
+    int rc = h->stats_from_particle0 ? MCL_OK : ensure_stats(h, st);
+    if (rc != MCL_OK) return rc;
+    rc = launch_step(h, nullptr, MCL_NO_RESAMPLE, true, st);
     h->stats_from_particle0 = false;
     return rc;
 }
@@ -504,6 +574,7 @@ int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_byte
     h->pose = reinterpret_cast<double *>(h->ws + L.off_pose);
     h->total = reinterpret_cast<unsigned long long *>(h->ws + L.off_total);
     h->trig = reinterpret_cast<TrigEntry *>(h->ws + L.off_trig);
+    h->wm_pub = reinterpret_cast<uint4 *>(h->ws + L.off_pub);
     h->delta = 1.0 / static_cast<double>(cfg->n_global);
     // the pair kernels stage up to 4096 landmarks (128 KiB) in dynamic shared memory
     const int max_dyn = 4096 * static_cast<int>(sizeof(double4));
@@ -529,6 +600,7 @@ int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_byte
     }
     cudaError_t e = cudaMemset(h->ws + L.off_tickets, 0, static_cast<size_t>(L.T) * 4 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_desc, 0, static_cast<size_t>(2) * L.T * L.tpt * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_pub, 0, static_cast<size_t>(L.T) * 2 * sizeof(uint4));
     if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_stats, 0, static_cast<size_t>(L.T) * sizeof(mcl_stats));
     if (e != cudaSuccess) {
         if (h->owns_ws) cudaFree(h->ws);
@@ -544,6 +616,7 @@ int mcl_destroy(mcl_filter *h) {
     cudaSetDevice(h->cfg.device);
     for (cudaEvent_t &e : h->ev)
         if (e) cudaEventDestroy(e);
+    if (h->dbg) cudaFree(h->dbg);
     if (h->owns_ws && h->ws) cudaFree(h->ws);
     delete h;
     return MCL_OK;
@@ -583,6 +656,7 @@ int mcl_init_particles(mcl_filter *h, const double *pose_host, void *stream) {
     k_init_stats<<<(L.T + 127) / 128, 128, 0, st>>>(h->stats, h->pose, static_cast<double>(h->cfg.n_global), L.T);
     MCL_LAUNCH_CHECK(h, "k_init_stats");
     h->have_particles = true;
+    h->stats_dirty = false;
     h->step = 0;
     return MCL_OK;
 }
@@ -667,7 +741,7 @@ int mcl_resample(mcl_filter *h, const double *ofs_host, uint32_t flags, void *st
     k_gather<<<dim3(bx, h->lay.T), 256, 0, st>>>(g);
     MCL_LAUNCH_CHECK(h, "k_gather");
     h->cur ^= 1;
-    return MCL_OK;
+    return MCL_OK;  // statistics are merged (the scan's statistics CTA) and updated (k_gather): not dirty
 }
 
 int mcl_predict_weight(mcl_filter *h, const double *z_host, const float *noise_dev, uint32_t flags, void *stream) {
@@ -711,6 +785,8 @@ int mcl_pose_moments(mcl_filter *h, void *stream) {
     int rc = use_device(h);
     if (rc != MCL_OK) return rc;
     if (!h->have_particles) return fail(h, MCL_ERR_STATE, "particles are not initialised");
+    rc = ensure_stats(h, S(stream));
+    if (rc != MCL_OK) return rc;
     CovParams p{};
     p.in = h->state[h->cur];
     p.stats = h->stats;
@@ -729,14 +805,18 @@ int mcl_get_stats(mcl_filter *h, mcl_stats *out_host, void *stream) {
     if (out_host == nullptr) return fail(h, MCL_ERR_ARG, "out_host is NULL");
     int rc = use_device(h);
     if (rc != MCL_OK) return rc;
+    rc = ensure_stats(h, S(stream));
+    if (rc != MCL_OK) return rc;
     MCL_CUDA(h, cudaMemcpyAsync(out_host, h->stats, static_cast<size_t>(h->lay.T) * sizeof(mcl_stats), cudaMemcpyDeviceToHost,
                                 S(stream)));
     MCL_CUDA(h, cudaStreamSynchronize(S(stream)));
+    for (int t = 0; t < h->lay.T; ++t) derive_stats(out_host[t]);  // log-normaliser, mean, covariance from the sums
     return MCL_OK;
 }
 
 int mcl_stats_dev(mcl_filter *h, const mcl_stats **out_dev) {
     if (h == nullptr || out_dev == nullptr) return MCL_ERR_ARG;
+    if (use_device(h) == MCL_OK) ensure_stats(h, nullptr);  // merged on the default stream
     *out_dev = h->stats;
     return MCL_OK;
 }
@@ -746,6 +826,8 @@ static int export_weights(mcl_filter *h, double *w_host, uint64_t *q_host, void 
     if (rc != MCL_OK) return rc;
     if (!h->have_particles) return fail(h, MCL_ERR_STATE, "particles are not initialised");
     cudaStream_t st = S(stream);
+    rc = ensure_stats(h, st);
+    if (rc != MCL_OK) return rc;
     const Layout &L = h->lay;
     // the idle state buffer (16 B per particle) is the staging area for the 8 B per particle export
     void *stage = h->state[h->cur ^ 1].x;
@@ -810,6 +892,27 @@ int mcl_profile_read(mcl_filter *h, double *ms3_host) {
 
 uint64_t mcl_launch_count(const mcl_filter *h) { return h ? h->launches : 0; }
 
+int mcl_debug_timeline(mcl_filter *h, uint64_t *stamps_host, int64_t capacity, int32_t *n_ctas) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    const size_t n_step = static_cast<size_t>(h->lay.T) * h->lay.bpt * kDbgSlots;
+    const size_t n_scan = static_cast<size_t>(h->lay.T) * (h->lay.tpt + 2) * kDbgSlots;
+    const size_t n = n_step + n_scan;  // k_step stamps, then k_scan stamps
+    if (h->dbg == nullptr) {  // first call arms the timeline; the next steps fill it
+        void *p = nullptr;
+        if (cudaMalloc(&p, n * sizeof(unsigned long long)) != cudaSuccess) return fail(h, MCL_ERR_NOMEM, "cudaMalloc failed");
+        cudaMemset(p, 0, n * sizeof(unsigned long long));
+        h->dbg = static_cast<unsigned long long *>(p);
+    }
+    if (n_ctas) *n_ctas = h->lay.T * (h->lay.bpt + h->lay.tpt + 2);
+    if (stamps_host == nullptr) return MCL_OK;
+    if (capacity < static_cast<int64_t>(n)) return fail(h, MCL_ERR_ARG, "stamps_host too small");
+    MCL_CUDA(h, cudaDeviceSynchronize());
+    MCL_CUDA(h, cudaMemcpy(stamps_host, h->dbg, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return MCL_OK;
+}
+
 // ---- particle-sharded single filter -----------------------------------------------------------
 int mcl_shard_total(mcl_filter *h, uint64_t *total_dev, void *stream) {
     if (h == nullptr) return MCL_ERR_ARG;
@@ -818,6 +921,8 @@ int mcl_shard_total(mcl_filter *h, uint64_t *total_dev, void *stream) {
     int rc = use_device(h);
     if (rc != MCL_OK) return rc;
     cudaStream_t st = S(stream);
+    rc = ensure_stats(h, st);
+    if (rc != MCL_OK) return rc;
     ScanParams sp;
     fill_scan(h, sp);
     sp.total = reinterpret_cast<unsigned long long *>(total_dev);
@@ -913,6 +1018,7 @@ int mcl_shard_set_global(mcl_filter *h, const mcl_stats *merged_host, void *stre
     MCL_CUDA(h, cudaMemcpyAsync(h->stats, merged_host, sizeof(mcl_stats), cudaMemcpyHostToDevice, S(stream)));
     MCL_CUDA(h, cudaStreamSynchronize(S(stream)));
     h->stats_from_particle0 = false;
+    h->stats_dirty = false;
     return MCL_OK;
 }
 

@@ -48,6 +48,38 @@ struct PrepOut {
 };
 
 // ---------------------------------------------------------------------------------------------
+// The transcendental part of mcl_stats from its raw sums: log-normaliser, weight of the MAP particle,
+// circular mean and covariance about the mean.  Host side of mcl_get_stats, and k_cov.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline double limit_angle_hd(double a) {
+    double r = fabs(a);
+    if (!(r < 1.0e300)) return a;
+    if (r > 64.0) r = fmod(r, kTwoPi);
+    while (r > kPi) r -= kTwoPi;
+    return (a < 0.0) ? -r : r;
+}
+__host__ __device__ inline void derive_stats(mcl_stats &s) {
+    if (s.derived) return;
+    const double s1 = s.sum_w;
+    s.log_norm = s.max_logw + log(s1);
+    s.max_weight = exp(s.raw[11] - s.max_logw) / s1;
+    const double inv = 1.0 / s1;
+    const double mdx = s.raw[0] * inv, mdy = s.raw[1] * inv, mdt = s.raw[2] * inv;
+    const double mth = atan2(s.raw[3], s.raw[4]);       // circular mean of the yaw
+    const double del = limit_angle_hd(mth - s.ref[2]);  // its offset from the reference pose of the sums
+    s.mean[0] = s.ref[0] + mdx;
+    s.mean[1] = s.ref[1] + mdy;
+    s.mean[2] = mth;
+    const double cxx = s.raw[5] * inv - mdx * mdx, cxy = s.raw[6] * inv - mdx * mdy, cyy = s.raw[7] * inv - mdy * mdy;
+    const double cxt = s.raw[8] * inv - mdx * mdt, cyt = s.raw[9] * inv - mdy * mdt;
+    const double ctt = s.raw[10] * inv - 2.0 * del * mdt + del * del;
+    s.cov[0] = cxx; s.cov[1] = cxy; s.cov[2] = cxt;
+    s.cov[3] = cxy; s.cov[4] = cyy; s.cov[5] = cyt;
+    s.cov[6] = cxt; s.cov[7] = cyt; s.cov[8] = ctt;
+    s.derived = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // mylib/limit.py:19-26 in fp64: r = |a|; while r > pi: r -= 2 pi; sign restored for a < 0.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double limit_angle(double a) {
@@ -65,6 +97,16 @@ __device__ __forceinline__ float wrap_residual(float d) {
     if (d > 3.14159265f) d -= 6.28318531f;
     if (d < -3.14159265f) d += 6.28318531f;
     return d;
+}
+
+// optional phase timeline (mcl_debug_timeline): thread 0 of a CTA stamps the global nanosecond timer
+constexpr int kDbgSlots = 12;
+__device__ __forceinline__ void dbg_stamp(unsigned long long *dbg, int slot) {
+    if (dbg != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        dbg[(static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * kDbgSlots + slot] = t;
+    }
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {

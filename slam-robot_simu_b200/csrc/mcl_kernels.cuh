@@ -74,17 +74,23 @@ __device__ __forceinline__ double comb_offset(const PrepParams &p, int t) {
 }
 
 // all kScanThreads threads of one block; red: >= 8 * 15 doubles of shared memory
-__device__ __noinline__ void prep_block(const PrepParams &p, const mcl_stats *stp, int t, int do_resample, double ofs,
-                                           double *red) {
+struct PrepIn {
+    double est[3];     // MAP pose of the previous step
+    double max_logw;   // maximum and sum of the stored weights (weight map)
+    double sum_w;
+};
+__device__ __noinline__ void prep_block(const PrepParams &p, const PrepIn &in, const TrigEntry *trig, int t,
+                                        int do_resample, double ofs, double *red) {
     const int tid = threadIdx.x;
     PrepOut *po = p.prep + t;
     // ---- reference pose: previous MAP estimate pushed through the noise-free motion (__f) ----
+    // (est is a stored fp32 pose; the table sincos keeps this once-per-step code short)
     double s0, c0;
-    sincos(stp->est[2], &s0, &c0);
+    sincos_tab(static_cast<float>(in.est[2]), trig, s0, c0);
     // the kernels subtract the reference in fp32: make it exactly representable
-    const double rx = static_cast<double>(static_cast<float>(stp->est[0] + p.vdt * c0));
-    const double ry = static_cast<double>(static_cast<float>(stp->est[1] + p.vdt * s0));
-    const double rth = static_cast<double>(static_cast<float>(limit_angle(stp->est[2] + p.wdt)));
+    const double rx = static_cast<double>(static_cast<float>(in.est[0] + p.vdt * c0));
+    const double ry = static_cast<double>(static_cast<float>(in.est[1] + p.vdt * s0));
+    const double rth = static_cast<double>(static_cast<float>(limit_angle(in.est[2] + p.wdt)));
 
     // ---- landmark table, moments, likelihood of the reference pose ----
     double acc[15];
@@ -92,7 +98,7 @@ __device__ __noinline__ void prep_block(const PrepParams &p, const mcl_stats *st
     for (int k = 0; k < 15; ++k) acc[k] = 0.0;
     if (p.z != nullptr) {
         double s, c;
-        sincos(rth, &s, &c);
+        sincos_tab(static_cast<float>(rth), trig, s, c);
         const double tx = -(s * rx - c * ry), ty = -(c * rx + s * ry);
         for (int l = tid; l < p.L; l += blockDim.x) {
             const double lx = p.lm[2 * l], ly = p.lm[2 * l + 1];
@@ -119,300 +125,14 @@ __device__ __noinline__ void prep_block(const PrepParams &p, const mcl_stats *st
         po->ref[0] = rx;
         po->ref[1] = ry;
         po->ref[2] = rth;
-        po->max_prev = stp->max_logw;
+        po->max_prev = in.max_logw;
         po->lik_const = p.lik_const;
-        const WeightMap wm = make_weight_map(stp->max_logw, stp->sum_w);
+        const WeightMap wm = make_weight_map(in.max_logw, in.sum_w);
         po->wq_m = wm.m;
         po->wq_scale = wm.scale;
         po->L = p.L;
         po->do_resample = do_resample;
         po->ofs = ofs;
-    }
-}
-
-// -------------------------------------------------------------------------------------------------
-// k_scan : per-step scalars + single-pass chained scan (decoupled look-back) over the fixed-point
-// weights + ancestors.
-// Tile descriptor = status (2 bits) << 62 | value, one 64-bit word, so status and value are read
-// atomically.  Tiles are handed out by an atomic ticket so a tile's predecessors are always running.
-// The look-back is block-wide (256 predecessors per round): when every tile of a 2^20-particle
-// filter starts in the same wave, the prefix reaches the last tile in two rounds instead of sixteen.
-// Descriptors are double-buffered: this launch clears the buffer the NEXT scan will use.
-//
-// Ancestors: every source's slot range [count_le(K_{j-1}), count_le(K_j)) comes from a branch-free
-// fp64 evaluation; the block then fills ancestors by slot -- owners mark their first slot in a
-// shared-memory window, an inclusive max-scan spreads the marks, stores are coalesced.
-// -------------------------------------------------------------------------------------------------
-struct ScanParams {
-    PrepParams prep;
-    int do_prep;                // 1: block 0 of each trial writes PrepOut
-    const float *lw;            // [T][ld]
-    const mcl_stats *stats;     // [T] statistics of the stored weights (weight map, ESS, estimate)
-    unsigned long long *desc;   // [T][tpt] tile descriptors of this launch (all zero on entry)
-    unsigned long long *desc_next;  // [T][tpt] cleared for the next launch (may be null)
-    unsigned int *tickets;      // [T][4]  (slot 0 = scan ticket)
-    uint32_t *anc;              // [T][ld] (slot - slot_first)
-    unsigned long long *total;  // optional [T] : inclusive total of the local weights
-    long long n, ld, n_global;  // local sources, stride, comb length
-    long long j_global_base;    // global index of local source 0 (sharded)
-    long long slot_first;       // anc is indexed by (global slot - slot_first)
-    long long anc_cap;          // capacity of anc per trial
-    unsigned long long k_offset;  // sum of the quantised weights of all lower-ranked shards
-    double delta;               // fl(1 / n_global)
-    int tpt;
-    int use_override;           // 1: always resample, ofs from ofs_override (sharded resampling)
-    int prep_only;              // 1: per-step scalars only (the sharded step resamples beforehand)
-    double ofs_override;
-    // kScanExpand (sharded filter): slots inside this shard's own output range [own_lo, own_hi) keep the
-    // ancestor path (anc[slot - own_lo]); slots owned by other ranks get the resampled POSE written to
-    // the send buffers: slots below own_lo at (slot - slot_first), slots from own_hi on at
-    // send_hi_off + (slot - max(own_hi, slot_first)); anc_cap = capacity of the send buffers.
-    long long own_lo, own_hi, send_hi_off, send_hi_base;
-    StateView src;
-    float *ox, *oy, *oth;
-};
-
-constexpr int kScanAncestors = 0;  // write the ancestor of every slot
-constexpr int kScanTotals = 1;     // only the inclusive total of the quantised weights
-constexpr int kScanExpand = 2;     // write the resampled pose of every slot (sender side of the sharded filter)
-
-enum : unsigned long long {
-    kDescAggregate = 1ull << 62,
-    kDescPrefix = 2ull << 62,
-    kDescValueMask = (1ull << 62) - 1ull
-};
-
-struct ScanShared {
-    double ofs;
-    float wq_m, wq_scale;
-    int resample;
-    unsigned int tile;
-};
-
-template <int MODE>
-__global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant__ ScanParams p) {
-    const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kScanThreads / 32;
-    __shared__ ScanShared s_sc;
-    __shared__ unsigned long long s_warp[NW];
-    __shared__ int s_first[NW];
-    __shared__ double s_slot[2];
-    __shared__ __align__(16) uint32_t s_mark[kScanTile];  // also the reduction scratch of prep_block
-    __shared__ uint32_t s_wmax[NW];
-
-    if (p.desc_next != nullptr && tid == 0) p.desc_next[static_cast<long long>(t) * p.tpt + blockIdx.x] = 0ull;
-    const mcl_stats *stp = p.stats + t;
-    if (tid == 0) {
-        const int rs = p.use_override ? 1 : decide_resample(p.prep.flags, stp->ess, p.prep.ess_threshold);
-        s_sc.resample = rs;
-        s_sc.ofs = p.use_override ? p.ofs_override : (rs ? comb_offset(p.prep, t) : 0.0);
-        const WeightMap w0 = make_weight_map(stp->max_logw, stp->sum_w);
-        s_sc.wq_m = w0.m;
-        s_sc.wq_scale = w0.scale;
-        s_sc.tile = (rs && !p.prep_only) ? atomicAdd(&p.tickets[t * 4 + 0], 1u) : 0u;
-    }
-    __syncthreads();
-    const int resample = s_sc.resample;
-    const double ofs = s_sc.ofs;
-    WeightMap wm;
-    wm.m = s_sc.wq_m;
-    wm.scale = s_sc.wq_scale;
-    const long long tile = s_sc.tile;
-    if (p.do_prep && blockIdx.x == 0) {
-        prep_block(p.prep, stp, t, resample, ofs, reinterpret_cast<double *>(s_mark));
-        __syncthreads();
-    }
-    if (!resample || p.prep_only) return;
-    if (tile >= p.tpt) return;  // never taken: scalars-only launches leave above
-    const long long j0 = tile * kScanTile + static_cast<long long>(tid) * kScanItems;
-    const float *lw = p.lw + static_cast<long long>(t) * p.ld;
-
-    // ---- load + quantise (8 consecutive items per thread, two 16-byte loads) ----
-    double qd[kScanItems];  // integer-valued: rint(w * 2^52)
-    if (j0 < p.n) {
-        // the state arrays are padded to a multiple of 128 elements, so the vector loads stay in bounds
-        const float4 a = *reinterpret_cast<const float4 *>(lw + j0);
-        const float4 b = *reinterpret_cast<const float4 *>(lw + j0 + 4);
-        const float v[kScanItems] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k) qd[k] = (j0 + k < p.n) ? quantize_weight_d(v[k], wm) : 0.0;
-    } else {
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k) qd[k] = 0.0;
-    }
-    double tsum_d = 0.0;  // sums of integers below 2^53 are exact in fp64
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) tsum_d += qd[k];
-    const unsigned long long tsum = static_cast<unsigned long long>(tsum_d);
-
-    // ---- block exclusive scan of the thread sums ----
-    unsigned long long incl = tsum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += n;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    unsigned long long warp_off = 0, tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-        const unsigned long long v = s_warp[w];
-        if (w < warp) warp_off += v;
-        tile_total += v;
-    }
-    const unsigned long long thread_excl = warp_off + incl - tsum;
-    __syncthreads();  // s_warp is reused by the look-back
-
-    // ---- decoupled look-back, block-wide ----
-    unsigned long long *desc = p.desc + static_cast<long long>(t) * p.tpt;
-    unsigned long long excl = 0;
-    if (tile == 0) {
-        if (tid == 0) atomicExch(&desc[0], kDescPrefix | tile_total);
-    } else {
-        if (tid == 0) atomicExch(&desc[tile], kDescAggregate | tile_total);
-        long long look = tile - 1;  // window covers tiles [look-255, look]
-        while (true) {
-            const long long idx = look - tid;
-            unsigned long long d = kDescPrefix;  // tiles before the first one: an empty prefix
-            if (idx >= 0) d = *reinterpret_cast<volatile unsigned long long *>(&desc[idx]);
-            while (!__syncthreads_and((d >> 62) != 0ull)) {
-                if ((d >> 62) == 0ull) d = *reinterpret_cast<volatile unsigned long long *>(&desc[idx]);
-            }
-            const unsigned int is_prefix = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
-            if (lane == 0) s_first[warp] = is_prefix ? (warp * 32 + __ffs(is_prefix) - 1) : 0x7fffffff;
-            __syncthreads();
-            int first = 0x7fffffff;  // nearest predecessor (smallest tid) that already holds a prefix
-#pragma unroll
-            for (int w = 0; w < NW; ++w) first = min(first, s_first[w]);
-            unsigned long long contrib = (tid <= first && idx >= 0) ? (d & kDescValueMask) : 0ull;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-            if (lane == 0) s_warp[warp] = contrib;
-            __syncthreads();
-#pragma unroll
-            for (int w = 0; w < NW; ++w) excl += s_warp[w];
-            __syncthreads();
-            if (first != 0x7fffffff) break;
-            look -= kScanThreads;
-        }
-        if (tid == 0) atomicExch(&desc[tile], kDescPrefix | (excl + tile_total));
-    }
-    if (tid == 0 && p.total != nullptr && tile == p.tpt - 1) p.total[t] = excl + tile_total;
-    if (MODE == kScanTotals) return;
-
-    // ---- slot range of every source ----
-    const double nd = static_cast<double>(p.n_global);
-    const CombFast cf = make_comb_fast(ofs, nd);
-    double Kd = static_cast<double>(p.k_offset + excl + thread_excl);
-    const double first_slot = count_le_fast(Kd, cf, p.delta, ofs);
-    double cur = first_slot;
-    uint32_t rel[kScanItems];  // first slot of source k relative to the thread's first slot
-    uint32_t owners = 0;       // bit k: source k owns at least one slot
-    // the last particle of the whole filter also takes every slot past the final cumulative weight
-    // (the reference would raise IndexError there; SURVEY.md section 5)
-    const long long k_last64 = p.n_global - 1 - p.j_global_base - j0;
-    const int k_last = (k_last64 >= 0 && k_last64 < kScanItems) ? static_cast<int>(k_last64) : -1;
-    const int n_valid = static_cast<int>(min(static_cast<long long>(kScanItems), max(0ll, p.n - j0)));
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        rel[k] = static_cast<uint32_t>(static_cast<int>(cur - first_slot));
-        Kd += qd[k];
-        double end = count_le_fast(Kd, cf, p.delta, ofs);
-        if (k == k_last) end = nd;
-        if (k < n_valid && end > cur) {
-            owners |= 1u << k;
-            cur = end;
-        }
-    }
-    // tile slot range [S0, S1): S0 from the first thread, S1 from the last thread holding sources
-    const long long n_in_tile = min(static_cast<long long>(kScanTile), p.n - tile * kScanTile);
-    const int last_tid = static_cast<int>((n_in_tile - 1) / kScanItems);
-    if (tid == 0) s_slot[0] = first_slot;
-    if (tid == last_tid) s_slot[1] = cur;
-    __syncthreads();
-    const double S0d = s_slot[0];
-    const long long S0 = static_cast<long long>(S0d), span = static_cast<long long>(s_slot[1] - S0d);
-    const uint32_t my_off = static_cast<uint32_t>(static_cast<long long>(first_slot - S0d));  // threads with sources: >= 0
-
-    uint32_t *anc = p.anc + static_cast<long long>(t) * p.ld;
-    uint32_t carry = 0;  // source (local index + 1) that owns the slot just before the window
-    for (long long cb = 0; cb < span; cb += kScanTile) {
-        // window of kScanTile slots starting at S0 + cb
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k) s_mark[k * kScanThreads + tid] = 0u;
-        __syncthreads();
-        if (owners) {
-            // slot positions relative to the window, modulo 2^32 (n_global < 2^31: no aliasing)
-            const uint32_t wofs = my_off - static_cast<uint32_t>(cb);
-#pragma unroll
-            for (int k = 0; k < kScanItems; ++k) {
-                const uint32_t pos = wofs + rel[k];
-                if (((owners >> k) & 1u) && pos < static_cast<uint32_t>(kScanTile))
-                    s_mark[pos] = static_cast<uint32_t>(tid * kScanItems + k + 1);
-            }
-        }
-        __syncthreads();
-        // inclusive max-scan over the window, 8 consecutive entries per thread
-        uint32_t v[kScanItems];
-        {
-            const uint4 a = *reinterpret_cast<const uint4 *>(&s_mark[tid * kScanItems]);
-            const uint4 b = *reinterpret_cast<const uint4 *>(&s_mark[tid * kScanItems + 4]);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        }
-#pragma unroll
-        for (int k = 1; k < kScanItems; ++k) v[k] = max(v[k], v[k - 1]);
-        uint32_t run = v[kScanItems - 1];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, run, o);
-            if (lane >= o) run = max(run, n);
-        }
-        if (lane == 31) s_wmax[warp] = run;
-        uint32_t before = __shfl_up_sync(0xffffffffu, run, 1);
-        if (lane == 0) before = 0u;
-        __syncthreads();
-        uint32_t wbefore = carry, wall = carry;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            const uint32_t m = s_wmax[w];
-            if (w < warp) wbefore = max(wbefore, m);
-            wall = max(wall, m);
-        }
-        before = max(before, wbefore);
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k) v[k] = max(v[k], before);
-        *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(v[4], v[5], v[6], v[7]);
-        carry = wall;
-        __syncthreads();
-        // coalesced stores
-        const int lim = static_cast<int>(min(static_cast<long long>(kScanTile), span - cb));
-        const uint32_t jbase = static_cast<uint32_t>(tile * kScanTile) - 1u;
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k) {
-            const int pos = k * kScanThreads + tid;
-            if (pos < lim) {
-                const long long slot = S0 + cb + pos;
-                const uint32_t j = jbase + s_mark[pos];
-                if (MODE == kScanExpand) {
-                    if (slot >= p.own_lo && slot < p.own_hi) {
-                        anc[slot - p.own_lo] = j;
-                    } else {
-                        const long long o = (slot < p.own_lo) ? slot - p.slot_first : p.send_hi_off + (slot - p.send_hi_base);
-                        if (o >= 0 && o < p.anc_cap) {
-                            p.ox[o] = p.src.x[j];
-                            p.oy[o] = p.src.y[j];
-                            p.oth[o] = p.src.th[j];
-                        }
-                    }
-                } else {
-                    anc[slot] = j;  // unsharded: slots are local indices, anc holds ld >= n of them
-                }
-            }
-        }
-        __syncthreads();
     }
 }
 
@@ -502,30 +222,25 @@ __device__ __forceinline__ float float_from_order_key(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// Block partial -> partials[]; the last block of the trial merges all partials into mcl_stats and
-// re-arms the tickets.  Must be called by all threads of the block (kStepThreads).
-struct FinishParams {
-    double *partials;       // [T][bpt][kPart]
-    unsigned int *tickets;  // [T][4]  (slot 0 = scan ticket, slot 1 = reduce ticket)
-    mcl_stats *stats;       // [T]
-    int bpt;
-    const float *ex, *ey, *eth;  // trial-offset arrays of the state the statistics describe
-    double ref_x, ref_y, ref_th;
-    int set_step;           // 1: also write resampled / step
-    int resampled;
-    int step;
-};
-
-__device__ __forceinline__ void stats_finish(WarpStats &ws, const FinishParams &f, int t) {
+// -------------------------------------------------------------------------------------------------
+// CTA partials and their merges.
+// Every k_step / k_reduce CTA leaves ONE 128-byte record {max, 13 sums relative to it, arg-max value, index}
+// in partials[] and exits -- no fence, no ticket, no "last CTA".  The records are merged where they are
+// consumed, each consumer reading only the columns it needs:
+//   merge_light  (max, sum w, sum w^2)  every tile CTA of the next k_scan: weight map + ESS gate
+//   merge_best   (arg-max)              the scalars CTA of k_scan: MAP pose -> reference pose
+//   merge_full   (all 14 columns)       the statistics CTA of k_scan, or k_merge on demand: mcl_stats
+// All merges run the same code on the same records in the same order: every CTA derives bit-identical values.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void partial_write(WarpStats &ws, double *pp, unsigned long long *dbg) {
     constexpr int NW = kStepThreads / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ double s_sum[NW][kNumSums];
     __shared__ float s_m[NW];
     __shared__ uint32_t s_bk[NW], s_bi[NW];
-    __shared__ int s_last;
-    __shared__ double s_fin[kNumSums + 1];
 
     ws.flush();
+    dbg_stamp(dbg, 3);
     double as = ws.asin_, ac = ws.acos_;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -551,7 +266,6 @@ __device__ __forceinline__ void stats_finish(WarpStats &ws, const FinishParams &
         float M = s_m[0];
 #pragma unroll
         for (int w = 1; w < NW; ++w) M = fmaxf(M, s_m[w]);
-        double *pp = f.partials + (static_cast<long long>(t) * f.bpt + blockIdx.x) * kPart;
         if (tid < kNumSums) {
             double acc = 0.0;
 #pragma unroll
@@ -569,98 +283,651 @@ __device__ __forceinline__ void stats_finish(WarpStats &ws, const FinishParams &
             pp[14] = static_cast<double>(float_from_order_key(bk));
             pp[15] = static_cast<double>(bi);
         }
-        __threadfence();
     }
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&f.tickets[t * 4 + 1], 1u) == static_cast<unsigned int>(gridDim.x) - 1u);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+    dbg_stamp(dbg, 4);
+}
 
-    // ---------------- last block of the trial: merge partials (fixed order) -> stats ----------------
-    const double *pp = f.partials + static_cast<long long>(t) * f.bpt * kPart;
-    const int nb = static_cast<int>(gridDim.x);
-    // warp w < 13 merges quantity w over the blocks (lane-strided, then a shuffle tree); all warps need MM first
-    double mm = -INFINITY;
-    for (int b = tid; b < nb; b += kStepThreads) mm = fmax(mm, __ldcg(pp + b * kPart));
+struct MergeScratch {  // shared memory of one merge (256 threads)
+    float m[8];
+    double a[8], b[8];
+    uint32_t k[8], i[8];
+};
+
+// (max, sum w, sum w^2) over the nb partial records of trial t; all 256 threads, result in every thread
+__device__ __noinline__ void merge_light(const double *pp, int nb, MergeScratch &sc, float &M, double &s1, double &s2) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float mx = -3.4028234e38f;
+    double a1 = 0.0, a2 = 0.0;
+    constexpr int kB = 4;
+    for (int b0 = tid; b0 < nb; b0 += 256 * kB) {
+        double m4[kB], p4[kB], q4[kB];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mm = fmax(mm, __shfl_xor_sync(0xffffffffu, mm, o));
-    __shared__ double s_mm[NW];
-    if (lane == 0) s_mm[warp] = mm;
-    __syncthreads();
-    double MM = s_mm[0];
+        for (int u = 0; u < kB; ++u) {  // clamped rows, masked below: the 12 loads are independent
+            const double *r = pp + min(b0 + u * 256, nb - 1) * kPart;
+            m4[u] = __ldcg(r);
+            p4[u] = __ldcg(r + 1);
+            q4[u] = __ldcg(r + 2);
+        }
 #pragma unroll
-    for (int w = 1; w < NW; ++w) MM = fmax(MM, s_mm[w]);
-    for (int q = warp; q < kNumSums + 1; q += NW) {
-        if (q < kNumSums) {
-            double acc = 0.0;
-            for (int b = lane; b < nb; b += 32) {
-                const double r = exp(__ldcg(pp + b * kPart) - MM);  // partial maxima are finite (sentinel -> 0)
-                acc = fma(__ldcg(pp + b * kPart + 1 + q), (q == 1) ? r * r : r, acc);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) s_fin[q] = acc;
-        } else {
-            float bv = -INFINITY;
-            uint32_t bi = 0xffffffffu;
-            for (int b = lane; b < nb; b += 32) {
-                const float v = static_cast<float>(__ldcg(pp + b * kPart + 14));
-                const uint32_t i = static_cast<uint32_t>(__ldcg(pp + b * kPart + 15));
-                if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-            }
-            const uint32_t k = float_order_key(bv);
-            const uint32_t wk = __reduce_max_sync(0xffffffffu, k);
-            const uint32_t wi = __reduce_min_sync(0xffffffffu, (k == wk) ? bi : 0xffffffffu);
-            if (lane == 0) {
-                s_bk[0] = wk;
-                s_bi[0] = wi;
+        for (int u = 0; u < kB; ++u) {
+            if (b0 + u * 256 < nb) {
+                const float mb = static_cast<float>(m4[u]);
+                if (mb > mx) {
+                    const float r = ex2_approx((mx - mb) * kLog2e);
+                    a1 *= static_cast<double>(r);
+                    a2 *= static_cast<double>(r * r);
+                    mx = mb;
+                }
+                const float r = ex2_approx((mb - mx) * kLog2e);
+                a1 = fma(p4[u], static_cast<double>(r), a1);
+                a2 = fma(q4[u], static_cast<double>(r * r), a2);
             }
         }
     }
+    // warp, then CTA: rescale to the common maximum and add
+    float wm = mx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+    {
+        const float r = ex2_approx((mx - wm) * kLog2e);
+        a1 *= static_cast<double>(r);
+        a2 *= static_cast<double>(r * r);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    __syncthreads();  // the scratch may still be in use by a previous merge
+    if (lane == 0) { sc.m[warp] = wm; sc.a[warp] = a1; sc.b[warp] = a2; }
     __syncthreads();
+    M = sc.m[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) M = fmaxf(M, sc.m[w]);
+    s1 = 0.0;
+    s2 = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const float r = ex2_approx((sc.m[w] - M) * kLog2e);
+        s1 = fma(sc.a[w], static_cast<double>(r), s1);
+        s2 = fma(sc.b[w], static_cast<double>(r * r), s2);
+    }
+}
+
+// arg-max over the records: stored log-weight of the MAP particle and its index (smallest index on ties)
+__device__ __noinline__ void merge_best(const double *pp, int nb, MergeScratch &sc, float &best_v, uint32_t &best_i) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t bk = 0u, bi = 0xffffffffu;
+    constexpr int kB = 4;
+    for (int b0 = tid; b0 < nb; b0 += 256 * kB) {
+        double v4[kB], i4[kB];
+#pragma unroll
+        for (int u = 0; u < kB; ++u) {
+            const double *r = pp + min(b0 + u * 256, nb - 1) * kPart;
+            v4[u] = __ldcg(r + 14);
+            i4[u] = __ldcg(r + 15);
+        }
+#pragma unroll
+        for (int u = 0; u < kB; ++u) {
+            if (b0 + u * 256 < nb) {
+                const uint32_t k = float_order_key(static_cast<float>(v4[u]));
+                const uint32_t i = static_cast<uint32_t>(i4[u]);
+                if (k > bk || (k == bk && i < bi)) { bk = k; bi = i; }
+            }
+        }
+    }
+    const uint32_t wk = __reduce_max_sync(0xffffffffu, bk);
+    const uint32_t wi = __reduce_min_sync(0xffffffffu, (bk == wk) ? bi : 0xffffffffu);
+    __syncthreads();
+    if (lane == 0) { sc.k[warp] = wk; sc.i[warp] = wi; }
+    __syncthreads();
+    bk = sc.k[0];
+    bi = sc.i[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w)
+        if (sc.k[w] > bk || (sc.k[w] == bk && sc.i[w] < bi)) { bk = sc.k[w]; bi = sc.i[w]; }
+    best_v = float_from_order_key(bk);
+    best_i = bi;
+}
+
+// All columns -> mcl_stats (sums, ESS, MAP index and pose).  One 256-thread CTA per trial; runs with a cold
+// instruction cache (once per step on one SM), hence small: rolled loops, no libm -- log-normaliser, mean and
+// covariance are derived from the sums where they are consumed (derive_stats).
+__device__ __noinline__ void merge_full(const double *pp, int nb, mcl_stats *st, const float *ex, const float *ey,
+                                        const float *eth, unsigned long long *dbg) {
+    constexpr int NW = kStepThreads / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double s_part[NW][kPart];
+    __shared__ float s_mx[NW];
+    __shared__ uint32_t s_bk[NW], s_bi[NW];
+    const int col = tid & (kPart - 1), row0 = tid >> 4;  // 16 threads read one 128-byte record
+    constexpr int kRows = kStepThreads / kPart;
+    dbg_stamp(dbg, 7);
+    // pass 1: the global maximum of the partial maxima (loads in explicit batches: one L2 round trip each)
+    constexpr int kBatch = 8;
+    float mx = -3.4028234e38f;
+    for (int b0 = row0; b0 < nb; b0 += kRows * kBatch) {
+        double m8[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) m8[u] = __ldcg(pp + min(b0 + u * kRows, nb - 1) * kPart);  // clamped: no branch
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) mx = fmaxf(mx, static_cast<float>(m8[u]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_mx[warp] = mx;
+    __syncthreads();
+    float MM = s_mx[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) MM = fmaxf(MM, s_mx[w]);
+    dbg_stamp(dbg, 8);
+    // pass 2: column `col` of every record, rescaled to MM (columns 1..13 are sums; column 2 carries squares)
+    double acc = 0.0;
+    uint32_t bkey = 0u, bidx = 0xffffffffu;
+    for (int b0 = row0; b0 < nb; b0 += kRows * kBatch) {
+        double m8[kBatch], v8[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {  // clamped rows, masked below: the 16 loads of a batch are independent
+            const int b = min(b0 + u * kRows, nb - 1);
+            m8[u] = __ldcg(pp + b * kPart);
+            v8[u] = __ldcg(pp + b * kPart + col);
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const bool ok = b0 + u * kRows < nb;
+            const float r = ok ? ex2_approx((static_cast<float>(m8[u]) - MM) * kLog2e) : 0.0f;  // empty CTA: sentinel -> 0
+            acc = fma(v8[u], static_cast<double>((col == 2) ? r * r : r), acc);
+            // arg-max: column 14 holds the value, column 15 (the next lane) the index; largest value, then
+            // smallest index (np.argmax, particle_filter.py:116)
+            const double idx_d = __shfl_down_sync(0xffffffffu, v8[u], 1);
+            if (col == 14 && ok) {
+                const uint32_t k = float_order_key(static_cast<float>(v8[u]));
+                const uint32_t i = static_cast<uint32_t>(idx_d);
+                if (k > bkey || (k == bkey && i < bidx)) { bkey = k; bidx = i; }
+            }
+        }
+    }
+    dbg_stamp(dbg, 9);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);  // lanes l and l + 16 hold the same column
+    if (lane < kPart) s_part[warp][lane] = acc;
+    {
+        const uint32_t wk = __reduce_max_sync(0xffffffffu, bkey);
+        const uint32_t wi = __reduce_min_sync(0xffffffffu, (bkey == wk) ? bidx : 0xffffffffu);
+        if (lane == 0) { s_bk[warp] = wk; s_bi[warp] = wi; }
+    }
+    __syncthreads();
+    if (tid >= 1 && tid <= kNumSums) {  // thread c sums column c over the warps
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) tot += s_part[w][tid];
+        if (tid == 1) st->sum_w = tot;
+        else if (tid == 2) st->sum_w2 = tot;
+        else st->raw[tid - 3] = tot;  // dx dy dth sin cos xx xy yy xth yth thth
+        if (tid <= 2) s_part[0][tid] = tot;
+    }
+    __syncthreads();
+    dbg_stamp(dbg, 10);
     if (tid == 0) {
-        const double *tot = s_fin;
-        const float bv = float_from_order_key(s_bk[0]);
-        const long long bi = s_bi[0];
-        mcl_stats *st = f.stats + t;
-        const double s1 = tot[0], s2 = tot[1];
-        st->max_logw = MM;
-        st->sum_w = s1;
-        st->sum_w2 = s2;
-        st->log_norm = MM + log(s1);
-        st->ess = s1 * s1 / s2;  // 1 / sum (w/s1)^2, particle_filter.py:210
-        st->max_weight = exp(static_cast<double>(bv) - MM) / s1;
-        st->max_idx = bi;
-        st->est[0] = __ldcg(f.ex + bi);
-        st->est[1] = __ldcg(f.ey + bi);
-        st->est[2] = __ldcg(f.eth + bi);
+        uint32_t bk = s_bk[0], bj = s_bi[0];
 #pragma unroll
-        for (int k = 0; k < 11; ++k) st->raw[k] = tot[2 + k];
-        st->raw[11] = 0.0;
-        st->ref[0] = f.ref_x; st->ref[1] = f.ref_y; st->ref[2] = f.ref_th;
-        // mean / covariance about the reference pose (single pass)
-        const double inv = 1.0 / s1;
-        const double mdx = tot[2] * inv, mdy = tot[3] * inv, mdt = tot[4] * inv;
-        const double mth = atan2(tot[5], tot[6]);         // circular mean of the yaw
-        const double del = limit_angle(mth - f.ref_th);    // its offset from the reference
-        st->mean[0] = f.ref_x + mdx;
-        st->mean[1] = f.ref_y + mdy;
-        st->mean[2] = mth;
-        const double cxx = tot[7] * inv - mdx * mdx, cxy = tot[8] * inv - mdx * mdy, cyy = tot[9] * inv - mdy * mdy;
-        const double cxt = tot[10] * inv - mdx * mdt, cyt = tot[11] * inv - mdy * mdt;
-        const double ctt = tot[12] * inv - 2.0 * del * mdt + del * del;
-        st->cov[0] = cxx; st->cov[1] = cxy; st->cov[2] = cxt;
-        st->cov[3] = cxy; st->cov[4] = cyy; st->cov[5] = cyt;
-        st->cov[6] = cxt; st->cov[7] = cyt; st->cov[8] = ctt;
-        if (f.set_step) {
-            st->resampled = f.resampled;
-            st->step = f.step;
-        }
-        // re-arm the tickets: every block of this trial has passed both
-        f.tickets[t * 4 + 0] = 0u;
-        f.tickets[t * 4 + 1] = 0u;
+        for (int w = 1; w < NW; ++w)
+            if (s_bk[w] > bk || (s_bk[w] == bk && s_bi[w] < bj)) { bk = s_bk[w]; bj = s_bi[w]; }
+        const double s1 = s_part[0][1], s2 = s_part[0][2];
+        st->max_logw = static_cast<double>(MM);
+        st->ess = s1 * s1 / s2;  // 1 / sum (w/s1)^2, particle_filter.py:210
+        st->raw[11] = static_cast<double>(float_from_order_key(bk));  // stored log-weight of the MAP particle
+        st->max_idx = bj;
+        st->est[0] = __ldcg(ex + bj);
+        st->est[1] = __ldcg(ey + bj);
+        st->est[2] = __ldcg(eth + bj);
+        st->derived = 0;  // log_norm, max_weight, mean, cov: derive_stats()
+        dbg_stamp(dbg, 6);
     }
+}
+
+// on-demand merge (mcl_get_stats and friends): one CTA per trial
+struct MergeParams {
+    const double *partials;
+    int bpt;
+    mcl_stats *stats;
+    StateView cur;
+    long long ld;
+};
+__global__ void __launch_bounds__(kStepThreads) k_merge(const MergeParams p) {
+    const int t = blockIdx.x;
+    const long long off = static_cast<long long>(t) * p.ld;
+    merge_full(p.partials + static_cast<long long>(t) * p.bpt * kPart, p.bpt, p.stats + t, p.cur.x + off, p.cur.y + off,
+               p.cur.th + off, nullptr);
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_scan : per-step scalars + single-pass chained scan (decoupled look-back) over the fixed-point
+// weights + ancestors.
+// Tile descriptor = status (2 bits) << 62 | value, one 64-bit word, so status and value are read
+// atomically.  Tiles are handed out by an atomic ticket so a tile's predecessors are always running.
+// The look-back is block-wide (256 predecessors per round): when every tile of a 2^20-particle
+// filter starts in the same wave, the prefix reaches the last tile in two rounds instead of sixteen.
+// Descriptors are double-buffered: this launch clears the buffer the NEXT scan will use.
+//
+// Ancestors: every source's slot range [count_le(K_{j-1}), count_le(K_j)) comes from a branch-free
+// fp64 evaluation; the block then fills ancestors by slot -- owners mark their first slot in a
+// shared-memory window, an inclusive max-scan spreads the marks, stores are coalesced.
+// -------------------------------------------------------------------------------------------------
+struct ScanParams {
+    PrepParams prep;
+    unsigned long long *dbg;    // optional phase timeline [T][tpt + 1][kDbgSlots]
+    int do_prep;                // 1: the LAST block of each trial's row (an extra one) only writes PrepOut
+    const TrigEntry *trig;
+    const float *lw;            // [T][ld]
+    mcl_stats *stats;           // [T] statistics of the stored weights (weight map, ESS, estimate)
+    // n_partials > 0: the statistics are still the CTA partials of the previous k_step / k_reduce: tiles merge
+    // (max, sum, sum^2), the scalars CTA the arg-max, and one more extra CTA merges everything into stats[]
+    const double *partials;     // [T][n_partials][kPart]
+    int n_partials;
+    uint4 *wm_pub;              // [T][2] {weight-map m, scale, resample gate, epoch}, {comb offset, epoch}: published by the tile with ticket 0
+    unsigned int epoch;         // scan launches of this handle so far (never 0: the words start as 0)
+    StateView cur;              // the stored state (MAP pose lookup)
+    unsigned long long *desc;   // [T][tpt] tile descriptors of this launch (all zero on entry)
+    unsigned long long *desc_next;  // [T][tpt] cleared for the next launch (may be null)
+    unsigned int *tickets;      // [T][4]  (slot 0 = scan ticket)
+    uint32_t *anc;              // [T][ld] (slot - slot_first)
+    unsigned long long *total;  // optional [T] : inclusive total of the local weights
+    long long n, ld, n_global;  // local sources, stride, comb length
+    long long j_global_base;    // global index of local source 0 (sharded)
+    long long slot_first;       // anc is indexed by (global slot - slot_first)
+    long long anc_cap;          // capacity of anc per trial
+    unsigned long long k_offset;  // sum of the quantised weights of all lower-ranked shards
+    double delta;               // fl(1 / n_global)
+    int tpt;
+    int use_override;           // 1: always resample, ofs from ofs_override (sharded resampling)
+    int persistent;             // 1: fewer tile CTAs than tiles: a CTA keeps taking tickets
+    double ofs_override;
+    // kScanExpand (sharded filter): slots inside this shard's own output range [own_lo, own_hi) keep the
+    // ancestor path (anc[slot - own_lo]); slots owned by other ranks get the resampled POSE written to
+    // the send buffers: slots below own_lo at (slot - slot_first), slots from own_hi on at
+    // send_hi_off + (slot - max(own_hi, slot_first)); anc_cap = capacity of the send buffers.
+    long long own_lo, own_hi, send_hi_off, send_hi_base;
+    StateView src;
+    float *ox, *oy, *oth;
+};
+
+constexpr int kDirectTiles = 1024;  // tiles that sum all predecessors' aggregates directly (2M particles)
+constexpr int kScanAncestors = 0;  // write the ancestor of every slot
+constexpr int kScanTotals = 1;     // only the inclusive total of the quantised weights
+constexpr int kScanExpand = 2;     // write the resampled pose of every slot (sender side of the sharded filter)
+
+enum : unsigned long long {
+    kDescAggregate = 1ull << 62,
+    kDescPrefix = 2ull << 62,
+    kDescValueMask = (1ull << 62) - 1ull
+};
+
+struct ScanShared {
+    double ofs;
+    float wq_m, wq_scale;
+    int resample;
+    unsigned int tile;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant__ ScanParams p) {
+    const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kScanThreads / 32;
+    __shared__ ScanShared s_sc;
+    __shared__ unsigned long long s_warp[NW];
+    __shared__ int s_first[NW];
+    __shared__ double s_slot[2];
+    __shared__ __align__(16) uint32_t s_mark[kScanTile];  // also the reduction scratch of prep_block
+    __shared__ uint32_t s_wmax[NW];
+
+    // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as every CTA of
+    // this grid has started; nothing is read or written before the previous kernel has completed.
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
+    // per-step scalars are the job of one extra CTA per trial: they are only needed by k_step, and their
+    // once-per-step code (cold instruction cache) must not delay a tile that every later tile waits for
+    dbg_stamp(p.dbg, 0);
+    const bool prep_cta = p.do_prep && blockIdx.x == gridDim.x - 1;
+    // ... and another extra CTA merges ALL columns of the partials into mcl_stats (host read-back, k_cov)
+    const bool stats_cta = p.do_prep && p.n_partials > 0 && blockIdx.x == gridDim.x - 2;
+    __shared__ MergeScratch s_merge;
+    const long long soff = static_cast<long long>(t) * p.ld;
+    const double *pp = p.partials + static_cast<long long>(t) * p.n_partials * kPart;
+    if (stats_cta) {
+        merge_full(pp, p.n_partials, p.stats + t, p.cur.x + soff, p.cur.y + soff, p.cur.th + soff, nullptr);
+        return;
+    }
+    const mcl_stats *stp = p.stats + t;
+    // Tiles take their ticket first.  When the statistics still live in the CTA partials, the tile with ticket
+    // 0 (the first to arrive, so certainly running) merges (max, sum, sum^2) and publishes what every tile
+    // needs -- weight map, resample gate, comb offset -- as two aligned 16-byte words tagged with this launch's
+    // epoch; the others poll them (one round trip, issued together with the ticket) -- 500 CTAs each reading
+    // all partials would hammer the same few L2 lines.
+    uint4 *pub = p.wm_pub + 2 * t;  // word A {m, scale, gate, epoch}, word B {ofs lo, ofs hi, epoch, 0}
+    if (tid == 0) {
+        const bool may_poll = p.n_partials > 0 && !prep_cta;
+        uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+        if (may_poll) {  // speculative first poll, in flight together with the ticket
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(pub));
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(pub + 1));
+        }
+        const unsigned int tk = prep_cta ? 0xffffffffu : atomicAdd(&p.tickets[t * 4 + 0], 1u);
+        s_sc.tile = tk;
+        if (may_poll && tk != 0u) {
+            while (a.w != p.epoch || b.z != p.epoch) {
+                __nanosleep(32);
+                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(pub));
+                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(pub + 1));
+            }
+            s_sc.wq_m = __uint_as_float(a.x);
+            s_sc.wq_scale = __uint_as_float(a.y);
+            s_sc.resample = static_cast<int>(a.z);
+            s_sc.ofs = __hiloint2double(static_cast<int>(b.y), static_cast<int>(b.x));
+        }
+    }
+    __syncthreads();
+    const bool merger = p.n_partials > 0 && (prep_cta || s_sc.tile == 0u);
+    double st_max = 0.0, st_sum = 1.0;
+    if (merger || p.n_partials == 0) {  // CTA-uniform: this CTA derives the scalars itself
+        double st_ess;
+        if (merger) {
+            float M;
+            double s1, s2;
+            merge_light(pp, p.n_partials, s_merge, M, s1, s2);
+            st_max = static_cast<double>(M);
+            st_sum = s1;
+            st_ess = s1 * s1 / s2;
+        } else {
+            st_max = stp->max_logw;
+            st_sum = stp->sum_w;
+            st_ess = stp->ess;
+        }
+        if (tid == 0) {
+            const int rs = p.use_override ? 1 : decide_resample(p.prep.flags, st_ess, p.prep.ess_threshold);
+            const WeightMap w0 = make_weight_map(st_max, st_sum);
+            const double o = p.use_override ? p.ofs_override : (rs ? comb_offset(p.prep, t) : 0.0);
+            s_sc.resample = rs;
+            s_sc.wq_m = w0.m;
+            s_sc.wq_scale = w0.scale;
+            s_sc.ofs = o;
+            if (merger && !prep_cta) {
+                const uint4 va = make_uint4(__float_as_uint(w0.m), __float_as_uint(w0.scale), static_cast<unsigned int>(rs), p.epoch);
+                const uint4 vb = make_uint4(static_cast<unsigned int>(__double2loint(o)), static_cast<unsigned int>(__double2hiint(o)), p.epoch, 0u);
+                asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(pub), "r"(va.x), "r"(va.y), "r"(va.z), "r"(va.w) : "memory");
+                asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(pub + 1), "r"(vb.x), "r"(vb.y), "r"(vb.z), "r"(vb.w) : "memory");
+            }
+        }
+        __syncthreads();
+    }
+    const int resample = s_sc.resample;
+    const double ofs = s_sc.ofs;
+    WeightMap wm;
+    wm.m = s_sc.wq_m;
+    wm.scale = s_sc.wq_scale;
+    dbg_stamp(p.dbg, 1);
+    if (prep_cta) {
+        PrepIn in;
+        in.max_logw = st_max;
+        in.sum_w = st_sum;
+        if (p.n_partials > 0) {
+            float bv;
+            uint32_t bi;
+            merge_best(pp, p.n_partials, s_merge, bv, bi);
+            in.est[0] = p.cur.x[soff + bi];
+            in.est[1] = p.cur.y[soff + bi];
+            in.est[2] = p.cur.th[soff + bi];
+        } else {
+            in.est[0] = stp->est[0];
+            in.est[1] = stp->est[1];
+            in.est[2] = stp->est[2];
+        }
+        prep_block(p.prep, in, p.trig, t, resample, ofs, reinterpret_cast<double *>(s_mark));
+        dbg_stamp(p.dbg, 6);
+        return;
+    }
+    if (!resample) return;
+    const float *lw = p.lw + static_cast<long long>(t) * p.ld;
+    // Persistent over tiles: a CTA keeps taking tickets, so the prologue above is paid once per CTA.
+    __shared__ unsigned int s_next[2];  // two slots by iteration parity: one barrier per tile is enough
+    int it = 0;
+    for (long long tile = s_sc.tile; tile < p.tpt; tile = s_next[it++ & 1]) {
+    if (tid == 0 && p.desc_next != nullptr) p.desc_next[static_cast<long long>(t) * p.tpt + tile] = 0ull;
+    const long long j0 = tile * kScanTile + static_cast<long long>(tid) * kScanItems;
+
+    // ---- load + quantise (8 consecutive items per thread, two 16-byte loads) ----
+    double qd[kScanItems];  // integer-valued: rint(w * 2^52)
+    if (j0 < p.n) {
+        // the state arrays are padded to a multiple of 128 elements, so the vector loads stay in bounds
+        const float4 a = *reinterpret_cast<const float4 *>(lw + j0);
+        const float4 b = *reinterpret_cast<const float4 *>(lw + j0 + 4);
+        const float v[kScanItems] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) qd[k] = (j0 + k < p.n) ? quantize_weight_d(v[k], wm) : 0.0;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) qd[k] = 0.0;
+    }
+    double tsum_d = 0.0;  // sums of integers below 2^53 are exact in fp64
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) tsum_d += qd[k];
+    const unsigned long long tsum = static_cast<unsigned long long>(tsum_d);
+
+    // ---- block exclusive scan of the thread sums ----
+    unsigned long long incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long warp_off = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const unsigned long long v = s_warp[w];
+        if (w < warp) warp_off += v;
+        tile_total += v;
+    }
+    const unsigned long long thread_excl = warp_off + incl - tsum;
+    __syncthreads();  // s_warp is reused by the look-back
+
+    dbg_stamp(p.dbg, 2);
+    // ---- decoupled look-back, block-wide ----
+    unsigned long long *desc = p.desc + static_cast<long long>(t) * p.tpt;
+    unsigned long long excl = 0;
+    if (tile == 0) {
+        if (tid == 0) atomicExch(&desc[0], kDescAggregate | tile_total);  // == its prefix; see the direct range
+    } else {
+        if (tid == 0) atomicExch(&desc[tile], kDescAggregate | tile_total);
+        long long look = tile - 1;  // window covers tiles [look-255, look]
+        if (tile <= kDirectTiles) {
+            // Small scans start all their tiles in one wave: waiting for a predecessor's PREFIX would
+            // serialise them in rounds of 256.  Every aggregate is published at about the same time, so sum
+            // ALL predecessors' aggregates instead (<= 4 independent loads per thread, one wait).
+            unsigned long long d[kDirectTiles / kScanThreads];
+            bool ready;
+            do {
+                ready = true;
+#pragma unroll
+                for (int r = 0; r < kDirectTiles / kScanThreads; ++r) {
+                    const long long idx = look - tid - r * kScanThreads;
+                    d[r] = (idx >= 0) ? *reinterpret_cast<volatile unsigned long long *>(&desc[idx]) : kDescPrefix;
+                    ready = ready && ((d[r] >> 62) != 0ull);
+                }
+            } while (!__syncthreads_and(ready));
+            unsigned long long contrib = 0;
+#pragma unroll
+            for (int r = 0; r < kDirectTiles / kScanThreads; ++r) {
+                // an aggregate (status 1) or a prefix (status 2) of tile idx both END with idx's own total only
+                // if we use aggregates; prefixes are converted back below
+                contrib += d[r] & kDescValueMask;
+            }
+            // NOTE: tiles publish their aggregate first and overwrite it with the inclusive prefix later; a
+            // prefix read here would double count.  Tiles in the direct range therefore never publish prefixes
+            // (see below): every descriptor read above is an aggregate.
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+            if (lane == 0) s_warp[warp] = contrib;
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < NW; ++w) excl += s_warp[w];
+            __syncthreads();
+        } else
+        while (true) {
+            const long long idx = look - tid;
+            unsigned long long d = kDescPrefix;  // tiles before the first one: an empty prefix
+            if (idx >= 0) d = *reinterpret_cast<volatile unsigned long long *>(&desc[idx]);
+            while (!__syncthreads_and((d >> 62) != 0ull)) {
+                if ((d >> 62) == 0ull) d = *reinterpret_cast<volatile unsigned long long *>(&desc[idx]);
+            }
+            const unsigned int is_prefix = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
+            if (lane == 0) s_first[warp] = is_prefix ? (warp * 32 + __ffs(is_prefix) - 1) : 0x7fffffff;
+            __syncthreads();
+            int first = 0x7fffffff;  // nearest predecessor (smallest tid) that already holds a prefix
+#pragma unroll
+            for (int w = 0; w < NW; ++w) first = min(first, s_first[w]);
+            unsigned long long contrib = (tid <= first && idx >= 0) ? (d & kDescValueMask) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+            if (lane == 0) s_warp[warp] = contrib;
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < NW; ++w) excl += s_warp[w];
+            __syncthreads();
+            if (first != 0x7fffffff) break;
+            look -= kScanThreads;
+        }
+        // tiles of the direct range keep their aggregate (later direct tiles sum aggregates); the LAST direct
+        // tile and everything after it publish inclusive prefixes for the classic look-back
+        if (tid == 0 && tile >= kDirectTiles) atomicExch(&desc[tile], kDescPrefix | (excl + tile_total));
+    }
+    if (tid == 0 && p.total != nullptr && tile == p.tpt - 1) p.total[t] = excl + tile_total;
+    // The next ticket is taken only now: a ticket held by a CTA that has not started the tile would stall
+    // every later tile's look-back.  Its round trip overlaps the ancestor phase below.
+    if (tid == 0) s_next[it & 1] = p.persistent ? atomicAdd(&p.tickets[t * 4 + 0], 1u) : 0xffffffffu;
+    dbg_stamp(p.dbg, 3);
+    if (MODE == kScanTotals) {
+        __syncthreads();  // s_next[] is read by the loop header; shared scratch is reused by the next tile
+        continue;
+    }
+
+    // ---- slot range of every source ----
+    const double nd = static_cast<double>(p.n_global);
+    const CombFast cf = make_comb_fast(ofs, nd);
+    double Kd = static_cast<double>(p.k_offset + excl + thread_excl);
+    const double first_slot = count_le_fast(Kd, cf, p.delta, ofs);
+    double cur = first_slot;
+    uint32_t rel[kScanItems];  // first slot of source k relative to the thread's first slot
+    uint32_t owners = 0;       // bit k: source k owns at least one slot
+    // the last particle of the whole filter also takes every slot past the final cumulative weight
+    // (the reference would raise IndexError there; SURVEY.md section 5)
+    const long long k_last64 = p.n_global - 1 - p.j_global_base - j0;
+    const int k_last = (k_last64 >= 0 && k_last64 < kScanItems) ? static_cast<int>(k_last64) : -1;
+    const int n_valid = static_cast<int>(min(static_cast<long long>(kScanItems), max(0ll, p.n - j0)));
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        rel[k] = static_cast<uint32_t>(static_cast<int>(cur - first_slot));
+        Kd += qd[k];
+        double end = count_le_fast(Kd, cf, p.delta, ofs);
+        if (k == k_last) end = nd;
+        if (k < n_valid && end > cur) {
+            owners |= 1u << k;
+            cur = end;
+        }
+    }
+    // tile slot range [S0, S1): S0 from the first thread, S1 from the last thread holding sources
+    const long long n_in_tile = min(static_cast<long long>(kScanTile), p.n - tile * kScanTile);
+    const int last_tid = static_cast<int>((n_in_tile - 1) / kScanItems);
+    if (tid == 0) s_slot[0] = first_slot;
+    if (tid == last_tid) s_slot[1] = cur;
+    __syncthreads();
+    const double S0d = s_slot[0];
+    const long long S0 = static_cast<long long>(S0d), span = static_cast<long long>(s_slot[1] - S0d);
+    const uint32_t my_off = static_cast<uint32_t>(static_cast<long long>(first_slot - S0d));  // threads with sources: >= 0
+
+    dbg_stamp(p.dbg, 4);
+    uint32_t *anc = p.anc + static_cast<long long>(t) * p.ld;
+    uint32_t carry = 0;  // source (local index + 1) that owns the slot just before the window
+    for (long long cb = 0; cb < span; cb += kScanTile) {
+        // window of kScanTile slots starting at S0 + cb
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) s_mark[k * kScanThreads + tid] = 0u;
+        __syncthreads();
+        if (owners) {
+            // slot positions relative to the window, modulo 2^32 (n_global < 2^31: no aliasing)
+            const uint32_t wofs = my_off - static_cast<uint32_t>(cb);
+#pragma unroll
+            for (int k = 0; k < kScanItems; ++k) {
+                const uint32_t pos = wofs + rel[k];
+                if (((owners >> k) & 1u) && pos < static_cast<uint32_t>(kScanTile))
+                    s_mark[pos] = static_cast<uint32_t>(tid * kScanItems + k + 1);
+            }
+        }
+        __syncthreads();
+        // inclusive max-scan over the window, 8 consecutive entries per thread
+        uint32_t v[kScanItems];
+        {
+            const uint4 a = *reinterpret_cast<const uint4 *>(&s_mark[tid * kScanItems]);
+            const uint4 b = *reinterpret_cast<const uint4 *>(&s_mark[tid * kScanItems + 4]);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
+#pragma unroll
+        for (int k = 1; k < kScanItems; ++k) v[k] = max(v[k], v[k - 1]);
+        uint32_t run = v[kScanItems - 1];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, run, o);
+            if (lane >= o) run = max(run, n);
+        }
+        if (lane == 31) s_wmax[warp] = run;
+        uint32_t before = __shfl_up_sync(0xffffffffu, run, 1);
+        if (lane == 0) before = 0u;
+        __syncthreads();
+        uint32_t wbefore = carry, wall = carry;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t m = s_wmax[w];
+            if (w < warp) wbefore = max(wbefore, m);
+            wall = max(wall, m);
+        }
+        before = max(before, wbefore);
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) v[k] = max(v[k], before);
+        *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(v[4], v[5], v[6], v[7]);
+        carry = wall;
+        __syncthreads();
+        // coalesced stores
+        const int lim = static_cast<int>(min(static_cast<long long>(kScanTile), span - cb));
+        const uint32_t jbase = static_cast<uint32_t>(tile * kScanTile) - 1u;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const int pos = k * kScanThreads + tid;
+            if (pos < lim) {
+                const long long slot = S0 + cb + pos;
+                const uint32_t j = jbase + s_mark[pos];
+                if (MODE == kScanExpand) {
+                    if (slot >= p.own_lo && slot < p.own_hi) {
+                        anc[slot - p.own_lo] = j;
+                    } else {
+                        const long long o = (slot < p.own_lo) ? slot - p.slot_first : p.send_hi_off + (slot - p.send_hi_base);
+                        if (o >= 0 && o < p.anc_cap) {
+                            p.ox[o] = p.src.x[j];
+                            p.oy[o] = p.src.y[j];
+                            p.oth[o] = p.src.th[j];
+                        }
+                    }
+                } else {
+                    anc[slot] = j;  // unsharded: slots are local indices, anc holds ld >= n of them
+                }
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();  // s_next (written at the top of this iteration) and the scratch are settled
+    }  // tiles
+    dbg_stamp(p.dbg, 5);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -680,6 +947,7 @@ struct StepParams {
     double *partials;      // [T][bpt][kPart]
     unsigned int *tickets; // [T][4]
     mcl_stats *stats;      // [T]
+    unsigned long long *dbg;  // optional phase timeline [T][bpt][kDbgSlots]
     uint32_t n;            // particles per trial
     uint32_t per;          // particles per block (multiple of kStepUnit)
     long long ld;
@@ -703,6 +971,9 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const Ste
     double4 *s_tab = reinterpret_cast<double4 *>(smem_raw);  // [L] (pair / RB only)
     __shared__ PrepOut s_prep;
 
+    cudaTriggerProgrammaticLaunchCompletion();  // see k_scan
+    cudaGridDependencySynchronize();
+    dbg_stamp(p.dbg, 0);
     if (tid < static_cast<int>(sizeof(PrepOut) / sizeof(double)))
         reinterpret_cast<double *>(&s_prep)[tid] = reinterpret_cast<const double *>(p.prep + t)[tid];
     __syncthreads();
@@ -736,6 +1007,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const Ste
 
     WarpStats ws;
     ws.init();
+    dbg_stamp(p.dbg, 1);
 
     // static contiguous partition of the trial's particles over the blocks (p.per is a multiple of 128,
     // so a warp's 128 particles are either all inside the block's range or all outside)
@@ -943,21 +1215,18 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const Ste
         }
     }
 
-    FinishParams f;
-    f.partials = p.partials;
-    f.tickets = p.tickets;
-    f.stats = p.stats;
-    f.bpt = p.bpt;
-    f.ex = ox;
-    f.ey = oy;
-    f.eth = oth;
-    f.ref_x = s_prep.ref[0];
-    f.ref_y = s_prep.ref[1];
-    f.ref_th = s_prep.ref[2];
-    f.set_step = 1;
-    f.resampled = resample;
-    f.step = static_cast<int>(p.step + 1u);
-    stats_finish(ws, f, t);
+    dbg_stamp(p.dbg, 2);
+    if (blockIdx.x == 0 && tid == 0) {
+        // what the merge of the partials cannot know; and re-arm the scan ticket (the scan has completed)
+        mcl_stats *st = p.stats + t;
+        st->ref[0] = s_prep.ref[0];
+        st->ref[1] = s_prep.ref[1];
+        st->ref[2] = s_prep.ref[2];
+        st->resampled = resample;
+        st->step = static_cast<int>(p.step + 1u);
+        p.tickets[t * 4 + 0] = 0u;
+    }
+    partial_write(ws, p.partials + (static_cast<long long>(t) * p.bpt + blockIdx.x) * kPart, p.dbg);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1004,21 +1273,14 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_reduce(const StepParams p, 
         }
         if (wb + stride < wb) break;  // 32-bit wrap guard for n close to 2^32
     }
-    FinishParams f;
-    f.partials = p.partials;
-    f.tickets = p.tickets;
-    f.stats = p.stats;
-    f.bpt = p.bpt;
-    f.ex = ix;
-    f.ey = iy;
-    f.eth = ith;
-    f.ref_x = ref_x;
-    f.ref_y = ref_y;
-    f.ref_th = ref_th;
-    f.set_step = 0;
-    f.resampled = 0;
-    f.step = 0;
-    stats_finish(ws, f, t);
+    if (blockIdx.x == 0 && tid == 0) {
+        mcl_stats *st = p.stats + t;
+        st->ref[0] = ref_x;
+        st->ref[1] = ref_y;
+        st->ref[2] = ref_th;
+        p.tickets[t * 4 + 0] = 0u;
+    }
+    partial_write(ws, p.partials + (static_cast<long long>(t) * p.bpt + blockIdx.x) * kPart, nullptr);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1056,15 +1318,15 @@ __global__ void __launch_bounds__(256) k_gather(const GatherParams p) {
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.tickets[t * 4 + 0] = 0u;  // re-arm the scan ticket (no k_step follows in the stage API)
-        mcl_stats *st = p.stats + t;
+        mcl_stats *st = p.stats + t;  // (merged before this launch: ensure_stats)
         st->resampled = rs;
         if (rs) {  // weights reset to 1/NP (:222): stored log-weights 0, normaliser log NP
-            st->log_norm = log(p.n_global);
             st->ess = p.n_global;
-            st->max_weight = 1.0 / p.n_global;
             st->max_logw = 0.0;
             st->sum_w = p.n_global;
             st->sum_w2 = p.n_global;
+            st->raw[11] = 0.0;
+            st->derived = 0;
         }
     }
 }
@@ -1085,8 +1347,14 @@ __global__ void __launch_bounds__(256) k_cov(const CovParams p) {
     const int t = blockIdx.y, tid = threadIdx.x;
     __shared__ double s_red[8 * 8];
     __shared__ int s_last;
-    const mcl_stats *st = p.stats + t;
-    const double mx = st->mean[0], my = st->mean[1], mth = st->mean[2], ln = st->log_norm;
+    __shared__ double s_mean[4];
+    if (tid == 0) {
+        mcl_stats d = p.stats[t];
+        derive_stats(d);
+        s_mean[0] = d.mean[0]; s_mean[1] = d.mean[1]; s_mean[2] = d.mean[2]; s_mean[3] = d.log_norm;
+    }
+    __syncthreads();
+    const double mx = s_mean[0], my = s_mean[1], mth = s_mean[2], ln = s_mean[3];
     const long long off = static_cast<long long>(t) * p.ld;
     double a[6] = {0, 0, 0, 0, 0, 0};
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + tid; i < p.n;
@@ -1114,6 +1382,10 @@ __global__ void __launch_bounds__(256) k_cov(const CovParams p) {
     block_sum<6>(s, s_red);
     if (tid == 0) {
         mcl_stats *o = p.stats + t;
+        o->mean[0] = mx; o->mean[1] = my; o->mean[2] = mth;
+        o->log_norm = ln;
+        o->max_weight = exp(o->raw[11] - o->max_logw) / o->sum_w;
+        o->derived = 1;  // exact two-pass moments: mcl_get_stats must not overwrite them
         o->cov[0] = s[0]; o->cov[1] = s[1]; o->cov[2] = s[3];
         o->cov[3] = s[1]; o->cov[4] = s[2]; o->cov[5] = s[4];
         o->cov[6] = s[3]; o->cov[7] = s[4]; o->cov[8] = s[5];
@@ -1139,10 +1411,8 @@ __global__ void k_init(StateView s, const double *pose, long long n, long long l
 __global__ void k_init_stats(mcl_stats *stats, const double *pose, double n_global, int T) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
-    mcl_stats z = {};
-    z.log_norm = log(n_global);  // stored log-weights are 0: w = exp(0 - log NP) = 1/NP (particle_filter.py:83-84)
+    mcl_stats z = {};  // stored log-weights are 0: w = exp(0 - log NP) = 1/NP (particle_filter.py:83-84)
     z.ess = n_global;
-    z.max_weight = 1.0 / n_global;
     z.max_idx = 0;
     z.sum_w = n_global; z.sum_w2 = n_global; z.max_logw = 0.0;
     for (int k = 0; k < 3; ++k) { z.est[k] = pose[3 * t + k]; z.mean[k] = pose[3 * t + k]; z.ref[k] = pose[3 * t + k]; }

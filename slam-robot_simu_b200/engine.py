@@ -235,6 +235,14 @@ class Filter:
         self._check(self.lib.mcl_profile_read(self._h, ms), "mcl_profile_read")
         return ms[0], ms[1], ms[2]
 
+    def debug_timeline(self):
+        """Arms (first call) / reads the k_step phase timeline: (n_ctas, 8) uint64 nanosecond stamps."""
+        n = C.c_int32(0)
+        self._check(self.lib.mcl_debug_timeline(self._h, None, 0, C.byref(n)), "mcl_debug_timeline")
+        out = np.zeros((n.value, 12), dtype=np.uint64)
+        self._check(self.lib.mcl_debug_timeline(self._h, out.ctypes.data, out.size, C.byref(n)), "mcl_debug_timeline")
+        return out
+
     def launch_count(self):
         return int(self.lib.mcl_launch_count(self._h))
 

@@ -108,6 +108,7 @@ def merge_stats(records, slot_bases):
     cov[0, 2] = cov[2, 0] = raw[8] * inv - mdx * mdt
     cov[1, 2] = cov[2, 1] = raw[9] * inv - mdy * mdt
     cov[2, 2] = raw[10] * inv - 2.0 * dl * mdt + dl * dl
+    raw[11] = bv  # stored log-weight of the MAP particle
     return dict(max_logw=M, sum_w=s1, sum_w2=s2, log_norm=M + math.log(s1), ess=s1 * s1 / s2,
                 max_weight=math.exp(bv - M) / s1, max_idx=int(slot_bases[bg] + records[bg]["max_idx"]),
                 est=np.asarray(records[bg]["est"], dtype=np.float64), mean=np.array([ref[0] + mdx, ref[1] + mdy, mth]),
@@ -262,6 +263,7 @@ class ShardedParticleFilter:
         s.max_logw = 0.0
         s.sum_w = float(self.n_global)
         s.sum_w2 = float(self.n_global)
+        s.derived = 1
         for k in range(3):
             s.est[k] = float(est[k])
             s.mean[k] = float(est[k])
@@ -279,6 +281,7 @@ class ShardedParticleFilter:
             s.cov[k] = merged["cov"].reshape(-1)[k]
         for k in range(12):
             s.raw[k] = merged["raw"][k]
+        s.derived = 1
         s.step = self.step_count
         self.flt.shard_set_global(s)
 

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Phase timelines of k_scan and k_step (mcl_debug_timeline): where the fixed time of a small step goes.
+
+    python tools/timeline.py [--n 1048576] [--workload c1]
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+STEP = ["start", "scalars", "loop", "flush", "partial"]
+SCAN = ["start", "prologue", "tile-scan", "look-back", "counts", "filled", "prep-done"]
+
+
+def show(title, t, names, t0):
+    rel = (t - t0) / 1e3
+    print(f"  {title}: {t.shape[0]} CTAs")
+    for s, nm in enumerate(names):
+        col = rel[:, s][(t[:, s] > 0) & (rel[:, s] > -50.0) & (rel[:, s] < 1000.0)]
+        if col.size:
+            print(f"    {nm:10s} min {col.min():7.2f}  median {np.median(col):7.2f}  max {col.max():7.2f}  (n={col.size})")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="c1")
+    ap.add_argument("--n", type=int, default=0)
+    a = ap.parse_args()
+    import torch
+
+    import slam_robot_simu_b200 as mcl
+
+    wl = dict(bench.WORKLOADS[a.workload])
+    if a.n:
+        wl["n"] = a.n
+    lm = bench.landmarks_for(wl["L"])
+    f = mcl.Filter(n_particles=wl["n"], n_trials=wl["T"], landmarks=lm, likelihood="moment", max_landmarks=wl["L"])
+    tr = bench.Truth(lm, seed=7, T=wl["T"])
+    f.init_particles(tr.pose())
+    cyc = torch.from_numpy(tr.cycle()).cuda()
+    for k in range(30):
+        f.step_dev(cyc[k], force_resample=True)
+    f.debug_timeline()  # arm
+    n_scan = wl["T"] * ((wl["n"] + 2047) // 2048 + 2)  # the api sizes the scan region for tpt + 1 CTAs
+    for rep in range(3):
+        junk = torch.empty(64 << 20, dtype=torch.float32, device="cuda").fill_(1.0)  # flush L2
+        torch.cuda.synchronize()
+        f.step_dev(cyc[30 + rep], force_resample=True)
+        t = f.debug_timeline().astype(np.int64)
+        ts, tc = t[:-n_scan], t[-n_scan:]
+        t0 = tc[:, 0][tc[:, 0] > 0].min()
+        print(f"--- step {rep}: microseconds after the first k_scan CTA started")
+        show("k_scan", tc, SCAN, t0)
+        show("k_step", ts, STEP, t0)
+        del junk
+
+
+if __name__ == "__main__":
+    main()
