@@ -26,7 +26,8 @@ if ROOT not in sys.path:
 L2_BYTES = 126 * 1024 * 1024
 BYTES_STEP_CANONICAL = 64  # fp32 SoA state, predict+weight 32 B + scan 4 B + gather 28 B
 BYTES_K_STEP = 32          # k_step as built: ancestor 4 B + gathered pose 12 B in, pose + log-weight 16 B out
-BYTES_K_SCAN = 8           # k_scan_ancestors: log-weight 4 B in, ancestor 4 B out
+BYTES_K_SCAN = 8           # k_scan: log-weight 4 B in, ancestor 4 B out
+NCU_TRAFFIC_K_STEP_BYTES_PER_PARTICLE = (469.743360e6 + 499.869696e6) / 33554432  # profiles/r01_h_ncu_32M_x64_summary.csv
 
 WORKLOADS = {
     # name: (particles per filter, landmarks, trials per GPU, description)
@@ -342,26 +343,7 @@ def run_b200(args, wl):
             print(json.dumps(line), flush=True)
         dist.destroy_process_group()
         return
-    state_bytes = 2 * 16 * n * T + 4 * n * T
-    replicas = max(1, min(64, math.ceil(2.2 * L2_BYTES / state_bytes)))  # rotate filters so every step is L2-cold
     K, W = args.steps, max(args.warmup, 3)
-
-    filters, zcyc_host, zcyc = [], [], []
-    for r in range(replicas):
-        f = mcl.Filter(n_particles=n, n_trials=T, landmarks=lm, likelihood=args.likelihood, device=local,
-                       seed=42 + 1000 * rank + r, max_landmarks=L)
-        tr = Truth(lm, seed=7 + 100 * rank + r * 17, T=T)
-        f.init_particles(tr.pose())
-        cyc = tr.cycle()  # (360, T, L, 2): replica r at filter step k sees cyc[k % 360]
-        filters.append(f)
-        zcyc_host.append(cyc)
-        zcyc.append(torch.from_numpy(cyc).to(dev))
-    torch.cuda.synchronize()
-    counts = [0] * replicas  # steps taken by each replica
-
-    def step_dev(r):
-        filters[r].step_dev(zcyc[r][counts[r] % Truth.PERIOD], force_resample=True)
-        counts[r] += 1
 
     def sync_all():
         torch.cuda.synchronize()
@@ -369,63 +351,98 @@ def run_b200(args, wl):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # untimed: 20 spreading steps per replica, then spin until the clocks are at their loaded
-    # state (W is a minimum, not a maximum)
-    for r in range(replicas):
-        for _ in range(20):
+    def timed_run(w_, K_, W_, spin_s):
+        """K_ timed steps of workload w_ with device-resident inputs; returns the numbers of the JSON line."""
+        n_, L_, T_ = w_["n"], w_["L"], w_["T"]
+        lm_ = landmarks_for(L_)
+        state_bytes = 2 * 16 * n_ * T_ + 4 * n_ * T_
+        replicas = max(1, min(64, math.ceil(2.2 * L2_BYTES / state_bytes)))  # rotate filters: every step is L2-cold
+        filters, zcyc_host, zcyc = [], [], []
+        for r in range(replicas):
+            f = mcl.Filter(n_particles=n_, n_trials=T_, landmarks=lm_, likelihood=args.likelihood, device=local,
+                           seed=42 + 1000 * rank + r, max_landmarks=L_)
+            tr = Truth(lm_, seed=7 + 100 * rank + r * 17, T=T_)
+            f.init_particles(tr.pose())
+            cyc = tr.cycle()  # (360, T, L, 2): replica r at filter step k sees cyc[k % 360]
+            filters.append(f)
+            zcyc_host.append(cyc)
+            zcyc.append(torch.from_numpy(cyc).to(dev))
+        torch.cuda.synchronize()
+        counts = [0] * replicas  # steps taken by each replica
+
+        def step_dev(r):
+            filters[r].step_dev(zcyc[r][counts[r] % Truth.PERIOD], force_resample=True)
+            counts[r] += 1
+
+        # untimed: 20 spreading steps per replica (SURVEY 8d), then spin until the clocks are at their loaded
+        # state (W is a minimum, not a maximum)
+        for r in range(replicas):
+            for _ in range(20):
+                step_dev(r)
+        t_spin = time.perf_counter()
+        i = 0
+        while time.perf_counter() - t_spin < spin_s:
+            step_dev(i % replicas)
+            i += 1
+            if i % 64 == 0:
+                torch.cuda.synchronize()
+        for i in range(W_):
+            step_dev(i % replicas)
+
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = sum(f.launch_count() for f in filters)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        sampler.active.set()
+        e0.record()
+        for i in range(K_):
+            step_dev((W_ + i) % replicas)
+        e1.record()
+        sync_all()
+        sampler.active.clear()
+        sampler.stop()
+        ms_ = e0.elapsed_time(e1)
+        launches_ = sum(f.launch_count() for f in filters) - launches0
+        if world > 1:
+            t = torch.tensor([ms_], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item())
+        value_ = float(n_) * T_ * K_ * world / (ms_ * 1e-3)
+
+        # per-kernel durations, measured live with CUDA events inside the library (same steps, L2-cold)
+        kt = np.zeros(3)
+        kn = min(K_, 200)
+        for f in filters:
+            f.profile(True)
+        for i in range(kn):
+            r = (W_ + i) % replicas
             step_dev(r)
-    t_spin = time.perf_counter()
-    i = 0
-    while time.perf_counter() - t_spin < 0.3:
-        step_dev(i % replicas)
-        i += 1
-        if i % 64 == 0:
-            torch.cuda.synchronize()
-    for i in range(W):
-        step_dev(i % replicas)
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = sum(f.launch_count() for f in filters)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    sampler.active.set()
-    e0.record()
-    for i in range(K):
-        step_dev((W + i) % replicas)
-    e1.record()
-    sync_all()
-    sampler.active.clear()
-    ms = e0.elapsed_time(e1)
-    launches = sum(f.launch_count() for f in filters) - launches0
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = float(n) * T * K * world / (ms * 1e-3)
-
-    # ---- per-kernel durations, measured live with CUDA events inside the library (same steps, L2-cold) ----
-    kt = np.zeros(3)
-    kn = min(K, 200)
-    for f in filters:
-        f.profile(True)
-    for i in range(kn):
-        r = (W + i) % replicas
-        step_dev(r)
-        kt += np.array(filters[r].profile_read())
-    ess_frac = float(np.mean([st.ess for st in filters[0].stats()])) / n
-    for f in filters:
-        f.profile(False)
-    kt /= kn
-    peak, peak_src = peaks()
-    ach = BYTES_K_STEP * n * T / (kt[2] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_step<0> (gather + predict + weight + reductions)", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_particle": BYTES_K_STEP,
+            kt += np.array(filters[r].profile_read())
+        ess_frac_ = float(np.mean([st.ess for st in filters[0].stats()])) / n_
+        for f in filters:
+            f.profile(False)
+        kt /= kn
+        peak, peak_src = peaks()
+        ach = BYTES_K_STEP * n_ * T_ / (kt[2] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_step (gather + predict + weight + statistics)", "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_K_STEP_BYTES_PER_PARTICLE * n_ * T_,
+                "traffic_source": "ncu --set full, 32M particles x 64 landmarks: dram__bytes_read + write of k_step per "
+                                  "particle (profiles/r01_h_ncu_32M_x64_summary.csv), scaled to this launch",
+                "peak_source": peak_src, "algorithmic_bytes_per_particle": BYTES_K_STEP,
                 "kernel_ms": {"k_scan": kt[1], "k_step": kt[2]},
-                "scan_achieved_GBps": BYTES_K_SCAN * n * T / (kt[1] * 1e-3) / 1e9,
+                "scan_achieved_GBps": BYTES_K_SCAN * n_ * T_ / (kt[1] * 1e-3) / 1e9,
+                "step_bytes_moved_per_particle": BYTES_K_STEP + BYTES_K_SCAN,
+                "step_moved_frac": (BYTES_K_STEP + BYTES_K_SCAN) * value_ / world / 1e9 / peak,
                 "step_canonical_bytes": BYTES_STEP_CANONICAL,
-                "step_canonical_frac": BYTES_STEP_CANONICAL * value / world / 1e9 / peak}
+                "step_canonical_frac": BYTES_STEP_CANONICAL * value_ / world / 1e9 / peak}
+        return dict(value=value_, ms=ms_, launches=launches_, roofline=roof, ess=ess_frac_, replicas=replicas,
+                    state_bytes=state_bytes, clocks=sampler.summary(), filters=filters, zcyc_host=zcyc_host, counts=counts)
+
+    main_run = timed_run(wl, K, W, 0.3)
+    value, ms, launches, roofline, ess_frac = (main_run[k] for k in ("value", "ms", "launches", "roofline", "ess"))
+    replicas, state_bytes, filters, zcyc_host, counts = (main_run[k] for k in ("replicas", "state_bytes", "filters", "zcyc_host", "counts"))
+    clocks = main_run["clocks"]
 
     # ---- end to end through the reference-facing API: host observation in, host estimate out, every step ----
     e2e = None
@@ -451,7 +468,7 @@ def run_b200(args, wl):
         e2e = {"value": float(n) * ke * world / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": 16 * L,
                "d2h_bytes_per_step": C.sizeof(mcl.mcl_stats), "steps": ke,
                "api": "ParticleFilter(period_ms, noise='philox', lazy_px=True, force_resample=True).main_pf()",
-               "note": "host truth motion + observation draw, H2D of z_l, 3 kernels, D2H of the mcl_stats block; px stays "
+               "note": "host truth motion + observation draw, H2D of z_l, k_scan + k_step + k_merge, D2H of the mcl_stats block; px stays "
                        "on the device until read (LazyParticles)"}
         del pf
     else:
@@ -468,14 +485,24 @@ def run_b200(args, wl):
 
         e2e = {"value": float(n) * T * ke * world / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": 16 * L * T,
                "d2h_bytes_per_step": C.sizeof(mcl.mcl_stats) * T, "steps": ke, "api": "Filter.step(z_host) + Filter.stats()"}
-    sampler.stop()
-
     sharded = None
     if world > 1 and not args.no_sharded:
-        del filters, zcyc
+        del filters, main_run
         torch.cuda.empty_cache()
         c3 = WORKLOADS["c3"]
         sharded = measure_sharded(mcl, torch, dist, dev, c3["n"], c3["L"], args.likelihood, 8, 3)
+    large = None
+    if world == 1 and args.workload == "c1" and not args.no_large:
+        # the per-GPU share of the metric's target configuration (1B particles x 64 landmarks over 8 GPUs): the
+        # same kernels at a size where launch and tail latencies no longer dominate
+        del filters, main_run
+        torch.cuda.empty_cache()
+        c3 = WORKLOADS["c3"]
+        lr = timed_run(c3, 12, 3, 0.1)
+        large = {"workload": c3["desc"], "value": lr["value"], "unit": "particle-steps/s", "ms_per_step": lr["ms"] / 12,
+                 "steps": 12, "ess_over_n": lr["ess"], "roofline": lr["roofline"]}
+        del lr
+        torch.cuda.empty_cache()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -489,8 +516,8 @@ def run_b200(args, wl):
                        "ess_over_n": ess_frac,
                        "l2": f"rotating {replicas} independent filter replicas ({replicas * state_bytes >> 20} MiB > 126 MiB L2)",
                        "parallelism": "single GPU" if world == 1 else f"{world} ranks, one independent filter each (no data-path collective)"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sharded_filter": sharded, "gpu_launches": int(launches),
-            "clocks": sampler.summary()}
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "large_filter": large, "sharded_filter": sharded,
+            "gpu_launches": int(launches), "clocks": clocks}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -507,6 +534,7 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="override the particle count of the workload (experiments)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the particle-sharded C3 measurement")
+    ap.add_argument("--no-large", action="store_true", help="N = 1, c1: skip the extra C3-shard measurement")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.n:

@@ -84,6 +84,11 @@ class ParticleFilter:
         self.__Q = np.diag([0.03, 0.03, np.deg2rad(2.0)]) ** 2  # :62-65
         self.__R = np.diag([0.3, 0.3]) ** 2  # :68-70
         self.__x_true = np.array([[self.__RADIUS_m], [0.0], [np.deg2rad(90.0)]])  # :74-79
+        # np.random.multivariate_normal(0, C, n) is standard_normal(n * d).reshape(n, d) @ (sqrt(s)[:, None] * v)
+        # with (u, s, v) = svd(C) recomputed on every call (numpy mtrand, legacy generator).  The factor is
+        # constant, so it is computed once; the draws below consume the np.random stream identically.
+        self.__Q_factor = self.__mvn_factor(self.__Q)
+        self.__R_factor = self.__mvn_factor(self.__R)
         self.__noise = noise
         self.__lazy = bool(lazy_px)
         self.__force = bool(force_resample)
@@ -95,6 +100,17 @@ class ParticleFilter:
         self.__flt.init_particles(self.__x_true[:, 0])  # :81-84
         self.__ess = float(self.__NP)  # 1 / sum((1/NP)^2)
         self.last_stats = None
+
+    @staticmethod
+    def __mvn_factor(cov):
+        _, s, v = np.linalg.svd(cov)
+        return np.sqrt(s)[:, None] * v
+
+    @staticmethod
+    def __mvn(factor, n):
+        """np.random.multivariate_normal(zeros, cov, n), same stream, without the per-call SVD."""
+        d = factor.shape[0]
+        return np.dot(np.random.standard_normal(n * d).reshape(n, d), factor)
 
     # -- host-side pieces the reference also runs once per step on one pose ---------------------
     def __f(self, x):
@@ -109,7 +125,7 @@ class ParticleFilter:
     def __observation(self, x_true):
         """particle_filter.py:144-154."""
         z_l = world2robot(x_true, self.__LM)
-        w = np.random.multivariate_normal([0.0, 0.0], self.__R, self.__LM.shape[0])
+        w = self.__mvn(self.__R_factor, self.__LM.shape[0])  # multivariate_normal([0, 0], R, L)
         return z_l + w
 
     @property
@@ -129,7 +145,7 @@ class ParticleFilter:
         if self.__noise == "numpy":
             if do_resample:
                 ofs = np.random.rand() * self.__NP_RECIP  # :214
-            v = np.random.multivariate_normal([0.0, 0.0, 0.0], self.__Q, self.__NP).T  # :165
+            v = self.__mvn(self.__Q_factor, self.__NP).T  # multivariate_normal([0, 0, 0], Q, NP).T (:165)
             noise = np.ascontiguousarray(v, dtype=np.float32)[:, None, :]
         z_l = self.__observation(self.__x_true)  # :110
 
