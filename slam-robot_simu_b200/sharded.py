@@ -3,7 +3,7 @@
 Rank g owns the contiguous global particles / output slots [g * m, (g + 1) * m), m = n_global / G.
 Predict + weight is local.  Two exchanges couple the shards:
 
-  * statistics -- every rank allgathers its 304-byte mcl_stats record and merges them on the host
+  * statistics -- every rank allgathers its 312-byte mcl_stats record and merges them on the host
     (`merge_stats`): global max, normaliser, ESS, arg-max, weighted mean / covariance.  The merged
     record goes back into every shard (mcl_shard_set_global), so all shards quantise their weights
     with the same map and take the same resampling decision;
