@@ -189,7 +189,7 @@ int mcl_get_ancestors(mcl_filter *h, uint32_t *anc_host, void *stream);
 int mcl_profile(mcl_filter *h, int enable);
 int mcl_profile_read(mcl_filter *h, double *ms3_host);
 uint64_t mcl_launch_count(const mcl_filter *h);
-/* Debug aid: the first call (stamps_host may be NULL) arms a per-CTA phase timeline of k_step; later calls
+/* Debug aid (needs a library built with -DMCL_TIMELINE, else MCL_ERR_STATE): the first call (stamps_host may be NULL) arms a per-CTA phase timeline of k_step; later calls
  * copy [n_ctas][12] global-timer nanosecond stamps of the most recent step (synchronises the device;
  * n_ctas = k_step CTAs followed by k_scan CTAs):
  * 0 start, 1 scalars loaded, 2 loop done, 3 warp sums flushed, 4 partial written, 5 ticket taken,

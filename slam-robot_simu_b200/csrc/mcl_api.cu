@@ -894,6 +894,10 @@ uint64_t mcl_launch_count(const mcl_filter *h) { return h ? h->launches : 0; }
 
 int mcl_debug_timeline(mcl_filter *h, uint64_t *stamps_host, int64_t capacity, int32_t *n_ctas) {
     if (h == nullptr) return MCL_ERR_ARG;
+#ifndef MCL_TIMELINE
+    (void)stamps_host; (void)capacity; (void)n_ctas;
+    return fail(h, MCL_ERR_STATE, "libmcl_b200.so was built without -DMCL_TIMELINE (MCL_TIMELINE=1 python build.py --force)");
+#endif
     int rc = use_device(h);
     if (rc != MCL_OK) return rc;
     const size_t n_step = static_cast<size_t>(h->lay.T) * h->lay.bpt * kDbgSlots;

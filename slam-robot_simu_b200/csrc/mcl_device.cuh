@@ -101,12 +101,18 @@ __device__ __forceinline__ float wrap_residual(float d) {
 
 // optional phase timeline (mcl_debug_timeline): thread 0 of a CTA stamps the global nanosecond timer
 constexpr int kDbgSlots = 12;
+// (compiled in only with -DMCL_TIMELINE: MCL_TIMELINE=1 python slam-robot_simu_b200/build.py --force)
 __device__ __forceinline__ void dbg_stamp(unsigned long long *dbg, int slot) {
+#ifdef MCL_TIMELINE
     if (dbg != nullptr && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         dbg[(static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * kDbgSlots + slot] = t;
     }
+#else
+    (void)dbg;
+    (void)slot;
+#endif
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {

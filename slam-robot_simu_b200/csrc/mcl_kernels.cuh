@@ -424,7 +424,8 @@ __device__ __noinline__ void merge_full(const double *pp, int nb, mcl_stats *st,
     // pass 2: column `col` of every record, rescaled to MM (columns 1..13 are sums; column 2 carries squares)
     double acc = 0.0;
     uint32_t bkey = 0u, bidx = 0xffffffffu;
-    for (int b0 = row0; b0 < nb; b0 += kRows * kBatch) {
+    for (int bb = 0; bb < nb; bb += kRows * kBatch) {  // CTA-uniform trip count: the loop body shuffles
+        const int b0 = bb + row0;
         double m8[kBatch], v8[kBatch];
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {  // clamped rows, masked below: the 16 loads of a batch are independent
@@ -1039,13 +1040,15 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const Ste
 #pragma unroll
                     for (int k = 0; k < kPPT; ++k) {
                         const uint32_t i = base + k;
-                        if (i >= p.win_lo && i < p.win_hi) {
-                            const uint32_t j = (i < p.n) ? a[k] : 0u;
+                        if (i >= p.n) {  // padding of the last, partial group
+                            x[k] = y[k] = th[k] = 0.0f;
+                        } else if (i >= p.win_lo && i < p.win_hi) {
+                            const uint32_t j = a[k];
                             x[k] = ix[j];
                             y[k] = iy[j];
                             th[k] = ith[j];
                         } else {
-                            const uint32_t r = (i < p.win_lo) ? i : min(i, p.n - 1u) - p.win_hi + p.win_lo;
+                            const uint32_t r = (i < p.win_lo) ? i : i - p.win_hi + p.win_lo;
                             x[k] = p.recv_x[r];
                             y[k] = p.recv_y[r];
                             th[k] = p.recv_th[r];

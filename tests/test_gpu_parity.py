@@ -562,3 +562,151 @@ def test_sharded_filter_two_gpus_nccl():
            "--master-port", "29641", os.path.join(root, "tests", "_nccl_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
     assert r.returncode == 0 and "nccl worker ok" in r.stdout, r.stdout[-3000:] + r.stderr[-4000:]
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases: tiny and ragged sizes, extreme landmark counts, mixed gates in a trial batch
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 127, 129, 2047, 2049])
+def test_tiny_and_ragged_particle_counts(mcl, n):
+    """Sizes around the vector width (4), the partition unit (128) and the scan tile (2048)."""
+    rng = np.random.RandomState(n)
+    lm = rng.uniform(-5, 5, (3, 2))
+    P = O.PFParams(100, n_particles=n, landmarks=lm)
+    truth = np.array([[1.0], [-1.0], [0.3]])
+    pos = (truth + rng.normal(0, 0.1, (3, n))).astype(np.float32)
+    lw = rng.normal(0, 1, n).astype(np.float32)
+    noise = (rng.normal(0, 1, (3, n)) * np.sqrt(np.diag(P.Q))[:, None]).astype(np.float32)
+    z = O.world2robot(truth, lm) + rng.normal(0, 0.3, (3, 2))
+    ofs = rng.rand() / n
+    f = mcl.Filter(n_particles=n, landmarks=lm)
+    f.set_particles(pos[0], pos[1], pos[2], lw)
+    q = f.qweights()[0]
+    f.step(z[None], ofs=ofs, noise=noise[:, None, :], force_resample=True)
+    anc = f.ancestors()[0].astype(np.int64)
+    np.testing.assert_array_equal(anc, O.resample_indices(O.dequantize_weights(q), ofs))
+    x, y, th, _ = f.get_particles()
+    got = np.stack([x[0], y[0], th[0]]).astype(np.float64)
+    np.testing.assert_allclose(got, O.predict(pos.astype(np.float64)[:, anc], noise.astype(np.float64), P), rtol=RTOL, atol=1e-6)
+    ll = O.loglik_cartesian(got, z, lm, 0.3, 0.3)
+    want_w, _ = O.update_weights_log(np.full(n, -np.log(float(n))), ll)
+    _assert_weights_close(f.weights()[0], want_w)
+    st = f.stats()[0]
+    assert st.max_idx == int(np.argmax(want_w)) or want_w[st.max_idx] >= want_w.max() * (1 - RTOL)
+    assert st.ess == pytest.approx(O.ess(want_w), rel=RTOL)
+
+
+def test_single_and_maximum_landmark_counts(mcl):
+    """L = 1 and L = 4096 (the capacity of the shared-memory landmark table)."""
+    rng = np.random.RandomState(4)
+    n = 4096
+    truth = np.array([[0.5], [0.25], [-0.8]])
+    for Lm in (1, 4096):
+        lm = rng.uniform(-20, 20, (Lm, 2))
+        spread = 0.3 / np.sqrt(Lm)
+        pos = (truth + rng.normal(0, 1, (3, n)) * np.array([[spread], [spread], [spread / 10]])).astype(np.float32)
+        pos[:, 0] = truth[:, 0].astype(np.float32)
+        z = O.world2robot(truth, lm) + rng.normal(0, 0.3, (Lm, 2))
+        out = {}
+        for lik in ("pair", "moment"):
+            f = mcl.Filter(n_particles=n, landmarks=lm, likelihood=lik, max_landmarks=max(Lm, 8))
+            f.set_particles(pos[0], pos[1], pos[2], None)
+            f.predict_weight(z[None], noise=np.zeros((3, 1, n), dtype=np.float32))
+            x, y, th, _ = f.get_particles()
+            out[lik] = f.weights()[0]
+        got_px = np.stack([x[0], y[0], th[0]]).astype(np.float64)
+        ll = O.loglik_cartesian(got_px, z, lm, 0.3, 0.3)
+        want_w, _ = O.update_weights_log(np.full(n, -np.log(float(n))), ll)
+        _assert_weights_close(out["pair"], want_w)
+        _assert_weights_close(out["moment"], want_w)
+    with pytest.raises(mcl.MclError):
+        mcl.Filter(n_particles=16, max_landmarks=4097)
+
+
+def test_anisotropic_observation_noise(mcl):
+    """sigma_x != sigma_y selects the 13-moment kernel; same weights as the pair kernel and the oracle."""
+    rng = np.random.RandomState(8)
+    n, Lm = 8192, 12
+    lm = rng.uniform(-15, 15, (Lm, 2))
+    truth = np.array([[2.0], [3.0], [1.9]])
+    pos = (truth + rng.normal(0, 1, (3, n)) * np.array([[0.1], [0.1], [0.02]])).astype(np.float32)
+    pos[:, 0] = truth[:, 0].astype(np.float32)
+    z = O.world2robot(truth, lm) + rng.normal(0, 1, (Lm, 2)) * np.array([0.2, 0.5])
+    res = {}
+    for lik in ("pair", "moment"):
+        f = mcl.Filter(n_particles=n, landmarks=lm, likelihood=lik, sigma_obs=[0.2, 0.5], max_landmarks=16)
+        f.set_particles(pos[0], pos[1], pos[2], None)
+        f.predict_weight(z[None], noise=np.zeros((3, 1, n), dtype=np.float32))
+        x, y, th, _ = f.get_particles()
+        res[lik] = f.weights()[0]
+    got_px = np.stack([x[0], y[0], th[0]]).astype(np.float64)
+    ll = O.loglik_cartesian(got_px, z, lm, 0.2, 0.5)
+    want_w, _ = O.update_weights_log(np.full(n, -np.log(float(n))), ll)
+    _assert_weights_close(res["pair"], want_w)
+    _assert_weights_close(res["moment"], want_w)
+
+
+def test_trial_batch_with_mixed_resampling_gates(mcl):
+    """ESS-gated step on a batch where some trials resample and some do not (particle_filter.py:211);
+    ragged n (not a multiple of the 128-particle stride unit)."""
+    T, n, Lm = 6, 1500, 5
+    rng = np.random.RandomState(21)
+    lm = rng.uniform(-8, 8, (Lm, 2))
+    truth = np.array([[1.0], [1.0], [0.2]])
+    P = O.PFParams(100, n_particles=n, landmarks=lm)
+    pos = (truth[:, None, :] + rng.normal(0, 0.05, (3, T, n))).astype(np.float32)
+    lw = np.zeros((T, n), dtype=np.float32)
+    for t in range(T):
+        if t % 2 == 0:  # degenerate weights: ESS ~ 3 << n / 100
+            lw[t] = -40.0
+            lw[t, rng.randint(0, n, 3)] = 0.0
+        else:  # healthy weights: ESS ~ n
+            lw[t] = rng.normal(0, 0.05, n)
+    noise = (rng.normal(0, 1, (3, T, n)) * np.sqrt(np.diag(P.Q))[:, None, None]).astype(np.float32)
+    z = np.stack([O.world2robot(truth, lm) + rng.normal(0, 0.3, (Lm, 2)) for _ in range(T)])
+    ofs = rng.rand(T) / n
+    f = mcl.Filter(n_particles=n, n_trials=T, landmarks=lm)
+    f.set_particles(pos[0], pos[1], pos[2], lw)
+    ess0 = [s.ess for s in f.stats()]
+    q = f.qweights()
+    f.step(z, ofs=ofs, noise=noise)  # gated, not forced
+    st = f.stats()
+    anc = f.ancestors()
+    x, y, th, _ = f.get_particles()
+    w = f.weights()
+    for t in range(T):
+        fired = ess0[t] < n / 100.0
+        assert fired == (t % 2 == 0) and st[t].resampled == int(fired)
+        src = pos[:, t].astype(np.float64)
+        if fired:
+            a = anc[t].astype(np.int64)
+            np.testing.assert_array_equal(a, O.resample_indices(O.dequantize_weights(q[t]), ofs[t]))
+            src = src[:, a]
+            prev = np.full(n, -np.log(float(n)))
+        else:
+            prev = np.log(_weights_from_logw32(lw[t]))
+        got = np.stack([x[t], y[t], th[t]]).astype(np.float64)
+        np.testing.assert_allclose(got, O.predict(src, noise[:, t].astype(np.float64), P), rtol=RTOL, atol=1e-6)
+        ll = O.loglik_cartesian(got, z[t], lm, 0.3, 0.3)
+        want_w, _ = O.update_weights_log(prev, ll)
+        _assert_weights_close(w[t], want_w)
+        assert st[t].ess == pytest.approx(O.ess(want_w), rel=RTOL)
+
+
+def test_yaw_wrap_at_the_seam_matches_limit_angle(mcl):
+    """Particles whose yaw + w dt lands on both sides of pi: the wrap decision is the fp64 one of mylib/limit.py."""
+    n = 4096
+    P = O.PFParams(100, n_particles=n)
+    rng = np.random.RandomState(12)
+    wdt = P.YAW_RATE_rps * P.DT_s
+    th = (np.pi - wdt + rng.uniform(-3e-6, 3e-6, n)).astype(np.float32)
+    th[::2] *= -1  # and the mirrored seam; also exercises the sign rule for negative angles
+    th[1::4] = (-np.pi - wdt + rng.uniform(-3e-6, 3e-6, n // 4)).astype(np.float32)
+    pos = np.stack([rng.normal(0, 1, n), rng.normal(0, 1, n), th]).astype(np.float32)
+    f = mcl.Filter(n_particles=n, landmarks=P.LM)
+    f.set_particles(pos[0], pos[1], pos[2], None)
+    f.predict_weight(np.zeros((1, 5, 2)), noise=np.zeros((3, 1, n), dtype=np.float32))
+    got = f.get_particles()[2][0].astype(np.float64)
+    want = O.predict(pos.astype(np.float64), np.zeros((3, n)), P)[2]
+    assert np.all(np.abs(got - want) < 1e-6)  # same side of the seam everywhere
+    assert (want > 3.0).any() and (want < -3.0).any()

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Phase timelines of k_scan and k_step (mcl_debug_timeline): where the fixed time of a small step goes.
 
+    MCL_TIMELINE=1 python slam-robot_simu_b200/build.py --force     # stamps are compiled out by default
     python tools/timeline.py [--n 1048576] [--workload c1]
 """
 import argparse
