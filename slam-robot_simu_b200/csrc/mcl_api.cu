@@ -26,7 +26,7 @@ struct Layout {
     int T, Lmax, tpt, bpt, cov_bpt;
     uint32_t per;
     size_t off_state[2], off_anc, off_desc, off_tickets, off_partials, off_cov, off_stats, off_prep, off_tab, off_lm,
-        off_z, off_ofs, off_pose, off_total, off_trig, off_pub, total;
+        off_z, off_ofs, off_pose, off_total, off_trig, off_pub, off_ready, total;
 };
 
 int make_layout(const mcl_config &c, int sm_count, Layout &L) {
@@ -69,6 +69,7 @@ int make_layout(const mcl_config &c, int sm_count, Layout &L) {
     L.off_pose = o;     o = align_up(o + static_cast<size_t>(L.T) * 3 * sizeof(double), kAlign);
     L.off_total = o;    o = align_up(o + static_cast<size_t>(L.T) * sizeof(unsigned long long), kAlign);
     L.off_pub = o;      o = align_up(o + static_cast<size_t>(L.T) * 2 * sizeof(uint4), kAlign);
+    L.off_ready = o;    o = align_up(o + static_cast<size_t>(2) * L.T * (kDirectTiles / 32) * sizeof(unsigned int), kAlign);
     L.off_trig = o;     o = align_up(o + static_cast<size_t>(kTrigEntries) * sizeof(TrigEntry), kAlign);
     L.total = o;
     return MCL_OK;
@@ -107,6 +108,7 @@ struct mcl_filter {
     unsigned long long *total = nullptr;
     TrigEntry *trig = nullptr;
     uint4 *wm_pub = nullptr;
+    unsigned int *ready[2] = {nullptr, nullptr};  // double-buffered like desc[]
     unsigned int scan_epoch = 0;
     int cur = 0;
     int L = 0;
@@ -236,6 +238,8 @@ void fill_scan(mcl_filter *h, ScanParams &p) {
     p.stats = h->stats;
     p.desc = h->desc[h->desc_cur];
     p.desc_next = nullptr;
+    p.ready = h->ready[h->desc_cur];
+    p.ready_next = nullptr;
     p.tickets = h->tickets;
     p.anc = h->anc;
     p.total = nullptr;
@@ -283,6 +287,7 @@ int launch_step_scan(mcl_filter *h, const double *z_dev, const double *ofs_dev, 
     sp.dbg = (h->dbg != nullptr && full) ? h->dbg + static_cast<size_t>(h->lay.T) * h->lay.bpt * kDbgSlots : nullptr;
     if (full) {
         sp.desc_next = h->desc[h->desc_cur ^ 1];
+        sp.ready_next = h->ready[h->desc_cur ^ 1];
         h->desc_cur ^= 1;
     }
     if (h->stats_dirty) {  // statistics still live in the CTA partials of the previous k_step / k_reduce
@@ -305,13 +310,13 @@ int launch_step_scan(mcl_filter *h, const double *z_dev, const double *ofs_dev, 
 
 // Sharded resampling: the scan runs outside a step, with the weight map of the (global) statistics.
 int launch_shard_scan(mcl_filter *h, ScanParams &sp, int mode, cudaStream_t st) {
-    k_reset_scan<<<(h->lay.tpt + 255) / 256, 256, 0, st>>>(sp.desc, h->tickets, h->lay.tpt);
+    k_reset_scan<<<(h->lay.tpt + 255) / 256, 256, 0, st>>>(sp.desc, sp.ready, h->tickets, h->lay.tpt);
     MCL_LAUNCH_CHECK(h, "k_reset_scan");
     dim3 grid(h->lay.tpt, 1);
     if (mode == kScanTotals) k_scan<kScanTotals><<<grid, kScanThreads, 0, st>>>(sp);
     else k_scan<kScanExpand><<<grid, kScanThreads, 0, st>>>(sp);
     MCL_LAUNCH_CHECK(h, "k_scan");
-    k_reset_scan<<<(h->lay.tpt + 255) / 256, 256, 0, st>>>(sp.desc, h->tickets, h->lay.tpt);
+    k_reset_scan<<<(h->lay.tpt + 255) / 256, 256, 0, st>>>(sp.desc, sp.ready, h->tickets, h->lay.tpt);
     MCL_LAUNCH_CHECK(h, "k_reset_scan");
     return MCL_OK;
 }
@@ -575,6 +580,8 @@ int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_byte
     h->total = reinterpret_cast<unsigned long long *>(h->ws + L.off_total);
     h->trig = reinterpret_cast<TrigEntry *>(h->ws + L.off_trig);
     h->wm_pub = reinterpret_cast<uint4 *>(h->ws + L.off_pub);
+    h->ready[0] = reinterpret_cast<unsigned int *>(h->ws + L.off_ready);
+    h->ready[1] = h->ready[0] + static_cast<size_t>(L.T) * (kDirectTiles / 32);
     h->delta = 1.0 / static_cast<double>(cfg->n_global);
     // the pair kernels stage up to 4096 landmarks (128 KiB) in dynamic shared memory
     const int max_dyn = 4096 * static_cast<int>(sizeof(double4));
@@ -600,6 +607,8 @@ int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_byte
     }
     cudaError_t e = cudaMemset(h->ws + L.off_tickets, 0, static_cast<size_t>(L.T) * 4 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_desc, 0, static_cast<size_t>(2) * L.T * L.tpt * sizeof(unsigned long long));
+    if (e == cudaSuccess)
+        e = cudaMemset(h->ws + L.off_ready, 0, static_cast<size_t>(2) * L.T * (kDirectTiles / 32) * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_pub, 0, static_cast<size_t>(L.T) * 2 * sizeof(uint4));
     if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_stats, 0, static_cast<size_t>(L.T) * sizeof(mcl_stats));
     if (e != cudaSuccess) {

@@ -530,6 +530,8 @@ struct ScanParams {
     StateView cur;              // the stored state (MAP pose lookup)
     unsigned long long *desc;   // [T][tpt] tile descriptors of this launch (all zero on entry)
     unsigned long long *desc_next;  // [T][tpt] cleared for the next launch (may be null)
+    unsigned int *ready;        // [T][32] bit per tile of the direct range: aggregate published (zero on entry)
+    unsigned int *ready_next;   // cleared for the next launch (may be null)
     unsigned int *tickets;      // [T][4]  (slot 0 = scan ticket)
     uint32_t *anc;              // [T][ld] (slot - slot_first)
     unsigned long long *total;  // optional [T] : inclusive total of the local weights
@@ -667,6 +669,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     wm.scale = s_sc.wq_scale;
     dbg_stamp(p.dbg, 1);
     if (prep_cta) {
+        if (p.ready_next != nullptr && tid < kDirectTiles / 32) p.ready_next[t * (kDirectTiles / 32) + tid] = 0u;
         PrepIn in;
         in.max_logw = st_max;
         in.sum_w = st_sum;
@@ -736,26 +739,46 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     // ---- decoupled look-back, block-wide ----
     unsigned long long *desc = p.desc + static_cast<long long>(t) * p.tpt;
     unsigned long long excl = 0;
+    // tiles of the direct range also raise a bit in ready[tile / 32] once their aggregate is visible
+    unsigned int *rdy = p.ready + t * (kDirectTiles / 32);
     if (tile == 0) {
-        if (tid == 0) atomicExch(&desc[0], kDescAggregate | tile_total);  // == its prefix; see the direct range
+        if (tid == 0) {
+            atomicExch(&desc[0], kDescAggregate | tile_total);  // == its prefix; see the direct range
+            __threadfence();
+            atomicOr(&rdy[0], 1u);
+        }
     } else {
-        if (tid == 0) atomicExch(&desc[tile], kDescAggregate | tile_total);
+        if (tid == 0) {
+            atomicExch(&desc[tile], kDescAggregate | tile_total);
+            if (tile < kDirectTiles) {
+                __threadfence();
+                atomicOr(&rdy[tile >> 5], 1u << (tile & 31));
+            }
+        }
         long long look = tile - 1;  // window covers tiles [look-255, look]
         if (tile <= kDirectTiles) {
             // Small scans start all their tiles in one wave: waiting for a predecessor's PREFIX would
             // serialise them in rounds of 256.  Every aggregate is published at about the same time, so sum
-            // ALL predecessors' aggregates instead (<= 4 independent loads per thread, one wait).
-            unsigned long long d[kDirectTiles / kScanThreads];
-            bool ready;
-            do {
-                ready = true;
-#pragma unroll
-                for (int r = 0; r < kDirectTiles / kScanThreads; ++r) {
-                    const long long idx = look - tid - r * kScanThreads;
-                    d[r] = (idx >= 0) ? *reinterpret_cast<volatile unsigned long long *>(&desc[idx]) : kDescPrefix;
-                    ready = ready && ((d[r] >> 62) != 0ull);
+            // ALL predecessors' aggregates instead (<= 4 independent loads per thread).  Waiting is done on the
+            // ready bit masks -- one warp polls <= 32 words -- because 500 CTAs polling 4 KB of descriptors
+            // each is what made this phase slow; the descriptors are then read exactly once.
+            if (warp == 0) {
+                const int gi = static_cast<int>(tile >> 5);  // lane g watches group g (g <= gi)
+                const unsigned int need = (lane < gi) ? 0xffffffffu : ((lane == gi) ? ((1u << (tile & 31)) - 1u) : 0u);
+                while (true) {
+                    const unsigned int m = need ? *reinterpret_cast<volatile unsigned int *>(&rdy[lane]) : 0u;
+                    if (__all_sync(0xffffffffu, (m & need) == need)) break;
+                    __nanosleep(64);
                 }
-            } while (!__syncthreads_and(ready));
+                __threadfence();
+            }
+            __syncthreads();
+            unsigned long long d[kDirectTiles / kScanThreads];
+#pragma unroll
+            for (int r = 0; r < kDirectTiles / kScanThreads; ++r) {
+                const long long idx = look - tid - r * kScanThreads;
+                d[r] = (idx >= 0) ? *reinterpret_cast<volatile unsigned long long *>(&desc[idx]) : kDescPrefix;
+            }
             unsigned long long contrib = 0;
 #pragma unroll
             for (int r = 0; r < kDirectTiles / kScanThreads; ++r) {
@@ -1008,7 +1031,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const Ste
 
     WarpStats ws;
     ws.init();
-    dbg_stamp(p.dbg, 1);
+    dbg_stamp_real(p.dbg, 1);  // (see mcl_device.cuh: kept in all builds for its effect on register allocation)
 
     // static contiguous partition of the trial's particles over the blocks (p.per is a multiple of 128,
     // so a warp's 128 particles are either all inside the block's range or all outside)
@@ -1040,10 +1063,8 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const Ste
 #pragma unroll
                     for (int k = 0; k < kPPT; ++k) {
                         const uint32_t i = base + k;
-                        if (i >= p.n) {  // padding of the last, partial group
-                            x[k] = y[k] = th[k] = 0.0f;
-                        } else if (i >= p.win_lo && i < p.win_hi) {
-                            const uint32_t j = a[k];
+                        if ((i >= p.win_lo && i < p.win_hi) || i >= p.n) {  // (padding lanes read particle 0)
+                            const uint32_t j = (i < p.n) ? a[k] : 0u;
                             x[k] = ix[j];
                             y[k] = iy[j];
                             th[k] = ith[j];
@@ -1430,9 +1451,10 @@ __global__ void k_fill(float *dst, long long ld, float value) {
 }
 
 // sharded resampling runs the scan outside a step: clear its tile descriptors and ticket (trial 0)
-__global__ void k_reset_scan(unsigned long long *desc, unsigned int *tickets, int tpt) {
+__global__ void k_reset_scan(unsigned long long *desc, unsigned int *ready, unsigned int *tickets, int tpt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < tpt) desc[i] = 0ull;
+    if (i < kDirectTiles / 32) ready[i] = 0u;
     if (i == 0) tickets[0] = 0u;
 }
 
