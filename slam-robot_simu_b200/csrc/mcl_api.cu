@@ -936,12 +936,12 @@ int mcl_shard_total(mcl_filter *h, uint64_t *total_dev, void *stream) {
     cudaStream_t st = S(stream);
     rc = ensure_stats(h, st);
     if (rc != MCL_OK) return rc;
-    ScanParams sp;
-    fill_scan(h, sp);
-    sp.total = reinterpret_cast<unsigned long long *>(total_dev);
-    sp.use_override = 1;
-    sp.ofs_override = 0.0;
-    return launch_shard_scan(h, sp, kScanTotals, st);
+    MCL_CUDA(h, cudaMemsetAsync(total_dev, 0, sizeof(uint64_t), st));
+    const int blocks = static_cast<int>(std::min<long long>((h->lay.n / 4 + 255) / 256 + 1, static_cast<long long>(h->sm_count) * 8));
+    k_shard_total<<<blocks, 256, 0, st>>>(h->state[h->cur].lw, h->lay.n, h->stats,
+                                            reinterpret_cast<unsigned long long *>(total_dev));
+    MCL_LAUNCH_CHECK(h, "k_shard_total");
+    return MCL_OK;
 }
 
 int mcl_shard_expand(mcl_filter *h, uint64_t k_offset, double ofs, float *send_x_dev, float *send_y_dev,

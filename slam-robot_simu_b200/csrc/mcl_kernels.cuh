@@ -1458,6 +1458,27 @@ __global__ void k_reset_scan(unsigned long long *desc, unsigned int *ready, unsi
     if (i == 0) tickets[0] = 0u;
 }
 
+// Sum of a shard's quantised weights under the (global) weight map of stats[0]: a plain streaming reduction.
+// Integer adds are exact and order-independent, so one 64-bit atomicAdd per warp is deterministic.
+__global__ void __launch_bounds__(256) k_shard_total(const float *lw, long long n, const mcl_stats *stats,
+                                                     unsigned long long *total) {
+    __shared__ WeightMap s_wm;
+    if (threadIdx.x == 0) s_wm = make_weight_map(stats[0].max_logw, stats[0].sum_w);
+    __syncthreads();
+    const WeightMap wm = s_wm;
+    unsigned long long acc = 0ull;
+    const long long n4 = n >> 2;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4 *>(lw)[i];
+        acc += quantize_weight(v.x, wm) + quantize_weight(v.y, wm) + quantize_weight(v.z, wm) + quantize_weight(v.w, wm);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) acc += quantize_weight(lw[(n4 << 2) + threadIdx.x], wm);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc != 0ull) atomicAdd(total, acc);
+}
+
 // normalised weights w = q 2^-52 (fp64) and the integers q the resampler scans
 __global__ void k_export_weights(const float *lw, const mcl_stats *stats, double *w, unsigned long long *q, long long n,
                                  long long ld) {
