@@ -848,15 +848,28 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     const long long k_last64 = p.n_global - 1 - p.j_global_base - j0;
     const int k_last = (k_last64 >= 0 && k_last64 < kScanItems) ? static_cast<int>(k_last64) : -1;
     const int n_valid = static_cast<int>(min(static_cast<long long>(kScanItems), max(0ll, p.n - j0)));
+    if (n_valid == kScanItems && k_last < 0) {  // all eight sources real, none is the filter's last: no per-item checks
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        rel[k] = static_cast<uint32_t>(static_cast<int>(cur - first_slot));
-        Kd += qd[k];
-        double end = count_le_fast(Kd, cf, p.delta, ofs);
-        if (k == k_last) end = nd;
-        if (k < n_valid && end > cur) {
-            owners |= 1u << k;
-            cur = end;
+        for (int k = 0; k < kScanItems; ++k) {
+            rel[k] = static_cast<uint32_t>(static_cast<int>(cur - first_slot));
+            Kd += qd[k];
+            const double end = count_le_fast(Kd, cf, p.delta, ofs);
+            if (end > cur) {
+                owners |= 1u << k;
+                cur = end;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            rel[k] = static_cast<uint32_t>(static_cast<int>(cur - first_slot));
+            Kd += qd[k];
+            double end = count_le_fast(Kd, cf, p.delta, ofs);
+            if (k == k_last) end = nd;
+            if (k < n_valid && end > cur) {
+                owners |= 1u << k;
+                cur = end;
+            }
         }
     }
     // tile slot range [S0, S1): S0 from the first thread, S1 from the last thread holding sources
