@@ -174,6 +174,8 @@ int mcl_get_stats(mcl_filter *h, mcl_stats *out_host, void *stream);
 /* Device address of the [n_trials] mcl_stats block (for callers that poll asynchronously).  On the device
  * only the sums, ess, max_idx and est are current (see `derived`). */
 int mcl_stats_dev(mcl_filter *h, const mcl_stats **out_dev);
+/* Enqueue, on `stream`, whatever merge is still pending so that the device block above is current. */
+int mcl_sync_stats(mcl_filter *h, void *stream);
 /* Normalised weights exp(logw - log_norm) as fp64 [n_trials][n_particles] (pw of :194-196). */
 int mcl_get_weights(mcl_filter *h, double *w_host, void *stream);
 /* The integers the resampler scans: rint(w * 2^52) as uint64 [n_trials][n_particles]. */

@@ -830,6 +830,13 @@ int mcl_stats_dev(mcl_filter *h, const mcl_stats **out_dev) {
     return MCL_OK;
 }
 
+int mcl_sync_stats(mcl_filter *h, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    return ensure_stats(h, S(stream));
+}
+
 static int export_weights(mcl_filter *h, double *w_host, uint64_t *q_host, void *stream) {
     int rc = use_device(h);
     if (rc != MCL_OK) return rc;

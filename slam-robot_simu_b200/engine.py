@@ -210,6 +210,15 @@ class Filter:
         self._check(self.lib.mcl_get_stats(self._h, arr, self._stream()), "mcl_get_stats")
         return list(arr)
 
+    def stats_dev_bytes(self):
+        """The [n_trials] mcl_stats block in device memory as a uint8 CUDA tensor (a view of the workspace).
+        Sums, ESS, MAP index and pose are current; log_norm / mean / cov are derived on the host by stats()."""
+        self._check(self.lib.mcl_sync_stats(self._h, self._stream()), "mcl_sync_stats")
+        ptr = C.c_void_p()
+        self._check(self.lib.mcl_stats_dev(self._h, C.byref(ptr)), "mcl_stats_dev")
+        off = ptr.value - self.workspace.data_ptr()
+        return self.workspace[off:off + self.T * C.sizeof(L.mcl_stats)]
+
     def weights(self):
         w = np.empty((self.T, self.n), dtype=np.float64)
         self._check(self.lib.mcl_get_weights(self._h, w.ctypes.data, self._stream()), "mcl_get_weights")

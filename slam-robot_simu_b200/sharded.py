@@ -246,6 +246,9 @@ class ShardedParticleFilter:
         self.cap = min(self.n_global, int(self.m * expand_factor) + 1024)
         self._alloc_expand()
         self.total_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self._totals_buf = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
+        self._gather_buf = None
+        self._stats_dtype = np.dtype(L.mcl_stats)
         self.step_count = 0
         self.global_stats = None
         self.last_ranges = None
@@ -286,21 +289,20 @@ class ShardedParticleFilter:
         self.flt.shard_set_global(s)
 
     def _merge(self):
-        import ctypes as C
-
+        """Allgather the shards' mcl_stats straight from device memory (the fields merge_stats reads -- sums,
+        maxima, MAP index and pose, reference pose -- are all written by the kernels) and merge on the host:
+        one collective and one device-to-host copy per step."""
         t = self.torch
-        st = self.flt.stats()[0]
-        buf = t.frombuffer(bytearray(bytes(st)), dtype=t.uint8).to(self.dev)
-        gathered = [t.empty_like(buf) for _ in range(self.world)]
-        self.dist.all_gather(gathered, buf, group=self.group)
+        mine = self.flt.stats_dev_bytes()  # uint8 view of this shard's record (runs the pending merge kernel)
+        if self._gather_buf is None:
+            self._gather_buf = t.empty(self.world * mine.numel(), dtype=t.uint8, device=self.dev)
+        self.dist.all_gather_into_tensor(self._gather_buf, mine, group=self.group)
+        rec = np.frombuffer(self._gather_buf.cpu().numpy().tobytes(), dtype=self._stats_dtype)
         recs = []
-        for g in gathered:
-            s = self._L.mcl_stats.from_buffer_copy(bytes(g.cpu().numpy()))
-            d = self._stats_to_dict(s)
-            # the stored log-weight of the shard's best particle IS its max_logw
-            d["best_logw"] = d["max_logw"]
-            recs.append(d)
-        assert C.sizeof(self._L.mcl_stats) == buf.numel()
+        for r in rec:
+            recs.append(dict(max_logw=float(r["max_logw"]), best_logw=float(r["max_logw"]), sum_w=float(r["sum_w"]),
+                             sum_w2=float(r["sum_w2"]), raw=np.array(r["raw"], dtype=np.float64), ref=np.array(r["ref"]),
+                             max_idx=int(r["max_idx"]), est=np.array(r["est"])))
         merged = merge_stats(recs, self.slot_bases)
         self.global_stats = merged
         self._install(merged)
@@ -323,9 +325,8 @@ class ShardedParticleFilter:
         off-rank slots are exchanged as poses.  Returns (recv arrays, n_prefix, n_suffix, ranges)."""
         t = self.torch
         self.flt.shard_total(self.total_dev)
-        totals = [t.empty_like(self.total_dev) for _ in range(self.world)]
-        self.dist.all_gather(totals, self.total_dev, group=self.group)
-        totals = [int(v) for v in t.cat(totals).tolist()]
+        self.dist.all_gather_into_tensor(self._totals_buf, self.total_dev, group=self.group)
+        totals = [int(v) for v in self._totals_buf.tolist()]
         ranges = shard_ranges(totals, self.n_global, ofs)
         send, _, _, _ = plan_offrank(ranges, self.n_global, self.world, self.rank)
         if sum(send) > self.cap:
