@@ -250,6 +250,18 @@ __device__ __forceinline__ CombFast make_comb_fast(double ofs, double nd) {
     f.nd = nd;
     return f;
 }
+// The fast count in integer registers: t = fma(K, a1, a0 + 1.5 2^36) is a rounded to the 2^-16 grid with the
+// integer round(a 2^16) in its mantissa, so floor(a) and the distance to the nearest integer are bit fields --
+// no floor, no fp64 compares, no conversion.  a0 + 1.5 2^36 is rounded once more (<= 2^-17), which puts the
+// total error at 1.04 grid steps: fractions within 2 steps of an integer are reported through `ok` (it becomes
+// 0) and the caller redoes those counts with count_le_fast.  a > -1, and a in (-1, 0) yields 0 (mod 2^32).
+constexpr double kCombMagic = 103079215104.0;  // 1.5 * 2^36
+__device__ __forceinline__ uint32_t count_le_bits(double Kd, double a1, double a0m, uint32_t &ok) {
+    const double t = fma(Kd, a1, a0m);
+    const uint32_t lo = static_cast<uint32_t>(__double2loint(t)), hi = static_cast<uint32_t>(__double2hiint(t));
+    ok = min(ok, (lo + 2u) & 0xfffcu);
+    return __funnelshift_r(lo, hi, 16) + 1u;
+}
 __device__ __forceinline__ double count_le_fast(double Kd, const CombFast &f, double delta, double ofs) {
     const double a = fma(Kd, f.a1, f.a0);
     const double g = floor(a);

@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     __shared__ ScanShared s_sc;
     __shared__ unsigned long long s_warp[NW];
     __shared__ int s_first[NW];
-    __shared__ double s_slot[2];
+    __shared__ uint32_t s_slot[2];
     __shared__ __align__(16) uint32_t s_mark[kScanTile];  // also the reduction scratch of prep_block
     __shared__ uint32_t s_wmax[NW];
 
@@ -705,8 +705,13 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
         const float4 a = *reinterpret_cast<const float4 *>(lw + j0);
         const float4 b = *reinterpret_cast<const float4 *>(lw + j0 + 4);
         const float v[kScanItems] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (j0 + kScanItems <= p.n) {
 #pragma unroll
-        for (int k = 0; k < kScanItems; ++k) qd[k] = (j0 + k < p.n) ? quantize_weight_d(v[k], wm) : 0.0;
+            for (int k = 0; k < kScanItems; ++k) qd[k] = quantize_weight_d(v[k], wm);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kScanItems; ++k) qd[k] = (j0 + k < p.n) ? quantize_weight_d(v[k], wm) : 0.0;
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) qd[k] = 0.0;
@@ -835,42 +840,54 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
         continue;
     }
 
-    // ---- slot range of every source ----
+    // ---- slot range of every source: u32 counts, non-owners carry rel = 2^31 (never inside a window) ----
     const double nd = static_cast<double>(p.n_global);
     const CombFast cf = make_comb_fast(ofs, nd);
-    double Kd = static_cast<double>(p.k_offset + excl + thread_excl);
-    const double first_slot = count_le_fast(Kd, cf, p.delta, ofs);
-    double cur = first_slot;
+    const double Kd0 = static_cast<double>(p.k_offset + excl + thread_excl);
     uint32_t rel[kScanItems];  // first slot of source k relative to the thread's first slot
-    uint32_t owners = 0;       // bit k: source k owns at least one slot
-    // the last particle of the whole filter also takes every slot past the final cumulative weight
-    // (the reference would raise IndexError there)
-    const long long k_last64 = p.n_global - 1 - p.j_global_base - j0;
-    const int k_last = (k_last64 >= 0 && k_last64 < kScanItems) ? static_cast<int>(k_last64) : -1;
-    const int n_valid = static_cast<int>(min(static_cast<long long>(kScanItems), max(0ll, p.n - j0)));
-    if (n_valid == kScanItems && k_last < 0) {  // all eight sources real, none is the filter's last: no per-item checks
+    uint32_t first_slot, cur;
+    // tiles that are full and do not hold the filter's last particle need no per-item checks (CTA-uniform)
+    const bool plain_tile = (tile + 1) * kScanTile <= p.n && (tile + 1) * kScanTile < p.n_global - p.j_global_base;
+    bool exact = !plain_tile;
+    if (plain_tile) {
+        const double a0m = cf.a0 + kCombMagic;
+        uint32_t ok = 0xffffffffu;
+        double Kd = Kd0;
+        first_slot = count_le_bits(Kd, cf.a1, a0m, ok);
+        cur = first_slot;
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) {
-            rel[k] = static_cast<uint32_t>(static_cast<int>(cur - first_slot));
             Kd += qd[k];
-            const double end = count_le_fast(Kd, cf, p.delta, ofs);
-            if (end > cur) {
-                owners |= 1u << k;
-                cur = end;
-            }
+            const uint32_t end = count_le_bits(Kd, cf.a1, a0m, ok);
+            rel[k] = (end != cur) ? cur - first_slot : 0x80000000u;
+            cur = end;
         }
-    } else {
+        // a count too close to a tooth, or past the end of the comb: this thread redoes its sources exactly
+        exact = (ok == 0u) || cur > static_cast<uint32_t>(p.n_global);
+    }
+    if (exact) {
+        // the last particle of the whole filter also takes every slot past the final cumulative weight
+        // (the reference would raise IndexError there)
+        const long long k_last64 = p.n_global - 1 - p.j_global_base - j0;
+        const int k_last = (k_last64 >= 0 && k_last64 < kScanItems) ? static_cast<int>(k_last64) : -1;
+        const int n_valid = static_cast<int>(min(static_cast<long long>(kScanItems), max(0ll, p.n - j0)));
+        double Kd = Kd0;
+        const double fs = count_le_fast(Kd, cf, p.delta, ofs);
+        double c = fs;
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) {
-            rel[k] = static_cast<uint32_t>(static_cast<int>(cur - first_slot));
             Kd += qd[k];
             double end = count_le_fast(Kd, cf, p.delta, ofs);
             if (k == k_last) end = nd;
-            if (k < n_valid && end > cur) {
-                owners |= 1u << k;
-                cur = end;
+            if (k < n_valid && end > c) {
+                rel[k] = static_cast<uint32_t>(static_cast<long long>(c - fs));
+                c = end;
+            } else {
+                rel[k] = 0x80000000u;
             }
         }
+        first_slot = static_cast<uint32_t>(static_cast<long long>(fs));
+        cur = static_cast<uint32_t>(static_cast<long long>(c));
     }
     // tile slot range [S0, S1): S0 from the first thread, S1 from the last thread holding sources
     const long long n_in_tile = min(static_cast<long long>(kScanTile), p.n - tile * kScanTile);
@@ -878,26 +895,28 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     if (tid == 0) s_slot[0] = first_slot;
     if (tid == last_tid) s_slot[1] = cur;
     __syncthreads();
-    const double S0d = s_slot[0];
-    const long long S0 = static_cast<long long>(S0d), span = static_cast<long long>(s_slot[1] - S0d);
-    const uint32_t my_off = static_cast<uint32_t>(static_cast<long long>(first_slot - S0d));  // threads with sources: >= 0
+    const uint32_t S0 = s_slot[0], S1 = s_slot[1];
+    // the ancestor array is written with 32-byte stores: the windows start at a multiple of 8 slots
+    const uint32_t W0 = (MODE == kScanAncestors) ? (S0 & ~7u) : S0;
+    const uint32_t span = (S1 > S0) ? S1 - W0 : 0u;
+    const uint32_t my_off = first_slot - W0;  // threads with sources: >= 0
 
     dbg_stamp(p.dbg, 4);
     uint32_t *anc = p.anc + static_cast<long long>(t) * p.ld;
     uint32_t carry = 0;  // source (local index + 1) that owns the slot just before the window
-    for (long long cb = 0; cb < span; cb += kScanTile) {
-        // window of kScanTile slots starting at S0 + cb
+    for (uint32_t cb = 0; cb < span; cb += kScanTile) {
+        // window of kScanTile slots starting at W0 + cb
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) s_mark[k * kScanThreads + tid] = 0u;
         __syncthreads();
-        if (owners) {
+        if (cur != first_slot) {
             // slot positions relative to the window, modulo 2^32 (n_global < 2^31: no aliasing)
-            const uint32_t wofs = my_off - static_cast<uint32_t>(cb);
+            const uint32_t wofs = my_off - cb;
+            const uint32_t id0 = static_cast<uint32_t>(tid * kScanItems + 1);
 #pragma unroll
             for (int k = 0; k < kScanItems; ++k) {
                 const uint32_t pos = wofs + rel[k];
-                if (((owners >> k) & 1u) && pos < static_cast<uint32_t>(kScanTile))
-                    s_mark[pos] = static_cast<uint32_t>(tid * kScanItems + k + 1);
+                if (pos < static_cast<uint32_t>(kScanTile)) s_mark[pos] = id0 + k;
             }
         }
         __syncthreads();
@@ -929,22 +948,37 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
             wall = max(wall, m);
         }
         before = max(before, wbefore);
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k) v[k] = max(v[k], before);
-        *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(v[4], v[5], v[6], v[7]);
         carry = wall;
-        __syncthreads();
-        // coalesced stores
-        const int lim = static_cast<int>(min(static_cast<long long>(kScanTile), span - cb));
         const uint32_t jbase = static_cast<uint32_t>(tile * kScanTile) - 1u;
+        if (MODE == kScanAncestors) {
+            // unsharded: slots are local indices, anc holds ld >= n of them; stores go straight from registers
 #pragma unroll
-        for (int k = 0; k < kScanItems; ++k) {
-            const int pos = k * kScanThreads + tid;
-            if (pos < lim) {
-                const long long slot = S0 + cb + pos;
-                const uint32_t j = jbase + s_mark[pos];
-                if (MODE == kScanExpand) {
+            for (int k = 0; k < kScanItems; ++k) v[k] = jbase + max(v[k], before);
+            const uint32_t slot0 = W0 + cb + static_cast<uint32_t>(tid * kScanItems);
+            if (slot0 >= S0 && slot0 + kScanItems <= S1) {
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(anc + slot0), "r"(v[0]), "r"(v[1]),
+                             "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                             : "memory");
+            } else {
+#pragma unroll
+                for (int k = 0; k < kScanItems; ++k)
+                    if (slot0 + k >= S0 && slot0 + k < S1) anc[slot0 + k] = v[k];
+            }
+            // no barrier here: the next window's zeroing of s_mark follows every thread's reads above
+        } else {
+#pragma unroll
+            for (int k = 0; k < kScanItems; ++k) v[k] = max(v[k], before);
+            *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(v[4], v[5], v[6], v[7]);
+            __syncthreads();
+            // coalesced stores
+            const int lim = static_cast<int>(min(static_cast<uint32_t>(kScanTile), span - cb));
+#pragma unroll
+            for (int k = 0; k < kScanItems; ++k) {
+                const int pos = k * kScanThreads + tid;
+                if (pos < lim) {
+                    const long long slot = static_cast<long long>(S0) + cb + pos;
+                    const uint32_t j = jbase + s_mark[pos];
                     if (slot >= p.own_lo && slot < p.own_hi) {
                         anc[slot - p.own_lo] = j;
                     } else {
@@ -955,12 +989,10 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
                             p.oth[o] = p.src.th[j];
                         }
                     }
-                } else {
-                    anc[slot] = j;  // unsharded: slots are local indices, anc holds ld >= n of them
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
     __syncthreads();  // s_next (written at the top of this iteration) and the scratch are settled
     }  // tiles
