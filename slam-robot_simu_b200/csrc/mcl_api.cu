@@ -368,6 +368,7 @@ int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool redu
     p.motion = c.motion;
     p.step = h->step;
     p.seed = c.seed;
+    p.rk = philox_round_keys(c.seed);
     p.vdt_f = static_cast<float>(c.vel * c.dt);
     p.wdt_f = static_cast<float>(c.yaw_rate * c.dt);
     p.wdt = c.yaw_rate * c.dt;

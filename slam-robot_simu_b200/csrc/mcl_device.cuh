@@ -159,6 +159,34 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
+// The same with the ten round keys precomputed (host side, philox_round_keys): in a kernel they are operands
+// from the parameter bank instead of 18 additions per call.
+struct PhiloxKeys {
+    uint32_t x[10], y[10];
+};
+__host__ __device__ inline PhiloxKeys philox_round_keys(unsigned long long seed) {
+    PhiloxKeys rk;
+    uint32_t kx = static_cast<uint32_t>(seed), ky = static_cast<uint32_t>(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        rk.x[r] = kx;
+        rk.y[r] = ky;
+        kx += 0x9E3779B9u;
+        ky += 0xBB67AE85u;
+    }
+    return rk;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys &rk) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = static_cast<unsigned long long>(0xD2511F53u) * c.x;
+        const unsigned long long p1 = static_cast<unsigned long long>(0xCD9E8D57u) * c.z;
+        const uint32_t hi0 = static_cast<uint32_t>(p0 >> 32), lo0 = static_cast<uint32_t>(p0);
+        const uint32_t hi1 = static_cast<uint32_t>(p1 >> 32), lo1 = static_cast<uint32_t>(p1);
+        c = make_uint4(hi1 ^ c.y ^ rk.x[r], lo1, hi0 ^ c.w ^ rk.y[r], lo0);
+    }
+    return c;
+}
+
 // Two standard normals from two 32-bit words: Box-Muller in fp32 on the MUFU pipe.  The top 23 bits
 // of each word become a float in [1,2) without touching the conversion unit; |n| <= 5.65.
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {

@@ -601,10 +601,13 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
         return;
     }
     const mcl_stats *stp = p.stats + t;
-    // Tiles take their ticket first.  When the statistics still live in the CTA partials, the tile with ticket
-    // 0 (the first to arrive, so certainly running) merges (max, sum, sum^2) and publishes what every tile
-    // needs -- weight map, resample gate, comb offset -- as two aligned 16-byte words tagged with this launch's
-    // epoch; the others poll them (one round trip, issued together with the ticket) -- 500 CTAs each reading
+    // One tile per CTA (single filters): tiles are numbered by blockIdx.x.  CTAs are dispatched in that order, so a
+    // tile's predecessors are always running (the assumption of every single-pass scan) and no ticket round trip
+    // precedes the first load.  Persistent CTAs (trial batches) take tickets.
+    const bool ordered = !p.persistent;
+    // When the statistics still live in the CTA partials, tile 0 (certainly running) merges (max, sum, sum^2)
+    // and publishes what every tile needs -- weight map, resample gate, comb offset -- as two aligned 16-byte
+    // words tagged with this launch's epoch; the others poll them (one round trip) -- 500 CTAs each reading
     // all partials would hammer the same few L2 lines.
     uint4 *pub = p.wm_pub + 2 * t;  // word A {m, scale, gate, epoch}, word B {ofs lo, ofs hi, epoch, 0}
     if (tid == 0) {
@@ -614,7 +617,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
             asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(pub));
             asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(pub + 1));
         }
-        const unsigned int tk = prep_cta ? 0xffffffffu : atomicAdd(&p.tickets[t * 4 + 0], 1u);
+        const unsigned int tk = prep_cta ? 0xffffffffu : (ordered ? blockIdx.x : atomicAdd(&p.tickets[t * 4 + 0], 1u));
         s_sc.tile = tk;
         if (may_poll && tk != 0u) {
             while (a.w != p.epoch || b.z != p.epoch) {
@@ -715,6 +718,11 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     } else {
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) qd[k] = 0.0;
+    }
+    // the first mark window is cleared here, off the critical path: the barriers of the block scan order it
+    if (MODE != kScanTotals) {
+        *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(0u, 0u, 0u, 0u);  // the thread's own 32 bytes
+        *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(0u, 0u, 0u, 0u);
     }
     double tsum_d = 0.0;  // sums of integers below 2^53 are exact in fp64
 #pragma unroll
@@ -906,9 +914,11 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     uint32_t carry = 0;  // source (local index + 1) that owns the slot just before the window
     for (uint32_t cb = 0; cb < span; cb += kScanTile) {
         // window of kScanTile slots starting at W0 + cb
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k) s_mark[k * kScanThreads + tid] = 0u;
-        __syncthreads();
+        if (cb > 0u) {  // (the first window was cleared before the block scan)
+            *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(0u, 0u, 0u, 0u);
+            __syncthreads();
+        }
         if (cur != first_slot) {
             // slot positions relative to the window, modulo 2^32 (n_global < 2^31: no aliasing)
             const uint32_t wofs = my_off - cb;
@@ -1025,6 +1035,7 @@ struct StepParams {
     int motion;
     uint32_t step;
     uint64_t seed;
+    PhiloxKeys rk;         // round keys of seed (Philox noise)
     float vdt_f, wdt_f;    // VEL*dt, YAW_RATE*dt
     double wdt;
     double vel, yaw_rate, dt;
@@ -1034,7 +1045,7 @@ struct StepParams {
 };
 
 template <int LIK, bool PHILOX>
-__global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const StepParams p) {
+__global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __grid_constant__ StepParams p) {
     const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double4 *s_tab = reinterpret_cast<double4 *>(smem_raw);  // [L] (pair / RB only)
@@ -1069,7 +1080,6 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const Ste
     const float *ix = p.in.x + off, *iy = p.in.y + off, *ith = p.in.th + off, *ilw = p.in.lw + off;
     float *ox = p.out.x + off, *oy = p.out.y + off, *oth = p.out.th + off, *olw = p.out.lw + off;
     const uint32_t *anc = p.anc + off;
-    const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
 
     // injected noise is the final draw v of particle_filter.py:165; Philox normals are unit and get sqrt(diag Q)
     const float nscale[3] = {PHILOX ? p.q_std[0] : 1.0f, PHILOX ? p.q_std[1] : 1.0f, PHILOX ? p.q_std[2] : 1.0f};
@@ -1148,9 +1158,9 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const Ste
                 // 2 Philox calls = 256 bits = twelve 21-bit uniforms = the 12 normals of this thread's 4 particles
                 const unsigned long long grp = static_cast<unsigned long long>(p.slot_base + base) >> 2;
                 const uint4 r0 = philox4x32_10(make_uint4(static_cast<uint32_t>(grp), static_cast<uint32_t>(grp >> 32) * 2u,
-                                                          p.step, static_cast<uint32_t>(t)), key);
+                                                          p.step, static_cast<uint32_t>(t)), p.rk);
                 const uint4 r1 = philox4x32_10(make_uint4(static_cast<uint32_t>(grp), static_cast<uint32_t>(grp >> 32) * 2u + 1u,
-                                                          p.step, static_cast<uint32_t>(t)), key);
+                                                          p.step, static_cast<uint32_t>(t)), p.rk);
                 const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
                 float nrm[12];
 #pragma unroll
