@@ -200,12 +200,17 @@ int mcl_debug_timeline(mcl_filter *h, uint64_t *stamps_host, int64_t capacity, i
 
 /* ---- particle-sharded single filter (n_trials == 1, one handle per GPU) -----------------------
  * The host exchanges the small records; see slam-robot_simu_b200/sharded.py.  Order per step:
- *   mcl_predict_weight on every shard -> allgather + merge of mcl_stats -> mcl_shard_set_global;
+ *   mcl_predict_weight on every shard -> allgather of mcl_stats -> mcl_shard_merge (or a host merge +
+ *   mcl_shard_set_global);
  *   when resampling: mcl_shard_total -> allgather of the totals -> mcl_shard_expand -> all-to-all
  *   of the off-rank poses -> mcl_shard_step (instead of mcl_predict_weight).
  * mcl_shard_set_global: install the merged statistics (global max_logw / sum_w define the weight
  * map, est the reference pose, ess the resampling gate). */
 int mcl_shard_set_global(mcl_filter *h, const mcl_stats *merged_host, void *stream);
+/* mcl_shard_merge: the same without the host -- records_dev holds the n_shards mcl_stats blocks (device memory,
+ * as allgathered from mcl_stats_dev after mcl_sync_stats; shard g owns particles [g n_particles, (g+1) n_particles));
+ * one small kernel merges them into this handle's statistics (device twin of sharded.merge_stats).  Asynchronous. */
+int mcl_shard_merge(mcl_filter *h, const mcl_stats *records_dev, int n_shards, void *stream);
 /* mcl_shard_total: sum of this shard's quantised weights under the global weight map -> *total_dev. */
 int mcl_shard_total(mcl_filter *h, uint64_t *total_dev, void *stream);
 /* mcl_shard_expand: with k_offset = sum of the totals of lower ranks, resample this shard's particles

@@ -117,6 +117,7 @@ PROTOTYPES = {
                                    _P(C.c_int64), _P(C.c_int64), _vp]),
     "mcl_shard_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_uint32, _vp]),
     "mcl_shard_set_global": (C.c_int, [_vp, _P(mcl_stats), _vp]),
+    "mcl_shard_merge": (C.c_int, [_vp, _vp, C.c_int, _vp]),
 }
 
 _lib = None

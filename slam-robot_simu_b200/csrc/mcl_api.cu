@@ -1030,6 +1030,26 @@ int mcl_shard_step(mcl_filter *h, const double *z_host, const float *noise_dev, 
     return MCL_OK;
 }
 
+int mcl_shard_merge(mcl_filter *h, const mcl_stats *records_dev, int n_shards, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (records_dev == nullptr || n_shards < 1) return fail(h, MCL_ERR_ARG, "records_dev is NULL or n_shards < 1");
+    if (h->lay.T != 1) return fail(h, MCL_ERR_STATE, "sharding needs n_trials == 1");
+    if (static_cast<long long>(n_shards) * h->cfg.n_particles != h->cfg.n_global)
+        return fail(h, MCL_ERR_ARG, "n_shards * n_particles != n_global (shards must be equal)");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    ShardMergeParams mp{};
+    mp.rec = records_dev;
+    mp.G = n_shards;
+    mp.m = h->cfg.n_particles;
+    mp.out = h->stats;
+    k_shard_merge<<<1, 32, 0, S(stream)>>>(mp);
+    MCL_LAUNCH_CHECK(h, "k_shard_merge");
+    h->stats_from_particle0 = false;
+    h->stats_dirty = false;
+    return MCL_OK;
+}
+
 int mcl_shard_set_global(mcl_filter *h, const mcl_stats *merged_host, void *stream) {
     if (h == nullptr) return MCL_ERR_ARG;
     if (merged_host == nullptr) return fail(h, MCL_ERR_ARG, "merged_host is NULL");

@@ -1515,6 +1515,67 @@ __global__ void k_reset_scan(unsigned long long *desc, unsigned int *ready, unsi
 
 // Sum of a shard's quantised weights under the (global) weight map of stats[0]: a plain streaming reduction.
 // Integer adds are exact and order-independent, so one 64-bit atomicAdd per warp is deterministic.
+// Sharded filter: merge the shards' mcl_stats records (allgathered, device memory) into the global statistics.
+// Device twin of sharded.merge_stats: shards share the reference pose of the moment sums (it derives from the
+// previous GLOBAL estimate), so their un-normalised sums add after rescaling to the global maximum; a shard
+// that used another reference (right after mcl_set_particles) is re-centred.  One thread: G is the GPU count.
+struct ShardMergeParams {
+    const mcl_stats *rec;  // [G]
+    int G;
+    long long m;           // particles per shard: global index of shard g's particle i is g * m + i
+    mcl_stats *out;        // this handle's statistics block (becomes the global one)
+};
+__global__ void k_shard_merge(const ShardMergeParams p) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double M = p.rec[0].max_logw;
+    for (int g = 1; g < p.G; ++g) M = fmax(M, p.rec[g].max_logw);
+    double s1 = 0.0, s2 = 0.0, raw[11];
+    for (int c = 0; c < 11; ++c) raw[c] = 0.0;
+    const double rx = p.rec[0].ref[0], ry = p.rec[0].ref[1], rt = p.rec[0].ref[2];
+    int bg = 0;
+    double bv = p.rec[0].max_logw;
+    for (int g = 0; g < p.G; ++g) {
+        const mcl_stats &r = p.rec[g];
+        const double sc = (r.sum_w > 0.0) ? exp(r.max_logw - M) : 0.0;
+        const double e = r.sum_w * sc;
+        s1 += e;
+        s2 += r.sum_w2 * sc * sc;
+        double a[11];
+        for (int c = 0; c < 11; ++c) a[c] = r.raw[c] * sc;
+        const double dx = r.ref[0] - rx, dy = r.ref[1] - ry, dt = limit_angle_hd(r.ref[2] - rt);
+        if (dx != 0.0 || dy != 0.0 || dt != 0.0) {
+            const double fx = a[0], fy = a[1], ft = a[2];
+            a[5] += 2.0 * dx * fx + dx * dx * e;
+            a[6] += dx * fy + dy * fx + dx * dy * e;
+            a[7] += 2.0 * dy * fy + dy * dy * e;
+            a[8] += dx * ft + dt * fx + dx * dt * e;
+            a[9] += dy * ft + dt * fy + dy * dt * e;
+            a[10] += 2.0 * dt * ft + dt * dt * e;
+            a[0] += dx * e;
+            a[1] += dy * e;
+            a[2] += dt * e;
+        }
+        for (int c = 0; c < 11; ++c) raw[c] += a[c];
+        if (r.max_logw > bv) {  // ties go to the lowest global index (np.argmax, particle_filter.py:116)
+            bv = r.max_logw;
+            bg = g;
+        }
+    }
+    const mcl_stats &b = p.rec[bg];
+    mcl_stats o = p.rec[0];  // ref, resampled, step: identical on every shard
+    o.max_logw = M;
+    o.sum_w = s1;
+    o.sum_w2 = s2;
+    o.ess = s1 * s1 / s2;
+    for (int c = 0; c < 11; ++c) o.raw[c] = raw[c];
+    o.raw[11] = bv;
+    o.max_idx = static_cast<uint32_t>(static_cast<long long>(bg) * p.m + b.max_idx);
+    for (int c = 0; c < 3; ++c) o.est[c] = b.est[c];
+    o.derived = 0;
+    derive_stats(o);
+    *p.out = o;
+}
+
 __global__ void __launch_bounds__(256) k_shard_total(const float *lw, long long n, const mcl_stats *stats,
                                                      unsigned long long *total) {
     __shared__ WeightMap s_wm;

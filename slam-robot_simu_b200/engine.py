@@ -276,6 +276,11 @@ class Filter:
                                             ptr(recv_yaw), int(n_prefix), int(n_suffix), self._flags(noise, False, False),
                                             self._stream()), "mcl_shard_step")
 
+    def shard_merge(self, records, n_shards):
+        """records: CUDA uint8 tensor holding the n_shards allgathered mcl_stats blocks."""
+        self._check(self.lib.mcl_shard_merge(self._h, C.c_void_p(records.data_ptr()), int(n_shards), self._stream()),
+                    "mcl_shard_merge")
+
     def shard_set_global(self, merged: L.mcl_stats):
         self._check(self.lib.mcl_shard_set_global(self._h, C.byref(merged), self._stream()), "mcl_shard_set_global")
 

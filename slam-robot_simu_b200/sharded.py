@@ -198,18 +198,30 @@ def exchange(arrays, first, count, n_global, group=None):
 
 def exchange_offrank(send_arrays, ranges, n_global, group=None):
     """All-to-all of the off-rank slots only.  `send_arrays`: [slots below my range | slots above it] as
-    written by mcl_shard_expand.  Returns (recv_arrays, n_prefix, n_suffix)."""
+    written by mcl_shard_expand.  Returns (recv_arrays, n_prefix, n_suffix).
+
+    All arrays travel in ONE batched group of point-to-point transfers (one NCCL launch), and only between
+    the pairs of ranks that actually exchange slots -- in a running filter those are the neighbours."""
     import torch
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     send, recv, n_prefix, n_suffix = plan_offrank(ranges, n_global, world, rank)
-    n_send, n_recv = sum(send), sum(recv)
-    out = []
-    for a in send_arrays:
-        o = torch.empty(max(n_recv, 1), dtype=a.dtype, device=a.device)
-        dist.all_to_all_single(o[:n_recv], a[:n_send].contiguous(), recv, send, group=group)
-        out.append(o)
+    n_recv = sum(recv)
+    out = [torch.empty(max(n_recv, 1), dtype=a.dtype, device=a.device) for a in send_arrays]
+    ops, so, ro = [], 0, 0
+    for g in range(world):
+        peer = g if group is None else dist.get_global_rank(group, g)
+        for a, o in zip(send_arrays, out):  # the same order on both sides of a pair: matched one by one
+            if send[g]:
+                ops.append(dist.P2POp(dist.isend, a[so:so + send[g]], peer, group))
+            if recv[g]:
+                ops.append(dist.P2POp(dist.irecv, o[ro:ro + recv[g]], peer, group))
+        so += send[g]
+        ro += recv[g]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
     return out, n_prefix, n_suffix
 
 
@@ -248,6 +260,7 @@ class ShardedParticleFilter:
         self.total_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self._totals_buf = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
         self._gather_buf = None
+        self._totals = None
         self._stats_dtype = np.dtype(L.mcl_stats)
         self.step_count = 0
         self.global_stats = None
@@ -273,46 +286,35 @@ class ShardedParticleFilter:
             s.ref[k] = float(est[k])
         return s
 
-    def _install(self, merged):
-        s = self._L.mcl_stats()
-        s.log_norm, s.ess, s.max_weight = merged["log_norm"], merged["ess"], merged["max_weight"]
-        s.max_idx = merged["max_idx"]
-        s.max_logw, s.sum_w, s.sum_w2 = merged["max_logw"], merged["sum_w"], merged["sum_w2"]
-        for k in range(3):
-            s.est[k], s.mean[k], s.ref[k] = merged["est"][k], merged["mean"][k], merged["ref"][k]
-        for k in range(9):
-            s.cov[k] = merged["cov"].reshape(-1)[k]
-        for k in range(12):
-            s.raw[k] = merged["raw"][k]
-        s.derived = 1
-        s.step = self.step_count
-        self.flt.shard_set_global(s)
-
     def _merge(self):
-        """Allgather the shards' mcl_stats straight from device memory (the fields merge_stats reads -- sums,
-        maxima, MAP index and pose, reference pose -- are all written by the kernels) and merge on the host:
-        one collective and one device-to-host copy per step."""
+        """Statistics of the state just written, with no host round trip in between: allgather of the shards'
+        mcl_stats straight from device memory -> merge on the device (mcl_shard_merge, twin of merge_stats) ->
+        this shard's total of the quantised weights under the merged weight map -> allgather of the totals.
+        The totals are what the NEXT step's resampling starts from; computing them here (0.1 ms, wasted only
+        when that step does not resample) leaves one host synchronisation per step -- the read-back below."""
         t = self.torch
         mine = self.flt.stats_dev_bytes()  # uint8 view of this shard's record (runs the pending merge kernel)
         if self._gather_buf is None:
             self._gather_buf = t.empty(self.world * mine.numel(), dtype=t.uint8, device=self.dev)
         self.dist.all_gather_into_tensor(self._gather_buf, mine, group=self.group)
-        rec = np.frombuffer(self._gather_buf.cpu().numpy().tobytes(), dtype=self._stats_dtype)
-        recs = []
-        for r in rec:
-            recs.append(dict(max_logw=float(r["max_logw"]), best_logw=float(r["max_logw"]), sum_w=float(r["sum_w"]),
-                             sum_w2=float(r["sum_w2"]), raw=np.array(r["raw"], dtype=np.float64), ref=np.array(r["ref"]),
-                             max_idx=int(r["max_idx"]), est=np.array(r["est"])))
-        merged = merge_stats(recs, self.slot_bases)
+        self.flt.shard_merge(self._gather_buf, self.world)
+        self._enqueue_totals()
+        merged = self._stats_to_dict(self.flt.stats()[0])  # device-to-host + synchronise
+        self._totals = [int(v) for v in self._totals_buf.tolist()]
         self.global_stats = merged
-        self._install(merged)
         return merged
+
+    def _enqueue_totals(self):
+        self.flt.shard_total(self.total_dev)
+        self.dist.all_gather_into_tensor(self._totals_buf, self.total_dev, group=self.group)
 
     # -- API ------------------------------------------------------------------------------------
     def init_particles(self, pose):
         pose = np.asarray(pose, dtype=np.float64).reshape(3)
         self.flt.init_particles(pose)
         self.flt.shard_set_global(self._uniform_stats(pose))
+        self._enqueue_totals()
+        self._totals = [int(v) for v in self._totals_buf.tolist()]
         self.global_stats = dict(ess=float(self.n_global), est=pose.copy(), log_norm=math.log(self.n_global))
 
     def set_local_particles(self, x, y, yaw, logw=None):
@@ -323,10 +325,7 @@ class ShardedParticleFilter:
     def _expand(self, ofs):
         """Global systematic resampling (particle_filter.py:212-222): local slots keep the ancestor path,
         off-rank slots are exchanged as poses.  Returns (recv arrays, n_prefix, n_suffix, ranges)."""
-        t = self.torch
-        self.flt.shard_total(self.total_dev)
-        self.dist.all_gather_into_tensor(self._totals_buf, self.total_dev, group=self.group)
-        totals = [int(v) for v in self._totals_buf.tolist()]
+        totals = self._totals  # allgathered at the end of the previous step (_merge)
         ranges = shard_ranges(totals, self.n_global, ofs)
         send, _, _, _ = plan_offrank(ranges, self.n_global, self.world, self.rank)
         if sum(send) > self.cap:

@@ -494,6 +494,16 @@ def test_sharded_step_matches_unsharded(mcl, G, kind):
     assert merged["log_norm"] == pytest.approx(s1.log_norm, abs=1e-7)
     np.testing.assert_allclose(merged["mean"], np.array(s1.mean[:]), rtol=1e-6)
     np.testing.assert_allclose(merged["cov"], np.array(s1.cov[:]).reshape(3, 3), rtol=1e-4, atol=1e-9)
+    # the device merge (mcl_shard_merge, what ShardedParticleFilter uses) against its host twin
+    recs_dev = torch.cat([f.stats_dev_bytes().clone() for f in fs])
+    fs[0].shard_merge(recs_dev, G)
+    dm = mcl.stats_to_dict(fs[0].stats()[0])
+    assert dm["max_idx"] == merged["max_idx"]
+    np.testing.assert_allclose(dm["est"], merged["est"], rtol=0, atol=0)
+    for key in ("ess", "log_norm", "sum_w", "sum_w2", "max_logw", "max_weight"):
+        assert dm[key] == pytest.approx(merged[key], rel=1e-12, abs=1e-300), key
+    np.testing.assert_allclose(dm["mean"], merged["mean"], rtol=1e-12)
+    np.testing.assert_allclose(dm["cov"], merged["cov"], rtol=1e-9, atol=1e-15)
     g_stats = mcl.mcl_stats()
     # install the UNSHARDED statistics so the weight map is bit-identical (the merged ones agree to ~1e-9,
     # which very rarely moves the fp32 scale by one ulp)
