@@ -572,6 +572,20 @@ struct ScanShared {
     unsigned int tile;
 };
 
+// kScanExpand: where the resampled particle of one global slot goes (see ScanParams::own_lo)
+__device__ __forceinline__ void expand_store(const ScanParams &p, uint32_t *anc, long long slot, uint32_t j) {
+    if (slot >= p.own_lo && slot < p.own_hi) {
+        anc[slot - p.own_lo] = j;
+    } else {
+        const long long o = (slot < p.own_lo) ? slot - p.slot_first : p.send_hi_off + (slot - p.send_hi_base);
+        if (o >= 0 && o < p.anc_cap) {
+            p.ox[o] = p.src.x[j];
+            p.oy[o] = p.src.y[j];
+            p.oth[o] = p.src.th[j];
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant__ ScanParams p) {
     const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -914,6 +928,35 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     uint32_t carry = 0;  // source (local index + 1) that owns the slot just before the window
     for (uint32_t cb = 0; cb < span; cb += kScanTile) {
         // window of kScanTile slots starting at W0 + cb
+        if (cb > 0u && span > 4u * kScanTile) {
+            // Degenerate weights: one source owns many windows.  A window in which no source starts is a
+            // constant fill with the carried owner -- one barrier and one store per thread instead of a scan.
+            bool starts = false;
+            const uint32_t wofs = my_off - cb;
+#pragma unroll
+            for (int k = 0; k < kScanItems; ++k) starts = starts || (wofs + rel[k] < static_cast<uint32_t>(kScanTile));
+            if (!__syncthreads_or(starts)) {
+                const uint32_t j = static_cast<uint32_t>(tile * kScanTile) - 1u + carry;
+                if (MODE == kScanAncestors) {
+                    const uint32_t slot0 = W0 + cb + static_cast<uint32_t>(tid * kScanItems);
+                    if (slot0 >= S0 && slot0 + kScanItems <= S1) {
+                        asm volatile("st.global.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(anc + slot0), "r"(j) : "memory");
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kScanItems; ++k)
+                            if (slot0 + k >= S0 && slot0 + k < S1) anc[slot0 + k] = j;
+                    }
+                } else {
+                    const int lim = static_cast<int>(min(static_cast<uint32_t>(kScanTile), span - cb));
+#pragma unroll
+                    for (int k = 0; k < kScanItems; ++k) {
+                        const int pos = k * kScanThreads + tid;
+                        if (pos < lim) expand_store(p, anc, static_cast<long long>(S0) + cb + pos, j);
+                    }
+                }
+                continue;
+            }
+        }
         if (cb > 0u) {  // (the first window was cleared before the block scan)
             *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(0u, 0u, 0u, 0u);
             *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(0u, 0u, 0u, 0u);
@@ -987,18 +1030,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
             for (int k = 0; k < kScanItems; ++k) {
                 const int pos = k * kScanThreads + tid;
                 if (pos < lim) {
-                    const long long slot = static_cast<long long>(S0) + cb + pos;
-                    const uint32_t j = jbase + s_mark[pos];
-                    if (slot >= p.own_lo && slot < p.own_hi) {
-                        anc[slot - p.own_lo] = j;
-                    } else {
-                        const long long o = (slot < p.own_lo) ? slot - p.slot_first : p.send_hi_off + (slot - p.send_hi_base);
-                        if (o >= 0 && o < p.anc_cap) {
-                            p.ox[o] = p.src.x[j];
-                            p.oy[o] = p.src.y[j];
-                            p.oth[o] = p.src.th[j];
-                        }
-                    }
+                    expand_store(p, anc, static_cast<long long>(S0) + cb + pos, jbase + s_mark[pos]);
                 }
             }
             __syncthreads();

@@ -99,6 +99,7 @@ class ParticleFilter:
                             vel=self.__VEL_mps, yaw_rate=self.__YAW_RATE_rps, dt=self.__DT_s)
         self.__flt.init_particles(self.__x_true[:, 0])  # :81-84
         self.__ess = float(self.__NP)  # 1 / sum((1/NP)^2)
+        self.__ahead = None
         self.last_stats = None
 
     @staticmethod
@@ -135,7 +136,12 @@ class ParticleFilter:
     def main_pf(self):
         """particle_filter.py:86-119."""
         flt = self.__flt
-        self.__x_true = self.__f(self.__x_true)  # :100
+        if self.__ahead is not None:  # prepared while the GPU ran the previous step (see below)
+            self.__x_true, z_ahead = self.__ahead
+            self.__ahead = None
+        else:
+            self.__x_true = self.__f(self.__x_true)  # :100
+            z_ahead = None
 
         # :104/:210-214 -- the gate is taken on the previous step's weights; the uniform offset is
         # drawn first (and only when resampling) so the np.random stream matches the reference
@@ -147,9 +153,15 @@ class ParticleFilter:
                 ofs = np.random.rand() * self.__NP_RECIP  # :214
             v = self.__mvn(self.__Q_factor, self.__NP).T  # multivariate_normal([0, 0, 0], Q, NP).T (:165)
             noise = np.ascontiguousarray(v, dtype=np.float32)[:, None, :]
-        z_l = self.__observation(self.__x_true)  # :110
+        z_l = z_ahead if z_ahead is not None else self.__observation(self.__x_true)  # :110
 
         flt.step(z_l[None], ofs=ofs, noise=noise, force_resample=do_resample, no_resample=not do_resample)
+        if self.__noise == "philox":
+            # The kernels are in flight: simulate the NEXT frame's ground truth and observation now (:100, :110 of
+            # the next call).  Neither depends on the filter, and with on-device noise the observation draw is the
+            # only consumer of np.random, so the stream is consumed in the same order, one frame early.
+            x_next = self.__f(self.__x_true)
+            self.__ahead = (x_next, self.__observation(x_next))
         st = flt.stats()[0]
         self.last_stats = st
         self.__ess = st.ess

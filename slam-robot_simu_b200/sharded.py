@@ -261,6 +261,7 @@ class ShardedParticleFilter:
         self._totals_buf = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
         self._gather_buf = None
         self._totals = None
+        self._ofs_ahead = None
         self._stats_dtype = np.dtype(L.mcl_stats)
         self.step_count = 0
         self.global_stats = None
@@ -343,13 +344,16 @@ class ShardedParticleFilter:
         z = np.asarray(z, dtype=np.float64).reshape(1, -1, 2)
         if resampled:
             if ofs is None:
-                ofs = philox_ofs(self.seed, self.step_count, self.n_global)
+                ahead = self._ofs_ahead
+                ofs = ahead[1] if ahead is not None and ahead[0] == self.step_count else philox_ofs(self.seed, self.step_count, self.n_global)
             recv, n_prefix, n_suffix = self._expand(ofs)
             self.flt.shard_step(z, recv[0], recv[1], recv[2], n_prefix, n_suffix, noise=noise)
             self._keep = recv
         else:
             self.flt.predict_weight(z, noise=noise)
         self.step_count += 1
+        # host work of the next step that does not need this step's results, done while the GPU is busy
+        self._ofs_ahead = (self.step_count, philox_ofs(self.seed, self.step_count, self.n_global))
         merged = self._merge()
         merged["resampled"] = int(resampled)
         return merged
