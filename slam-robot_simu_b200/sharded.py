@@ -232,7 +232,7 @@ class ShardedParticleFilter:
     """n_global particles, contiguous shards of n_global / world_size per rank."""
 
     def __init__(self, n_global, landmarks, period_ms=100.0, likelihood="moment", seed=42, group=None, device=None,
-                 ess_div=100.0, expand_factor=0.125, **cfg):
+                 ess_div=100.0, expand_factor=0.125, speculate=True, **cfg):
         import torch
         import torch.distributed as dist
 
@@ -259,6 +259,10 @@ class ShardedParticleFilter:
         self._alloc_expand()
         self.total_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self._totals_buf = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
+        self._totals_host = torch.zeros(self.world, dtype=torch.int64, pin_memory=True)
+        self.speculate = bool(speculate)
+        self._spec = None
+        self._force_last = False
         self._gather_buf = None
         self._totals = None
         self._ofs_ahead = None
@@ -300,14 +304,22 @@ class ShardedParticleFilter:
         self.dist.all_gather_into_tensor(self._gather_buf, mine, group=self.group)
         self.flt.shard_merge(self._gather_buf, self.world)
         self._enqueue_totals()
-        merged = self._stats_to_dict(self.flt.stats()[0])  # device-to-host + synchronise
-        self._totals = [int(v) for v in self._totals_buf.tolist()]
+        merged = self._stats_to_dict(self.flt.stats()[0])  # device-to-host + synchronise (the totals ride along)
+        self._totals = [int(v) for v in self._totals_host.tolist()]
         self.global_stats = merged
+        self._spec = None
+        if self.speculate and (self._force_last or merged["ess"] < self.ess_threshold) and self._ofs_ahead is not None \
+                and self._ofs_ahead[0] == self.step_count:
+            # The next step will resample (its gate is this ESS), and everything its resampling needs is known:
+            # start it now, so that the host work between two steps hides behind the scan instead of idling the GPU.
+            ofs = self._ofs_ahead[1]
+            self._spec = (self.step_count, ofs) + self._expand(ofs)
         return merged
 
     def _enqueue_totals(self):
         self.flt.shard_total(self.total_dev)
         self.dist.all_gather_into_tensor(self._totals_buf, self.total_dev, group=self.group)
+        self._totals_host.copy_(self._totals_buf, non_blocking=True)  # pinned: complete at the next stream sync
 
     # -- API ------------------------------------------------------------------------------------
     def init_particles(self, pose):
@@ -315,7 +327,9 @@ class ShardedParticleFilter:
         self.flt.init_particles(pose)
         self.flt.shard_set_global(self._uniform_stats(pose))
         self._enqueue_totals()
-        self._totals = [int(v) for v in self._totals_buf.tolist()]
+        self.torch.cuda.current_stream().synchronize()
+        self._totals = [int(v) for v in self._totals_host.tolist()]
+        self._spec = None
         self.global_stats = dict(ess=float(self.n_global), est=pose.copy(), log_norm=math.log(self.n_global))
 
     def set_local_particles(self, x, y, yaw, logw=None):
@@ -346,11 +360,17 @@ class ShardedParticleFilter:
             if ofs is None:
                 ahead = self._ofs_ahead
                 ofs = ahead[1] if ahead is not None and ahead[0] == self.step_count else philox_ofs(self.seed, self.step_count, self.n_global)
-            recv, n_prefix, n_suffix = self._expand(ofs)
+            spec = self._spec
+            if spec is not None and spec[0] == self.step_count and spec[1] == ofs:
+                recv, n_prefix, n_suffix = spec[2:]  # started at the end of the previous step
+            else:
+                recv, n_prefix, n_suffix = self._expand(ofs)
             self.flt.shard_step(z, recv[0], recv[1], recv[2], n_prefix, n_suffix, noise=noise)
             self._keep = recv
         else:
             self.flt.predict_weight(z, noise=noise)
+        self._spec = None
+        self._force_last = bool(force_resample)
         self.step_count += 1
         # host work of the next step that does not need this step's results, done while the GPU is busy
         self._ofs_ahead = (self.step_count, philox_ofs(self.seed, self.step_count, self.n_global))

@@ -51,9 +51,34 @@ def main():
     wrap(sf.flt, "shard_total", "shard_total (enqueue)")
     wrap(sf.flt, "stats", "stats() = D2H + WAIT for the GPU")
     wrap(sf.dist, "all_gather_into_tensor", "allgathers (enqueue)")
+    # GPU-side phases: CUDA events on the current stream after each enqueue
+    phases = ["expand (reset + scan + reset)", "exchange (NCCL p2p group)", "shard_step (prep + k_step)",
+              "k_merge", "allgather stats", "k_shard_merge", "k_shard_total", "allgather totals"]
+    evs = []
+
+    def stamp(obj, name):
+        fn = getattr(obj, name)
+
+        def inner(*a, **k):
+            r = fn(*a, **k)
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            evs.append(e)
+            return r
+        setattr(obj, name, inner)
+
+    if os.environ.get("GPU_PHASES", "1") == "1":
+        stamp(sf.flt, "shard_expand")
+        stamp(sh, "exchange_offrank")
+        stamp(sf.flt, "shard_step")
+        stamp(sf.flt, "stats_dev_bytes")
+        stamp(sf.dist, "all_gather_into_tensor")
+        stamp(sf.flt, "shard_merge")
+        stamp(sf.flt, "shard_total")
     for k in range(5):
         sf.step(cyc[k % bench.Truth.PERIOD], force_resample=True)
     marks.clear()
+    evs.clear()
     K = 20
     torch.cuda.synchronize()
     dist.barrier()
@@ -62,6 +87,19 @@ def main():
         sf.step(cyc[k % bench.Truth.PERIOD], force_resample=True)
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / K
+    if rank == 0 and evs:
+        per = len(phases)
+        assert len(evs) == per * K, (len(evs), per, K)
+        acc = [0.0] * per
+        gap = 0.0
+        for i in range(K):
+            for j in range(1, per):
+                acc[j] += evs[i * per + j - 1].elapsed_time(evs[i * per + j])
+            if i > 0:
+                gap += evs[i * per - 1].elapsed_time(evs[i * per])  # last stamp of step i-1 -> end of expand of step i
+        for j in range(1, per):
+            print(f"  GPU {phases[j]:36s} {acc[j] / K * 1e3:8.1f} us")
+        print(f"  GPU {'end of step -> end of next expand':36s} {gap / (K - 1) * 1e3:8.1f} us  (idle + " + phases[0] + ")")
     if rank == 0:
         print(f"wall per step {wall * 1e3:.3f} ms")
         tot = 0.0
