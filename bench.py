@@ -298,7 +298,7 @@ def measure_sharded(mcl, torch, dist, dev, n_per_gpu, L, likelihood, steps, warm
            "value": n_global * steps / dt, "unit": "particle-steps/s", "ms_per_step": dt / steps * 1e3, "steps": steps,
            "ess_over_n": g["ess"] / n_global,
            "max_slots_sent_off_rank_per_step": float(t[1].item()) / steps,
-           "collectives": "allgather(mcl_stats 312 B) + allgather(u64 weight total) + 3 x all_to_all_single(fp32 poses of off-rank slots)"}
+           "collectives": "allgather(mcl_stats 312 B) -> device merge; allgather(u64 weight total); one batched NCCL P2P group for the fp32 poses of off-rank slots"}
     del sf
     torch.cuda.empty_cache()
     return out

@@ -270,6 +270,26 @@ class ShardedParticleFilter:
         self.step_count = 0
         self.global_stats = None
         self.last_ranges = None
+        self._connect_peers()
+
+    def _connect_peers(self):
+        """NCCL sets up a point-to-point connection the first time a pair of ranks exchanges data (milliseconds).
+        Which pairs exchange slots depends on the weights, so every pair is connected once, here."""
+        t, dist = self.torch, self.dist
+        if self.world == 1:
+            return
+        sbuf = t.zeros(self.world, dtype=t.float32, device=self.dev)
+        rbuf = t.empty(self.world, dtype=t.float32, device=self.dev)
+        ops = []
+        for g in range(self.world):
+            if g == self.rank:
+                continue
+            peer = g if self.group is None else dist.get_global_rank(self.group, g)
+            ops.append(dist.P2POp(dist.isend, sbuf[g:g + 1], peer, self.group))
+            ops.append(dist.P2POp(dist.irecv, rbuf[g:g + 1], peer, self.group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        t.cuda.current_stream().synchronize()
 
     def _alloc_expand(self):
         t = self.torch
