@@ -10,7 +10,8 @@ Parity status: the reference ships no tests or golden vectors (SURVEY.md section
 restatement is pinned against outputs of the *unmodified reference class* run in the authoring
 container behind ``oracle/mpl_stub.py``; the generator is ``tests/golden/make_golden.py`` and
 the vectors live in ``tests/golden/*.npz`` (checked by ``tests/test_oracle_golden.py``).
-The range/bearing likelihood (``loglik_rb``) has no counterpart in the reference: parity unpinned.
+The range/bearing likelihoods (``loglik_rb``, ``loglik_rb_fan``) have no counterpart in the reference: parity
+unpinned for them; the scan sensor they consume (``scan_sensor``) is pinned (``tests/golden/scan_sensor.npz``).
 """
 from __future__ import annotations
 
@@ -340,6 +341,74 @@ def loglik_rb(px_est, z_rb, LM, sigma_d, sigma_phi, chunk=1 << 15):
         ephi = limit_angle_vec(z_rb[None, :, 1] - phi) / sigma_phi
         out[s:s + chunk] = -0.5 * (ed ** 2 + ephi ** 2).sum(axis=1)
     return out - L * math.log(2 * math.pi * sigma_d * sigma_phi)
+
+
+# --------------------------------------------------------------------------------------
+# the fan-shaped scan sensor (graph_based_slam.py:128-167) and the range/bearing
+# likelihood with its visibility gate.  The SENSOR is pinned (tests/golden/scan_sensor.npz is
+# written by the unmodified ScanSensor.scan); the LIKELIHOOD has no reference counterpart --
+# the reference uses these observations in a graph optimiser, not a particle filter -- and is
+# defined here: parity unpinned.
+# --------------------------------------------------------------------------------------
+def fan_visible(robot_lm, scan_range, scan_angle):
+    """graph_based_slam.py:150-160: inside the scan range and inside the fan of +-scan_angle about the
+    heading (the robot looks along +y of its own frame, mylib/transform.py:12)."""
+    dist = np.linalg.norm(robot_lm, axis=-1)
+    scan_rad = BASE_ANG - scan_angle
+    return (dist <= scan_range) & (robot_lm[..., 1] >= np.absolute(robot_lm[..., 0]) * np.tan(scan_rad))
+
+
+def scan_sensor(pose, LM, scan_range, scan_angle, r_dist, dir_sigma, orient_sigma, rng=np.random):
+    """ScanSensor.scan (graph_based_slam.py:128-167).  Returns (ids, noisy (n,3), clean (n,3)) with columns
+    (distance, direction, orientation); draws np.random.normal in the reference's order (:163-165)."""
+    p = world2robot(pose, LM)
+    dist = np.linalg.norm(p, axis=1)
+    dirs = np.arctan2(p[:, 1], p[:, 0])
+    orient = np.ones(p.shape[0]) * (BASE_ANG - pose[2, 0])
+    flg = fan_visible(p, scan_range, scan_angle)
+    ids, noisy, clean = [], [], []
+    for i in np.nonzero(flg)[0]:
+        d = rng.normal(dist[i], dist[i] * r_dist)
+        a = limit_angle(rng.normal(dirs[i], dir_sigma))
+        o = limit_angle(rng.normal(orient[i], orient_sigma))
+        ids.append(int(i))
+        noisy.append((d, a, o))
+        clean.append((dist[i], dirs[i], orient[i]))
+    return np.array(ids, dtype=np.int64), np.array(noisy).reshape(-1, 3), np.array(clean).reshape(-1, 3)
+
+
+def rb_fan_table(ids, noisy, L):
+    """(L, 2) observation table of the engine: (distance, direction) per landmark, NaN where not detected."""
+    z = np.full((L, 2), np.nan)
+    if len(ids):
+        z[ids, 0] = noisy[:, 0]
+        z[ids, 1] = noisy[:, 1]
+    return z
+
+
+def loglik_rb_fan(px_est, z_rb, LM, scan_range, scan_angle, r_dist, dir_sigma, miss_chi2, chunk=1 << 14):
+    """Sum over the DETECTED landmarks l (finite z_rb[l, 0]) of
+         -1/2 [ (d_obs - d_i)^2 / (d_obs r_dist)^2 + limit_angle(phi_obs - phi_i)^2 / dir_sigma^2 ]
+    when the landmark lies inside particle i's own fan (fan_visible from the particle's pose), and of
+    -1/2 miss_chi2 when it does not: the particle predicts it cannot see what was seen.  The distance noise
+    follows the sensor, sigma_d = distance * R_Dist (:163).  No normalisation constant (it is the same for
+    every particle)."""
+    N = px_est.shape[1]
+    obs = np.nonzero(np.isfinite(z_rb[:, 0]))[0]
+    out = np.zeros(N)
+    if obs.size == 0:
+        return out
+    lm, zo = LM[obs], z_rb[obs]
+    sd = zo[:, 0] * r_dist
+    for s in range(0, N, chunk):
+        p = world2robot_batch(px_est[:, s:s + chunk], lm)
+        d = np.sqrt(p[..., 0] ** 2 + p[..., 1] ** 2)
+        phi = np.arctan2(p[..., 1], p[..., 0])
+        ed = (zo[None, :, 0] - d) / sd[None, :]
+        ephi = limit_angle_vec(zo[None, :, 1] - phi) / dir_sigma
+        vis = fan_visible(p, scan_range, scan_angle)
+        out[s:s + chunk] = -0.5 * np.where(vis, ed ** 2 + ephi ** 2, miss_chi2).sum(axis=1)
+    return out
 
 
 # --------------------------------------------------------------------------------------
