@@ -62,7 +62,8 @@ class Truth:
 
     PERIOD = 360
 
-    def __init__(self, lm, seed, T=1, dt=0.1):
+    def __init__(self, lm, seed, T=1, dt=0.1, fan=False):
+        self.fan = bool(fan)  # observations of the fan-shaped scan sensor (graph_based_slam.py:128-167) instead
         self.lm = np.asarray(lm, dtype=np.float64)
         self.rng = np.random.RandomState(seed)
         self.dt = dt
@@ -88,6 +89,16 @@ class Truth:
         s, c = np.sin(th), np.cos(th)
         dx, dy = self.lm[None, :, 0] - x, self.lm[None, :, 1] - y
         z = np.stack([s * dx - c * dy, c * dx + s * dy], axis=2)
+        if self.fan:
+            # (distance, direction) of the landmarks inside the fan (15 m, +-80 deg), noise as the reference's Robot
+            # sets it (5 % of the distance, 2 deg; graph_based_slam.py:604); NaN rows where nothing is detected
+            d = np.hypot(z[..., 0], z[..., 1])
+            phi = np.arctan2(z[..., 1], z[..., 0])
+            seen = (d <= 15.0) & (z[..., 1] >= np.abs(z[..., 0]) * np.tan(np.pi / 2 - np.deg2rad(80.0)))
+            dn = self.rng.normal(d, 0.05 * d)
+            pn = phi + self.rng.normal(0.0, np.deg2rad(2.0), phi.shape)
+            pn = (pn + np.pi) % (2 * np.pi) - np.pi
+            return np.where(seen[..., None], np.stack([dn, pn], axis=2), np.nan)
         return z + self.rng.normal(0.0, 0.3, z.shape)
 
     def cycle(self):
@@ -361,7 +372,7 @@ def run_b200(args, wl):
         for r in range(replicas):
             f = mcl.Filter(n_particles=n_, n_trials=T_, landmarks=lm_, likelihood=args.likelihood, device=local,
                            seed=42 + 1000 * rank + r, max_landmarks=L_)
-            tr = Truth(lm_, seed=7 + 100 * rank + r * 17, T=T_)
+            tr = Truth(lm_, seed=7 + 100 * rank + r * 17, T=T_, fan=(args.likelihood == "rb_fan"))
             f.init_particles(tr.pose())
             cyc = tr.cycle()  # (360, T, L, 2): replica r at filter step k sees cyc[k % 360]
             filters.append(f)
@@ -518,6 +529,14 @@ def run_b200(args, wl):
                        "parallelism": "single GPU" if world == 1 else f"{world} ranks, one independent filter each (no data-path collective)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "large_filter": large, "sharded_filter": sharded,
             "gpu_launches": int(launches), "clocks": clocks}
+    if args.likelihood in ("pair", "rb_fan"):
+        # the likelihood-bound configurations (C4): what the pair loop sustains.  rb_fan scores only the landmarks
+        # the fan sensor detected (NaN rows of the observation are skipped); pair scores all L in fp64.
+        seen = float(np.mean([np.isfinite(c[..., 0]).sum(axis=-1).mean() for c in zcyc_host])) if args.likelihood == "rb_fan" else float(L)
+        k_ms = roofline["kernel_ms"]["k_step"]
+        line["pair_loop"] = {"landmarks_scored_per_step": seen, "pairs_per_s": n * T * seen / (k_ms * 1e-3),
+                             "arithmetic": "fp32 + MUFU (rcp, sqrt), branch-free atan2" if args.likelihood == "rb_fan" else "fp64, 8 operations per pair",
+                             "bound": "FP32/SFU issue" if args.likelihood == "rb_fan" else "FP64 pipe"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -530,7 +549,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
-    ap.add_argument("--likelihood", default="moment", choices=["pair", "moment"])
+    ap.add_argument("--likelihood", default="moment", choices=["pair", "moment", "rb_fan"])
     ap.add_argument("--n", type=int, default=0, help="override the particle count of the workload (experiments)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the particle-sharded C3 measurement")

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MCL_ABI_VERSION 1
+#define MCL_ABI_VERSION 2
 
 typedef struct mcl_filter mcl_filter; /* opaque */
 
@@ -49,8 +49,13 @@ typedef enum mcl_status {
 typedef enum mcl_likelihood {
     MCL_LIK_PAIR = 0,   /* every particle x every landmark, fp64, landmarks staged in shared memory */
     MCL_LIK_MOMENT = 1, /* same result from 13 per-step landmark moments (exact identity), O(1)/particle */
-    MCL_LIK_RB = 2      /* range/bearing residuals with limit_angle wrap (extension; sensor model
+    MCL_LIK_RB = 2,     /* range/bearing residuals with limit_angle wrap (extension; sensor model
                            graph_based_slam.py:150-167) */
+    MCL_LIK_RB_FAN = 3  /* the fan-shaped scan sensor (ScanSensor, graph_based_slam.py:73-167): only DETECTED
+                           landmarks are scored (z rows with a NaN distance are skipped), distance noise grows
+                           with the distance (:163), and a landmark outside the particle's own fan (:155-160)
+                           costs fan_miss_chi2 / 2 instead of its residuals.  fp32 per pair (MUFU sqrt, atan2f):
+                           the likelihood-heavy kernel; sigma_obs = (R_Dist gain, direction sigma [rad]) */
 } mcl_likelihood;
 
 typedef enum mcl_motion {
@@ -85,6 +90,10 @@ typedef struct mcl_config {
     /* particle sharding of ONE filter over several handles/GPUs (n_trials must be 1):     */
     int64_t n_global;       /* particles in the whole filter (== n_particles if unsharded) */
     int64_t slot_base;      /* global index of this handle's first particle                */
+    /* MCL_LIK_RB_FAN (graph_based_slam.py:155-160, :901-902):                              */
+    double fan_range;       /* scan range [m] (SCN_SENS_RANGE_m = 15)                      */
+    double fan_half_angle;  /* half opening angle of the fan [rad] (SCN_SENS_ANGLE_rps = 80 deg) */
+    double fan_miss_chi2;   /* chi^2 charged for a detected landmark outside the particle's fan */
 } mcl_config;
 
 /* Per-trial scalars of one step; the reference returns max_idx/max_val/x_est from main_pf
@@ -153,7 +162,8 @@ int mcl_get_particles(mcl_filter *h, float *x, float *y, float *yaw, float *logw
 int mcl_resample(mcl_filter *h, const double *ofs_host, uint32_t flags, void *stream);
 
 /* __predict (:156-168) + __likelihood/__normalize (:170-198, :226-237) + MAP estimate (:115-117).
- * z_host: [n_trials][L][2] fp64 observations z_l (:151-153) -- (range, bearing) in MCL_LIK_RB.
+ * z_host: [n_trials][L][2] fp64 observations z_l (:151-153) -- (range, bearing) in MCL_LIK_RB and
+ * MCL_LIK_RB_FAN (there a NaN range marks a landmark the sensor did not detect).
  * noise_dev: device fp32 [3][n_trials][n_particles] = the draw v of :165 (rows x, y, yaw), or NULL
  * with MCL_PHILOX_NOISE.  For MCL_MOTION_B the three rows are standard normals (vel, omg, gam). */
 int mcl_predict_weight(mcl_filter *h, const double *z_host, const float *noise_dev, uint32_t flags, void *stream);

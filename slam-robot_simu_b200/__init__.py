@@ -12,6 +12,7 @@ _lib.load()  # fail loudly at import time when the CUDA library has not been bui
 from .engine import Filter, default_config, stats_to_dict  # noqa: E402
 from .particle_filter import ParticleFilter, LazyParticles  # noqa: E402
 from .sharded import ShardedParticleFilter  # noqa: E402
+from .scan_sensor import ScanSensor  # noqa: E402
 
-__all__ = ["Filter", "ParticleFilter", "LazyParticles", "ShardedParticleFilter", "MclError", "mcl_config", "mcl_stats", "default_config",
+__all__ = ["Filter", "ParticleFilter", "LazyParticles", "ShardedParticleFilter", "ScanSensor", "MclError", "mcl_config", "mcl_stats", "default_config",
            "stats_to_dict"]

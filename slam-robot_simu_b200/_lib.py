@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmcl_b200.so")
 
-MCL_ABI_VERSION = 1
+MCL_ABI_VERSION = 2
 
 MCL_OK = 0
 MCL_ERR_ARG = -1
@@ -23,6 +23,7 @@ MCL_ERR_NODEVICE = -5
 MCL_LIK_PAIR = 0
 MCL_LIK_MOMENT = 1
 MCL_LIK_RB = 2
+MCL_LIK_RB_FAN = 3
 MCL_MOTION_A = 0
 MCL_MOTION_B = 1
 
@@ -56,6 +57,9 @@ class mcl_config(C.Structure):
         ("seed", C.c_uint64),
         ("n_global", C.c_int64),
         ("slot_base", C.c_int64),
+        ("fan_range", C.c_double),
+        ("fan_half_angle", C.c_double),
+        ("fan_miss_chi2", C.c_double),
     ]
 
 

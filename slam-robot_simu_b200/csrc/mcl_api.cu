@@ -78,7 +78,10 @@ int make_layout(const mcl_config &c, int sm_count, Layout &L) {
 int validate(const mcl_config *c) {
     if (c == nullptr || c->struct_size != sizeof(mcl_config)) return MCL_ERR_ARG;
     if (!(c->dt > 0.0) || !(c->sigma_obs[0] > 0.0) || !(c->sigma_obs[1] > 0.0)) return MCL_ERR_ARG;
-    if (c->likelihood < MCL_LIK_PAIR || c->likelihood > MCL_LIK_RB) return MCL_ERR_ARG;
+    if (c->likelihood < MCL_LIK_PAIR || c->likelihood > MCL_LIK_RB_FAN) return MCL_ERR_ARG;
+    if (c->likelihood == MCL_LIK_RB_FAN &&
+        !(c->fan_range > 0.0 && c->fan_half_angle > 0.0 && c->fan_half_angle < kPi / 2 && c->fan_miss_chi2 >= 0.0))
+        return MCL_ERR_ARG;
     if (c->motion < MCL_MOTION_A || c->motion > MCL_MOTION_B) return MCL_ERR_ARG;
     if (c->n_global < c->n_particles || c->slot_base < 0 || c->slot_base + c->n_particles > c->n_global)
         return MCL_ERR_ARG;
@@ -226,7 +229,12 @@ void fill_prep(mcl_filter *h, PrepParams &p, const double *z_dev, const double *
     p.wdt = c.yaw_rate * c.dt;
     p.inv_s0sq = 1.0 / (c.sigma_obs[0] * c.sigma_obs[0]);
     p.inv_s1sq = 1.0 / (c.sigma_obs[1] * c.sigma_obs[1]);
-    p.lik_const = -static_cast<double>(h->L) * std::log(2.0 * kPi * c.sigma_obs[0] * c.sigma_obs[1]);
+    p.lik_const = (c.likelihood == MCL_LIK_RB_FAN) ? 0.0 : -static_cast<double>(h->L) * std::log(2.0 * kPi * c.sigma_obs[0] * c.sigma_obs[1]);
+    p.fan_range = c.fan_range;
+    p.fan_tan = std::tan(kPi / 2 - c.fan_half_angle);  // ry >= |rx| tan(pi/2 - angle), graph_based_slam.py:156-158
+    p.fan_miss = c.fan_miss_chi2;
+    p.r_dist = c.sigma_obs[0];
+    p.dir_sigma = c.sigma_obs[1];
     p.inv_n = h->delta;
     p.seed = c.seed;
     p.step = h->step;
@@ -330,6 +338,7 @@ void launch_step_lik(const StepParams &p, dim3 grid, size_t smem, bool philox, c
 int step_variant(const mcl_config &c) {
     if (c.likelihood == MCL_LIK_PAIR) return kLikPair;
     if (c.likelihood == MCL_LIK_RB) return kLikRB;
+    if (c.likelihood == MCL_LIK_RB_FAN) return kLikRBFan;
     return (c.sigma_obs[0] == c.sigma_obs[1]) ? kLikMomentIso : kLikMomentGen;
 }
 
@@ -378,6 +387,11 @@ int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool redu
     for (int k = 0; k < 3; ++k) p.q_std[k] = static_cast<float>(c.q_std[k]);
     p.inv_s0sq = 1.0 / (c.sigma_obs[0] * c.sigma_obs[0]);
     p.inv_s1sq = 1.0 / (c.sigma_obs[1] * c.sigma_obs[1]);
+    p.fan_r2 = static_cast<float>(c.fan_range * c.fan_range);
+    p.fan_tan = static_cast<float>(std::tan(kPi / 2 - c.fan_half_angle));
+    p.fan_inv_r = static_cast<float>(1.0 / c.sigma_obs[0]);
+    p.fan_inv_sphi = static_cast<float>(1.0 / c.sigma_obs[1]);
+    p.fan_miss = static_cast<float>(c.fan_miss_chi2);
     {
         // motion_model.py:43-48: sigma = a_i v^2 + a_j w^2 and np.random.normal(0, sigma ** 2)
         const double v2 = c.vel * c.vel, w2 = c.yaw_rate * c.yaw_rate;
@@ -400,6 +414,7 @@ int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool redu
     switch (step_variant(c)) {
         case kLikPair: launch_step_lik<kLikPair>(p, grid, smem, philox, st, pdl); break;
         case kLikRB: launch_step_lik<kLikRB>(p, grid, smem, philox, st, pdl); break;
+        case kLikRBFan: launch_step_lik<kLikRBFan>(p, grid, smem, philox, st, pdl); break;
         case kLikMomentIso: launch_step_lik<kLikMomentIso>(p, grid, 0, philox, st, pdl); break;
         default: launch_step_lik<kLikMomentGen>(p, grid, 0, philox, st, pdl); break;
     }
@@ -499,6 +514,9 @@ int mcl_config_default(mcl_config *cfg, double period_ms) {
     cfg->seed = 42;
     cfg->n_global = cfg->n_particles;
     cfg->slot_base = 0;
+    cfg->fan_range = 15.0;              // graph_based_slam.py:901
+    cfg->fan_half_angle = 80.0 * deg;   // :902
+    cfg->fan_miss_chi2 = 18.0;          // two 3-sigma residuals
     return MCL_OK;
 }
 
@@ -590,6 +608,8 @@ int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_byte
     cudaFuncSetAttribute(k_step<kLikPair, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
     cudaFuncSetAttribute(k_step<kLikRB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
     cudaFuncSetAttribute(k_step<kLikRB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    cudaFuncSetAttribute(k_step<kLikRBFan, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    cudaFuncSetAttribute(k_step<kLikRBFan, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
     // sin/cos table of sincos_tab: entry k-128 holds sin, cos of k*pi/32 and the correction -k*(pi/32 - HI)
     {
         static TrigEntry tab[kTrigEntries];

@@ -141,6 +141,29 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return y;
 }
 
+// atan2 in ~22 branch-free fp32 instructions (atan2f is ~60 with its special-case branches): octant reduction
+// a = min/max in [0, 1] (MUFU.RCP), odd minimax polynomial of degree 15 (1.4e-7 rad evaluated in fp32),
+// quadrant fix-up by selects.  (0, 0) -> 0.  Used per (particle, landmark) pair by the fan-sensor likelihood.
+__device__ __forceinline__ float atan2_fast(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(fmaxf(ax, ay), 1.0e-30f), mn = fminf(ax, ay);
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));
+    const float a = mn * rc, s = a * a;
+    float p = -4.054567019e-03f;
+    p = fmaf(p, s, 2.186295735e-02f);
+    p = fmaf(p, s, -5.591232636e-02f);
+    p = fmaf(p, s, 9.642197334e-02f);
+    p = fmaf(p, s, -1.390862957e-01f);
+    p = fmaf(p, s, 1.994656566e-01f);
+    p = fmaf(p, s, -3.332986079e-01f);
+    p = fmaf(p, s, 9.999993356e-01f);
+    float r = a * p;
+    r = (ay > ax) ? 1.57079632679489662f - r : r;
+    r = (x < 0.0f) ? 3.14159265358979324f - r : r;
+    return copysignf(r, y);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11), counter-based: the noise of particle i at step k does not
 // depend on launch geometry or on how the filter is sharded.

@@ -23,6 +23,7 @@ constexpr int kLikPair = 0;       // per (particle, landmark) pair, landmarks st
 constexpr int kLikMomentIso = 1;  // 8 per-step moments, sigma_x == sigma_y (the reference's R)
 constexpr int kLikMomentGen = 2;  // 13 per-step moments, sigma_x != sigma_y
 constexpr int kLikRB = 3;         // range / bearing residuals with limit_angle wrap
+constexpr int kLikRBFan = 4;      // fan-shaped scan sensor: detected landmarks only, visibility gate, fp32 per pair
 
 __device__ __forceinline__ void pair_residual_c(double s, double c, double tx, double ty, double4 t, double &ex,
                                                 double &ey) {
@@ -40,6 +41,33 @@ __device__ __forceinline__ void pair_residual_rb(double s, double c, double tx, 
     ephi = limit_angle(t.w - atan2(ry, rx));
 }
 
+// The fan sensor (MCL_LIK_RB_FAN).  Table entry t = (lx, ly, 1 / (d_obs r_dist), phi_obs) of a DETECTED landmark;
+// (rx, ry) its position in the particle's frame.  Returns the chi^2 of the pair: the two normalised residuals
+//   (d_obs - d) / (d_obs r_dist) = 1/r_dist - d t.z        (distance noise grows with the distance, :163)
+//   limit_angle(phi_obs - phi) / dir_sigma
+// when the landmark is inside the particle's own fan (d <= range and ry >= |rx| tan(pi/2 - angle), :155-160),
+// else `miss`.  Same expression in fp64 (reference pose, once per step) and in fp32 (every pair).
+template <typename F>
+__device__ __forceinline__ F fan_pair_chi2(F rx, F ry, F tz, F tw, F range2, F fan_tan, F inv_r, F inv_sphi, F miss);
+template <>
+__device__ __forceinline__ double fan_pair_chi2<double>(double rx, double ry, double tz, double tw, double range2,
+                                                        double fan_tan, double inv_r, double inv_sphi, double miss) {
+    const double d2 = fma(rx, rx, ry * ry);
+    const bool vis = d2 <= range2 && ry >= fabs(rx) * fan_tan;
+    const double ed = inv_r - sqrt(d2) * tz;
+    const double ep = limit_angle(tw - atan2(ry, rx)) * inv_sphi;
+    return vis ? fma(ed, ed, ep * ep) : miss;
+}
+template <>
+__device__ __forceinline__ float fan_pair_chi2<float>(float rx, float ry, float tz, float tw, float range2, float fan_tan,
+                                                      float inv_r, float inv_sphi, float miss) {
+    const float d2 = fmaf(rx, rx, ry * ry);
+    const bool vis = d2 <= range2 && ry >= fabsf(rx) * fan_tan;
+    const float ed = fmaf(-sqrt_approx(d2), tz, inv_r);
+    const float ep = wrap_residual(tw - atan2_fast(ry, rx)) * inv_sphi;
+    return vis ? fmaf(ed, ed, ep * ep) : miss;
+}
+
 // -------------------------------------------------------------------------------------------------
 // per-step scalars ("prep"), executed by block 0 of each trial inside k_scan
 // -------------------------------------------------------------------------------------------------
@@ -53,6 +81,7 @@ struct PrepParams {
     uint32_t flags;
     int likelihood;
     double ess_threshold, vdt, wdt, inv_s0sq, inv_s1sq, lik_const, inv_n;
+    double fan_range, fan_tan, fan_miss, r_dist, dir_sigma;  // MCL_LIK_RB_FAN
     uint64_t seed;
     uint32_t step;
 };
@@ -96,7 +125,48 @@ __device__ __noinline__ void prep_block(const PrepParams &p, const PrepIn &in, c
     double acc[15];
 #pragma unroll
     for (int k = 0; k < 15; ++k) acc[k] = 0.0;
-    if (p.z != nullptr) {
+    int L_out = p.L;
+    if (p.z != nullptr && p.likelihood == MCL_LIK_RB_FAN) {
+        // Detected landmarks (finite, positive distance) are compacted into the table -- the pair loop of k_step
+        // then runs over them only -- and the reference pose is scored with the same expression in fp64.
+        __shared__ int s_cnt[32];
+        double s, c;
+        sincos_tab(static_cast<float>(rth), trig, s, c);
+        const int lane = tid & 31, warp = tid >> 5, nw = (static_cast<int>(blockDim.x) + 31) >> 5;
+        const double range2 = p.fan_range * p.fan_range, inv_r = 1.0 / p.r_dist, inv_sphi = 1.0 / p.dir_sigma;
+        int base = 0;
+        for (int l0 = 0; l0 < p.L; l0 += blockDim.x) {
+            const int l = l0 + tid;
+            double zd = 0.0, zp = 0.0;
+            bool seen = false;
+            if (l < p.L) {
+                zd = p.z[(static_cast<long long>(t) * p.L + l) * 2];
+                zp = p.z[(static_cast<long long>(t) * p.L + l) * 2 + 1];
+                seen = zd > 0.0 && zd < 1.0e300 && zp == zp;  // NaN fails every comparison
+            }
+            const unsigned int b = __ballot_sync(0xffffffffu, seen);
+            if (lane == 0) s_cnt[warp] = __popc(b);
+            __syncthreads();
+            int pos = base, tot = 0;
+            for (int w = 0; w < nw; ++w) {
+                if (w < warp) pos += s_cnt[w];
+                tot += s_cnt[w];
+            }
+            pos += __popc(b & ((1u << lane) - 1u));
+            if (seen) {
+                const double lx = p.lm[2 * l], ly = p.lm[2 * l + 1];
+                const double4 e = make_double4(lx, ly, 1.0 / (zd * p.r_dist), zp);
+                p.tab[static_cast<long long>(t) * p.Lmax + pos] = e;
+                const double dx = lx - rx, dy = ly - ry;
+                acc[13] += fan_pair_chi2<double>(s * dx - c * dy, c * dx + s * dy, e.z, e.w, range2, p.fan_tan, inv_r,
+                                                 inv_sphi, p.fan_miss);
+            }
+            base += tot;
+            __syncthreads();
+        }
+        L_out = base;
+        block_sum<15>(acc, red);
+    } else if (p.z != nullptr) {
         double s, c;
         sincos_tab(static_cast<float>(rth), trig, s, c);
         const double tx = -(s * rx - c * ry), ty = -(c * rx + s * ry);
@@ -121,7 +191,8 @@ __device__ __noinline__ void prep_block(const PrepParams &p, const PrepIn &in, c
     if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < 13; ++k) po->mom[k] = acc[k];
-        po->c_shift = (p.z != nullptr) ? (-0.5 * (acc[13] * p.inv_s0sq + acc[14] * p.inv_s1sq) + p.lik_const) : 0.0;
+        if (p.likelihood == MCL_LIK_RB_FAN) po->c_shift = -0.5 * acc[13];  // residuals are already normalised
+        else po->c_shift = (p.z != nullptr) ? (-0.5 * (acc[13] * p.inv_s0sq + acc[14] * p.inv_s1sq) + p.lik_const) : 0.0;
         po->ref[0] = rx;
         po->ref[1] = ry;
         po->ref[2] = rth;
@@ -130,7 +201,7 @@ __device__ __noinline__ void prep_block(const PrepParams &p, const PrepIn &in, c
         const WeightMap wm = make_weight_map(in.max_logw, in.sum_w);
         po->wq_m = wm.m;
         po->wq_scale = wm.scale;
-        po->L = p.L;
+        po->L = L_out;
         po->do_resample = do_resample;
         po->ofs = ofs;
     }
@@ -1073,6 +1144,7 @@ struct StepParams {
     double vel, yaw_rate, dt;
     float q_std[3];
     double inv_s0sq, inv_s1sq;
+    float fan_r2, fan_tan, fan_inv_r, fan_inv_sphi, fan_miss;  // MCL_LIK_RB_FAN
     double mb_sig[3];      // motion B: the three "sigma ** 2" scales (motion_model.py:43-48)
 };
 
@@ -1093,6 +1165,16 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
     if (LIK == kLikPair || LIK == kLikRB) {
         const double4 *g = p.tab + static_cast<long long>(t) * p.Lmax;
         for (int l = tid; l < L; l += kStepThreads) s_tab[l] = g[l];
+        __syncthreads();
+    }
+    float4 *s_tabf = reinterpret_cast<float4 *>(smem_raw);  // [L detected] (fan sensor: fp32 per pair)
+    if (LIK == kLikRBFan) {
+        const double4 *g = p.tab + static_cast<long long>(t) * p.Lmax;
+        for (int l = tid; l < L; l += kStepThreads) {
+            const double4 e = g[l];
+            s_tabf[l] = make_float4(static_cast<float>(e.x), static_cast<float>(e.y), static_cast<float>(e.z),
+                                    static_cast<float>(e.w));
+        }
         __syncthreads();
     }
     const int resample = s_prep.do_resample;
@@ -1252,9 +1334,30 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
             }
 
             // ---------------- weight: log-likelihood of the STORED (fp32) pose, fp64 arithmetic ----------------
+            float fan_chi2[kPPT] = {0.f, 0.f, 0.f, 0.f};
+            if (LIK == kLikRBFan) {
+                // the fan sensor is scored in fp32, one table entry against the thread's four particles at a time
+                float sf[kPPT], cf[kPPT];
+#pragma unroll
+                for (int k = 0; k < kPPT; ++k) {
+                    sincos_tab(th[k], p.trig, s[k], c[k]);
+                    sf[k] = static_cast<float>(s[k]);
+                    cf[k] = static_cast<float>(c[k]);
+                }
+#pragma unroll 2
+                for (int l = 0; l < L; ++l) {
+                    const float4 e = s_tabf[l];
+#pragma unroll
+                    for (int k = 0; k < kPPT; ++k) {
+                        const float dx = e.x - x[k], dy = e.y - y[k];
+                        fan_chi2[k] += fan_pair_chi2<float>(fmaf(sf[k], dx, -cf[k] * dy), fmaf(cf[k], dx, sf[k] * dy), e.z, e.w,
+                                                            p.fan_r2, p.fan_tan, p.fan_inv_r, p.fan_inv_sphi, p.fan_miss);
+                    }
+                }
+            }
 #pragma unroll
             for (int k = 0; k < kPPT; ++k) {
-                sincos_tab(th[k], p.trig, s[k], c[k]);
+                if (LIK != kLikRBFan) sincos_tab(th[k], p.trig, s[k], c[k]);
                 const double xd = x[k], yd = y[k];
                 double ll;
                 if (LIK == kLikMomentIso) {
@@ -1280,6 +1383,8 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
                     const double q0 = Saa + 2.0 * tx * Sa + Ld * tx * tx;
                     const double q1 = Sbb + 2.0 * ty * Sb + Ld * ty * ty;
                     ll = fma(half0, q0, half1 * q1);
+                } else if (LIK == kLikRBFan) {
+                    ll = -0.5 * static_cast<double>(fan_chi2[k]);
                 } else {
                     const double tx = -(s[k] * xd - c[k] * yd), ty = -(c[k] * xd + s[k] * yd);
                     double q0 = 0.0, q1 = 0.0;

@@ -33,7 +33,7 @@ class Filter:
     def __init__(self, n_particles=1000, n_trials=1, period_ms=100.0, landmarks=None, likelihood="pair",
                  motion="a", device=0, seed=42, ess_threshold=None, q_std=None, sigma_obs=None,
                  max_landmarks=None, n_global=None, slot_base=0, motion_b_alpha=None, vel=None, yaw_rate=None,
-                 dt=None):
+                 dt=None, fan_range=None, fan_half_angle=None, fan_miss_chi2=None):
         torch = _torch()
         self.lib = L.load()
         cfg = default_config(period_ms)
@@ -43,7 +43,14 @@ class Filter:
         cfg.n_global = int(n_global if n_global is not None else n_particles)
         cfg.slot_base = int(slot_base)
         cfg.seed = int(seed)
-        cfg.likelihood = {"pair": L.MCL_LIK_PAIR, "moment": L.MCL_LIK_MOMENT, "rb": L.MCL_LIK_RB}[likelihood]
+        cfg.likelihood = {"pair": L.MCL_LIK_PAIR, "moment": L.MCL_LIK_MOMENT, "rb": L.MCL_LIK_RB,
+                          "rb_fan": L.MCL_LIK_RB_FAN}[likelihood]
+        if likelihood == "rb_fan" and sigma_obs is None:
+            # ScanSensor noise as the reference's Robot sets it (graph_based_slam.py:604): 5 % of the distance, 2 deg
+            sigma_obs = [0.05, np.deg2rad(2.0)]
+        for name, val in (("fan_range", fan_range), ("fan_half_angle", fan_half_angle), ("fan_miss_chi2", fan_miss_chi2)):
+            if val is not None:
+                setattr(cfg, name, float(val))
         cfg.motion = {"a": L.MCL_MOTION_A, "b": L.MCL_MOTION_B}[motion]
         # ESS_TH = NP / 100 (particle_filter.py:33)
         cfg.ess_threshold = float(ess_threshold) if ess_threshold is not None else cfg.n_global / 100.0

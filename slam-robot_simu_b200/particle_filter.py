@@ -92,10 +92,20 @@ class ParticleFilter:
         self.__noise = noise
         self.__lazy = bool(lazy_px)
         self.__force = bool(force_resample)
+        self.__sensor = None
+        sigma_obs = [np.sqrt(self.__R[0][0]), np.sqrt(self.__R[1][1])]
+        if likelihood == "rb_fan":
+            # the robot carries the fan-shaped scan sensor of graph_based_slam.py:73-167 with the
+            # noise its Robot class sets (:604); the filter scores (distance, direction) of the detected landmarks
+            from .scan_sensor import ScanSensor
+
+            self.__sensor = ScanSensor(15.0, np.deg2rad(80.0), self.__LM)  # :901-902
+            self.__sensor.setNoiseParam(5, 2, 2)
+            sigma_obs = [self.__sensor.r_dist, self.__sensor.dir_sigma]
         self.__flt = Filter(n_particles=self.__NP, n_trials=1, period_ms=period_ms, landmarks=self.__LM,
                             likelihood=likelihood, motion="a", device=device, seed=seed,
                             ess_threshold=self.__ESS_TH,
-                            q_std=np.sqrt(np.diag(self.__Q)), sigma_obs=[np.sqrt(self.__R[0][0]), np.sqrt(self.__R[1][1])],
+                            q_std=np.sqrt(np.diag(self.__Q)), sigma_obs=sigma_obs,
                             vel=self.__VEL_mps, yaw_rate=self.__YAW_RATE_rps, dt=self.__DT_s)
         self.__flt.init_particles(self.__x_true[:, 0])  # :81-84
         self.__ess = float(self.__NP)  # 1 / sum((1/NP)^2)
@@ -124,7 +134,9 @@ class ParticleFilter:
         return x_next
 
     def __observation(self, x_true):
-        """particle_filter.py:144-154."""
+        """particle_filter.py:144-154 (or ScanSensor.scan, graph_based_slam.py:128-167, in the fan-sensor mode)."""
+        if self.__sensor is not None:
+            return self.__sensor.scan(x_true)[0]
         z_l = world2robot(x_true, self.__LM)
         w = self.__mvn(self.__R_factor, self.__LM.shape[0])  # multivariate_normal([0, 0], R, L)
         return z_l + w

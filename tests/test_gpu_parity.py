@@ -720,3 +720,84 @@ def test_yaw_wrap_at_the_seam_matches_limit_angle(mcl):
     want = O.predict(pos.astype(np.float64), np.zeros((3, n)), P)[2]
     assert np.all(np.abs(got - want) < 1e-6)  # same side of the seam everywhere
     assert (want > 3.0).any() and (want < -3.0).any()
+
+
+def _fan_case(rng, n, Lm, spread):
+    lm = rng.uniform(-14, 14, (Lm, 2))
+    truth = np.array([[1.5], [-2.0], [0.6]])
+    pos = (truth + rng.normal(0, 1, (3, n)) * np.array([[spread], [spread], [0.25 * spread]])).astype(np.float32)
+    return lm, truth, pos
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Lm,spread", [(24, 0.3), (200, 2.0)])
+def test_rb_fan_likelihood_matches_oracle(mcl, Lm, spread):
+    """the fan-sensor likelihood (fp32 per pair, detected landmarks only, visibility gate) against
+    the fp64 oracle on the same stored poses.  The gate is a step function, so particles that sit within 1e-4 of a
+    gate boundary for some landmark are excluded (fp32 may legitimately take the other side)."""
+    rng = np.random.RandomState(Lm)
+    n = 4096
+    lm, truth, pos = _fan_case(rng, n, Lm, spread)
+    rng_obs = np.random.RandomState(Lm + 1)
+    ids, noisy, _ = O.scan_sensor(truth, lm, 15.0, np.deg2rad(80.0), 0.05, np.deg2rad(2.0), np.deg2rad(2.0), rng=rng_obs)
+    assert 2 <= ids.size < Lm
+    z = O.rb_fan_table(ids, noisy, Lm)
+    f = mcl.Filter(n_particles=n, landmarks=lm, likelihood="rb_fan", max_landmarks=Lm, q_std=[1e-9, 1e-9, 1e-9])
+    f.set_particles(pos[0], pos[1], pos[2], None)
+    f.predict_weight(z[None], noise=np.zeros((3, 1, n), np.float32))
+    x, y, th, lw = f.get_particles()
+    got_px = np.stack([x[0], y[0], th[0]]).astype(np.float64)
+    want = O.loglik_rb_fan(got_px, z, lm, 15.0, np.deg2rad(80.0), 0.05, np.deg2rad(2.0), 18.0)
+    # robust particles: every detected landmark clearly inside or clearly outside the particle's fan
+    p = O.world2robot_batch(got_px, lm[ids])
+    d = np.sqrt(p[..., 0] ** 2 + p[..., 1] ** 2)
+    m_range = np.abs(d - 15.0)
+    m_ang = np.abs(p[..., 1] - np.abs(p[..., 0]) * np.tan(np.pi / 2 - np.deg2rad(80.0)))
+    robust = (np.minimum(m_range, m_ang) > 1e-3).all(axis=1)
+    assert robust.mean() > 0.95
+    got = lw[0].astype(np.float64)
+    # stored log-weights are relative to one per-step constant: compare differences to the best particle
+    k = int(np.argmax(np.where(robust, want, -np.inf)))
+    dg, dw = got - got[k], want - want[k]
+    tol = 2e-3 + 2e-6 * np.abs(dw)  # fp32 residuals, MUFU sqrt, atan2f; chi^2 up to ~1e4 per particle
+    bad = robust & (np.abs(dg - dw) > tol)
+    assert not bad.any(), (int(bad.sum()), float(np.abs(dg - dw)[robust].max()))
+    st = f.stats()[0]
+    assert st.max_idx == int(np.argmax(got))
+
+
+@pytest.mark.gpu
+def test_rb_fan_gate_and_empty_scan(mcl):
+    """Nothing detected -> the step leaves the weights uniform; a particle that looks away from every detected
+    landmark pays exactly fan_miss_chi2 / 2 per landmark; a full step with resampling runs in this mode."""
+    rng = np.random.RandomState(9)
+    n, Lm = 2048, 32
+    lm, truth, pos = _fan_case(rng, n, Lm, 0.05)
+    f = mcl.Filter(n_particles=n, landmarks=lm, likelihood="rb_fan", max_landmarks=Lm, fan_miss_chi2=8.0,
+                   q_std=[1e-9, 1e-9, 1e-9], vel=0.0, yaw_rate=0.0)
+    f.set_particles(pos[0], pos[1], pos[2], None)
+    f.predict_weight(np.full((1, Lm, 2), np.nan), noise=np.zeros((3, 1, n), np.float32))
+    np.testing.assert_allclose(f.weights()[0], 1.0 / n, rtol=1e-6)
+    # exact observation from the truth; half of the particles turned around
+    ids, _, clean = O.scan_sensor(truth, lm, 15.0, np.deg2rad(80.0), 0.05, 0.03, 0.03, rng=np.random.RandomState(1))
+    z = O.rb_fan_table(ids, clean, Lm)
+    pos2 = np.repeat(truth.astype(np.float32), n, axis=1)
+    pos2[2, n // 2:] += np.float32(np.pi)
+    f.set_particles(pos2[0], pos2[1], pos2[2], None)
+    f.predict_weight(z[None], noise=np.zeros((3, 1, n), np.float32))
+    _, _, _, lw = f.get_particles()
+    front, back = lw[0][: n // 2].astype(np.float64), lw[0][n // 2:].astype(np.float64)
+    assert np.ptp(front) < 1e-3 and np.ptp(back) < 1e-6
+    assert front.mean() - back.mean() == pytest.approx(0.5 * 8.0 * ids.size, abs=2e-3)
+    # a normal step (resampling forced) in this mode
+    f2 = mcl.Filter(n_particles=n, landmarks=lm, likelihood="rb_fan", max_landmarks=Lm)
+    f2.init_particles(truth[:, 0])
+    sens = mcl.ScanSensor(15.0, np.deg2rad(80.0), lm)
+    sens.setNoiseParam(5, 2, 2)
+    np.random.seed(3)
+    for _ in range(5):
+        zt, _ = sens.scan(truth)
+        f2.step(zt[None], force_resample=True)
+    st = f2.stats()[0]
+    assert np.isfinite(st.ess) and 1.0 <= st.ess <= n
+    assert np.hypot(st.est[0] - truth[0, 0], st.est[1] - truth[1, 0]) < 3.0

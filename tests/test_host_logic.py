@@ -46,13 +46,15 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_struct_layout_matches_the_header(pkg, tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include "mcl.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu\\n",'
-                   'sizeof(mcl_config),sizeof(mcl_stats),offsetof(mcl_stats,raw),offsetof(mcl_config,seed));return 0;}\n')
+    src.write_text('#include "mcl.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+                   'sizeof(mcl_config),sizeof(mcl_stats),offsetof(mcl_stats,raw),offsetof(mcl_config,seed),'
+                   'offsetof(mcl_config,fan_miss_chi2));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     L = pkg._lib
-    assert got == [C.sizeof(L.mcl_config), C.sizeof(L.mcl_stats), L.mcl_stats.raw.offset, L.mcl_config.seed.offset]
+    assert got == [C.sizeof(L.mcl_config), C.sizeof(L.mcl_stats), L.mcl_stats.raw.offset, L.mcl_config.seed.offset,
+                   L.mcl_config.fan_miss_chi2.offset]
 
 
 def test_config_defaults_are_the_reference_literals(pkg):
@@ -111,6 +113,25 @@ def test_host_mirror_of_the_reference_helpers(pkg, golden_dir):
     assert np.array_equal(got, h["lim_out"])
     for p, want in zip(h["w2r_pose"], h["w2r_out"]):
         np.testing.assert_allclose(pf.world2robot(p, h["w2r_lm"]), want, rtol=0, atol=1e-12)
+
+
+def test_scan_sensor_mirror_against_reference_golden(pkg, golden_dir):
+    """The product's host-side ScanSensor (scan_sensor.py) against the unmodified reference class
+    (graph_based_slam.py:73-167; tests/golden/make_golden_scan.py): same detections, same draws."""
+    g = np.load(os.path.join(golden_dir, "scan_sensor.npz"))
+    for c in range(int(g["n_cases"])):
+        lm = g[f"c{c}_lm"]
+        sens = pkg.ScanSensor(float(g["scan_range"]), float(g["scan_angle"]), lm)
+        sens.setNoiseParam(5, 2, 2)
+        np.random.seed(int(g[f"c{c}_seed"]))
+        z, ids = sens.scan(g[f"c{c}_pose"])
+        np.testing.assert_array_equal(ids, g[f"c{c}_ids"])
+        np.testing.assert_array_equal(z[ids], g[f"c{c}_noisy"][:, :2])
+        assert np.isnan(z[:, 0]).sum() == lm.shape[0] - ids.size
+        z0, _ = sens.scan(g[f"c{c}_pose"], noise=False)
+        np.testing.assert_array_equal(z0[ids], g[f"c{c}_clean"][:, :2])
+    cfg = pkg.default_config(100.0)
+    assert cfg.fan_range == 15.0 and cfg.fan_half_angle == pytest.approx(np.deg2rad(80.0), rel=1e-15)  # :901-902
 
 
 def test_philox_known_answers(pkg):

@@ -31,7 +31,7 @@ def main():
         wl["n"] = a.n
     lm = bench.landmarks_for(wl["L"])
     f = mcl.Filter(n_particles=wl["n"], n_trials=wl["T"], landmarks=lm, likelihood=a.likelihood, max_landmarks=wl["L"])
-    tr = bench.Truth(lm, seed=7, T=wl["T"])
+    tr = bench.Truth(lm, seed=7, T=wl["T"], fan=(a.likelihood == "rb_fan"))
     f.init_particles(tr.pose())
     for _ in range(a.steps):
         tr.advance()
