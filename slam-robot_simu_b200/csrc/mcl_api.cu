@@ -26,7 +26,7 @@ struct Layout {
     int T, Lmax, tpt, bpt, cov_bpt;
     uint32_t per;
     size_t off_state[2], off_anc, off_desc, off_tickets, off_partials, off_cov, off_stats, off_prep, off_tab, off_lm,
-        off_z, off_ofs, off_pose, off_total, off_trig, off_pub, off_ready, total;
+        off_z, off_ofs, off_pose, off_total, off_trig, off_pub, off_ready, off_seg, total;
 };
 
 int make_layout(const mcl_config &c, int sm_count, Layout &L) {
@@ -71,6 +71,7 @@ int make_layout(const mcl_config &c, int sm_count, Layout &L) {
     L.off_pub = o;      o = align_up(o + static_cast<size_t>(L.T) * 2 * sizeof(uint4), kAlign);
     L.off_ready = o;    o = align_up(o + static_cast<size_t>(2) * L.T * (kDirectTiles / 32) * sizeof(unsigned int), kAlign);
     L.off_trig = o;     o = align_up(o + static_cast<size_t>(kTrigEntries) * sizeof(TrigEntry), kAlign);
+    L.off_seg = o;      o = align_up(o + static_cast<size_t>(kMaxSegments) * sizeof(unsigned long long), kAlign);
     L.total = o;
     return MCL_OK;
 }
@@ -110,6 +111,8 @@ struct mcl_filter {
     double *lm = nullptr, *z = nullptr, *ofs = nullptr, *pose = nullptr;
     unsigned long long *total = nullptr;
     TrigEntry *trig = nullptr;
+    unsigned long long *seg = nullptr;  // [kMaxSegments] weight totals of the tile segments of mcl_shard_total
+    int tiles_per_seg = 1;
     uint4 *wm_pub = nullptr;
     unsigned int *ready[2] = {nullptr, nullptr};  // double-buffered like desc[]
     unsigned int scan_epoch = 0;
@@ -119,6 +122,8 @@ struct mcl_filter {
     bool have_particles = false;
     bool stats_from_particle0 = false;  // next reduce-only pass takes its reference pose from particle 0
     bool stats_dirty = false;           // the CTA partials of the last k_step / k_reduce are newer than stats[]
+    bool tile_prefix_valid = false;     // desc[desc_cur] holds the tile prefixes of the CURRENT weights (mcl_shard_total)
+    bool desc_stale = false;            // desc[desc_cur] holds tile sums, not the zeros a look-back scan starts from
     double delta = 0.0;                 // fl(1 / n_global), NP_RECIP (particle_filter.py:32)
     std::string err;
     uint64_t launches = 0;
@@ -294,6 +299,12 @@ int launch_step_scan(mcl_filter *h, const double *z_dev, const double *ofs_dev, 
     sp.trig = h->trig;
     sp.dbg = (h->dbg != nullptr && full) ? h->dbg + static_cast<size_t>(h->lay.T) * h->lay.bpt * kDbgSlots : nullptr;
     if (full) {
+        if (h->desc_stale) {  // tile sums of an mcl_shard_total that no expansion consumed
+            k_reset_scan<<<(h->lay.tpt + 255) / 256, 256, 0, st>>>(sp.desc, sp.ready, h->tickets, h->lay.tpt);
+            MCL_LAUNCH_CHECK(h, "k_reset_scan");
+            h->desc_stale = false;
+            h->tile_prefix_valid = false;
+        }
         sp.desc_next = h->desc[h->desc_cur ^ 1];
         sp.ready_next = h->ready[h->desc_cur ^ 1];
         h->desc_cur ^= 1;
@@ -318,8 +329,16 @@ int launch_step_scan(mcl_filter *h, const double *z_dev, const double *ofs_dev, 
 
 // Sharded resampling: the scan runs outside a step, with the weight map of the (global) statistics.
 int launch_shard_scan(mcl_filter *h, ScanParams &sp, int mode, cudaStream_t st) {
-    k_reset_scan<<<(h->lay.tpt + 255) / 256, 256, 0, st>>>(sp.desc, sp.ready, h->tickets, h->lay.tpt);
-    MCL_LAUNCH_CHECK(h, "k_reset_scan");
+    if (mode == kScanExpand && h->tile_prefix_valid) {
+        sp.tile_prefix = sp.desc;  // written by mcl_shard_total for exactly these weights: no look-back
+        sp.seg_prefix = h->seg;
+        sp.tiles_per_seg = h->tiles_per_seg;
+    } else {
+        k_reset_scan<<<(h->lay.tpt + 255) / 256, 256, 0, st>>>(sp.desc, sp.ready, h->tickets, h->lay.tpt);
+        MCL_LAUNCH_CHECK(h, "k_reset_scan");
+    }
+    h->tile_prefix_valid = false;
+    h->desc_stale = false;  // the trailing k_reset_scan below leaves zeros
     dim3 grid(h->lay.tpt, 1);
     if (mode == kScanTotals) k_scan<kScanTotals><<<grid, kScanThreads, 0, st>>>(sp);
     else k_scan<kScanExpand><<<grid, kScanThreads, 0, st>>>(sp);
@@ -350,6 +369,7 @@ struct StepWindow {
 int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool reduce_only, cudaStream_t st,
                 const StepWindow *win = nullptr) {
     const mcl_config &c = h->cfg;
+    h->tile_prefix_valid = false;  // the weights (or their statistics) are about to change
     StepParams p{};
     p.in = h->state[h->cur];
     p.out = h->state[h->cur ^ 1];
@@ -598,6 +618,7 @@ int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_byte
     h->pose = reinterpret_cast<double *>(h->ws + L.off_pose);
     h->total = reinterpret_cast<unsigned long long *>(h->ws + L.off_total);
     h->trig = reinterpret_cast<TrigEntry *>(h->ws + L.off_trig);
+    h->seg = reinterpret_cast<unsigned long long *>(h->ws + L.off_seg);
     h->wm_pub = reinterpret_cast<uint4 *>(h->ws + L.off_pub);
     h->ready[0] = reinterpret_cast<unsigned int *>(h->ws + L.off_ready);
     h->ready[1] = h->ready[0] + static_cast<size_t>(L.T) * (kDirectTiles / 32);
@@ -686,6 +707,7 @@ int mcl_init_particles(mcl_filter *h, const double *pose_host, void *stream) {
     k_init_stats<<<(L.T + 127) / 128, 128, 0, st>>>(h->stats, h->pose, static_cast<double>(h->cfg.n_global), L.T);
     MCL_LAUNCH_CHECK(h, "k_init_stats");
     h->have_particles = true;
+    h->tile_prefix_valid = false;
     h->stats_dirty = false;
     h->step = 0;
     return MCL_OK;
@@ -718,6 +740,7 @@ int mcl_set_particles(mcl_filter *h, const float *x, const float *y, const float
     }
     if (!on_device) MCL_CUDA(h, cudaStreamSynchronize(st));  // pageable host sources may go away
     h->have_particles = true;
+    h->tile_prefix_valid = false;
     if (skip_stats) return MCL_OK;  // the caller installs statistics itself (mcl_shard_set_global)
     h->stats_from_particle0 = true;
     return reduce_only_pass(h, st);
@@ -965,10 +988,22 @@ int mcl_shard_total(mcl_filter *h, uint64_t *total_dev, void *stream) {
     rc = ensure_stats(h, st);
     if (rc != MCL_OK) return rc;
     MCL_CUDA(h, cudaMemsetAsync(total_dev, 0, sizeof(uint64_t), st));
-    const int blocks = static_cast<int>(std::min<long long>((h->lay.n / 4 + 255) / 256 + 1, static_cast<long long>(h->sm_count) * 8));
-    k_shard_total<<<blocks, 256, 0, st>>>(h->state[h->cur].lw, h->lay.n, h->stats,
-                                            reinterpret_cast<unsigned long long *>(total_dev));
+    // the tile sums go where the scan keeps its descriptors (unused when the tile prefixes are known); the
+    // expansion clears them again
+    // Every CTA sums one contiguous segment of tiles and leaves each tile's prefix WITHIN the segment; a one-CTA
+    // kernel then turns the (at most 1024) segment totals into prefixes.
+    unsigned long long *tiles = h->desc[h->desc_cur];
+    const int blocks_max = std::min(kMaxSegments, h->sm_count * 8);
+    h->tiles_per_seg = (h->lay.tpt + blocks_max - 1) / blocks_max;
+    const int blocks = (h->lay.tpt + h->tiles_per_seg - 1) / h->tiles_per_seg;
+    k_shard_total<<<blocks, kScanThreads, 0, st>>>(h->state[h->cur].lw, h->lay.n, h->stats,
+                                                    reinterpret_cast<unsigned long long *>(total_dev), tiles, h->seg,
+                                                    h->lay.tpt, h->tiles_per_seg);
     MCL_LAUNCH_CHECK(h, "k_shard_total");
+    k_tile_prefix<<<1, 1024, 0, st>>>(h->seg, blocks);
+    MCL_LAUNCH_CHECK(h, "k_tile_prefix");
+    h->tile_prefix_valid = true;
+    h->desc_stale = true;
     return MCL_OK;
 }
 
@@ -1065,6 +1100,7 @@ int mcl_shard_merge(mcl_filter *h, const mcl_stats *records_dev, int n_shards, v
     mp.out = h->stats;
     k_shard_merge<<<1, 32, 0, S(stream)>>>(mp);
     MCL_LAUNCH_CHECK(h, "k_shard_merge");
+    h->tile_prefix_valid = false;
     h->stats_from_particle0 = false;
     h->stats_dirty = false;
     return MCL_OK;
@@ -1078,6 +1114,7 @@ int mcl_shard_set_global(mcl_filter *h, const mcl_stats *merged_host, void *stre
     if (rc != MCL_OK) return rc;
     MCL_CUDA(h, cudaMemcpyAsync(h->stats, merged_host, sizeof(mcl_stats), cudaMemcpyHostToDevice, S(stream)));
     MCL_CUDA(h, cudaStreamSynchronize(S(stream)));
+    h->tile_prefix_valid = false;
     h->stats_from_particle0 = false;
     h->stats_dirty = false;
     return MCL_OK;

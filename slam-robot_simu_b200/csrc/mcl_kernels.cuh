@@ -606,6 +606,11 @@ struct ScanParams {
     unsigned int *tickets;      // [T][4]  (slot 0 = scan ticket)
     uint32_t *anc;              // [T][ld] (slot - slot_first)
     unsigned long long *total;  // optional [T] : inclusive total of the local weights
+    // kScanExpand after mcl_shard_total: exclusive prefix of every tile's weight (that pass summed the tiles
+    // anyway) -- tiles then need no look-back and no descriptors at all
+    const unsigned long long *tile_prefix;  // [tpt] weight before the tile inside its segment
+    const unsigned long long *seg_prefix;   // [segments] weight before the segment
+    int tiles_per_seg;
     long long n, ld, n_global;  // local sources, stride, comb length
     long long j_global_base;    // global index of local source 0 (sharded)
     long long slot_first;       // anc is indexed by (global slot - slot_first)
@@ -839,7 +844,10 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     unsigned long long excl = 0;
     // tiles of the direct range also raise a bit in ready[tile / 32] once their aggregate is visible
     unsigned int *rdy = p.ready + t * (kDirectTiles / 32);
-    if (tile == 0) {
+    const bool have_prefix = (MODE == kScanExpand) && p.tile_prefix != nullptr;
+    if (have_prefix) {
+        excl = __ldg(p.seg_prefix + tile / p.tiles_per_seg) + __ldg(p.tile_prefix + tile);
+    } else if (tile == 0) {
         if (tid == 0) {
             atomicExch(&desc[0], kDescAggregate | tile_total);  // == its prefix; see the direct range
             __threadfence();
@@ -1713,23 +1721,70 @@ __global__ void k_shard_merge(const ShardMergeParams p) {
     *p.out = o;
 }
 
-__global__ void __launch_bounds__(256) k_shard_total(const float *lw, long long n, const mcl_stats *stats,
-                                                     unsigned long long *total) {
+// Sharded filter, first pass of the global resampling: the shard's total of the quantised weights (atomicAdd into
+// *total).  The tiles are those of k_scan; every CTA takes one contiguous segment of them and leaves, tile by
+// tile, the weight that precedes the tile inside the segment (tile_prefix) and the segment's total (seg_total).
+// k_tile_prefix turns the segment totals into prefixes, so the second pass (k_scan<kScanExpand>) starts every
+// tile at seg_prefix[segment] + tile_prefix[tile] -- no look-back, no descriptors.
+constexpr int kMaxSegments = 1024;
+__global__ void __launch_bounds__(kScanThreads) k_shard_total(const float *lw, long long n, const mcl_stats *stats,
+                                                              unsigned long long *total, unsigned long long *tile_prefix,
+                                                              unsigned long long *seg_total, int tpt, int tiles_per_seg) {
     __shared__ WeightMap s_wm;
-    if (threadIdx.x == 0) s_wm = make_weight_map(stats[0].max_logw, stats[0].sum_w);
+    __shared__ unsigned long long s_part[2][kScanThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_wm = make_weight_map(stats[0].max_logw, stats[0].sum_w);
     __syncthreads();
     const WeightMap wm = s_wm;
-    unsigned long long acc = 0ull;
-    const long long n4 = n >> 2;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const float4 v = reinterpret_cast<const float4 *>(lw)[i];
-        acc += quantize_weight(v.x, wm) + quantize_weight(v.y, wm) + quantize_weight(v.z, wm) + quantize_weight(v.w, wm);
-    }
-    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) acc += quantize_weight(lw[(n4 << 2) + threadIdx.x], wm);
+    unsigned long long run = 0ull;  // thread 0: weight of the segment's tiles so far
+    const long long t0 = static_cast<long long>(blockIdx.x) * tiles_per_seg;
+    const long long t1 = min(static_cast<long long>(tpt), t0 + tiles_per_seg);
+    int par = 0;
+    for (long long tile = t0; tile < t1; ++tile, par ^= 1) {
+        const long long j0 = tile * kScanTile + static_cast<long long>(tid) * kScanItems;
+        unsigned long long acc = 0ull;
+        if (j0 < n) {  // the state arrays are padded to a multiple of 128 elements: the vector loads stay in bounds
+            const float4 a = *reinterpret_cast<const float4 *>(lw + j0);
+            const float4 b = *reinterpret_cast<const float4 *>(lw + j0 + 4);
+            const float v[kScanItems] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0 && acc != 0ull) atomicAdd(total, acc);
+            for (int k = 0; k < kScanItems; ++k)
+                if (j0 + k < n) acc += quantize_weight(v[k], wm);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_part[par][warp] = acc;
+        __syncthreads();  // one barrier per tile: the two halves of s_part alternate
+        if (tid == 0) {
+            unsigned long long s = 0ull;
+#pragma unroll
+            for (int w = 0; w < kScanThreads / 32; ++w) s += s_part[par][w];
+            tile_prefix[tile] = run;
+            run += s;
+        }
+    }
+    if (tid == 0) {
+        seg_total[blockIdx.x] = run;
+        if (run != 0ull) atomicAdd(total, run);
+    }
+}
+
+// in-place exclusive prefix of v[0..n), n <= 1024: one CTA, one element per thread
+__global__ void __launch_bounds__(1024) k_tile_prefix(unsigned long long *v, int n) {
+    __shared__ unsigned long long s_w[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long x = (tid < n) ? v[tid] : 0ull;
+    unsigned long long incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    unsigned long long off = 0ull;
+    for (int w = 0; w < warp; ++w) off += s_w[w];
+    if (tid < n) v[tid] = off + incl - x;
 }
 
 // normalised weights w = q 2^-52 (fp64) and the integers q the resampler scans
