@@ -997,8 +997,12 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     if (tid == last_tid) s_slot[1] = cur;
     __syncthreads();
     const uint32_t S0 = s_slot[0], S1 = s_slot[1];
-    // the ancestor array is written with 32-byte stores: the windows start at a multiple of 8 slots
-    const uint32_t W0 = (MODE == kScanAncestors) ? (S0 & ~7u) : S0;
+    // the ancestor array is written with 32-byte stores: the windows start where (slot - first slot of anc[]) is a
+    // multiple of 8 (anc[] starts at slot 0, or at own_lo in the sharded expansion)
+    const uint32_t anc_lo = (MODE == kScanAncestors) ? 0u : static_cast<uint32_t>(p.own_lo);
+    const uint32_t mis = (S0 - anc_lo) & 7u;
+    const bool aligned = mis <= S0;
+    const uint32_t W0 = aligned ? S0 - mis : S0;
     const uint32_t span = (S1 > S0) ? S1 - W0 : 0u;
     const uint32_t my_off = first_slot - W0;  // threads with sources: >= 0
 
@@ -1007,6 +1011,10 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     uint32_t carry = 0;  // source (local index + 1) that owns the slot just before the window
     for (uint32_t cb = 0; cb < span; cb += kScanTile) {
         // window of kScanTile slots starting at W0 + cb
+        // registers -> anc[] directly when the whole window belongs to this handle's ancestor array (always, unsharded)
+        const bool reg_store = (MODE == kScanAncestors) ||
+                               (aligned && static_cast<long long>(W0) + cb >= p.own_lo &&
+                                static_cast<long long>(W0) + cb + kScanTile <= p.own_hi);
         if (cb > 0u && span > 4u * kScanTile) {
             // Degenerate weights: one source owns many windows.  A window in which no source starts is a
             // constant fill with the carried owner -- one barrier and one store per thread instead of a scan.
@@ -1016,21 +1024,22 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
             for (int k = 0; k < kScanItems; ++k) starts = starts || (wofs + rel[k] < static_cast<uint32_t>(kScanTile));
             if (!__syncthreads_or(starts)) {
                 const uint32_t j = static_cast<uint32_t>(tile * kScanTile) - 1u + carry;
-                if (MODE == kScanAncestors) {
+                if (reg_store) {
                     const uint32_t slot0 = W0 + cb + static_cast<uint32_t>(tid * kScanItems);
                     if (slot0 >= S0 && slot0 + kScanItems <= S1) {
-                        asm volatile("st.global.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(anc + slot0), "r"(j) : "memory");
+                        asm volatile("st.global.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(anc + (slot0 - anc_lo)), "r"(j) : "memory");
                     } else {
 #pragma unroll
                         for (int k = 0; k < kScanItems; ++k)
-                            if (slot0 + k >= S0 && slot0 + k < S1) anc[slot0 + k] = j;
+                            if (slot0 + k >= S0 && slot0 + k < S1) anc[slot0 + k - anc_lo] = j;
                     }
                 } else {
                     const int lim = static_cast<int>(min(static_cast<uint32_t>(kScanTile), span - cb));
 #pragma unroll
                     for (int k = 0; k < kScanItems; ++k) {
                         const int pos = k * kScanThreads + tid;
-                        if (pos < lim) expand_store(p, anc, static_cast<long long>(S0) + cb + pos, j);
+                        const long long slot = static_cast<long long>(W0) + cb + pos;
+                        if (pos < lim && slot >= S0) expand_store(p, anc, slot, j);
                     }
                 }
                 continue;
@@ -1082,19 +1091,20 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
         before = max(before, wbefore);
         carry = wall;
         const uint32_t jbase = static_cast<uint32_t>(tile * kScanTile) - 1u;
-        if (MODE == kScanAncestors) {
-            // unsharded: slots are local indices, anc holds ld >= n of them; stores go straight from registers
+        if (reg_store) {
+            // slots of this handle's own ancestor array (unsharded: all of them; anc holds ld >= n slots): the
+            // stores go straight from registers
 #pragma unroll
             for (int k = 0; k < kScanItems; ++k) v[k] = jbase + max(v[k], before);
             const uint32_t slot0 = W0 + cb + static_cast<uint32_t>(tid * kScanItems);
             if (slot0 >= S0 && slot0 + kScanItems <= S1) {
-                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(anc + slot0), "r"(v[0]), "r"(v[1]),
-                             "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(anc + (slot0 - anc_lo)), "r"(v[0]),
+                             "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                              : "memory");
             } else {
 #pragma unroll
                 for (int k = 0; k < kScanItems; ++k)
-                    if (slot0 + k >= S0 && slot0 + k < S1) anc[slot0 + k] = v[k];
+                    if (slot0 + k >= S0 && slot0 + k < S1) anc[slot0 + k - anc_lo] = v[k];
             }
             // no barrier here: the next window's zeroing of s_mark follows every thread's reads above
         } else {
@@ -1108,9 +1118,8 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
 #pragma unroll
             for (int k = 0; k < kScanItems; ++k) {
                 const int pos = k * kScanThreads + tid;
-                if (pos < lim) {
-                    expand_store(p, anc, static_cast<long long>(S0) + cb + pos, jbase + s_mark[pos]);
-                }
+                const long long slot = static_cast<long long>(W0) + cb + pos;
+                if (pos < lim && slot >= S0) expand_store(p, anc, slot, jbase + s_mark[pos]);
             }
             __syncthreads();
         }
