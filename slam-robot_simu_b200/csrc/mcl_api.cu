@@ -340,6 +340,13 @@ int launch_shard_scan(mcl_filter *h, ScanParams &sp, int mode, cudaStream_t st) 
     h->tile_prefix_valid = false;
     h->desc_stale = false;  // the trailing k_reset_scan below leaves zeros
     dim3 grid(h->lay.tpt, 1);
+    static const bool persistent_expand = [] { const char *e = std::getenv("MCL_EXPAND_PERSISTENT"); return e == nullptr || e[0] != '0'; }();
+    if (sp.tile_prefix != nullptr && persistent_expand) {
+        // tiles are independent once their prefixes are known: persistent CTAs (tickets) pay the kernel prologue once
+        // per CTA instead of once per tile (expand 0.55 -> 0.50 ms at 125 M particles)
+        sp.persistent = 1;
+        grid.x = std::min(h->lay.tpt, h->sm_count * 4);
+    }
     if (mode == kScanTotals) k_scan<kScanTotals><<<grid, kScanThreads, 0, st>>>(sp);
     else k_scan<kScanExpand><<<grid, kScanThreads, 0, st>>>(sp);
     MCL_LAUNCH_CHECK(h, "k_scan");
