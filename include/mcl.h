@@ -181,6 +181,11 @@ int mcl_pose_moments(mcl_filter *h, void *stream);
 /* ---- results ---------------------------------------------------------------------------------
  * Copies [n_trials] mcl_stats to host memory and synchronises the stream. */
 int mcl_get_stats(mcl_filter *h, mcl_stats *out_host, void *stream);
+/* The same in two halves, so the host can work while the step runs: mcl_get_stats_begin enqueues the pending
+ * merge, the copy into a pinned buffer of the handle and an event, and returns at once; mcl_get_stats_end waits
+ * for that event only and fills out_host (log_norm / max_weight / mean / cov derived on the host as above). */
+int mcl_get_stats_begin(mcl_filter *h, void *stream);
+int mcl_get_stats_end(mcl_filter *h, mcl_stats *out_host);
 /* Device address of the [n_trials] mcl_stats block (for callers that poll asynchronously).  On the device
  * only the sums, ess, max_idx and est are current (see `derived`). */
 int mcl_stats_dev(mcl_filter *h, const mcl_stats **out_dev);

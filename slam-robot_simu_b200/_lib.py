@@ -108,6 +108,8 @@ PROTOTYPES = {
     "mcl_pose_moments": (C.c_int, [_vp, _vp]),
     "mcl_get_stats": (C.c_int, [_vp, _P(mcl_stats), _vp]),
     "mcl_stats_dev": (C.c_int, [_vp, _P(_vp)]),
+    "mcl_get_stats_begin": (C.c_int, [_vp, _vp]),
+    "mcl_get_stats_end": (C.c_int, [_vp, _P(mcl_stats)]),
     "mcl_sync_stats": (C.c_int, [_vp, _vp]),
     "mcl_get_weights": (C.c_int, [_vp, _vp, _vp]),
     "mcl_get_qweights": (C.c_int, [_vp, _vp, _vp]),

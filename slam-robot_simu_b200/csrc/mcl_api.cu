@@ -121,6 +121,9 @@ struct mcl_filter {
     uint32_t step = 0;
     bool have_particles = false;
     bool stats_from_particle0 = false;  // next reduce-only pass takes its reference pose from particle 0
+    mcl_stats *stats_pinned = nullptr;  // pinned landing buffer of mcl_get_stats_begin/_end
+    cudaEvent_t stats_event = nullptr;
+    bool stats_pending = false;
     bool stats_dirty = false;           // the CTA partials of the last k_step / k_reduce are newer than stats[]
     bool tile_prefix_valid = false;     // desc[desc_cur] holds the tile prefixes of the CURRENT weights (mcl_shard_total)
     bool desc_stale = false;            // desc[desc_cur] holds tile sums, not the zeros a look-back scan starts from
@@ -674,6 +677,8 @@ int mcl_destroy(mcl_filter *h) {
     cudaSetDevice(h->cfg.device);
     for (cudaEvent_t &e : h->ev)
         if (e) cudaEventDestroy(e);
+    if (h->stats_event) cudaEventDestroy(h->stats_event);
+    if (h->stats_pinned) cudaFreeHost(h->stats_pinned);
     if (h->dbg) cudaFree(h->dbg);
     if (h->owns_ws && h->ws) cudaFree(h->ws);
     delete h;
@@ -871,6 +876,36 @@ int mcl_get_stats(mcl_filter *h, mcl_stats *out_host, void *stream) {
                                 S(stream)));
     MCL_CUDA(h, cudaStreamSynchronize(S(stream)));
     for (int t = 0; t < h->lay.T; ++t) derive_stats(out_host[t]);  // log-normaliser, mean, covariance from the sums
+    return MCL_OK;
+}
+
+int mcl_get_stats_begin(mcl_filter *h, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    const size_t bytes = static_cast<size_t>(h->lay.T) * sizeof(mcl_stats);
+    if (h->stats_pinned == nullptr) {  // first use: the landing buffer and the event of the read-back
+        MCL_CUDA(h, cudaHostAlloc(reinterpret_cast<void **>(&h->stats_pinned), bytes, cudaHostAllocDefault));
+        MCL_CUDA(h, cudaEventCreateWithFlags(&h->stats_event, cudaEventDisableTiming));
+    }
+    rc = ensure_stats(h, S(stream));
+    if (rc != MCL_OK) return rc;
+    MCL_CUDA(h, cudaMemcpyAsync(h->stats_pinned, h->stats, bytes, cudaMemcpyDeviceToHost, S(stream)));
+    MCL_CUDA(h, cudaEventRecord(h->stats_event, S(stream)));
+    h->stats_pending = true;
+    return MCL_OK;
+}
+
+int mcl_get_stats_end(mcl_filter *h, mcl_stats *out_host) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (out_host == nullptr) return fail(h, MCL_ERR_ARG, "out_host is NULL");
+    if (!h->stats_pending) return fail(h, MCL_ERR_STATE, "mcl_get_stats_end without mcl_get_stats_begin");
+    MCL_CUDA(h, cudaEventSynchronize(h->stats_event));
+    h->stats_pending = false;
+    for (int t = 0; t < h->lay.T; ++t) {
+        out_host[t] = h->stats_pinned[t];
+        derive_stats(out_host[t]);  // log-normaliser, mean, covariance from the sums
+    }
     return MCL_OK;
 }
 

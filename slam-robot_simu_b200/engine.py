@@ -106,7 +106,7 @@ class Filter:
     @staticmethod
     def _f64(a, shape):
         a = np.ascontiguousarray(a, dtype=np.float64)
-        if a.size != int(np.prod(shape)):
+        if a.size != math.prod(shape):
             raise ValueError(f"expected {shape}, got {a.shape}")
         return a
 
@@ -215,6 +215,16 @@ class Filter:
     def stats(self):
         arr = (L.mcl_stats * self.T)()
         self._check(self.lib.mcl_get_stats(self._h, arr, self._stream()), "mcl_get_stats")
+        return list(arr)
+
+    def stats_begin(self):
+        """First half of stats(): enqueue the merge and the copy into a pinned buffer of the handle, return at once.
+        The host is free until stats_end() -- ParticleFilter.main_pf simulates the next frame's observation there."""
+        self._check(self.lib.mcl_get_stats_begin(self._h, self._stream()), "mcl_get_stats_begin")
+
+    def stats_end(self):
+        arr = (L.mcl_stats * self.T)()
+        self._check(self.lib.mcl_get_stats_end(self._h, arr), "mcl_get_stats_end")
         return list(arr)
 
     def stats_dev_bytes(self):

@@ -168,13 +168,14 @@ class ParticleFilter:
         z_l = z_ahead if z_ahead is not None else self.__observation(self.__x_true)  # :110
 
         flt.step(z_l[None], ofs=ofs, noise=noise, force_resample=do_resample, no_resample=not do_resample)
+        flt.stats_begin()  # merge + device-to-host copy of the statistics block, enqueued behind the step
         if self.__noise == "philox":
             # The kernels are in flight: simulate the NEXT frame's ground truth and observation now (:100, :110 of
             # the next call).  Neither depends on the filter, and with on-device noise the observation draw is the
             # only consumer of np.random, so the stream is consumed in the same order, one frame early.
             x_next = self.__f(self.__x_true)
             self.__ahead = (x_next, self.__observation(x_next))
-        st = flt.stats()[0]
+        st = flt.stats_end()[0]
         self.last_stats = st
         self.__ess = st.ess
 
