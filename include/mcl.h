@@ -213,6 +213,13 @@ uint64_t mcl_launch_count(const mcl_filter *h);
  * 6 statistics written, 7..10 stages of the merge (last CTA only). */
 int mcl_debug_timeline(mcl_filter *h, uint64_t *stamps_host, int64_t capacity, int32_t *n_ctas);
 
+/* ---- checkpoint ------------------------------------------------------------------
+ * The state of a filter is its particles (mcl_get_particles, log-weights included), its [n_trials] mcl_stats
+ * (mcl_get_stats: weight map, ESS gate, MAP pose = next reference pose) and the step counter (mcl_stats.step; the
+ * Philox counter).  mcl_restore installs the last two after mcl_set_particles(..., MCL_SET_SKIP_STATS): the
+ * restored filter continues bit-identically to the one that was saved. */
+int mcl_restore(mcl_filter *h, const mcl_stats *stats_host, uint32_t step, void *stream);
+
 /* ---- particle-sharded single filter (n_trials == 1, one handle per GPU) -----------------------
  * The host exchanges the small records; see slam-robot_simu_b200/sharded.py.  Order per step:
  *   mcl_predict_weight on every shard -> allgather of mcl_stats -> mcl_shard_merge (or a host merge +

@@ -124,6 +124,7 @@ PROTOTYPES = {
     "mcl_shard_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_uint32, _vp]),
     "mcl_shard_set_global": (C.c_int, [_vp, _P(mcl_stats), _vp]),
     "mcl_shard_merge": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "mcl_restore": (C.c_int, [_vp, _P(mcl_stats), C.c_uint32, _vp]),
 }
 
 _lib = None

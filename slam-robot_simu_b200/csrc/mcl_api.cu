@@ -1127,6 +1127,22 @@ int mcl_shard_step(mcl_filter *h, const double *z_host, const float *noise_dev, 
     return MCL_OK;
 }
 
+int mcl_restore(mcl_filter *h, const mcl_stats *stats_host, uint32_t step, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (stats_host == nullptr) return fail(h, MCL_ERR_ARG, "stats_host is NULL");
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "mcl_restore follows mcl_set_particles (MCL_SET_SKIP_STATS)");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    MCL_CUDA(h, cudaMemcpyAsync(h->stats, stats_host, static_cast<size_t>(h->lay.T) * sizeof(mcl_stats),
+                                cudaMemcpyHostToDevice, S(stream)));
+    MCL_CUDA(h, cudaStreamSynchronize(S(stream)));
+    h->step = step;
+    h->stats_from_particle0 = false;
+    h->stats_dirty = false;
+    h->tile_prefix_valid = false;
+    return MCL_OK;
+}
+
 int mcl_shard_merge(mcl_filter *h, const mcl_stats *records_dev, int n_shards, void *stream) {
     if (h == nullptr) return MCL_ERR_ARG;
     if (records_dev == nullptr || n_shards < 1) return fail(h, MCL_ERR_ARG, "records_dev is NULL or n_shards < 1");

@@ -68,6 +68,11 @@ class Filter:
             cfg.dt = float(dt)
         lm = None if landmarks is None else np.ascontiguousarray(landmarks, dtype=np.float64).reshape(-1, 2)
         cfg.max_landmarks = int(max_landmarks if max_landmarks is not None else max(1, 0 if lm is None else len(lm), 8))
+        self._create(cfg, lm)
+
+    def _create(self, cfg, lm):
+        torch = _torch()
+        self.lib = L.load()
         self.cfg = cfg
         self.n = cfg.n_particles
         self.T = cfg.n_trials
@@ -84,6 +89,31 @@ class Filter:
         self.n_landmarks = 0
         if lm is not None:
             self.set_landmarks(lm)
+
+    # ------------------------------------------------------------------ checkpoint
+    def save(self, path):
+        """Everything a bit-identical continuation needs, as one .npz: config, landmarks, particles with their
+        log-weights, the statistics block (weight map, gate, MAP pose) and the step counter."""
+        x, y, th, lw = self.get_particles()
+        st = (L.mcl_stats * self.T)(*self.stats())
+        np.savez(path, config=np.frombuffer(bytes(self.cfg), dtype=np.uint8), landmarks=self.landmarks,
+                 x=x, y=y, yaw=th, logw=lw, stats=np.frombuffer(bytes(st), dtype=np.uint8), step=np.int64(st[0].step),
+                 abi=np.int64(L.MCL_ABI_VERSION))
+
+    @classmethod
+    def load(cls, path, device=None):
+        with np.load(path) as z:
+            if int(z["abi"]) != L.MCL_ABI_VERSION:
+                raise ValueError(f"{path}: written with ABI {int(z['abi'])}, this library is ABI {L.MCL_ABI_VERSION}")
+            cfg = L.mcl_config.from_buffer_copy(z["config"].tobytes())
+            if device is not None:
+                cfg.device = int(device)
+            self = cls.__new__(cls)
+            self._create(cfg, np.ascontiguousarray(z["landmarks"], dtype=np.float64))
+            self.set_particles(z["x"], z["y"], z["yaw"], z["logw"], skip_stats=True)
+            st = (L.mcl_stats * self.T).from_buffer_copy(z["stats"].tobytes())
+            self._check(self.lib.mcl_restore(self._h, st, int(z["step"]), self._stream()), "mcl_restore")
+        return self
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):

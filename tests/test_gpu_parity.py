@@ -801,3 +801,76 @@ def test_rb_fan_gate_and_empty_scan(mcl):
     st = f2.stats()[0]
     assert np.isfinite(st.ess) and 1.0 <= st.ess <= n
     assert np.hypot(st.est[0] - truth[0, 0], st.est[1] - truth[1, 0]) < 3.0
+
+
+class _AxStub:
+    def __init__(self, log):
+        self.log = log
+
+    def __getattr__(self, name):
+        def call(*a, **k):
+            self.log.append((name, a, k))
+        return call
+
+
+class _PltStub(_AxStub):
+    def subplot2grid(self, *a, **k):
+        return _AxStub(self.log)
+
+
+@pytest.mark.gpu
+def test_animation_caller_consumes_the_dropin(mcl):
+    """the reference's animation loop (particle_filter.py:248-328), restated in
+    examples/animate_pf.py, runs frame by frame against the GPU class: the 7-tuple, px read lazily and
+    sub-sampled for drawing, the covariance ellipse.  (matplotlib is not needed: a recording stub stands in.)"""
+    import importlib.util
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("animate_pf", os.path.join(root, "examples", "animate_pf.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    np.random.seed(0)
+    pf = mcl.ParticleFilter(100, n_particles=50000, noise="philox", likelihood="moment", lazy_px=True)
+    log = []
+    anim = mod.Animator(pf, 100, _PltStub(log), max_scatter=4000)
+    for i in range(3):
+        out = anim.frame(i)
+    assert out["n_drawn"] == 4000 and out["time_s"] == pytest.approx(0.3)
+    assert 0 <= out["w_idx"] < 50000 and 0.0 < out["w_val"] <= 1.0
+    assert np.all(np.linalg.eigvalsh(out["cov"][0:2, 0:2]) > 0)
+    names = [c[0] for c in log]
+    assert names.count("scatter") >= 3 * 8 and "quiver" in names and "annotate" in names
+    e = mod.ellipse_points(np.diag([4.0, 1.0]), chi2=1.0)
+    assert np.abs(e[0]).max() == pytest.approx(2.0, rel=1e-3) and np.abs(e[1]).max() == pytest.approx(1.0, rel=1e-2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("trials", [1, 3])
+def test_checkpoint_restores_a_bit_identical_filter(mcl, tmp_path, trials):
+    """Filter.save / Filter.load -- the restored filter continues exactly like the saved one
+    (same Philox counters, same weight map, same reference pose), gated resampling included."""
+    n, Lm = 20000, 7
+    rng = np.random.RandomState(4)
+    lm = rng.uniform(-10, 10, (Lm, 2))
+    tr = __import__("bench").Truth(lm, seed=2, T=trials)
+    f = mcl.Filter(n_particles=n, n_trials=trials, landmarks=lm, likelihood="moment", seed=99)
+    f.init_particles(tr.pose())
+    zs = []
+    for _ in range(12):
+        tr.advance()
+        zs.append(tr.observe())
+    for k in range(6):
+        f.step(zs[k])  # ESS-gated: some of these steps resample, some do not
+    path = str(tmp_path / "ckpt.npz")
+    f.save(path)
+    g = mcl.Filter.load(path)
+    assert g.n == n and g.T == trials and g.n_landmarks == Lm
+    for k in range(6, 12):
+        f.step(zs[k])
+        g.step(zs[k])
+    for a, b in zip(f.get_particles(), g.get_particles()):
+        np.testing.assert_array_equal(a, b)
+    sa, sb = f.stats(), g.stats()
+    for t in range(trials):
+        assert sa[t].max_idx == sb[t].max_idx and sa[t].ess == sb[t].ess and sa[t].step == sb[t].step == 12
+        assert sa[t].resampled == sb[t].resampled
