@@ -27,7 +27,7 @@ L2_BYTES = 126 * 1024 * 1024
 BYTES_STEP_CANONICAL = 64  # fp32 SoA state, predict+weight 32 B + scan 4 B + gather 28 B
 BYTES_K_STEP = 32          # k_step as built: ancestor 4 B + gathered pose 12 B in, pose + log-weight 16 B out
 BYTES_K_SCAN = 8           # k_scan: log-weight 4 B in, ancestor 4 B out
-NCU_TRAFFIC_K_STEP_BYTES_PER_PARTICLE = (469.743360e6 + 499.869696e6) / 33554432  # profiles/r01_h_ncu_32M_x64_summary.csv
+NCU_TRAFFIC_K_STEP_BYTES_PER_PARTICLE = (528.388608e6 + 501.015552e6) / 33554432  # profiles/r01_r_ncu_32M_x64_k_step_summary.csv
 
 WORKLOADS = {
     # name: (particles per filter, landmarks, trials per GPU, description)
@@ -439,7 +439,7 @@ def run_b200(args, wl):
         roof = {"bound": "hbm", "kernel": "k_step (gather + predict + weight + statistics)", "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_K_STEP_BYTES_PER_PARTICLE * n_ * T_,
                 "traffic_source": "ncu --set full, 32M particles x 64 landmarks: dram__bytes_read + write of k_step per "
-                                  "particle (profiles/r01_h_ncu_32M_x64_summary.csv), scaled to this launch",
+                                  "particle (profiles/r01_r_ncu_32M_x64_k_step_summary.csv), scaled to this launch",
                 "peak_source": peak_src, "algorithmic_bytes_per_particle": BYTES_K_STEP,
                 "kernel_ms": {"k_scan": kt[1], "k_step": kt[2]},
                 "scan_achieved_GBps": BYTES_K_SCAN * n_ * T_ / (kt[1] * 1e-3) / 1e9,
