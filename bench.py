@@ -284,7 +284,18 @@ def measure_sharded(mcl, torch, dist, dev, n_per_gpu, L, likelihood, steps, warm
     sf = mcl.ShardedParticleFilter(n_global, lm, likelihood=likelihood, seed=4711, max_landmarks=L)
     sf.init_particles(truth.pose()[0])
     k = 0
+    # untimed: at least `warmup` steps AND at least 0.6 s of them -- a sharded step is ~2 ms, so a handful of steps
+    # ends before the clocks of all GPUs have left their idle state (W is a minimum, not a maximum)
+    t_warm = time.perf_counter()
     for _ in range(max(warmup, 3)):
+        sf.step(cyc[k % Truth.PERIOD], force_resample=True)
+        k += 1
+    torch.cuda.synchronize()
+    # the steps contain collectives, so every rank must take the SAME number of extra steps: agree on it first
+    per_step = torch.tensor([(time.perf_counter() - t_warm) / max(warmup, 3)], device=dev, dtype=torch.float64)
+    dist.all_reduce(per_step, op=dist.ReduceOp.MAX)
+    extra = int(min(400, max(0.0, 0.6 / max(float(per_step.item()), 1e-4) - max(warmup, 3))))
+    for _ in range(extra):
         sf.step(cyc[k % Truth.PERIOD], force_resample=True)
         k += 1
     torch.cuda.synchronize()
