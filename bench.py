@@ -140,20 +140,30 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
             getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
         }
+        self._names = names
         while not self._stop_evt.is_set():
             if self.active.is_set():
-                try:
-                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                    try:
-                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                    except Exception:
-                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                    for bit, name in names.items():
-                        if r & bit:
-                            self.reasons.add(name)
-                except Exception:
-                    pass
+                self.sample_once()
             time.sleep(0.002)
+
+    def sample_once(self):
+        """One reading (also usable without the thread: a host-driven loop must not share the driver with NVML)."""
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = getattr(self, "_names", None) or {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                                                  0x4: "sw_power_cap"}
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
     def stop(self):
         self._stop_evt.set()
@@ -301,6 +311,12 @@ def measure_sharded(mcl, torch, dist, dev, n_per_gpu, L, likelihood, steps, warm
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
+    # The sharded step is host-driven, and NVML queries share the driver with the launches (a polling thread
+    # slowed the step 2.5x): the clocks are read once right before and once right after the timed steps, while the
+    # GPU is still loaded by them.
+    sampler = ClockSampler(dev.index)
+    sampler.sample_once()
+    launches0 = sf.flt.launch_count()
     t0 = time.perf_counter()
     moved = 0
     for _ in range(steps):
@@ -313,12 +329,14 @@ def measure_sharded(mcl, torch, dist, dev, n_per_gpu, L, likelihood, steps, warm
     dist.barrier()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    sampler.sample_once()
+    launches = sf.flt.launch_count() - launches0
     t = torch.tensor([dt, float(moved)], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t[0].item())
     out = {"workload": f"one filter of {n_global} particles x {L} landmarks over {world} GPUs, global systematic resampling",
            "value": n_global * steps / dt, "unit": "particle-steps/s", "ms_per_step": dt / steps * 1e3, "steps": steps,
-           "ess_over_n": g["ess"] / n_global,
+           "ess_over_n": g["ess"] / n_global, "gpu_launches_rank0": int(launches), "clocks_rank0": sampler.summary(),
            "max_slots_sent_off_rank_per_step": float(t[1].item()) / steps,
            "collectives": "allgather(mcl_stats 312 B) -> device merge; allgather(u64 weight total); one batched NCCL P2P group for the fp32 poses of off-rank slots"}
     del sf
@@ -361,7 +379,7 @@ def run_b200(args, wl):
                                                   "h2d_bytes_per_step": 16 * L + 304, "d2h_bytes_per_step": 304 + 8 + 16,
                                                   "note": "the sharded step is host-mediated: its timing already includes the "
                                                           "observation upload and the statistics read-back of every step"},
-                    "sharded_filter": sh, "gpu_launches": None}
+                    "sharded_filter": sh, "gpu_launches": sh["gpu_launches_rank0"] * world, "clocks": sh["clocks_rank0"]}
             print(json.dumps(line), flush=True)
         dist.destroy_process_group()
         return
