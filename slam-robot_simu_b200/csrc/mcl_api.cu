@@ -350,8 +350,7 @@ int launch_shard_scan(mcl_filter *h, ScanParams &sp, int mode, cudaStream_t st) 
         sp.persistent = 1;
         grid.x = std::min(h->lay.tpt, h->sm_count * 4);
     }
-    if (mode == kScanTotals) k_scan<kScanTotals><<<grid, kScanThreads, 0, st>>>(sp);
-    else k_scan<kScanExpand><<<grid, kScanThreads, 0, st>>>(sp);
+    k_scan<kScanExpand><<<grid, kScanThreads, 0, st>>>(sp);
     MCL_LAUNCH_CHECK(h, "k_scan");
     k_reset_scan<<<(h->lay.tpt + 255) / 256, 256, 0, st>>>(sp.desc, sp.ready, h->tickets, h->lay.tpt);
     MCL_LAUNCH_CHECK(h, "k_reset_scan");

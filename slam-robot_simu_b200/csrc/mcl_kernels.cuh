@@ -632,7 +632,6 @@ struct ScanParams {
 
 constexpr int kDirectTiles = 1024;  // tiles that sum all predecessors' aggregates directly (2M particles)
 constexpr int kScanAncestors = 0;  // write the ancestor of every slot
-constexpr int kScanTotals = 1;     // only the inclusive total of the quantised weights
 constexpr int kScanExpand = 2;     // write the resampled pose of every slot (sender side of the sharded filter)
 
 enum : unsigned long long {
@@ -810,10 +809,8 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
         for (int k = 0; k < kScanItems; ++k) qd[k] = 0.0;
     }
     // the first mark window is cleared here, off the critical path: the barriers of the block scan order it
-    if (MODE != kScanTotals) {
-        *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(0u, 0u, 0u, 0u);  // the thread's own 32 bytes
-        *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(0u, 0u, 0u, 0u);
-    }
+    *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(0u, 0u, 0u, 0u);  // the thread's own 32 bytes
+    *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(0u, 0u, 0u, 0u);
     double tsum_d = 0.0;  // sums of integers below 2^53 are exact in fp64
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) tsum_d += qd[k];
@@ -936,11 +933,6 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     // every later tile's look-back.  Its round trip overlaps the ancestor phase below.
     if (tid == 0) s_next[it & 1] = p.persistent ? atomicAdd(&p.tickets[t * 4 + 0], 1u) : 0xffffffffu;
     dbg_stamp(p.dbg, 3);
-    if (MODE == kScanTotals) {
-        __syncthreads();  // s_next[] is read by the loop header; shared scratch is reused by the next tile
-        continue;
-    }
-
     // ---- slot range of every source: u32 counts, non-owners carry rel = 2^31 (never inside a window) ----
     const double nd = static_cast<double>(p.n_global);
     const CombFast cf = make_comb_fast(ofs, nd);
