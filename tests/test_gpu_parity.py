@@ -445,12 +445,22 @@ def test_error_paths(mcl):
 def test_sharded_step_matches_unsharded(mcl, G, kind):
     """G shards (G handles on this one GPU, the all-to-all done by hand) take one full step --
     global resampling, predict, weight -- and end with exactly the particles of the unsharded filter."""
+    _sharded_step_case(mcl, G, kind, 1 << 16)
+
+
+def test_sharded_step_with_segmented_tile_prefixes(mcl):
+    """The same at a size where mcl_shard_total's CTAs each sum SEVERAL scan tiles (more than 1024 tiles per
+    shard: 4.2 M particles), so the expansion starts its tiles from segment prefix + tile prefix."""
+    _sharded_step_case(mcl, 2, "spread", 1 << 23)
+
+
+def _sharded_step_case(mcl, G, kind, n):
     import importlib
 
     import torch
 
     sh = importlib.import_module("slam-robot_simu_b200.sharded")
-    n, Lm = 1 << 16, 6
+    Lm = 6
     m = n // G
     rng = np.random.RandomState(G + len(kind))
     lm = rng.uniform(-10, 10, (Lm, 2))
