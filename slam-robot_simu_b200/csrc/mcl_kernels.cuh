@@ -596,7 +596,7 @@ struct ScanParams {
     // (max, sum, sum^2), the scalars CTA the arg-max, and one more extra CTA merges everything into stats[]
     const double *partials;     // [T][n_partials][kPart]
     int n_partials;
-    uint4 *wm_pub;              // [T][2] {weight-map m, scale, resample gate, epoch}, {comb offset, epoch}: published by the tile with ticket 0
+    uint4 *wm_pub;              // [T][2] {weight-map m, scale, resample gate, epoch}, {comb offset, epoch}: published by tile 0
     unsigned int epoch;         // scan launches of this handle so far (never 0: the words start as 0)
     StateView cur;              // the stored state (MAP pose lookup)
     unsigned long long *desc;   // [T][tpt] tile descriptors of this launch (all zero on entry)
