@@ -3,19 +3,23 @@
 Rank g owns the contiguous global particles / output slots [g * m, (g + 1) * m), m = n_global / G.
 Predict + weight is local.  Two exchanges couple the shards:
 
-  * statistics -- every rank allgathers its 312-byte mcl_stats record and merges them on the host
-    (`merge_stats`): global max, normaliser, ESS, arg-max, weighted mean / covariance.  The merged
-    record goes back into every shard (mcl_shard_set_global), so all shards quantise their weights
-    with the same map and take the same resampling decision;
-  * resampling -- allgather of the per-shard integer weight totals gives every shard the cumulative
-    offset of its first particle; because the weights are integers on a 2^-52 grid the global scan is
-    exact, and each shard computes, with GLOBAL slot numbers, the resampled pose of every slot its own
-    particles fill (mcl_shard_expand).  Ancestors are monotone, so that is one contiguous slot range
-    per shard (`shard_ranges` derives all of them from the totals).  Slots inside a shard's own range
-    keep the local ancestor/gather path; only the slots owned by other ranks are materialised as poses
-    and travel in one variable-count all-to-all per pose array (`plan_offrank`, NCCL over NVLink).
-    mcl_shard_step then predicts + weights [received prefix | locally gathered middle | received suffix].
+  * statistics -- every rank allgathers its 312-byte mcl_stats record straight from device memory and merges
+    the records on the device (mcl_shard_merge; `merge_stats` below is its host twin, used by the CPU
+    tests): global max, normaliser, ESS, arg-max, weighted mean / covariance.  All shards then quantise
+    their weights with the same map and take the same resampling decision;
+  * resampling -- a first pass (mcl_shard_total) sums the shard's integer weights, tile by tile; the allgather
+    of the totals gives every shard the cumulative offset of its first particle; because the weights are
+    integers on a 2^-52 grid the global scan is exact, and each shard computes, with GLOBAL slot numbers, the
+    resampled pose of every slot its own particles fill (mcl_shard_expand, every scan tile starting from the
+    prefixes of the first pass).  Ancestors are monotone, so that is one contiguous slot range per shard
+    (`shard_ranges` derives all of them from the totals).  Slots inside a shard's own range keep the local
+    ancestor/gather path; only the slots owned by other ranks are materialised as poses and travel in one
+    batched group of NCCL point-to-point transfers (`plan_offrank`, `exchange_offrank`).  mcl_shard_step then
+    predicts + weights [received prefix | locally gathered middle | received suffix].
     The result is bit-identical to the unsharded filter, and to the reference walk of :212-221.
+
+A step synchronises with the host once (the read-back of the merged statistics and the totals); when those say
+the next step will resample, its expansion is started right away so the host work between two steps is hidden.
 
 The pure-host pieces (`merge_stats`, `plan_exchange`, `exchange`, `philox_ofs`) import neither CUDA
 nor the C library and are what the world_size-2 gloo tests exercise on CPU.
