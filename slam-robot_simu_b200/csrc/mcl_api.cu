@@ -285,7 +285,7 @@ int ensure_stats(mcl_filter *h, cudaStream_t st) {
     m.stats = h->stats;
     m.cur = h->state[h->cur];
     m.ld = h->lay.ld;
-    k_merge<<<h->lay.T, kStepThreads, 0, st>>>(m);
+    launch_pdl(k_merge, dim3(h->lay.T), dim3(kStepThreads), 0, st, pdl_enabled() && !h->profiling, m);
     MCL_LAUNCH_CHECK(h, "k_merge");
     h->stats_dirty = false;
     return MCL_OK;

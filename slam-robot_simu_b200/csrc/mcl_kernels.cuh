@@ -566,6 +566,7 @@ struct MergeParams {
     long long ld;
 };
 __global__ void __launch_bounds__(kStepThreads) k_merge(const MergeParams p) {
+    cudaGridDependencySynchronize();  // launched programmatically behind k_step: its launch latency is hidden
     const int t = blockIdx.x;
     const long long off = static_cast<long long>(t) * p.ld;
     merge_full(p.partials + static_cast<long long>(t) * p.bpt * kPart, p.bpt, p.stats + t, p.cur.x + off, p.cur.y + off,
