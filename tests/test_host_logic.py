@@ -169,3 +169,25 @@ def test_sharded_host_logic_under_gloo_world_size_2():
            "--master-port", "29617", os.path.join(ROOT, "tests", "_gloo_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "gloo worker ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_bench_fan_observations_follow_the_sensor_gate():
+    """bench.Truth(fan=True) -- the synthetic input of the C4 fan-sensor line -- detects exactly the landmarks the
+    reference's gate admits (oracle.fan_visible, graph_based_slam.py:155-160) and keeps (distance, direction)."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    lm = bench.landmarks_for(256)
+    tr = bench.Truth(lm, seed=3, T=2, fan=True)
+    for _ in range(5):
+        tr.advance()
+    z = tr.observe()
+    assert z.shape == (2, 256, 2)
+    for t in range(2):
+        pose = tr.pose()[t].reshape(3, 1)
+        p = O.world2robot(pose, lm)
+        vis = O.fan_visible(p, 15.0, np.deg2rad(80.0))
+        assert np.array_equal(np.isfinite(z[t, :, 0]), vis) and 0 < vis.sum() < 256
+        d = np.hypot(p[vis, 0], p[vis, 1])
+        assert np.all(np.abs(z[t, vis, 0] / d - 1.0) < 0.3)  # 5 % distance noise
+        assert np.all(np.abs(O.limit_angle_vec(z[t, vis, 1] - np.arctan2(p[vis, 1], p[vis, 0]))) < 0.25)  # 2 deg noise
