@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MCL_ABI_VERSION 2
+#define MCL_ABI_VERSION 3
 
 typedef struct mcl_filter mcl_filter; /* opaque */
 
@@ -199,9 +199,9 @@ int mcl_get_qweights(mcl_filter *h, uint64_t *q_host, void *stream);
 int mcl_get_ancestors(mcl_filter *h, uint32_t *anc_host, void *stream);
 
 /* ---- measurement hooks (bench.py) -----------------------------------------------------------------
- * mcl_profile(h, 1): every following mcl_step* call brackets its three kernels (k_prep, k_scan_ancestors,
- * k_step) with CUDA events on the caller's stream.  mcl_profile_read synchronises on the last step and
- * returns that step's kernel durations in milliseconds: ms[0] prep, ms[1] scan, ms[2] step.
+ * mcl_profile(h, 1): every following mcl_step* call brackets its two kernels (k_scan, k_step) with CUDA
+ * events on the caller's stream.  mcl_profile_read synchronises on the last step and returns that step's
+ * kernel durations in milliseconds: ms[0] = 0 (historic: a separate prep kernel), ms[1] k_scan, ms[2] k_step.
  * mcl_launch_count: kernels launched through this handle since creation. */
 int mcl_profile(mcl_filter *h, int enable);
 int mcl_profile_read(mcl_filter *h, double *ms3_host);
@@ -251,6 +251,56 @@ int mcl_shard_expand(mcl_filter *h, uint64_t k_offset, double ofs, float *send_x
 int mcl_shard_step(mcl_filter *h, const double *z_host, const float *noise_dev, const float *recv_x_dev,
                    const float *recv_y_dev, const float *recv_yaw_dev, int64_t n_prefix, int64_t n_suffix, uint32_t flags,
                    void *stream);
+
+/* ---- particle-sharded single filter, DEVICE-DRIVEN (peer memory over NVLink / NVSwitch) -------------------------
+ * The same step as the calls above with no host in the loop: statistics records, weight totals and the resampled
+ * poses of off-rank slots are written by the producing kernels straight into the peers' memory, flags carry the
+ * step number, slot ranges are derived on the device, and nothing synchronises with the host.  Semantics are those
+ * of particle_filter.py:210-224 on the GLOBAL weights; results are bit-identical to the host-driven calls above.
+ *
+ *   mcl_shard_peer_alloc    allocates this shard's peer-visible region (mailbox + receive staging of n_particles
+ *                           poses) with cudaMalloc and returns its CUDA IPC handle (64 bytes; may be NULL).
+ *   mcl_shard_peer_connect  maps the peers' regions: `ipc_handles` = the n_shards handles in rank order (other
+ *                           processes, one per GPU), or `local_peers` = the n_shards handles of THIS process
+ *                           (several devices, or several shards on one device as the tests do).  Exactly one of
+ *                           the two is non-NULL.
+ *   mcl_shard_step_peer     main_pf minus the ground-truth line for this shard: [totals -> exchange -> expansion ->
+ *                           exchange] when the step resamples (MCL_FORCE_RESAMPLE, or the ESS gate the previous
+ *                           statistics exchange left on the device), predict + weight, statistics exchange.
+ *                           ofs_host: one comb offset (rand() * NP_RECIP) or NULL = the Philox draw of the
+ *                           unsharded filter.  `stages`: MCL_STAGE_ALL for a real step.  The one-GPU emulation
+ *                           calls the four stages separately, each for all shards in turn, so that every "push"
+ *                           precedes the matching "wait" on a single stream.
+ *   mcl_shard_sync_peer     the statistics exchange alone (after mcl_set_particles), stages MCL_STAGE_C | _D.
+ *   mcl_shard_get_plan      synchronises and copies the plan of the last step (diagnostics, error flag).
+ * Statistics: mcl_get_stats / _begin / _end return the GLOBAL record after a step. */
+#define MCL_IPC_HANDLE_BYTES 64
+#define MCL_MAX_SHARDS 16
+#define MCL_STAGE_A 1u /* integer weight totals; push them                                   */
+#define MCL_STAGE_B 2u /* wait for the totals; plan; expansion; push "done"                  */
+#define MCL_STAGE_C 4u /* wait for "done"; predict + weight; push the statistics record      */
+#define MCL_STAGE_D 8u /* wait for the records; merge; resampling gate of the next step      */
+#define MCL_STAGE_ALL 15u
+
+typedef struct mcl_shard_plan {
+    uint64_t k_offset;   /* sum of the integer weight totals of all lower-ranked shards                 */
+    double ofs;          /* comb offset of the step (particle_filter.py:214)                            */
+    int64_t first_slot;  /* global slots [first_slot, first_slot + n_slots) are filled by this shard    */
+    int64_t n_slots;
+    uint64_t totals[MCL_MAX_SHARDS];
+    uint32_t win_lo, win_hi; /* own output slots [win_lo, win_hi) gather locally, the rest came from peers */
+    int32_t gate;        /* 1: the merged ESS is below the threshold (:211) -> the next step resamples  */
+    int32_t resampled;   /* whether the step `epoch` resampled                                          */
+    int32_t error;       /* 1: a wait on a peer timed out (sticky)                                      */
+    uint32_t epoch;
+} mcl_shard_plan;
+
+int mcl_shard_peer_alloc(mcl_filter *h, int rank, int n_shards, unsigned char *ipc_handle_out);
+int mcl_shard_peer_connect(mcl_filter *h, const unsigned char *ipc_handles, mcl_filter *const *local_peers);
+int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_host, const float *noise_dev,
+                        uint32_t flags, uint32_t stages, void *stream);
+int mcl_shard_sync_peer(mcl_filter *h, uint32_t stages, void *stream);
+int mcl_shard_get_plan(mcl_filter *h, mcl_shard_plan *out_host, void *stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmcl_b200.so")
 
-MCL_ABI_VERSION = 2
+MCL_ABI_VERSION = 3
 
 MCL_OK = 0
 MCL_ERR_ARG = -1
@@ -30,6 +30,10 @@ MCL_MOTION_B = 1
 MCL_FORCE_RESAMPLE = 1
 MCL_NO_RESAMPLE = 2
 MCL_PHILOX_NOISE = 4
+
+MCL_IPC_HANDLE_BYTES = 64
+MCL_MAX_SHARDS = 16
+MCL_STAGE_A, MCL_STAGE_B, MCL_STAGE_C, MCL_STAGE_D, MCL_STAGE_ALL = 1, 2, 4, 8, 15
 
 
 class MclError(RuntimeError):
@@ -84,6 +88,22 @@ class mcl_stats(C.Structure):
     ]
 
 
+class mcl_shard_plan(C.Structure):
+    _fields_ = [
+        ("k_offset", C.c_uint64),
+        ("ofs", C.c_double),
+        ("first_slot", C.c_int64),
+        ("n_slots", C.c_int64),
+        ("totals", C.c_uint64 * MCL_MAX_SHARDS),
+        ("win_lo", C.c_uint32),
+        ("win_hi", C.c_uint32),
+        ("gate", C.c_int32),
+        ("resampled", C.c_int32),
+        ("error", C.c_int32),
+        ("epoch", C.c_uint32),
+    ]
+
+
 _P = C.POINTER
 _vp = C.c_void_p
 
@@ -125,6 +145,11 @@ PROTOTYPES = {
     "mcl_shard_set_global": (C.c_int, [_vp, _P(mcl_stats), _vp]),
     "mcl_shard_merge": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "mcl_restore": (C.c_int, [_vp, _P(mcl_stats), C.c_uint32, _vp]),
+    "mcl_shard_peer_alloc": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "mcl_shard_peer_connect": (C.c_int, [_vp, _vp, _P(_vp)]),
+    "mcl_shard_step_peer": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp]),
+    "mcl_shard_sync_peer": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "mcl_shard_get_plan": (C.c_int, [_vp, _P(mcl_shard_plan), _vp]),
 }
 
 _lib = None

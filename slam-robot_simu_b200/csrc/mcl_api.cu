@@ -121,9 +121,11 @@ struct mcl_filter {
     uint32_t step = 0;
     bool have_particles = false;
     bool stats_from_particle0 = false;  // next reduce-only pass takes its reference pose from particle 0
-    mcl_stats *stats_pinned = nullptr;  // pinned landing buffer of mcl_get_stats_begin/_end
-    cudaEvent_t stats_event = nullptr;
-    bool stats_pending = false;
+    // pinned landing buffers of mcl_get_stats_begin/_end: a ring of two, so the read-back of step k can still be
+    // in flight while step k + 1 is enqueued (the host then never idles the GPU waiting for statistics)
+    mcl_stats *stats_pinned[2] = {nullptr, nullptr};
+    cudaEvent_t stats_event[2] = {nullptr, nullptr};
+    uint64_t stats_begun = 0, stats_ended = 0;
     bool stats_dirty = false;           // the CTA partials of the last k_step / k_reduce are newer than stats[]
     bool tile_prefix_valid = false;     // desc[desc_cur] holds the tile prefixes of the CURRENT weights (mcl_shard_total)
     bool desc_stale = false;            // desc[desc_cur] holds tile sums, not the zeros a look-back scan starts from
@@ -133,6 +135,24 @@ struct mcl_filter {
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long *dbg = nullptr;  // optional k_step phase timeline (mcl_debug_timeline)
+    // pinned staging ring of the per-step host inputs (z, ofs): cudaMemcpyAsync from pageable memory may wait for
+    // the stream, which would put a host synchronisation into every step
+    static constexpr int kStageSlots = 4;
+    unsigned char *stage_pin[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t stage_ev[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+    bool stage_used[kStageSlots] = {false, false, false, false};
+    size_t stage_bytes = 0;
+    int stage_next = 0;
+    // device-driven sharded filter (mcl_shard_peer_*): the peer-visible region (mailbox + receive staging), the
+    // peers' mapped regions, the plan the exchange kernels keep on the device
+    unsigned char *peer_region = nullptr;
+    size_t peer_region_bytes = 0;
+    int peer_rank = -1, peer_G = 0;
+    bool peer_connected = false;
+    void *peer_ipc_opened[kMaxShards] = {};
+    PeerView *peer_view = nullptr;  // device copy
+    ShardPlan *plan = nullptr;      // device
+    uint32_t xchg_epoch = 0;        // exchange rounds so far (never reset: the flags in the boxes only grow)
 };
 
 namespace {
@@ -376,7 +396,7 @@ struct StepWindow {
 };
 
 int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool reduce_only, cudaStream_t st,
-                const StepWindow *win = nullptr) {
+                const StepWindow *win = nullptr, const ShardPlan *plan = nullptr) {
     const mcl_config &c = h->cfg;
     h->tile_prefix_valid = false;  // the weights (or their statistics) are about to change
     StepParams p{};
@@ -388,6 +408,7 @@ int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool redu
     p.recv_x = win ? win->x : nullptr;
     p.recv_y = win ? win->y : nullptr;
     p.recv_th = win ? win->th : nullptr;
+    p.plan = plan;
     p.noise = noise_dev;
     p.prep = h->prep;
     p.tab = h->tab;
@@ -489,12 +510,34 @@ int step_impl(mcl_filter *h, const double *z_dev, const double *ofs_dev, const f
 }
 
 int stage_inputs(mcl_filter *h, const double *z_host, const double *ofs_host, cudaStream_t st) {
-    if (z_host != nullptr) {
-        const size_t bytes = static_cast<size_t>(h->lay.T) * h->L * 2 * sizeof(double);
-        MCL_CUDA(h, cudaMemcpyAsync(h->z, z_host, bytes, cudaMemcpyHostToDevice, st));
+    if (z_host == nullptr && ofs_host == nullptr) return MCL_OK;
+    const size_t zb = static_cast<size_t>(h->lay.T) * h->L * 2 * sizeof(double);
+    const size_t ob = static_cast<size_t>(h->lay.T) * sizeof(double);
+    const size_t need = static_cast<size_t>(h->lay.T) * h->lay.Lmax * 2 * sizeof(double) + ob;
+    if (h->stage_bytes < need) {  // first use
+        for (int i = 0; i < mcl_filter::kStageSlots; ++i) {
+            if (h->stage_pin[i]) cudaFreeHost(h->stage_pin[i]);
+            h->stage_pin[i] = nullptr;
+            h->stage_used[i] = false;
+            MCL_CUDA(h, cudaHostAlloc(reinterpret_cast<void **>(&h->stage_pin[i]), need, cudaHostAllocDefault));
+            if (h->stage_ev[i] == nullptr) MCL_CUDA(h, cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming));
+        }
+        h->stage_bytes = need;
     }
-    if (ofs_host != nullptr)
-        MCL_CUDA(h, cudaMemcpyAsync(h->ofs, ofs_host, static_cast<size_t>(h->lay.T) * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int slot = h->stage_next;
+    h->stage_next = (slot + 1) % mcl_filter::kStageSlots;
+    if (h->stage_used[slot]) MCL_CUDA(h, cudaEventSynchronize(h->stage_ev[slot]));  // the copy that last read this slot
+    unsigned char *pin = h->stage_pin[slot];
+    if (z_host != nullptr) {
+        std::memcpy(pin, z_host, zb);
+        MCL_CUDA(h, cudaMemcpyAsync(h->z, pin, zb, cudaMemcpyHostToDevice, st));
+    }
+    if (ofs_host != nullptr) {
+        std::memcpy(pin + need - ob, ofs_host, ob);
+        MCL_CUDA(h, cudaMemcpyAsync(h->ofs, pin + need - ob, ob, cudaMemcpyHostToDevice, st));
+    }
+    MCL_CUDA(h, cudaEventRecord(h->stage_ev[slot], st));
+    h->stage_used[slot] = true;
     return MCL_OK;
 }
 
@@ -554,7 +597,19 @@ int mcl_workspace_bytes(const mcl_config *cfg, size_t *bytes) {
     int rc = validate(cfg);
     if (rc != MCL_OK) return fail(nullptr, rc, "invalid mcl_config");
     Layout L;
-    rc = make_layout(*cfg, 148, L);  // layout caps assume the B200's 148 SMs; mcl_create re-checks
+    // the layout depends on the SM count only through the number of k_step CTAs (partials: 128 B each); size for
+    // the device the filter will run on when one is visible, else for the B200's 148 SMs
+    int sms = 148;
+    {
+        int count = 0;
+        cudaDeviceProp prop;
+        if (cudaGetDeviceCount(&count) == cudaSuccess && cfg->device >= 0 && cfg->device < count &&
+            cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess)
+            sms = prop.multiProcessorCount;
+        else
+            cudaGetLastError();
+    }
+    rc = make_layout(*cfg, sms, L);
     if (rc != MCL_OK) return fail(nullptr, rc, "invalid sizes in mcl_config");
     *bytes = L.total;
     return MCL_OK;
@@ -578,7 +633,7 @@ int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_byte
     if (h == nullptr) return fail(nullptr, MCL_ERR_NOMEM, "host allocation failed");
     h->cfg = *cfg;
     h->sm_count = prop.multiProcessorCount;
-    rc = make_layout(*cfg, 148, h->lay);
+    rc = make_layout(*cfg, h->sm_count, h->lay);
     if (rc != MCL_OK) {
         delete h;
         return fail(nullptr, rc, "invalid sizes in mcl_config");
@@ -676,9 +731,20 @@ int mcl_destroy(mcl_filter *h) {
     cudaSetDevice(h->cfg.device);
     for (cudaEvent_t &e : h->ev)
         if (e) cudaEventDestroy(e);
-    if (h->stats_event) cudaEventDestroy(h->stats_event);
-    if (h->stats_pinned) cudaFreeHost(h->stats_pinned);
+    for (int i = 0; i < 2; ++i) {
+        if (h->stats_event[i]) cudaEventDestroy(h->stats_event[i]);
+        if (h->stats_pinned[i]) cudaFreeHost(h->stats_pinned[i]);
+    }
     if (h->dbg) cudaFree(h->dbg);
+    for (int i = 0; i < mcl_filter::kStageSlots; ++i) {
+        if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
+        if (h->stage_pin[i]) cudaFreeHost(h->stage_pin[i]);
+    }
+    for (void *p : h->peer_ipc_opened)
+        if (p) cudaIpcCloseMemHandle(p);
+    if (h->peer_view) cudaFree(h->peer_view);
+    if (h->plan) cudaFree(h->plan);
+    if (h->peer_region) cudaFree(h->peer_region);
     if (h->owns_ws && h->ws) cudaFree(h->ws);
     delete h;
     return MCL_OK;
@@ -882,27 +948,32 @@ int mcl_get_stats_begin(mcl_filter *h, void *stream) {
     if (h == nullptr) return MCL_ERR_ARG;
     int rc = use_device(h);
     if (rc != MCL_OK) return rc;
+    if (h->stats_begun - h->stats_ended >= 2) return fail(h, MCL_ERR_STATE, "two statistics read-backs are already pending");
     const size_t bytes = static_cast<size_t>(h->lay.T) * sizeof(mcl_stats);
-    if (h->stats_pinned == nullptr) {  // first use: the landing buffer and the event of the read-back
-        MCL_CUDA(h, cudaHostAlloc(reinterpret_cast<void **>(&h->stats_pinned), bytes, cudaHostAllocDefault));
-        MCL_CUDA(h, cudaEventCreateWithFlags(&h->stats_event, cudaEventDisableTiming));
+    if (h->stats_pinned[0] == nullptr) {  // first use: the landing buffers and the events of the read-backs
+        for (int i = 0; i < 2; ++i) {
+            MCL_CUDA(h, cudaHostAlloc(reinterpret_cast<void **>(&h->stats_pinned[i]), bytes, cudaHostAllocDefault));
+            MCL_CUDA(h, cudaEventCreateWithFlags(&h->stats_event[i], cudaEventDisableTiming));
+        }
     }
     rc = ensure_stats(h, S(stream));
     if (rc != MCL_OK) return rc;
-    MCL_CUDA(h, cudaMemcpyAsync(h->stats_pinned, h->stats, bytes, cudaMemcpyDeviceToHost, S(stream)));
-    MCL_CUDA(h, cudaEventRecord(h->stats_event, S(stream)));
-    h->stats_pending = true;
+    const int slot = static_cast<int>(h->stats_begun & 1u);
+    MCL_CUDA(h, cudaMemcpyAsync(h->stats_pinned[slot], h->stats, bytes, cudaMemcpyDeviceToHost, S(stream)));
+    MCL_CUDA(h, cudaEventRecord(h->stats_event[slot], S(stream)));
+    h->stats_begun += 1;
     return MCL_OK;
 }
 
 int mcl_get_stats_end(mcl_filter *h, mcl_stats *out_host) {
     if (h == nullptr) return MCL_ERR_ARG;
     if (out_host == nullptr) return fail(h, MCL_ERR_ARG, "out_host is NULL");
-    if (!h->stats_pending) return fail(h, MCL_ERR_STATE, "mcl_get_stats_end without mcl_get_stats_begin");
-    MCL_CUDA(h, cudaEventSynchronize(h->stats_event));
-    h->stats_pending = false;
+    if (h->stats_begun == h->stats_ended) return fail(h, MCL_ERR_STATE, "mcl_get_stats_end without mcl_get_stats_begin");
+    const int slot = static_cast<int>(h->stats_ended & 1u);  // the OLDEST pending read-back
+    MCL_CUDA(h, cudaEventSynchronize(h->stats_event[slot]));
+    h->stats_ended += 1;
     for (int t = 0; t < h->lay.T; ++t) {
-        out_host[t] = h->stats_pinned[t];
+        out_host[t] = h->stats_pinned[slot][t];
         derive_stats(out_host[t]);  // log-normaliser, mean, covariance from the sums
     }
     return MCL_OK;
@@ -910,7 +981,9 @@ int mcl_get_stats_end(mcl_filter *h, mcl_stats *out_host) {
 
 int mcl_stats_dev(mcl_filter *h, const mcl_stats **out_dev) {
     if (h == nullptr || out_dev == nullptr) return MCL_ERR_ARG;
-    if (use_device(h) == MCL_OK) ensure_stats(h, nullptr);  // merged on the default stream
+    // the block is current only after mcl_sync_stats(h, stream) (or a stats read-back) on the caller's stream: a merge
+    // launched from here would run on the default stream and could race with the step that is still in flight
+    if (h->stats_dirty) return fail(h, MCL_ERR_STATE, "mcl_stats_dev: call mcl_sync_stats(h, stream) first (a merge is pending)");
     *out_dev = h->stats;
     return MCL_OK;
 }
@@ -1039,7 +1112,7 @@ int mcl_shard_total(mcl_filter *h, uint64_t *total_dev, void *stream) {
     const int blocks = (h->lay.tpt + h->tiles_per_seg - 1) / h->tiles_per_seg;
     k_shard_total<<<blocks, kScanThreads, 0, st>>>(h->state[h->cur].lw, h->lay.n, h->stats,
                                                     reinterpret_cast<unsigned long long *>(total_dev), tiles, h->seg,
-                                                    h->lay.tpt, h->tiles_per_seg);
+                                                    h->lay.tpt, h->tiles_per_seg, nullptr, 0u);
     MCL_LAUNCH_CHECK(h, "k_shard_total");
     k_tile_prefix<<<1, 1024, 0, st>>>(h->seg, blocks);
     MCL_LAUNCH_CHECK(h, "k_tile_prefix");
@@ -1174,6 +1247,275 @@ int mcl_shard_set_global(mcl_filter *h, const mcl_stats *merged_host, void *stre
     h->tile_prefix_valid = false;
     h->stats_from_particle0 = false;
     h->stats_dirty = false;
+    return MCL_OK;
+}
+
+
+// ---- device-driven sharded filter (peer memory) ---------------------------------------------------
+namespace {
+struct PeerRegion {
+    size_t off_box, off_rx, off_ry, off_rth, total;
+};
+PeerRegion peer_region_layout(long long ld) {
+    PeerRegion r;
+    size_t o = 0;
+    r.off_box = o; o = align_up(o + sizeof(PeerBox), kAlign);
+    r.off_rx = o;  o = align_up(o + static_cast<size_t>(ld) * sizeof(float), kAlign);
+    r.off_ry = o;  o = align_up(o + static_cast<size_t>(ld) * sizeof(float), kAlign);
+    r.off_rth = o; o = align_up(o + static_cast<size_t>(ld) * sizeof(float), kAlign);
+    r.total = o;
+    return r;
+}
+int peer_ready(mcl_filter *h) {
+    if (h->peer_region == nullptr || !h->peer_connected)
+        return fail(h, MCL_ERR_STATE, "mcl_shard_peer_alloc / mcl_shard_peer_connect have not been called");
+    return MCL_OK;
+}
+void fill_xchg(mcl_filter *h, XchgParams &x, uint32_t flags, int mode) {
+    x = XchgParams{};
+    x.pv = h->peer_view;
+    x.plan = h->plan;
+    x.stats = h->stats;
+    x.epoch = h->xchg_epoch;
+    x.flags = flags;
+    x.mode = mode;
+    x.ess_threshold = h->cfg.ess_threshold;
+    x.seed = h->cfg.seed;
+    x.step = h->step;
+    x.n_global = h->cfg.n_global;
+    x.delta = h->delta;
+}
+// statistics exchange: push = merge of the own partials + record to every box, wait = merge of all records
+int launch_xchg_stats(mcl_filter *h, int mode, cudaStream_t st) {
+    XchgParams x;
+    fill_xchg(h, x, 0u, mode);
+    if ((mode & kXchgPush) && h->stats_dirty) {
+        x.partials = h->partials;
+        x.n_partials = h->lay.bpt;
+        x.cur = h->state[h->cur];
+        h->stats_dirty = false;
+    }
+    k_xchg_stats<<<1, kStepThreads, 0, st>>>(x);
+    MCL_LAUNCH_CHECK(h, "k_xchg_stats");
+    h->stats_from_particle0 = false;
+    h->tile_prefix_valid = false;
+    return MCL_OK;
+}
+}  // namespace
+
+int mcl_shard_peer_alloc(mcl_filter *h, int rank, int n_shards, unsigned char *ipc_handle_out) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (n_shards < 1 || n_shards > kMaxShards || rank < 0 || rank >= n_shards)
+        return fail(h, MCL_ERR_ARG, "rank / n_shards out of range (at most MCL_MAX_SHARDS shards)");
+    if (h->lay.T != 1) return fail(h, MCL_ERR_STATE, "sharding needs n_trials == 1");
+    if (static_cast<long long>(n_shards) * h->cfg.n_particles != h->cfg.n_global ||
+        static_cast<long long>(rank) * h->cfg.n_particles != h->cfg.slot_base)
+        return fail(h, MCL_ERR_ARG, "shards must be equal: n_shards * n_particles == n_global, slot_base == rank * n_particles");
+    if (h->peer_region != nullptr) return fail(h, MCL_ERR_STATE, "mcl_shard_peer_alloc was already called");
+    static_assert(sizeof(cudaIpcMemHandle_t) == MCL_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    const PeerRegion r = peer_region_layout(h->lay.ld);
+    void *p = nullptr;
+    // cudaMalloc, not the caller's workspace: an IPC handle names a whole allocation
+    if (cudaMalloc(&p, r.total) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(h, MCL_ERR_NOMEM, "cudaMalloc of the peer region failed");
+    }
+    MCL_CUDA(h, cudaMemset(p, 0, r.total));
+    h->peer_region = static_cast<unsigned char *>(p);
+    h->peer_region_bytes = r.total;
+    h->peer_rank = rank;
+    h->peer_G = n_shards;
+    void *q = nullptr;
+    MCL_CUDA(h, cudaMalloc(&q, sizeof(PeerView)));
+    h->peer_view = static_cast<PeerView *>(q);
+    MCL_CUDA(h, cudaMalloc(&q, sizeof(ShardPlan)));
+    MCL_CUDA(h, cudaMemset(q, 0, sizeof(ShardPlan)));
+    h->plan = static_cast<ShardPlan *>(q);
+    if (ipc_handle_out != nullptr) {
+        cudaIpcMemHandle_t ih;
+        MCL_CUDA(h, cudaIpcGetMemHandle(&ih, p));
+        std::memcpy(ipc_handle_out, &ih, sizeof ih);
+    }
+    return MCL_OK;
+}
+
+int mcl_shard_peer_connect(mcl_filter *h, const unsigned char *ipc_handles, mcl_filter *const *local_peers) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if ((ipc_handles == nullptr) == (local_peers == nullptr))
+        return fail(h, MCL_ERR_ARG, "exactly one of ipc_handles / local_peers must be given");
+    if (h->peer_region == nullptr) return fail(h, MCL_ERR_STATE, "mcl_shard_peer_alloc has not been called");
+    if (h->peer_connected) return fail(h, MCL_ERR_STATE, "mcl_shard_peer_connect was already called");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    const PeerRegion r = peer_region_layout(h->lay.ld);
+    PeerView pv{};
+    pv.me = h->peer_rank;
+    pv.G = h->peer_G;
+    pv.m = h->cfg.n_particles;
+    for (int g = 0; g < h->peer_G; ++g) {
+        unsigned char *base = nullptr;
+        if (g == h->peer_rank) {
+            base = h->peer_region;
+        } else if (local_peers != nullptr) {
+            mcl_filter *o = local_peers[g];
+            if (o == nullptr || o->peer_region == nullptr || o->peer_G != h->peer_G || o->peer_rank != g ||
+                o->cfg.n_particles != h->cfg.n_particles)
+                return fail(h, MCL_ERR_ARG, "local_peers[g] is not shard g of this filter (mcl_shard_peer_alloc first)");
+            if (o->cfg.device != h->cfg.device) {
+                int can = 0;
+                MCL_CUDA(h, cudaDeviceCanAccessPeer(&can, h->cfg.device, o->cfg.device));
+                if (!can) return fail(h, MCL_ERR_NODEVICE, "no peer access between the shards' devices");
+                cudaError_t e = cudaDeviceEnablePeerAccess(o->cfg.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) MCL_CUDA(h, e);
+                cudaGetLastError();
+            }
+            base = o->peer_region;
+        } else {
+            cudaIpcMemHandle_t ih;
+            std::memcpy(&ih, ipc_handles + static_cast<size_t>(g) * MCL_IPC_HANDLE_BYTES, sizeof ih);
+            void *p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                char buf[256];
+                snprintf(buf, sizeof buf, "cudaIpcOpenMemHandle of shard %d failed: %s", g, cudaGetErrorString(e));
+                return fail(h, MCL_ERR_CUDA, buf);
+            }
+            h->peer_ipc_opened[g] = p;
+            base = static_cast<unsigned char *>(p);
+        }
+        pv.box[g] = reinterpret_cast<PeerBox *>(base + r.off_box);
+        pv.rx[g] = reinterpret_cast<float *>(base + r.off_rx);
+        pv.ry[g] = reinterpret_cast<float *>(base + r.off_ry);
+        pv.rth[g] = reinterpret_cast<float *>(base + r.off_rth);
+    }
+    MCL_CUDA(h, cudaMemcpy(h->peer_view, &pv, sizeof pv, cudaMemcpyHostToDevice));
+    h->peer_connected = true;
+    return MCL_OK;
+}
+
+int mcl_shard_sync_peer(mcl_filter *h, uint32_t stages, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    int rc = peer_ready(h);
+    if (rc != MCL_OK) return rc;
+    rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    const bool push = (stages & MCL_STAGE_C) != 0, wait = (stages & MCL_STAGE_D) != 0;
+    if (!push && !wait) return fail(h, MCL_ERR_ARG, "stages must contain MCL_STAGE_C and / or MCL_STAGE_D");
+    if (push) h->xchg_epoch += 1;
+    return launch_xchg_stats(h, (push ? kXchgPush : 0) | (wait ? kXchgWait : 0), S(stream));
+}
+
+int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_host, const float *noise_dev,
+                        uint32_t flags, uint32_t stages, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    int rc = peer_ready(h);
+    if (rc != MCL_OK) return rc;
+    if ((stages & MCL_STAGE_ALL) == 0 || (stages & ~MCL_STAGE_ALL) != 0) return fail(h, MCL_ERR_ARG, "bad stages");
+    if (h->L <= 0) return fail(h, MCL_ERR_STATE, "mcl_set_landmarks has not been called");
+    if (!h->have_particles) return fail(h, MCL_ERR_STATE, "particles are not initialised");
+    if ((stages & MCL_STAGE_C) && z_host == nullptr) return fail(h, MCL_ERR_ARG, "z_host is NULL");
+    if ((stages & MCL_STAGE_C) && noise_dev == nullptr && !(flags & MCL_PHILOX_NOISE))
+        return fail(h, MCL_ERR_ARG, "noise_dev is NULL and MCL_PHILOX_NOISE is not set");
+    rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    cudaStream_t st = S(stream);
+    const bool A = stages & MCL_STAGE_A, B = stages & MCL_STAGE_B, Cc = stages & MCL_STAGE_C, D = stages & MCL_STAGE_D;
+    const bool may_resample = !(flags & MCL_NO_RESAMPLE);
+    if (A) {
+        if (h->stats_dirty) return fail(h, MCL_ERR_STATE, "statistics were not exchanged: mcl_shard_sync_peer first");
+        h->xchg_epoch += 1;
+    }
+    if (may_resample && A) {
+        // first pass over the weights under the GLOBAL map: tile prefixes inside contiguous segments + segment totals
+        const int blocks_max = std::min(kMaxSegments, h->sm_count * 8);
+        h->tiles_per_seg = (h->lay.tpt + blocks_max - 1) / blocks_max;
+        const int blocks = (h->lay.tpt + h->tiles_per_seg - 1) / h->tiles_per_seg;
+        k_shard_total<<<blocks, kScanThreads, 0, st>>>(h->state[h->cur].lw, h->lay.n, h->stats, nullptr, h->desc[h->desc_cur],
+                                                        h->seg, h->lay.tpt, h->tiles_per_seg, h->plan, flags);
+        MCL_LAUNCH_CHECK(h, "k_shard_total");
+        h->desc_stale = true;
+    }
+    if (may_resample && (A || B)) {
+        XchgParams x;
+        fill_xchg(h, x, flags, (A ? kXchgPush : 0) | (B ? kXchgWait : 0));
+        x.seg = h->seg;
+        x.n_seg = (h->lay.tpt + h->tiles_per_seg - 1) / h->tiles_per_seg;
+        x.have_ofs = ofs_host != nullptr;
+        x.ofs_host = ofs_host ? ofs_host[0] : 0.0;
+        k_xchg_total<<<1, 1024, 0, st>>>(x);
+        MCL_LAUNCH_CHECK(h, "k_xchg_total");
+    }
+    if (may_resample && B) {
+        // second pass: global slot numbers, every tile starting from segment prefix + tile prefix (no look-back);
+        // own slots -> ancestors, off-rank slots -> poses into the owner's staging
+        ScanParams sp;
+        fill_scan(h, sp);
+        sp.use_override = 1;
+        sp.own_lo = h->cfg.slot_base;
+        sp.own_hi = h->cfg.slot_base + h->cfg.n_particles;
+        sp.src = h->state[h->cur];
+        sp.plan = h->plan;
+        sp.pv = h->peer_view;
+        sp.xflags = flags;
+        sp.tile_prefix = sp.desc;
+        sp.seg_prefix = h->seg;
+        sp.tiles_per_seg = h->tiles_per_seg;
+        sp.persistent = 1;
+        dim3 grid(std::min(h->lay.tpt, h->sm_count * 4), 1);
+        k_scan<kScanExpand><<<grid, kScanThreads, 0, st>>>(sp);
+        MCL_LAUNCH_CHECK(h, "k_scan");
+    }
+    if (may_resample && (B || Cc)) {
+        XchgParams x;
+        fill_xchg(h, x, flags, (B ? kXchgPush : 0) | (Cc ? kXchgWait : 0));
+        k_xchg_done<<<1, 32, 0, st>>>(x);
+        MCL_LAUNCH_CHECK(h, "k_xchg_done");
+    }
+    if (Cc) {
+        rc = stage_inputs(h, z_host, nullptr, st);
+        if (rc != MCL_OK) return rc;
+        // per-step scalars; the gate comes from the plan
+        {
+            ScanParams sp;
+            fill_scan(h, sp);
+            fill_prep(h, sp.prep, h->z, nullptr, flags);
+            sp.do_prep = 1;
+            sp.trig = h->trig;
+            sp.plan = h->plan;
+            sp.xflags = flags;
+            launch_pdl(k_scan<kScanAncestors>, dim3(1, 1), dim3(kScanThreads), 0, st, false, sp);
+            MCL_LAUNCH_CHECK(h, "k_scan");
+        }
+        StepWindow win;
+        win.lo = 0u;
+        win.hi = static_cast<uint32_t>(h->lay.n);
+        const PeerRegion pr = peer_region_layout(h->lay.ld);
+        win.x = reinterpret_cast<const float *>(h->peer_region + pr.off_rx);
+        win.y = reinterpret_cast<const float *>(h->peer_region + pr.off_ry);
+        win.th = reinterpret_cast<const float *>(h->peer_region + pr.off_rth);
+        rc = launch_step(h, noise_dev, flags, false, st, &win, h->plan);
+        if (rc != MCL_OK) return rc;
+        h->cur ^= 1;
+        h->step += 1;
+    }
+    if (Cc || D) {
+        rc = launch_xchg_stats(h, (Cc ? kXchgPush : 0) | (D ? kXchgWait : 0), st);
+        if (rc != MCL_OK) return rc;
+    }
+    return MCL_OK;
+}
+
+int mcl_shard_get_plan(mcl_filter *h, mcl_shard_plan *out_host, void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (out_host == nullptr) return fail(h, MCL_ERR_ARG, "out_host is NULL");
+    if (h->plan == nullptr) return fail(h, MCL_ERR_STATE, "mcl_shard_peer_alloc has not been called");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    MCL_CUDA(h, cudaMemcpyAsync(out_host, h->plan, sizeof(mcl_shard_plan), cudaMemcpyDeviceToHost, S(stream)));
+    MCL_CUDA(h, cudaStreamSynchronize(S(stream)));
     return MCL_OK;
 }
 

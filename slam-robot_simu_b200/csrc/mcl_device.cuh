@@ -360,6 +360,71 @@ __device__ __forceinline__ void sincos_tab(float th, const TrigEntry *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// Particle-sharded filter, device-driven exchange over peer memory (NVLink / NVSwitch).
+// Every shard owns one PeerBox plus a receive staging area in memory its peers can write (cudaMalloc + CUDA IPC
+// between processes, plain pointers inside one process).  A shard WRITES into its peers' boxes and POLLS only its
+// own: record / total / "expansion done" flags carry the step number (never reset), data before flag with a
+// system-scope fence in between.  Nothing on this path goes through the host or through NCCL.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxShards = 16;
+
+struct PeerBox {
+    mcl_stats rec[kMaxShards];              // rec[g]: statistics record of shard g for the step in flag_stats[g]
+    unsigned long long total[kMaxShards];   // total[g]: integer weight total of shard g for the step in flag_total[g]
+    unsigned int flag_stats[kMaxShards];
+    unsigned int flag_total[kMaxShards];
+    unsigned int flag_done[kMaxShards];     // shard g has written every pose it owes this shard (step number)
+    unsigned int pad[16];
+};
+
+// Per-step plan of a shard's resampling, derived ON THE DEVICE from the exchanged totals (local memory): the public
+// struct of include/mcl.h.
+using ShardPlan = mcl_shard_plan;
+static_assert(kMaxShards == MCL_MAX_SHARDS, "mcl.h and the kernels disagree on the shard limit");
+
+// Where a shard reaches its peers (device memory, constant for the handle's lifetime).
+struct PeerView {
+    PeerBox *box[kMaxShards];                                    // box[me] is local
+    float *rx[kMaxShards], *ry[kMaxShards], *rth[kMaxShards];    // receive staging of shard g, indexed by g's LOCAL slot
+    int me, G;
+    long long m;                                                 // particles (= output slots) per shard
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Wait until *flag has reached `epoch` (flags only grow).  A peer that never arrives must not hang the GPU: after
+// kPeerTimeoutNs the wait gives up and raises the plan's sticky error, which every later wait honours at once.
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ void peer_wait(const unsigned int *flag, unsigned int epoch, ShardPlan *plan) {
+    if (*reinterpret_cast<volatile int *>(&plan->error)) return;
+    const unsigned long long t0 = global_timer_ns();
+    while (static_cast<int>(ld_acquire_sys(flag) - epoch) < 0) {
+        __nanosleep(200);
+        if (global_timer_ns() - t0 > kPeerTimeoutNs) {
+            *reinterpret_cast<volatile int *>(&plan->error) = 1;
+            return;
+        }
+    }
+}
+// whether the step resamples: host flags first, else the gate the previous statistics exchange left in the plan
+__device__ __forceinline__ int plan_resample(uint32_t flags, const ShardPlan *plan) {
+    if (flags & MCL_NO_RESAMPLE) return 0;
+    if (flags & MCL_FORCE_RESAMPLE) return 1;
+    return *reinterpret_cast<const volatile int *>(&plan->gate);
+}
+
+// ---------------------------------------------------------------------------------------------
 // block-wide sum of NV doubles (256 threads); result valid in all threads.
 // smem must hold (blockDim/32) * NV doubles.
 // ---------------------------------------------------------------------------------------------

@@ -1,12 +1,12 @@
 // Kernels of the MCL step (sm_100a).  One translation unit: included by mcl_api.cu.
 //
 // A filter step is TWO launches:
-//   k_scan   block 0 of every trial first derives the per-step scalars (resample gate, comb offset,
-//            reference pose, landmark table + moments, likelihood shift); then all blocks run the
-//            decoupled look-back scan of the 64-bit fixed-point weights and write the ancestor of
-//            every slot.  Trials that do not resample leave after the scalars.
-//   k_step   [gather through the ancestors] + predict + weight + statistics partials; the last
-//            block of a trial merges the partials into mcl_stats.
+//   k_scan   tile CTAs run the decoupled look-back scan of the 64-bit fixed-point weights and write the ancestor
+//            of every slot (trials that do not resample leave early); two extra CTAs per trial derive the per-step
+//            scalars (resample gate, comb offset, reference pose, landmark table + moments, likelihood shift) and
+//            merge the previous step's CTA partials into mcl_stats.
+//   k_step   [gather through the ancestors] + predict + weight + statistics; every CTA leaves one 128-byte partial
+//            record -- the records are merged where they are consumed (next k_scan, k_merge, k_xchg_stats).
 // Stage / utility kernels: k_reduce (statistics only), k_gather (stand-alone resampling gather),
 // k_cov (exact two-pass covariance), k_export_weights, k_init*, k_fill, k_reset_scan.
 #pragma once
@@ -629,6 +629,11 @@ struct ScanParams {
     long long own_lo, own_hi, send_hi_off, send_hi_base;
     StateView src;
     float *ox, *oy, *oth;
+    // kScanExpand, device-driven (mcl_shard_step_peer): gate, comb offset and k_offset come from the plan the
+    // totals exchange left in device memory, and off-rank poses go straight into their owner's receive staging
+    const ShardPlan *plan;
+    const PeerView *pv;
+    uint32_t xflags;            // host flags of the step (MCL_FORCE_RESAMPLE / MCL_NO_RESAMPLE)
 };
 
 constexpr int kDirectTiles = 1024;  // tiles that sum all predecessors' aggregates directly (2M particles)
@@ -652,6 +657,13 @@ struct ScanShared {
 __device__ __forceinline__ void expand_store(const ScanParams &p, uint32_t *anc, long long slot, uint32_t j) {
     if (slot >= p.own_lo && slot < p.own_hi) {
         anc[slot - p.own_lo] = j;
+    } else if (p.plan != nullptr) {
+        // the slot's owner and its index there (off-rank slots are ~1e-4 of all: the division is off the hot path)
+        const uint32_t m = static_cast<uint32_t>(p.pv->m), s32 = static_cast<uint32_t>(slot);
+        const uint32_t g = s32 / m, l = s32 - g * m;
+        p.pv->rx[g][l] = p.src.x[j];
+        p.pv->ry[g][l] = p.src.y[j];
+        p.pv->rth[g][l] = p.src.th[j];
     } else {
         const long long o = (slot < p.own_lo) ? slot - p.slot_first : p.send_hi_off + (slot - p.send_hi_base);
         if (o >= 0 && o < p.anc_cap) {
@@ -739,9 +751,11 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
             st_ess = stp->ess;
         }
         if (tid == 0) {
-            const int rs = p.use_override ? 1 : decide_resample(p.prep.flags, st_ess, p.prep.ess_threshold);
+            const bool planned = p.plan != nullptr;
+            const int rs = planned ? plan_resample(p.xflags, p.plan)
+                                   : (p.use_override ? 1 : decide_resample(p.prep.flags, st_ess, p.prep.ess_threshold));
             const WeightMap w0 = make_weight_map(st_max, st_sum);
-            const double o = p.use_override ? p.ofs_override : (rs ? comb_offset(p.prep, t) : 0.0);
+            const double o = planned ? p.plan->ofs : (p.use_override ? p.ofs_override : (rs ? comb_offset(p.prep, t) : 0.0));
             s_sc.resample = rs;
             s_sc.wq_m = w0.m;
             s_sc.wq_scale = w0.scale;
@@ -782,13 +796,23 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
         dbg_stamp(p.dbg, 6);
         return;
     }
+    // The descriptors the NEXT scan launch starts from are cleared whether or not this trial resamples: a launch
+    // that skipped the clear would leave the previous resampling's aggregates / prefixes in the buffer the launch
+    // after it looks back through (tiles past the direct range accept any non-zero status at once).
+    if (p.desc_next != nullptr) {
+        const int n_tile_ctas = static_cast<int>(gridDim.x) - (p.do_prep ? (p.n_partials > 0 ? 2 : 1) : 0);
+        unsigned long long *dn = p.desc_next + static_cast<long long>(t) * p.tpt;
+        for (long long i = static_cast<long long>(blockIdx.x) * kScanThreads + tid; i < p.tpt;
+             i += static_cast<long long>(n_tile_ctas) * kScanThreads)
+            dn[i] = 0ull;
+    }
     if (!resample) return;
+    const unsigned long long k_offset = (MODE == kScanExpand && p.plan != nullptr) ? p.plan->k_offset : p.k_offset;
     const float *lw = p.lw + static_cast<long long>(t) * p.ld;
     // Persistent over tiles: a CTA keeps taking tickets, so the prologue above is paid once per CTA.
     __shared__ unsigned int s_next[2];  // two slots by iteration parity: one barrier per tile is enough
     int it = 0;
     for (long long tile = s_sc.tile; tile < p.tpt; tile = s_next[it++ & 1]) {
-    if (tid == 0 && p.desc_next != nullptr) p.desc_next[static_cast<long long>(t) * p.tpt + tile] = 0ull;
     const long long j0 = tile * kScanTile + static_cast<long long>(tid) * kScanItems;
 
     // ---- load + quantise (8 consecutive items per thread, two 16-byte loads) ----
@@ -937,7 +961,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     // ---- slot range of every source: u32 counts, non-owners carry rel = 2^31 (never inside a window) ----
     const double nd = static_cast<double>(p.n_global);
     const CombFast cf = make_comb_fast(ofs, nd);
-    const double Kd0 = static_cast<double>(p.k_offset + excl + thread_excl);
+    const double Kd0 = static_cast<double>(k_offset + excl + thread_excl);
     uint32_t rel[kScanItems];  // first slot of source k relative to the thread's first slot
     uint32_t first_slot, cur;
     // tiles that are full and do not hold the filter's last particle need no per-item checks (CTA-uniform)
@@ -1119,6 +1143,8 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     }
     __syncthreads();  // s_next (written at the top of this iteration) and the scratch are settled
     }  // tiles
+    // poses written into peers' memory must be visible there before the "done" flag of the next kernel
+    if (MODE == kScanExpand && p.plan != nullptr) __threadfence_system();
     dbg_stamp(p.dbg, 5);
 }
 
@@ -1132,6 +1158,9 @@ struct StepParams {
     // poses arrive in recv_* ([prefix | suffix]).  Unsharded: win_lo = 0, win_hi = n.
     uint32_t win_lo, win_hi;
     const float *recv_x, *recv_y, *recv_th;
+    // device-driven sharded step: the window comes from the plan in device memory and the receive staging is
+    // indexed by the output slot itself (recv[i] instead of the packed [prefix | suffix])
+    const ShardPlan *plan;
     const float *noise;    // [3][T][n] dense, or null
     const PrepOut *prep;   // [T]
     const double4 *tab;    // [T][Lmax]
@@ -1164,12 +1193,17 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double4 *s_tab = reinterpret_cast<double4 *>(smem_raw);  // [L] (pair / RB only)
     __shared__ PrepOut s_prep;
+    __shared__ uint32_t s_win[2];
 
     cudaTriggerProgrammaticLaunchCompletion();  // see k_scan
     cudaGridDependencySynchronize();
     dbg_stamp(p.dbg, 0);
     if (tid < static_cast<int>(sizeof(PrepOut) / sizeof(double)))
         reinterpret_cast<double *>(&s_prep)[tid] = reinterpret_cast<const double *>(p.prep + t)[tid];
+    if (tid == 64) {
+        s_win[0] = (p.plan != nullptr) ? p.plan->win_lo : p.win_lo;
+        s_win[1] = (p.plan != nullptr) ? p.plan->win_hi : p.win_hi;
+    }
     __syncthreads();
     const int L = s_prep.L;
     if (LIK == kLikPair || LIK == kLikRB) {
@@ -1230,7 +1264,8 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
             if (resample) {
                 const uint4 a4 = *reinterpret_cast<const uint4 *>(anc + base);
                 const uint32_t a[kPPT] = {a4.x, a4.y, a4.z, a4.w};
-                if (base >= p.win_lo && base + kPPT <= p.win_hi) {
+                const uint32_t win_lo = s_win[0], win_hi = s_win[1];
+                if (base >= win_lo && base + kPPT <= win_hi) {
 #pragma unroll
                     for (int k = 0; k < kPPT; ++k) {
                         const uint32_t j = (base + k < p.n) ? a[k] : 0u;
@@ -1242,13 +1277,13 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
 #pragma unroll
                     for (int k = 0; k < kPPT; ++k) {
                         const uint32_t i = base + k;
-                        if ((i >= p.win_lo && i < p.win_hi) || i >= p.n) {  // (padding lanes read particle 0)
+                        if ((i >= win_lo && i < win_hi) || i >= p.n) {  // (padding lanes read particle 0)
                             const uint32_t j = (i < p.n) ? a[k] : 0u;
                             x[k] = ix[j];
                             y[k] = iy[j];
                             th[k] = ith[j];
                         } else {
-                            const uint32_t r = (i < p.win_lo) ? i : i - p.win_hi + p.win_lo;
+                            const uint32_t r = (p.plan != nullptr || i < win_lo) ? i : i - win_hi + win_lo;
                             x[k] = p.recv_x[r];
                             y[k] = p.recv_y[r];
                             th[k] = p.recv_th[r];
@@ -1672,8 +1707,7 @@ struct ShardMergeParams {
     long long m;           // particles per shard: global index of shard g's particle i is g * m + i
     mcl_stats *out;        // this handle's statistics block (becomes the global one)
 };
-__global__ void k_shard_merge(const ShardMergeParams p) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+__device__ __noinline__ void shard_merge_records(const ShardMergeParams p, bool derive) {
     double M = p.rec[0].max_logw;
     for (int g = 1; g < p.G; ++g) M = fmax(M, p.rec[g].max_logw);
     double s1 = 0.0, s2 = 0.0, raw[11];
@@ -1719,8 +1753,174 @@ __global__ void k_shard_merge(const ShardMergeParams p) {
     o.max_idx = static_cast<uint32_t>(static_cast<long long>(bg) * p.m + b.max_idx);
     for (int c = 0; c < 3; ++c) o.est[c] = b.est[c];
     o.derived = 0;
-    derive_stats(o);
+    if (derive) derive_stats(o);  // (libm, once per step on one thread: the device-driven step leaves it to the host)
     *p.out = o;
+}
+__global__ void k_shard_merge(const ShardMergeParams p) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    shard_merge_records(p, true);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Device-driven exchange of the sharded filter (mcl_shard_step_peer): three single-CTA kernels between the big ones.
+// Each has a PUSH half (write into the peers' boxes, then raise the step number there) and a WAIT half (poll the own
+// box until every peer's step number has arrived, then derive what the next kernel needs).  A real step launches
+// both halves as one kernel; the one-GPU emulation of the tests launches all shards' PUSH halves before any WAIT
+// half, on one stream, so nothing ever spins there.
+// -------------------------------------------------------------------------------------------------
+constexpr int kXchgPush = 1, kXchgWait = 2;
+
+struct XchgParams {
+    const PeerView *pv;
+    ShardPlan *plan;
+    mcl_stats *stats;           // this handle's statistics block (trial 0)
+    uint32_t epoch;             // step number + 1 of the step being exchanged
+    uint32_t flags;             // host flags of the step
+    int mode;                   // kXchgPush | kXchgWait
+    // k_xchg_stats
+    const double *partials;     // CTA partials of the k_step / k_reduce just run (n_partials = 0: stats[] is current)
+    int n_partials;
+    StateView cur;
+    double ess_threshold;
+    // k_xchg_total
+    unsigned long long *seg;    // [n_seg] segment totals of k_shard_total -> exclusive prefixes
+    int n_seg;
+    double ofs_host;            // injected comb offset (have_ofs) ...
+    int have_ofs;               // ... else drawn with Philox exactly like the unsharded filter (comb_offset)
+    uint64_t seed;
+    uint32_t step;
+    long long n_global;
+    double delta;               // fl(1 / n_global)
+};
+
+// statistics: merge the own CTA partials -> push the 312-byte record to every shard -> wait for all records -> merge
+// them (all shards compute bit-identical global statistics) -> resampling gate of the next step.
+__global__ void __launch_bounds__(kStepThreads) k_xchg_stats(const XchgParams p) {
+    const int tid = threadIdx.x;
+    const PeerView &pv = *p.pv;
+    constexpr int kWords = static_cast<int>(sizeof(mcl_stats) / sizeof(unsigned long long));
+    static_assert(sizeof(mcl_stats) % sizeof(unsigned long long) == 0, "mcl_stats is copied in 8-byte words");
+    if (p.mode & kXchgPush) {
+        if (p.n_partials > 0)
+            merge_full(p.partials, p.n_partials, p.stats, p.cur.x, p.cur.y, p.cur.th, nullptr);
+        __syncthreads();
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(p.stats);
+        for (int i = tid; i < pv.G * kWords; i += blockDim.x) {
+            const int g = i / kWords, w = i - g * kWords;
+            reinterpret_cast<unsigned long long *>(&pv.box[g]->rec[pv.me])[w] = __ldcg(src + w);
+        }
+        __syncthreads();
+        if (tid < pv.G) {
+            __threadfence_system();
+            st_release_sys(&pv.box[tid]->flag_stats[pv.me], p.epoch);
+        }
+    }
+    if (p.mode & kXchgWait) {
+        PeerBox *mine = pv.box[pv.me];
+        if (tid < pv.G) peer_wait(&mine->flag_stats[tid], p.epoch, p.plan);
+        __syncthreads();
+        if (tid == 0) {
+            ShardMergeParams mp;
+            mp.rec = mine->rec;
+            mp.G = pv.G;
+            mp.m = pv.m;
+            mp.out = p.stats;
+            shard_merge_records(mp, false);
+            p.plan->gate = (p.stats->ess < p.ess_threshold) ? 1 : 0;  // particle_filter.py:211, on the GLOBAL ESS
+        }
+    }
+}
+
+// totals: segment totals -> prefixes (the expansion starts every tile from them), the shard's total -> every shard;
+// then, from all totals: k_offset, the comb offset, the slots this shard fills and the part of its own output
+// range it gathers locally -- what the host used to derive after a device-to-host copy (sharded.shard_ranges).
+__global__ void __launch_bounds__(1024) k_xchg_total(const XchgParams p) {
+    __shared__ unsigned long long s_w[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const PeerView &pv = *p.pv;
+    if (!plan_resample(p.flags, p.plan)) {
+        if (tid == 0 && (p.mode & kXchgWait)) {
+            p.plan->resampled = 0;
+            p.plan->epoch = p.epoch;
+        }
+        return;
+    }
+    if (p.mode & kXchgPush) {
+        const unsigned long long x = (tid < p.n_seg) ? p.seg[tid] : 0ull;
+        unsigned long long incl = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        unsigned long long off = 0ull, total = 0ull;
+        for (int w = 0; w < 32; ++w) {
+            if (w < warp) off += s_w[w];
+            total += s_w[w];
+        }
+        if (tid < p.n_seg) p.seg[tid] = off + incl - x;
+        if (tid < pv.G) {
+            pv.box[tid]->total[pv.me] = total;
+            __threadfence_system();
+            st_release_sys(&pv.box[tid]->flag_total[pv.me], p.epoch);
+        }
+    }
+    if (p.mode & kXchgWait) {
+        PeerBox *mine = pv.box[pv.me];
+        if (tid < pv.G) peer_wait(&mine->flag_total[tid], p.epoch, p.plan);
+        __syncthreads();
+        if (tid == 0) {
+            ShardPlan *pl = p.plan;
+            double ofs = p.ofs_host;
+            if (!p.have_ofs) {  // mcl::comb_offset of the unsharded filter: same seed and step -> same draw on every shard
+                const uint4 r = philox4x32_10(make_uint4(0xFFFFFFFFu, 0u, p.step, 0u),
+                                              make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32)));
+                ofs = __dmul_rn(philox_uniform01(r), p.delta);
+            }
+            const double nd = static_cast<double>(p.n_global);
+            unsigned long long k = 0ull, k_me = 0ull;
+            long long first = 0, end = 0;
+            for (int g = 0; g < pv.G; ++g) {
+                const unsigned long long tg = *reinterpret_cast<volatile unsigned long long *>(&mine->total[g]);
+                pl->totals[g] = tg;
+                if (g == pv.me) {
+                    k_me = k;
+                    first = static_cast<long long>(count_le(static_cast<double>(k), p.delta, ofs, nd));
+                }
+                k += tg;
+                // the last shard also takes every slot past the final cumulative weight
+                if (g == pv.me) end = (g == pv.G - 1) ? p.n_global : static_cast<long long>(count_le(static_cast<double>(k), p.delta, ofs, nd));
+            }
+            const long long lo = static_cast<long long>(pv.me) * pv.m;
+            long long wl = first - lo, wh = end - lo;
+            wl = wl < 0 ? 0 : (wl > pv.m ? pv.m : wl);
+            wh = wh < 0 ? 0 : (wh > pv.m ? pv.m : wh);
+            if (wh < wl) wh = wl;
+            pl->k_offset = k_me;
+            pl->ofs = ofs;
+            pl->first_slot = first;
+            pl->n_slots = end - first;
+            pl->win_lo = static_cast<uint32_t>(wl);
+            pl->win_hi = static_cast<uint32_t>(wh);
+            pl->resampled = 1;
+            pl->epoch = p.epoch;
+        }
+    }
+}
+
+// done: every pose this shard owed its peers is in their staging (the expansion ended with a system fence) ->
+// raise the step number in every box; wait until every peer has done the same for this shard.
+__global__ void __launch_bounds__(32) k_xchg_done(const XchgParams p) {
+    const int tid = threadIdx.x;
+    const PeerView &pv = *p.pv;
+    if (!plan_resample(p.flags, p.plan)) return;
+    if ((p.mode & kXchgPush) && tid < pv.G) {
+        __threadfence_system();
+        st_release_sys(&pv.box[tid]->flag_done[pv.me], p.epoch);
+    }
+    if ((p.mode & kXchgWait) && tid < pv.G) peer_wait(&pv.box[pv.me]->flag_done[tid], p.epoch, p.plan);
 }
 
 // Sharded filter, first pass of the global resampling: the shard's total of the quantised weights (atomicAdd into
@@ -1731,10 +1931,12 @@ __global__ void k_shard_merge(const ShardMergeParams p) {
 constexpr int kMaxSegments = 1024;
 __global__ void __launch_bounds__(kScanThreads) k_shard_total(const float *lw, long long n, const mcl_stats *stats,
                                                               unsigned long long *total, unsigned long long *tile_prefix,
-                                                              unsigned long long *seg_total, int tpt, int tiles_per_seg) {
+                                                              unsigned long long *seg_total, int tpt, int tiles_per_seg,
+                                                              const ShardPlan *plan, uint32_t flags) {
     __shared__ WeightMap s_wm;
     __shared__ unsigned long long s_part[2][kScanThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (plan != nullptr && !plan_resample(flags, plan)) return;  // device-driven step: gated on the device
     if (tid == 0) s_wm = make_weight_map(stats[0].max_logw, stats[0].sum_w);
     __syncthreads();
     const WeightMap wm = s_wm;
@@ -1767,7 +1969,7 @@ __global__ void __launch_bounds__(kScanThreads) k_shard_total(const float *lw, l
     }
     if (tid == 0) {
         seg_total[blockIdx.x] = run;
-        if (run != 0ull) atomicAdd(total, run);
+        if (run != 0ull && total != nullptr) atomicAdd(total, run);
     }
 }
 

@@ -115,6 +115,13 @@ class Filter:
             self._check(self.lib.mcl_restore(self._h, st, int(z["step"]), self._stream()), "mcl_restore")
         return self
 
+    def restore_stats(self, stats, step):
+        """Install a statistics block (list of mcl_stats, or one) and the step counter: mcl_restore."""
+        if isinstance(stats, L.mcl_stats):
+            stats = [stats]
+        st = (L.mcl_stats * self.T)(*stats)
+        self._check(self.lib.mcl_restore(self._h, st, int(step), self._stream()), "mcl_restore")
+
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
         return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
@@ -327,6 +334,40 @@ class Filter:
         """records: CUDA uint8 tensor holding the n_shards allgathered mcl_stats blocks."""
         self._check(self.lib.mcl_shard_merge(self._h, C.c_void_p(records.data_ptr()), int(n_shards), self._stream()),
                     "mcl_shard_merge")
+
+    # ------------------------------------------------------------------ device-driven sharded filter (peer memory)
+    def peer_alloc(self, rank, n_shards):
+        """Allocate this shard's peer-visible region; -> its 64-byte CUDA IPC handle."""
+        buf = (C.c_ubyte * L.MCL_IPC_HANDLE_BYTES)()
+        self._check(self.lib.mcl_shard_peer_alloc(self._h, int(rank), int(n_shards), buf), "mcl_shard_peer_alloc")
+        return bytes(buf)
+
+    def peer_connect_ipc(self, handles):
+        """handles: the n_shards IPC handles in rank order (other processes)."""
+        blob = b"".join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self.lib.mcl_shard_peer_connect(self._h, buf, None), "mcl_shard_peer_connect")
+
+    def peer_connect_local(self, filters):
+        """filters: the n_shards Filter objects of this process, in rank order."""
+        arr = (C.c_void_p * len(filters))(*[f._h for f in filters])
+        self._check(self.lib.mcl_shard_peer_connect(self._h, None, arr), "mcl_shard_peer_connect")
+
+    def step_peer(self, z, ofs=None, noise=None, force_resample=False, no_resample=False, stages=L.MCL_STAGE_ALL):
+        zz = self._f64(z, (1, self.n_landmarks, 2))
+        o = None if ofs is None else (C.c_double * 1)(float(ofs))
+        self._check(self.lib.mcl_shard_step_peer(self._h, zz.ctypes.data, o, self._noise_ptr(noise),
+                                                 self._flags(noise, force_resample, no_resample), int(stages), self._stream()),
+                    "mcl_shard_step_peer")
+
+    def sync_peer(self, stages=L.MCL_STAGE_C | L.MCL_STAGE_D):
+        self._check(self.lib.mcl_shard_sync_peer(self._h, int(stages), self._stream()), "mcl_shard_sync_peer")
+
+    def shard_plan(self):
+        """The plan of the last device-driven step (synchronises)."""
+        pl = L.mcl_shard_plan()
+        self._check(self.lib.mcl_shard_get_plan(self._h, C.byref(pl), self._stream()), "mcl_shard_get_plan")
+        return pl
 
     def shard_set_global(self, merged: L.mcl_stats):
         self._check(self.lib.mcl_shard_set_global(self._h, C.byref(merged), self._stream()), "mcl_shard_set_global")

@@ -18,8 +18,18 @@ Predict + weight is local.  Two exchanges couple the shards:
     predicts + weights [received prefix | locally gathered middle | received suffix].
     The result is bit-identical to the unsharded filter, and to the reference walk of :212-221.
 
-A step synchronises with the host once (the read-back of the merged statistics and the totals); when those say
-the next step will resample, its expansion is started right away so the host work between two steps is hidden.
+Two transports carry those exchanges:
+
+  * ``transport="peer"`` (default when CUDA IPC works): DEVICE-DRIVEN.  Every shard owns a mailbox and a receive
+    staging area its peers can write (cudaMalloc + CUDA IPC, mapped once at construction).  The kernels that produce
+    the statistics record, the weight total and the off-rank poses write them straight into the peers' memory over
+    NVLink and raise a step-numbered flag; three single-CTA kernels wait on the own mailbox and derive gate, comb
+    offset, k_offset and slot ranges on the device.  A step is one C call that only enqueues kernels
+    (mcl_shard_step_peer): no NCCL, no host synchronisation; the merged statistics are read back asynchronously
+    and may be consumed one step late (``lag=1``).
+  * ``transport="nccl"``: the host-driven step of round 1 (allgather of records and totals, host planning, batched
+    NCCL point-to-point), kept as the fallback and as the cross-check of the peer path.  It synchronises with the
+    host once per step; when the statistics say the next step will resample, its expansion is started right away.
 
 The pure-host pieces (`merge_stats`, `plan_exchange`, `exchange`, `philox_ofs`) import neither CUDA
 nor the C library and are what the world_size-2 gloo tests exercise on CPU.
@@ -236,7 +246,7 @@ class ShardedParticleFilter:
     """n_global particles, contiguous shards of n_global / world_size per rank."""
 
     def __init__(self, n_global, landmarks, period_ms=100.0, likelihood="moment", seed=42, group=None, device=None,
-                 ess_div=100.0, expand_factor=0.125, speculate=True, **cfg):
+                 ess_div=100.0, expand_factor=0.125, speculate=True, transport="auto", lag=0, **cfg):
         import torch
         import torch.distributed as dist
 
@@ -260,7 +270,7 @@ class ShardedParticleFilter:
         # only slots owned by OTHER ranks are materialised as poses: the send buffers hold `cap` slots and
         # grow when a step needs more (worst case n_global - m, when one shard holds all the weight)
         self.cap = min(self.n_global, int(self.m * expand_factor) + 1024)
-        self._alloc_expand()
+        self.ex = None  # allocated by the first host-driven expansion (the peer transport never needs them)
         self.total_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self._totals_buf = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
         self._totals_host = torch.zeros(self.world, dtype=torch.int64, pin_memory=True)
@@ -274,7 +284,41 @@ class ShardedParticleFilter:
         self.step_count = 0
         self.global_stats = None
         self.last_ranges = None
-        self._connect_peers()
+        if transport not in ("auto", "peer", "nccl"):
+            raise ValueError("transport must be 'auto', 'peer' or 'nccl'")
+        self.lag = int(lag)
+        self.transport, self.transport_note = self._connect_peer_memory(transport)
+        if self.transport == "nccl":
+            self._connect_peers()
+
+    def _connect_peer_memory(self, want):
+        """Map every shard's peer-visible region into this process (CUDA IPC).  All ranks must agree on the
+        outcome, so the success flags are all-reduced; 'auto' falls back to NCCL when any rank fails."""
+        t, dist = self.torch, self.dist
+        if want == "nccl":
+            return "nccl", "requested"
+        ok, why = 1, ""
+        try:
+            handle = self.flt.peer_alloc(self.rank, self.world)
+        except Exception as e:  # noqa: BLE001
+            ok, why, handle = 0, f"peer_alloc: {e}", bytes(self._L.MCL_IPC_HANDLE_BYTES)
+        mine = t.tensor(list(handle), dtype=t.uint8, device=self.dev)
+        allh = t.empty(self.world * mine.numel(), dtype=t.uint8, device=self.dev)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        blob = bytes(allh.cpu().tolist())
+        handles = [blob[g * len(handle):(g + 1) * len(handle)] for g in range(self.world)]
+        if ok:
+            try:
+                self.flt.peer_connect_ipc(handles)
+            except Exception as e:  # noqa: BLE001
+                ok, why = 0, f"peer_connect: {e}"
+        flag = t.tensor([ok], dtype=t.int32, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            return "peer", "CUDA IPC peer mappings"
+        if want == "peer":
+            raise RuntimeError(f"transport='peer' is not available on rank {self.rank}: {why or 'another rank failed'}")
+        return "nccl", f"fallback: {why or 'another rank could not map peer memory'}"
 
     def _connect_peers(self):
         """NCCL sets up a point-to-point connection the first time a pair of ranks exchanges data (milliseconds).
@@ -349,6 +393,11 @@ class ShardedParticleFilter:
     def init_particles(self, pose):
         pose = np.asarray(pose, dtype=np.float64).reshape(3)
         self.flt.init_particles(pose)
+        self._pending = 0
+        if self.transport == "peer":
+            # the freshly initialised statistics already describe the GLOBAL uniform filter (ESS = n_global)
+            self.global_stats = dict(ess=float(self.n_global), est=pose.copy(), log_norm=math.log(self.n_global))
+            return
         self.flt.shard_set_global(self._uniform_stats(pose))
         self._enqueue_totals()
         self.torch.cuda.current_stream().synchronize()
@@ -359,6 +408,10 @@ class ShardedParticleFilter:
     def set_local_particles(self, x, y, yaw, logw=None):
         """This rank's m particles (numpy or CUDA tensors); all ranks then merge their statistics."""
         self.flt.set_particles(x, y, yaw, logw)
+        if self.transport == "peer":
+            self.flt.sync_peer()
+            self.global_stats = self._stats_to_dict(self.flt.stats()[0])
+            return self.global_stats
         return self._merge()
 
     def _expand(self, ofs):
@@ -369,6 +422,8 @@ class ShardedParticleFilter:
         send, _, _, _ = plan_offrank(ranges, self.n_global, self.world, self.rank)
         if sum(send) > self.cap:
             self.cap = min(self.n_global, max(2 * self.cap, sum(send) + 1024))
+            self.ex = None
+        if self.ex is None:
             self._alloc_expand()
         self.flt.shard_expand(sum(totals[:self.rank]), ofs, *self.ex, want_range=False)
         recv, n_prefix, n_suffix = exchange_offrank(self.ex, ranges, self.n_global, self.group)
@@ -378,8 +433,10 @@ class ShardedParticleFilter:
     def step(self, z, ofs=None, noise=None, force_resample=False):
         """main_pf minus the ground-truth line: resample (gated on the global ESS) -> predict -> weight ->
         merged statistics.  `noise`: this rank's (3, 1, m) slice of the draw, or None for Philox."""
-        resampled = force_resample or (self.global_stats["ess"] < self.ess_threshold)
         z = np.asarray(z, dtype=np.float64).reshape(1, -1, 2)
+        if self.transport == "peer":
+            return self._step_peer(z, ofs, noise, force_resample)
+        resampled = force_resample or (self.global_stats["ess"] < self.ess_threshold)
         if resampled:
             if ofs is None:
                 ahead = self._ofs_ahead
@@ -402,6 +459,94 @@ class ShardedParticleFilter:
         merged["resampled"] = int(resampled)
         return merged
 
+    def _step_peer(self, z, ofs, noise, force_resample):
+        """One C call enqueues the whole step; the gate is taken on the device.  The merged statistics come back
+        through a two-deep ring of pinned buffers: with lag = 1 the record returned is the one of the PREVIOUS step
+        (None after the first), and the host never waits for the step it has just enqueued."""
+        self.flt.step_peer(z, ofs=ofs, noise=noise, force_resample=force_resample)
+        self.flt.stats_begin()
+        self._pending = getattr(self, "_pending", 0) + 1
+        self.step_count += 1
+        merged = None
+        while self._pending > self.lag:
+            merged = self._stats_to_dict(self.flt.stats_end()[0])
+            self._pending -= 1
+        if merged is not None:
+            self.global_stats = merged
+        return merged
+
+    def drain(self):
+        """Wait for the statistics of every enqueued step; -> the newest record."""
+        merged = None
+        while getattr(self, "_pending", 0) > 0:
+            merged = self._stats_to_dict(self.flt.stats_end()[0])
+            self._pending -= 1
+        if merged is not None:
+            self.global_stats = merged
+        return self.global_stats
+
+    def plan(self):
+        """Device-side plan of the last peer step (synchronises): slot range, window, gate, error flag."""
+        pl = self.flt.shard_plan()
+        if pl.error:
+            raise RuntimeError(f"rank {self.rank}: a wait on a peer shard timed out (plan.error)")
+        return pl
+
     def local_particles(self, device=False):
         x, y, th, lw = self.flt.get_particles(device=device)
         return x[0], y[0], th[0], lw[0]
+
+
+class LocalShardedFilter:
+    """The same sharded filter driven by ONE process: shard g is a Filter on devices[g] (several GPUs of the box,
+    or -- as the tests do -- several shards on one GPU).  The peers' regions are plain pointers (peer access is
+    enabled between devices); each step runs the four stages of mcl_shard_step_peer for all shards in turn, so every
+    "push" is enqueued before the matching "wait" and a single stream never spins on itself."""
+
+    def __init__(self, n_global, landmarks, n_shards, devices=None, period_ms=100.0, likelihood="moment", seed=42,
+                 ess_div=100.0, **cfg):
+        from . import _lib as L
+        from .engine import Filter, stats_to_dict
+
+        self._L, self._stats_to_dict = L, stats_to_dict
+        if n_global % n_shards or (n_global // n_shards) % 4:
+            raise ValueError("n_global must be a multiple of 4 * n_shards")
+        self.G, self.n_global, self.m = int(n_shards), int(n_global), int(n_global) // int(n_shards)
+        devices = [0] * self.G if devices is None else [int(d) for d in devices]
+        self.shards = [Filter(n_particles=self.m, n_trials=1, period_ms=period_ms, landmarks=landmarks, likelihood=likelihood,
+                              device=devices[g], seed=seed, n_global=self.n_global, slot_base=g * self.m,
+                              ess_threshold=self.n_global / ess_div, **cfg) for g in range(self.G)]
+        for g, f in enumerate(self.shards):
+            f.peer_alloc(g, self.G)
+        for f in self.shards:
+            f.peer_connect_local(self.shards)
+
+    def init_particles(self, pose):
+        for f in self.shards:
+            f.init_particles(pose)
+
+    def set_particles(self, x, y, yaw, logw=None):
+        """Global arrays of n_global elements; shard g takes [g m, (g + 1) m)."""
+        for g, f in enumerate(self.shards):
+            sl = slice(g * self.m, (g + 1) * self.m)
+            f.set_particles(x[sl], y[sl], yaw[sl], None if logw is None else logw[sl])
+        for stage in (self._L.MCL_STAGE_C, self._L.MCL_STAGE_D):
+            for f in self.shards:
+                f.sync_peer(stage)
+
+    def step(self, z, ofs=None, noise=None, force_resample=False, no_resample=False):
+        """noise: (3, 1, n_global) or None (Philox).  -> the merged statistics (of shard 0; all shards agree)."""
+        L = self._L
+        for stage in (L.MCL_STAGE_A, L.MCL_STAGE_B, L.MCL_STAGE_C, L.MCL_STAGE_D):
+            for g, f in enumerate(self.shards):
+                nz = None if noise is None else noise[:, :, g * self.m:(g + 1) * self.m]
+                f.step_peer(z, ofs=ofs, noise=nz if stage == L.MCL_STAGE_C else None, force_resample=force_resample,
+                            no_resample=no_resample, stages=stage)
+        return self.stats()
+
+    def stats(self, shard=0):
+        return self._stats_to_dict(self.shards[shard].stats()[0])
+
+    def particles(self):
+        parts = [f.get_particles() for f in self.shards]
+        return tuple(np.concatenate([p[k][0] for p in parts]) for k in range(4))

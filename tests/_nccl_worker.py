@@ -1,5 +1,6 @@
-"""2+ GPU worker: ShardedParticleFilter (NCCL allgather + all-to-all) against the unsharded Filter run on
-rank 0 with the same Philox seed: identical particles after every step, identical statistics."""
+"""2+ GPU worker: ShardedParticleFilter -- transport from MCL_TRANSPORT: "peer" (device-driven, CUDA IPC peer memory)
+or "nccl" (host-driven allgather + point-to-point) -- against the unsharded Filter run on rank 0 with the same Philox
+seed: identical particles after every step, identical statistics.  Prints "<transport> worker ok"."""
 import os
 import sys
 
@@ -24,7 +25,9 @@ def main():
     m = n // world
     lm = bench.landmarks_for(L)
     truth = bench.Truth(lm, seed=3)
-    sf = ShardedParticleFilter(n, lm, likelihood="moment", seed=11)
+    transport = os.environ.get("MCL_TRANSPORT", "nccl")
+    sf = ShardedParticleFilter(n, lm, likelihood="moment", seed=11, transport=transport)
+    assert sf.transport == transport, (sf.transport, sf.transport_note)
     sf.init_particles(truth.pose()[0])
     ref = None
     if rank == 0:
@@ -35,6 +38,10 @@ def main():
         truth.advance()
         z = truth.observe()
         force = k % 3 != 1  # mix resampling and non-resampling steps
+        if rank == 0 and k > 0:
+            # the unsharded filter quantises with the shards' MERGED statistics (its own merge groups the fp32 partial
+            # sums differently: equal to ~1e-9, which very rarely moves the fp32 scale of the weight map by one ulp)
+            ref.restore_stats(sf.flt.stats()[0], k)
         g = sf.step(z, force_resample=force)
         x, y, th, lw = sf.local_particles()
         parts = [torch.from_numpy(np.stack([x, y, th, lw])).cuda()]
@@ -58,7 +65,7 @@ def main():
     dist.broadcast(flag, 0)
     dist.barrier()
     if rank == 0 and ok:
-        print("nccl worker ok", flush=True)
+        print(f"{transport} worker ok", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) else 1)
 

@@ -189,6 +189,37 @@ def test_resampling_indices_bit_exact(mcl, n, kind):
     assert f.stats()[0].ess == pytest.approx(n)
 
 
+def test_scan_descriptors_survive_a_skipped_resampling(mcl):
+    """More than 1024 scan tiles (look-back through prefixes), device ESS gate: resample -> gate holds -> resample.
+    The launch whose gate held must still clear the descriptor buffer the third launch scans with."""
+    n = 4_500_003
+    rng = np.random.RandomState(5)
+    pos = rng.normal(0, 1, (3, n)).astype(np.float32)
+    f = mcl.Filter(n_particles=n, landmarks=[[0.0, 0.0]])
+    for rnd, peaked in enumerate([True, False, True]):
+        if peaked:
+            lw = -0.5 * ((np.arange(n) - (0.3 + 0.2 * rnd) * n) / (0.0005 * n)) ** 2 + rng.normal(0, 0.5, n)
+        else:
+            lw = rng.normal(0, 0.1, n)
+        lw = (lw - lw.max()).astype(np.float32)
+        f.set_particles(pos[0], pos[1], pos[2], lw)
+        q = f.qweights()[0]
+        ess = f.stats()[0].ess
+        ofs = rng.rand() * (1 / n)
+        f.resample(ofs=ofs)  # gate on the device: ess < n / 100
+        assert (ess < n / 100) == peaked
+        if peaked:
+            anc = f.ancestors()[0].astype(np.int64)
+            want = O.resample_indices(O.dequantize_weights(q), ofs, clamp=True)
+            np.testing.assert_array_equal(anc, want)
+            x, _, _, _ = f.get_particles()
+            np.testing.assert_array_equal(x[0], pos[0][anc])
+        else:
+            x, _, _, lw1 = f.get_particles()
+            np.testing.assert_array_equal(x[0], pos[0])
+            np.testing.assert_array_equal(lw1[0], lw)
+
+
 def test_ess_gate_skips_resampling(mcl):
     n = 2048
     rng = np.random.RandomState(5)
@@ -568,20 +599,23 @@ def _sharded_step_case(mcl, G, kind, n):
             fs[heavy].shard_expand(sum(totals[:heavy]), ofs, *ex)
 
 
-def test_sharded_filter_two_gpus_nccl():
-    """The real thing: ShardedParticleFilter over NCCL on 2 GPUs == the unsharded filter (Philox noise)."""
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_sharded_filter_two_gpus(transport):
+    """The real thing: ShardedParticleFilter over 2 GPUs (one process each) == the unsharded filter (Philox noise).
+    "peer": device-driven exchange through CUDA IPC peer memory; "nccl": the host-driven fallback."""
     import subprocess
     import sys
 
     import torch
 
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2); bench.py --gpus N repeats this check in-line (sharded_filter.parity)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29641", os.path.join(root, "tests", "_nccl_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
-    assert r.returncode == 0 and "nccl worker ok" in r.stdout, r.stdout[-3000:] + r.stderr[-4000:]
+           "--master-port", "29641" if transport == "nccl" else "29643", os.path.join(root, "tests", "_nccl_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, MASTER_ADDR="127.0.0.1", MCL_TRANSPORT=transport))
+    assert r.returncode == 0 and f"{transport} worker ok" in r.stdout, r.stdout[-3000:] + r.stderr[-4000:]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -884,3 +918,115 @@ def test_checkpoint_restores_a_bit_identical_filter(mcl, tmp_path, trials):
     for t in range(trials):
         assert sa[t].max_idx == sb[t].max_idx and sa[t].ess == sb[t].ess and sa[t].step == sb[t].step == 12
         assert sa[t].resampled == sb[t].resampled
+
+
+# ---------------------------------------------------------------------------------------------
+# device-driven sharded filter (peer memory): G shards on this one GPU, no host in the loop
+# ---------------------------------------------------------------------------------------------
+def _peer_case(mcl, G, kind, n, steps=1):
+    Lm = 6
+    m = n // G
+    rng = np.random.RandomState(100 + G + len(kind))
+    lm = rng.uniform(-10, 10, (Lm, 2))
+    truth = np.array([[2.0], [1.0], [0.4]])
+    pos = (rng.normal(0, 1, (3, n)) * np.array([[0.2], [0.2], [0.05]]) + truth).astype(np.float32)
+    if kind == "spread":
+        lw = (-0.5 * ((np.arange(n) - 0.3 * n) / (0.05 * n)) ** 2 + rng.normal(0, 1.0, n)).astype(np.float32)
+    elif kind == "left_heavy":  # nearly all the weight in the first shard: it fills slots of every other rank
+        lw = (np.where(np.arange(n) < m // 3, 0.0, -30.0) + rng.normal(0, 1.0, n)).astype(np.float32)
+    else:  # right_heavy: the last shard fills everybody's slots (suffix path of every lower rank)
+        lw = (np.where(np.arange(n) >= n - m // 3, 0.0, -30.0) + rng.normal(0, 1.0, n)).astype(np.float32)
+    sf = mcl.LocalShardedFilter(n, lm, G, likelihood="pair")
+    sf.set_particles(pos[0], pos[1], pos[2], lw)
+    f1 = mcl.Filter(n_particles=n, landmarks=lm, likelihood="pair")
+    f1.set_particles(pos[0], pos[1], pos[2], lw, skip_stats=True)
+    for k in range(steps):
+        # the unsharded filter takes the MERGED statistics of the shards, so both quantise with the same weight map
+        # (its own merge groups the fp32 partial sums differently: equal to ~1e-9, not bitwise)
+        g_stats = sf.shards[0].stats()[0]
+        for f in sf.shards[1:]:
+            o = f.stats()[0]
+            assert (o.max_logw, o.sum_w, o.sum_w2, o.ess, o.max_idx) == (g_stats.max_logw, g_stats.sum_w, g_stats.sum_w2, g_stats.ess, g_stats.max_idx)
+        f1.restore_stats(g_stats, k)
+        q = np.concatenate([f.qweights()[0] for f in sf.shards])
+        assert np.array_equal(q, f1.qweights()[0])
+        ofs = rng.rand() / n
+        noise = (rng.normal(0, 1, (3, 1, n)) * np.array([0.03, 0.03, 0.035])[:, None, None]).astype(np.float32)
+        z = O.world2robot(truth, lm) + rng.normal(0, 0.3, (Lm, 2))
+        force = (k % 3 != 1)
+        sf.step(z[None], ofs=ofs, noise=noise, force_resample=force, no_resample=not force)
+        f1.step(z[None], ofs=ofs, noise=noise, force_resample=force, no_resample=not force)
+        for f in sf.shards:
+            pl = f.shard_plan()
+            assert pl.error == 0 and pl.resampled == int(force)
+        x1, y1, t1, l1 = f1.get_particles()
+        xs, ys, ts, ls = sf.particles()
+        if force:
+            anc1 = f1.ancestors()[0].astype(np.int64)
+            want = O.resample_indices_literal(O.dequantize_weights(q), ofs)
+            assert np.array_equal(anc1, want)
+            # the plan every shard derived on the device against the host twin of round 1
+            sh = importlib.import_module("slam-robot_simu_b200.sharded")
+            totals = [int(q[g * m:(g + 1) * m].sum()) for g in range(G)]
+            ranges = sh.shard_ranges(totals, n, ofs)
+            for g, f in enumerate(sf.shards):
+                pl = f.shard_plan()
+                assert [int(v) for v in pl.totals[:G]] == totals
+                assert (pl.first_slot, pl.n_slots) == ranges[g]
+                assert pl.k_offset == sum(totals[:g])
+        np.testing.assert_array_equal(xs, x1[0])
+        np.testing.assert_array_equal(ys, y1[0])
+        np.testing.assert_array_equal(ts, t1[0])
+        np.testing.assert_array_equal(ls, l1[0])
+        s1 = f1.stats()[0]
+        sg = sf.stats()
+        assert sg["max_idx"] == s1.max_idx and sg["ess"] == pytest.approx(s1.ess, rel=1e-6)
+        assert sg["log_norm"] == pytest.approx(s1.log_norm, abs=1e-7)
+
+
+import importlib  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("G", [2, 4, 8])
+@pytest.mark.parametrize("kind", ["spread", "left_heavy", "right_heavy"])
+def test_peer_sharded_step_matches_unsharded(mcl, G, kind):
+    """SURVEY 8(e), device-driven: statistics, totals and off-rank poses travel through peer memory, gate / k_offset /
+    slot ranges are derived on the device -- the particles equal the unsharded filter's bit for bit."""
+    _peer_case(mcl, G, kind, 1 << 16, steps=4)
+
+
+@pytest.mark.gpu
+def test_peer_sharded_step_with_segmented_tile_prefixes(mcl):
+    _peer_case(mcl, 2, "spread", 1 << 23, steps=2)
+
+
+@pytest.mark.gpu
+def test_peer_sharded_philox_run_with_device_gate(mcl):
+    """A free-running sharded filter (Philox noise, ESS gate taken on the device, no host decision anywhere) against
+    the unsharded filter fed the shards' merged statistics before every step: identical particles, identical gates."""
+    n, G, Lm = 1 << 17, 4, 16
+    bench = importlib.import_module("bench")
+    lm = bench.landmarks_for(Lm)
+    truth = bench.Truth(lm, seed=3)
+    sf = mcl.LocalShardedFilter(n, lm, G, likelihood="moment", seed=11)
+    sf.init_particles(truth.pose()[0])
+    ref = mcl.Filter(n_particles=n, landmarks=lm, likelihood="moment", seed=11, max_landmarks=Lm)
+    ref.init_particles(truth.pose()[0])
+    fired = 0
+    for k in range(14):
+        truth.advance()
+        z = truth.observe()
+        if k > 0:
+            ref.restore_stats(sf.shards[0].stats()[0], k)
+        sf.step(z)
+        ref.step(z)
+        x1, y1, t1, l1 = ref.get_particles()
+        xs, ys, ts, ls = sf.particles()
+        np.testing.assert_array_equal(xs, x1[0])
+        np.testing.assert_array_equal(ts, t1[0])
+        np.testing.assert_array_equal(ls, l1[0])
+        r1 = ref.stats()[0].resampled
+        assert all(f.shard_plan().resampled == r1 for f in sf.shards)
+        fired += r1
+    assert 0 < fired < 14  # the gate both fired and held
