@@ -27,14 +27,26 @@ L2_BYTES = 126 * 1024 * 1024
 BYTES_STEP_CANONICAL = 64  # fp32 SoA state, predict+weight 32 B + scan 4 B + gather 28 B
 BYTES_K_STEP = 32          # k_step as built: ancestor 4 B + gathered pose 12 B in, pose + log-weight 16 B out
 BYTES_K_SCAN = 8           # k_scan: log-weight 4 B in, ancestor 4 B out
-NCU_TRAFFIC_K_STEP_BYTES_PER_PARTICLE = (528.388608e6 + 501.015552e6) / 33554432  # profiles/r01_r_ncu_32M_x64_k_step_summary.csv
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_step launch, per particle, from `ncu --set full` captures of the
+# workload named by the key (tools/ncu_case.py; summaries under profiles/).  Workloads without a capture report null.
+NCU_TRAFFIC = {
+    ("c3", "moment"): ((528.388608e6 + 501.015552e6) / 33554432,
+                       "ncu --set full of k_step at 32M particles x 64 landmarks (profiles/r01_r_ncu_32M_x64_k_step_summary.csv), per particle x this launch"),
+}
+HAVE_RB32 = False
+PAIR_LOOPS = {
+    "pair": {"arithmetic": "fp64, 8 operations per pair", "bound": "FP64 pipe"},
+    "rb": {"arithmetic": "fp64, libm sqrt / atan2, all landmarks scored", "bound": "FP64 pipe"},
+    "rb32": {"arithmetic": "fp32 + MUFU (rcp, sqrt), branch-free atan2, ALL landmarks scored", "bound": "FP32/SFU issue"},
+    "rb_fan": {"arithmetic": "fp32 + MUFU (rcp, sqrt), branch-free atan2, detected landmarks only", "bound": "FP32/SFU issue"},
+}
 
 WORKLOADS = {
     # name: (particles per filter, landmarks, trials per GPU, description)
-    "c1": dict(n=1 << 20, L=16, T=1, desc="C1 single filter 2^20 particles x 16 landmarks"),
-    "c2": dict(n=16384, L=16, T=4096, desc="C2 4096 independent trials x 16384 particles x 16 landmarks"),
-    "c3": dict(n=125_000_000, L=64, T=1, desc="C3 one 125M-particle shard x 64 landmarks (1B over 8 GPUs)"),
-    "c4": dict(n=16 << 20, L=1024, T=1, desc="C4 16M particles x 1024 landmarks (FP-bound likelihood)"),
+    "c1": dict(key="c1", n=1 << 20, L=16, T=1, desc="C1 single filter 2^20 particles x 16 landmarks"),
+    "c2": dict(key="c2", n=16384, L=16, T=4096, desc="C2 4096 independent trials x 16384 particles x 16 landmarks"),
+    "c3": dict(key="c3", n=125_000_000, L=64, T=1, desc="C3 one 125M-particle shard x 64 landmarks (1B over 8 GPUs)"),
+    "c4": dict(key="c4", n=16 << 20, L=1024, T=1, desc="C4 16M particles x 1024 landmarks (FP-bound likelihood)"),
 }
 
 
@@ -62,7 +74,8 @@ class Truth:
 
     PERIOD = 360
 
-    def __init__(self, lm, seed, T=1, dt=0.1, fan=False):
+    def __init__(self, lm, seed, T=1, dt=0.1, fan=False, rb=False):
+        self.rb = bool(rb)    # (distance, direction) of ALL landmarks, no visibility gate (MCL_LIK_RB; C4 as named)
         self.fan = bool(fan)  # observations of the fan-shaped scan sensor (graph_based_slam.py:128-167) instead
         self.lm = np.asarray(lm, dtype=np.float64)
         self.rng = np.random.RandomState(seed)
@@ -89,6 +102,13 @@ class Truth:
         s, c = np.sin(th), np.cos(th)
         dx, dy = self.lm[None, :, 0] - x, self.lm[None, :, 1] - y
         z = np.stack([s * dx - c * dy, c * dx + s * dy], axis=2)
+        if self.rb:
+            # the sensor model of graph_based_slam.py:150-167 without the gate: d ~ N(d, d R_Dist), phi ~ N(phi, sigma)
+            d = np.hypot(z[..., 0], z[..., 1])
+            phi = np.arctan2(z[..., 1], z[..., 0])
+            dn = self.rng.normal(d, 0.05 * d)
+            pn = phi + self.rng.normal(0.0, np.deg2rad(2.0), phi.shape)
+            return np.stack([dn, (pn + np.pi) % (2 * np.pi) - np.pi], axis=2)
         if self.fan:
             # (distance, direction) of the landmarks inside the fan (15 m, +-80 deg), noise as the reference's Robot
             # sets it (5 % of the distance, 2 deg; graph_based_slam.py:604); NaN rows where nothing is detected
@@ -177,52 +197,77 @@ class ClockSampler(threading.Thread):
 # reference arm / CPU baseline: the numpy oracle (a port of the reference's step; the reference itself is
 # a per-particle Python loop that cannot finish these shapes) on the host cores
 # ======================================================================================================
-def _cpu_chunk(args):
+_SH = {}  # arrays shared with the worker processes (anonymous shared mappings, inherited through fork)
+
+
+def _shared(shape, dtype):
+    import multiprocessing as mp
+
+    n = int(np.prod(shape))
+    raw = mp.RawArray("b", n * np.dtype(dtype).itemsize)
+    return np.frombuffer(raw, dtype=dtype, count=n).reshape(shape)
+
+
+def _cpu_slice(args):
+    """One worker's share of a step, entirely inside the shared arrays (nothing is pickled but five scalars):
+    gather through the ancestors (:216-221), noise draw + motion (:165-166), log-likelihood (:185-192)."""
     from oracle import pf_oracle as O
 
-    px, v, z, lm, dt = args
-    P = O.PFParams(dt * 1000.0, n_particles=px.shape[1], landmarks=lm)
+    a, b, src, seed, step = args
+    S = _SH
+    P = S["P"]
+    px = S["px"][src][:, S["anc"][a:b]]
+    rng = np.random.RandomState((seed * 1000003 + step * 7919 + a) % (2 ** 32))
+    v = rng.multivariate_normal([0.0, 0.0, 0.0], P.Q, b - a).T
     px2 = O.predict(px, v, P)
-    ll = O.loglik_cartesian(px2, z, lm, 0.3, 0.3)
-    return px2, ll
+    S["px"][1 - src][:, a:b] = px2
+    S["ll"][a:b] = O.loglik_cartesian(px2, S["z"], S["lm"], 0.3, 0.3)
+    return 0
 
 
 def cpu_step_runner(n, L, procs):
-    """Returns step() -> seconds for ONE oracle step over n particles x L landmarks, `procs` processes.
+    """Returns step() -> seconds for ONE oracle step over n particles x L landmarks on `procs` processes.
 
-    Order as particle_filter.py:86-119: resample (cumsum + comb search + gather) -> predict (numpy
-    noise draw + motion) -> weight (log-domain likelihood, normalise) -> arg-max."""
+    Order as particle_filter.py:86-119: resample (cumsum + comb search on one core, gather in the workers) ->
+    predict (numpy noise draw + motion) -> weight (log-domain likelihood; normalisation on one core) -> arg-max.
+    Particles, ancestors, observations and log-likelihoods live in shared memory the forked workers inherit, so a
+    step moves no particle data between processes."""
     from oracle import pf_oracle as O
 
     lm = landmarks_for(L)
     truth = Truth(lm, seed=5)
     rng = np.random.RandomState(11)
     P = O.PFParams(100.0, n_particles=n, landmarks=lm)
-    state = dict(px=np.tile(P.x0, (1, n)) + rng.normal(0, 0.05, (3, n)), pw=np.full(n, 1.0 / n))
+    S = _SH
+    S.clear()
+    S.update(P=P, lm=lm, px=[_shared((3, n), np.float64), _shared((3, n), np.float64)], anc=_shared((n,), np.int64),
+             ll=_shared((n,), np.float64), z=_shared((L, 2), np.float64))
+    S["px"][0][:] = np.tile(P.x0, (1, n)) + rng.normal(0, 0.05, (3, n))
+    state = dict(src=0, pw=np.full(n, 1.0 / n), k=0)
     pool = None
     if procs > 1:
         import multiprocessing as mp
 
-        pool = mp.get_context("fork").Pool(procs)
+        pool = mp.get_context("fork").Pool(procs)  # after the shared arrays exist: the children inherit them
+    cuts = np.linspace(0, n, max(procs, 1) * 4 + 1).astype(int)  # 4 slices per process: load balance
 
     def step():
         t0 = time.perf_counter()
         truth.advance()
         ofs = rng.rand() / n
-        anc = O.resample_indices(state["pw"], ofs)
-        px = state["px"][:, anc]
-        v = rng.multivariate_normal([0.0, 0.0, 0.0], P.Q, n).T
-        z = truth.observe()[0]
+        S["anc"][:] = O.resample_indices(state["pw"], ofs)
+        S["z"][:] = truth.observe()[0]
+        jobs = [(int(a), int(b), state["src"], 11, state["k"]) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
         if pool is None:
-            px2, ll = _cpu_chunk((px, v, z, lm, 0.1))
+            for j in jobs:
+                _cpu_slice(j)
         else:
-            cuts = np.linspace(0, n, procs + 1).astype(int)
-            parts = pool.map(_cpu_chunk, [(px[:, a:b], v[:, a:b], z, lm, 0.1) for a, b in zip(cuts[:-1], cuts[1:])])
-            px2 = np.concatenate([p[0] for p in parts], axis=1)
-            ll = np.concatenate([p[1] for p in parts])
-        w, _ = O.update_weights_log(np.full(n, -math.log(n)), ll)
-        state["px"], state["pw"] = px2, w
-        O.map_estimate(px2, w)
+            pool.map(_cpu_slice, jobs, chunksize=1)
+        state["src"] = 1 - state["src"]
+        state["k"] += 1
+        w, _ = O.update_weights_log(np.full(n, -math.log(n)), S["ll"])
+        state["pw"] = w
+        O.map_estimate(S["px"][state["src"]], w)
         return time.perf_counter() - t0
 
     def close():
@@ -283,68 +328,149 @@ def run_reference(args, wl):
 # ======================================================================================================
 # the B200 arm
 # ======================================================================================================
-def measure_sharded(mcl, torch, dist, dev, n_per_gpu, L, likelihood, steps, warmup):
-    """One filter of world * n_per_gpu particles sharded over the ranks: allgather of statistics and
-    weight totals + variable-count all-to-all of the resampled poses (NCCL), forced resampling."""
+def _read_clocks(sampler, n=3):
+    """A few NVML readings taken while the GPU still works through what has been enqueued (never from a polling
+    thread inside the timed region: NVML queries share the driver with the launches)."""
+    for _ in range(n):
+        sampler.sample_once()
+
+
+def sharded_parity_check(mcl, torch, dist, dev, transport, n=1 << 18, L=16, steps=8):
+    """A small sharded filter over the LIVE process group against the unsharded filter on rank 0: particles and
+    log-weights must be equal bit for bit after every step (mixed resampling / non-resampling steps, Philox noise).
+    The unsharded filter takes the shards' merged statistics before each step, so both quantise the weights with the
+    same map (its own merge groups the fp32 partial sums differently: equal to ~1e-9, not bitwise).
+    -> (ok, text).  Also used by tests/_nccl_worker.py."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    lm = landmarks_for(L)
+    truth = Truth(lm, seed=3)
+    sf = mcl.ShardedParticleFilter(n, lm, likelihood="moment", seed=11, transport=transport, max_landmarks=L)
+    sf.init_particles(truth.pose()[0])
+    ref = None
+    if rank == 0:
+        ref = mcl.Filter(n_particles=n, landmarks=lm, likelihood="moment", seed=11, max_landmarks=L, device=dev.index)
+        ref.init_particles(truth.pose()[0])
+    ok, bad = True, ""
+    for k in range(steps):
+        truth.advance()
+        z = truth.observe()
+        force = k % 3 != 1
+        if rank == 0 and k > 0:
+            ref.restore_stats(sf.flt.stats()[0], k)
+        sf.step(z, force_resample=force)
+        g = sf.drain() if sf.transport == "peer" else sf.global_stats
+        x, y, th, lw = sf.local_particles(device=True)
+        mine = torch.stack([x, y, th, lw])
+        allp = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allp, mine)
+        if rank == 0:
+            ref.step(z, force_resample=force, no_resample=not force)
+            rx, ry, rt, rl = ref.get_particles()
+            got = torch.cat(allp, dim=1).cpu().numpy()
+            st = ref.stats()[0]
+            same = all(np.array_equal(got[i], a[0]) for i, a in enumerate((rx, ry, rt, rl)))
+            close = abs(g["ess"] / st.ess - 1) < 1e-6 and g["max_idx"] == st.max_idx and abs(g["log_norm"] - st.log_norm) < 1e-7
+            if not (same and close):
+                ok = False
+                bad = bad or f"step {k}: particles equal={same} statistics close={close}"
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    ok = bool(int(flag.item()))
+    del sf
+    return ok, (f"bit-identical to the unsharded filter over {steps} steps ({n} particles, {world} shards, transport {transport})"
+                if ok else f"MISMATCH: {bad}")
+
+
+def measure_sharded(mcl, torch, dist, dev, n_per_gpu, L, likelihood, steps, warmup, transport="auto", min_seconds=0.5):
+    """One filter of world * n_per_gpu particles sharded over the ranks, forced global resampling every step.
+    transport "peer": device-driven exchange through peer memory (no NCCL, no host synchronisation in a step);
+    "nccl": the host-driven step.  Timed on the device (CUDA events, blocks of `steps` steps, median block, MAX over
+    ranks) and, around the same steps, by the host clock (the end-to-end number)."""
     world, rank = dist.get_world_size(), dist.get_rank()
     n_global = n_per_gpu * world
     lm = landmarks_for(L)
     truth = Truth(lm, seed=77)  # the same observations on every rank
     cyc = truth.cycle()
-    sf = mcl.ShardedParticleFilter(n_global, lm, likelihood=likelihood, seed=4711, max_landmarks=L)
+    sf = mcl.ShardedParticleFilter(n_global, lm, likelihood=likelihood, seed=4711, max_landmarks=L, transport=transport, lag=1)
     sf.init_particles(truth.pose()[0])
     k = 0
-    # untimed: at least `warmup` steps AND at least 0.6 s of them -- a sharded step is ~2 ms, so a handful of steps
-    # ends before the clocks of all GPUs have left their idle state (W is a minimum, not a maximum)
+
+    def run(count):
+        nonlocal k
+        for _ in range(count):
+            sf.step(cyc[k % Truth.PERIOD], force_resample=True)
+            k += 1
+
+    # untimed: at least `warmup` steps AND at least 0.6 s of them (clocks of all GPUs leave their idle state)
+    W = max(warmup, 3)
     t_warm = time.perf_counter()
-    for _ in range(max(warmup, 3)):
-        sf.step(cyc[k % Truth.PERIOD], force_resample=True)
-        k += 1
+    run(W)
+    sf.drain()
     torch.cuda.synchronize()
-    # the steps contain collectives, so every rank must take the SAME number of extra steps: agree on it first
-    per_step = torch.tensor([(time.perf_counter() - t_warm) / max(warmup, 3)], device=dev, dtype=torch.float64)
-    dist.all_reduce(per_step, op=dist.ReduceOp.MAX)
-    extra = int(min(400, max(0.0, 0.6 / max(float(per_step.item()), 1e-4) - max(warmup, 3))))
-    for _ in range(extra):
-        sf.step(cyc[k % Truth.PERIOD], force_resample=True)
-        k += 1
+    per_step = torch.tensor([(time.perf_counter() - t_warm) / W], device=dev, dtype=torch.float64)
+    dist.all_reduce(per_step, op=dist.ReduceOp.MAX)  # every rank must take the SAME number of steps
+    per_step = max(float(per_step.item()), 1e-4)
+    run(int(min(600, max(0.0, 0.6 / per_step))))
+    sf.drain()
+    n_blocks = int(min(400, max(1, math.ceil(min_seconds / (per_step * steps)))))
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
-    # The sharded step is host-driven, and NVML queries share the driver with the launches (a polling thread
-    # slowed the step 2.5x): the clocks are read once right before and once right after the timed steps, while the
-    # GPU is still loaded by them.
     sampler = ClockSampler(dev.index)
-    sampler.sample_once()
     launches0 = sf.flt.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_blocks)]
     t0 = time.perf_counter()
-    moved = 0
-    for _ in range(steps):
-        g = sf.step(cyc[k % Truth.PERIOD], force_resample=True)
-        k += 1
-        first, count = sf.last_ranges[rank]
-        lo, hi = rank * sf.m, (rank + 1) * sf.m
-        moved += count - max(0, min(first + count, hi) - max(first, lo))
+    for e0, e1 in evs:
+        e0.record()
+        run(steps)
+        e1.record()
+    _read_clocks(sampler)
+    g = sf.drain()
     torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
     dist.barrier()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    sampler.sample_once()
     launches = sf.flt.launch_count() - launches0
-    t = torch.tensor([dt, float(moved)], device=dev, dtype=torch.float64)
+    block_ms = float(np.median([e0.elapsed_time(e1) for e0, e1 in evs]))
+    t = torch.tensor([block_ms, wall], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t[0].item())
+    block_ms, wall = float(t[0].item()), float(t[1].item())
+    # per-kernel durations of a few more steps (CUDA events inside the library, same stream)
+    kern = None
+    moved = None
+    if sf.transport == "peer":
+        sf.flt.profile(True)
+        acc = np.zeros(5)
+        for _ in range(8):
+            run(1)
+            acc += np.array(sf.flt.profile_read_peer())
+        sf.drain()
+        sf.flt.profile(False)
+        acc /= 8
+        kern = {"totals_pass+exchange": acc[0], "expansion+exchange": acc[1], "scalars": acc[2], "k_step": acc[3], "statistics_exchange": acc[4]}
+        pl = sf.plan()
+        moved = int(sf.m - (pl.win_hi - pl.win_lo))
+    mv = torch.tensor([float(moved or 0)], device=dev, dtype=torch.float64)
+    dist.all_reduce(mv, op=dist.ReduceOp.MAX)
     out = {"workload": f"one filter of {n_global} particles x {L} landmarks over {world} GPUs, global systematic resampling",
-           "value": n_global * steps / dt, "unit": "particle-steps/s", "ms_per_step": dt / steps * 1e3, "steps": steps,
+           "value": n_global * steps / (block_ms * 1e-3), "unit": "particle-steps/s", "ms_per_step": block_ms / steps, "steps": steps,
+           "blocks": n_blocks, "timed_seconds": block_ms * n_blocks * 1e-3,
+           "e2e_value": n_global * steps * n_blocks / wall, "e2e_ms_per_step": wall / (steps * n_blocks) * 1e3,
            "ess_over_n": g["ess"] / n_global, "gpu_launches_rank0": int(launches), "clocks_rank0": sampler.summary(),
-           "max_slots_sent_off_rank_per_step": float(t[1].item()) / steps,
-           "collectives": "allgather(mcl_stats 312 B) -> device merge; allgather(u64 weight total); one batched NCCL P2P group for the fp32 poses of off-rank slots"}
+           "transport": sf.transport, "transport_note": sf.transport_note, "kernel_ms_rank0": kern,
+           "max_slots_received_from_peers_last_step": float(mv.item()),
+           "exchange": ("statistics record (320 B), u64 weight total and off-rank poses written by the producing kernels into the "
+                        "peers' memory (CUDA IPC mappings, NVLink); step-numbered flags; gate / k_offset / slot ranges derived on "
+                        "the device; no NCCL call and no host synchronisation inside a step; statistics read back one step late"
+                        if sf.transport == "peer" else
+                        "allgather(mcl_stats) -> device merge; allgather(u64 total); D2H + host planning; one batched NCCL P2P group")}
     del sf
     torch.cuda.empty_cache()
     return out
 
 
 def run_b200(args, wl):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
@@ -358,31 +484,7 @@ def run_b200(args, wl):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-
-    n, L, T = wl["n"], wl["L"], wl["T"]
-    lm = landmarks_for(L)
-    if world > 1 and args.workload == "c3":
-        sh = measure_sharded(mcl, torch, dist, dev, n, L, args.likelihood, args.steps, args.warmup)
-        if rank == 0:
-            peak, peak_src = peaks()
-            line = {"metric": "particle-steps/s (predict+weight+resample)", "value": sh["value"], "unit": "particle-steps/s",
-                    "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": sh["ms_per_step"],
-                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                    "dtype": "f32 state / f64 likelihood / u64 scan", "data": "synthetic",
-                    "config": {"workload": sh["workload"], "likelihood": args.likelihood, "noise": "philox4x32-10 on device",
-                               "resampling": "forced every step, global", "ess_over_n": sh["ess_over_n"],
-                               "l2": f"{36 * n >> 20} MiB of state per GPU > 126 MiB L2", "parallelism": f"particle-sharded x{world}"},
-                    "roofline": {"bound": "hbm", "achieved": BYTES_STEP_CANONICAL * sh["value"] / world / 1e9, "peak": peak,
-                                 "unit": "GB/s", "frac": BYTES_STEP_CANONICAL * sh["value"] / world / 1e9 / peak, "traffic": None,
-                                 "peak_source": peak_src, "note": "whole step per GPU at the canonical 64 B per particle-step"},
-                    "cpu_baseline": None, "e2e": {"value": sh["value"], "unit": "particle-steps/s",
-                                                  "h2d_bytes_per_step": 16 * L + 304, "d2h_bytes_per_step": 304 + 8 + 16,
-                                                  "note": "the sharded step is host-mediated: its timing already includes the "
-                                                          "observation upload and the statistics read-back of every step"},
-                    "sharded_filter": sh, "gpu_launches": sh["gpu_launches_rank0"] * world, "clocks": sh["clocks_rank0"]}
-            print(json.dumps(line), flush=True)
-        dist.destroy_process_group()
-        return
+    peak, peak_src = peaks()
     K, W = args.steps, max(args.warmup, 3)
 
     def sync_all():
@@ -391,17 +493,18 @@ def run_b200(args, wl):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed_run(w_, K_, W_, spin_s):
-        """K_ timed steps of workload w_ with device-resident inputs; returns the numbers of the JSON line."""
-        n_, L_, T_ = w_["n"], w_["L"], w_["T"]
+    def timed_run(w_, K_, W_, spin_s, likelihood, min_seconds=0.25, keep=False, trials=None):
+        """Blocks of K_ timed steps of workload w_ with device-resident inputs (at least min_seconds of them; the
+        MEDIAN block is reported, MAX over ranks); returns the numbers of the JSON line."""
+        n_, L_, T_ = w_["n"], w_["L"], (trials if trials is not None else w_["T"])
         lm_ = landmarks_for(L_)
         state_bytes = 2 * 16 * n_ * T_ + 4 * n_ * T_
         replicas = max(1, min(64, math.ceil(2.2 * L2_BYTES / state_bytes)))  # rotate filters: every step is L2-cold
         filters, zcyc_host, zcyc = [], [], []
         for r in range(replicas):
-            f = mcl.Filter(n_particles=n_, n_trials=T_, landmarks=lm_, likelihood=args.likelihood, device=local,
+            f = mcl.Filter(n_particles=n_, n_trials=T_, landmarks=lm_, likelihood=likelihood, device=local,
                            seed=42 + 1000 * rank + r, max_landmarks=L_)
-            tr = Truth(lm_, seed=7 + 100 * rank + r * 17, T=T_, fan=(args.likelihood == "rb_fan"))
+            tr = Truth(lm_, seed=7 + 100 * rank + r * 17, T=T_, fan=(likelihood == "rb_fan"), rb=(likelihood in ("rb", "rb32")))
             f.init_particles(tr.pose())
             cyc = tr.cycle()  # (360, T, L, 2): replica r at filter step k sees cyc[k % 360]
             filters.append(f)
@@ -414,11 +517,15 @@ def run_b200(args, wl):
             filters[r].step_dev(zcyc[r][counts[r] % Truth.PERIOD], force_resample=True)
             counts[r] += 1
 
-        # untimed: 20 spreading steps per replica, then spin until the clocks are at their loaded
-        # state (W is a minimum, not a maximum)
+        # untimed: 20 spreading steps per replica, then spin until the clocks are at their loaded state
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         for r in range(replicas):
             for _ in range(20):
                 step_dev(r)
+        e1.record()
+        torch.cuda.synchronize()
+        est_ms = max(e0.elapsed_time(e1) / (20 * replicas), 1e-3)
         t_spin = time.perf_counter()
         i = 0
         while time.perf_counter() - t_spin < spin_s:
@@ -428,22 +535,27 @@ def run_b200(args, wl):
                 torch.cuda.synchronize()
         for i in range(W_):
             step_dev(i % replicas)
-
+        n_blocks = int(min(2000, max(1, math.ceil(min_seconds * 1e3 / (est_ms * K_)))))
+        if world > 1:  # the same number of blocks on every rank
+            nb = torch.tensor([n_blocks], device=dev)
+            dist.all_reduce(nb, op=dist.ReduceOp.MAX)
+            n_blocks = int(nb.item())
         sampler = ClockSampler(local)
-        sampler.start()
         launches0 = sum(f.launch_count() for f in filters)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_blocks)]
         sync_all()
-        sampler.active.set()
-        e0.record()
-        for i in range(K_):
-            step_dev((W_ + i) % replicas)
-        e1.record()
+        i = W_
+        for b0, b1 in evs:
+            b0.record()
+            for _ in range(K_):
+                step_dev(i % replicas)
+                i += 1
+            b1.record()
+        _read_clocks(sampler)  # all launches are enqueued; the GPU is still working through them
         sync_all()
-        sampler.active.clear()
-        sampler.stop()
-        ms_ = e0.elapsed_time(e1)
-        launches_ = sum(f.launch_count() for f in filters) - launches0
+        blocks = [b0.elapsed_time(b1) for b0, b1 in evs]
+        ms_ = float(np.median(blocks))
+        launches_ = (sum(f.launch_count() for f in filters) - launches0) // n_blocks
         if world > 1:
             t = torch.tensor([ms_], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -452,64 +564,133 @@ def run_b200(args, wl):
 
         # per-kernel durations, measured live with CUDA events inside the library (same steps, L2-cold)
         kt = np.zeros(3)
-        kn = min(K_, 200)
+        kn = int(min(200, max(8, 0.05e3 / est_ms)))
         for f in filters:
             f.profile(True)
-        for i in range(kn):
-            r = (W_ + i) % replicas
+        for j in range(kn):
+            r = (i + j) % replicas
             step_dev(r)
             kt += np.array(filters[r].profile_read())
         ess_frac_ = float(np.mean([st.ess for st in filters[0].stats()])) / n_
         for f in filters:
             f.profile(False)
         kt /= kn
-        peak, peak_src = peaks()
         ach = BYTES_K_STEP * n_ * T_ / (kt[2] * 1e-3) / 1e9
+        tr_bpp, tr_src = NCU_TRAFFIC.get((w_.get("key"), likelihood), (None, "no ncu --set full capture of this workload"))
         roof = {"bound": "hbm", "kernel": "k_step (gather + predict + weight + statistics)", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_K_STEP_BYTES_PER_PARTICLE * n_ * T_,
-                "traffic_source": "ncu --set full, 32M particles x 64 landmarks: dram__bytes_read + write of k_step per "
-                                  "particle (profiles/r01_r_ncu_32M_x64_k_step_summary.csv), scaled to this launch",
-                "peak_source": peak_src, "algorithmic_bytes_per_particle": BYTES_K_STEP,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None if tr_bpp is None else tr_bpp * n_ * T_,
+                "traffic_source": tr_src, "peak_source": peak_src, "algorithmic_bytes_per_particle": BYTES_K_STEP,
                 "kernel_ms": {"k_scan": kt[1], "k_step": kt[2]},
                 "scan_achieved_GBps": BYTES_K_SCAN * n_ * T_ / (kt[1] * 1e-3) / 1e9,
+                "scan_frac": BYTES_K_SCAN * n_ * T_ / (kt[1] * 1e-3) / 1e9 / peak,
                 "step_bytes_moved_per_particle": BYTES_K_STEP + BYTES_K_SCAN,
                 "step_moved_frac": (BYTES_K_STEP + BYTES_K_SCAN) * value_ / world / 1e9 / peak,
                 "step_canonical_bytes": BYTES_STEP_CANONICAL,
                 "step_canonical_frac": BYTES_STEP_CANONICAL * value_ / world / 1e9 / peak}
-        return dict(value=value_, ms=ms_, launches=launches_, roofline=roof, ess=ess_frac_, replicas=replicas,
-                    state_bytes=state_bytes, clocks=sampler.summary(), filters=filters, zcyc_host=zcyc_host, counts=counts)
+        out = dict(value=value_, ms=ms_, launches=launches_, roofline=roof, ess=ess_frac_, replicas=replicas, blocks=n_blocks,
+                   timed_seconds=float(np.sum(blocks)) * 1e-3, state_bytes=state_bytes, clocks=sampler.summary(),
+                   landmarks_seen=float(np.mean([np.isfinite(c[..., 0]).sum(axis=-1).mean() for c in zcyc_host])))
+        if keep:
+            out.update(filters=filters, zcyc_host=zcyc_host, counts=counts)
+        else:
+            del filters, zcyc
+            torch.cuda.empty_cache()
+        return out
 
-    main_run = timed_run(wl, K, W, 0.3)
+    def extra_line(w_, lr, K_):
+        return {"workload": w_["desc"], "value": lr["value"], "unit": "particle-steps/s", "ms_per_step": lr["ms"] / K_,
+                "steps": K_, "blocks": lr["blocks"], "ess_over_n": lr["ess"], "roofline": lr["roofline"]}
+
+    def pair_loop(w_, lr, likelihood):
+        k_ms = lr["roofline"]["kernel_ms"]["k_step"]
+        seen = lr["landmarks_seen"] if likelihood == "rb_fan" else float(w_["L"])
+        return {"landmarks_scored_per_step": seen, "pairs_per_s": w_["n"] * w_["T"] * seen / (k_ms * 1e-3), **PAIR_LOOPS[likelihood]}
+
+    # ------------------------------------------------------------------------------------------------------
+    # N > 1: the headline is ONE filter sharded over the N GPUs (BASELINE.json configs[3]); extras: one independent
+    # C1 filter per rank (no data-path collective), C2's trials split by rank, and the same 125 M shard run alone
+    # ------------------------------------------------------------------------------------------------------
+    if world > 1:
+        c3 = WORKLOADS["c3"]
+        n_shard = args.n if args.n else c3["n"]
+        parity_ok, parity_txt = sharded_parity_check(mcl, torch, dist, dev, args.transport)
+        sh = measure_sharded(mcl, torch, dist, dev, n_shard, c3["L"], args.likelihood, K, W, transport=args.transport)
+        sh["parity"] = parity_txt
+        extras = {}
+        if not args.no_extras:
+            lr = timed_run(c3, 12, 3, 0.1, args.likelihood, min_seconds=0.1)
+            extras["one_gpu_shard_alone"] = extra_line(c3, lr, 12)
+            lr = timed_run(WORKLOADS["c1"], max(K, 20), W, 0.2, args.likelihood)
+            extras["replicas_c1"] = dict(extra_line(WORKLOADS["c1"], lr, max(K, 20)),
+                                         parallelism=f"{world} ranks, one independent C1 filter each (no data-path collective)")
+            c2 = WORKLOADS["c2"]
+            lr = timed_run(c2, 12, 3, 0.1, args.likelihood, min_seconds=0.1, trials=c2["T"] // world)
+            extras["c2_trials_split_by_rank"] = dict(extra_line(c2, lr, 12), scaling="strong",
+                                                     parallelism=f"{c2['T']} trials, {c2['T'] // world} per rank, no collective")
+        if rank == 0:
+            frac = BYTES_STEP_CANONICAL * sh["value"] / world / 1e9 / peak
+            kern = sh.get("kernel_ms_rank0") or {}
+            k_step_ms = kern.get("k_step")
+            line = {"metric": "particle-steps/s (predict+weight+resample)", "value": sh["value"], "unit": "particle-steps/s",
+                    "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": sh["ms_per_step"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "f32 state / f64 likelihood / u64 scan", "data": "synthetic",
+                    "config": {"workload": sh["workload"], "likelihood": args.likelihood, "noise": "philox4x32-10 on device",
+                               "resampling": "forced every step, global", "ess_over_n": sh["ess_over_n"],
+                               "l2": f"{36 * n_shard >> 20} MiB of state per GPU > 126 MiB L2", "parallelism": f"particle-sharded x{world}",
+                               "transport": sh["transport"], "timing": f"median of {sh['blocks']} blocks of {K} steps, CUDA events, MAX over ranks",
+                               "note": "N = 1 runs C1 (one 2^20-particle filter); the weak-scaling base of THIS line is extras.one_gpu_shard_alone"},
+                    "roofline": {"bound": "hbm", "kernel": "k_step (gather + predict + weight + statistics), rank 0, inside the sharded step",
+                                 "achieved": None if not k_step_ms else BYTES_K_STEP * n_shard / (k_step_ms * 1e-3) / 1e9, "peak": peak,
+                                 "unit": "GB/s", "frac": None if not k_step_ms else BYTES_K_STEP * n_shard / (k_step_ms * 1e-3) / 1e9 / peak,
+                                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_particle": BYTES_K_STEP,
+                                 "kernel_ms": kern, "step_canonical_bytes": BYTES_STEP_CANONICAL, "step_canonical_frac": frac,
+                                 "note": "step_canonical_frac = whole step per GPU at SURVEY 8(d)'s canonical 64 B per particle-step"},
+                    "cpu_baseline": None,
+                    "e2e": {"value": sh["e2e_value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 16 * c3["L"],
+                            "d2h_bytes_per_step": C.sizeof(mcl.mcl_stats), "ms_per_step": sh["e2e_ms_per_step"],
+                            "api": "ShardedParticleFilter(..., lag=1).step(z_host, force_resample=True)",
+                            "note": "host clock around the same steps: observation upload every step, merged statistics read back every "
+                                    "step through a two-deep pinned ring (consumed one step late)"},
+                    "sharded_filter": sh, "extras": extras, "gpu_launches": sh["gpu_launches_rank0"] * world, "clocks": sh["clocks_rank0"]}
+            if not parity_ok:
+                line["error"] = "sharded filter differs from the unsharded one: " + parity_txt
+            print(json.dumps(line), flush=True)
+        dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------------------------------------------
+    # N = 1
+    # ------------------------------------------------------------------------------------------------------
+    n, L, T = wl["n"], wl["L"], wl["T"]
+    lm = landmarks_for(L)
+    main_run = timed_run(wl, K, W, 0.3, args.likelihood, keep=True)
     value, ms, launches, roofline, ess_frac = (main_run[k] for k in ("value", "ms", "launches", "roofline", "ess"))
     replicas, state_bytes, filters, zcyc_host, counts = (main_run[k] for k in ("replicas", "state_bytes", "filters", "zcyc_host", "counts"))
     clocks = main_run["clocks"]
+    n_blocks_main, timed_s_main, seen_main = main_run["blocks"], main_run["timed_seconds"], main_run["landmarks_seen"]
 
     # ---- end to end through the reference-facing API: host observation in, host estimate out, every step ----
     e2e = None
-    if T == 1:
+    if T == 1 and args.likelihood != "rb":
         sync_all()
         pf = mcl.ParticleFilter(100, n_particles=n, landmarks=lm, noise="philox", likelihood=args.likelihood,
                                 lazy_px=True, force_resample=True, device=local, seed=4242 + rank)
         for _ in range(max(W, 20)):
             pf.main_pf()
-        ke = min(K, 500)
+        ke = int(min(20000, max(K, 0.25 / 60e-6)))
         sync_all()
         t0 = time.perf_counter()
         for _ in range(ke):
             out = pf.main_pf()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        import ctypes as C
-
-        e2e = {"value": float(n) * ke * world / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": 16 * L,
-               "d2h_bytes_per_step": C.sizeof(mcl.mcl_stats), "steps": ke,
+        e2e = {"value": float(n) * ke / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": 16 * L,
+               "d2h_bytes_per_step": C.sizeof(mcl.mcl_stats), "steps": ke, "ms_per_step": dt / ke * 1e3,
                "api": "ParticleFilter(period_ms, noise='philox', lazy_px=True, force_resample=True).main_pf()",
-               "note": "host truth motion + observation draw, H2D of z_l, k_scan + k_step + k_merge, D2H of the mcl_stats block; px stays "
-                       "on the device until read (LazyParticles)"}
+               "note": "host truth motion + observation draw, H2D of z_l, k_scan + k_step + k_merge, D2H of the mcl_stats block of THIS "
+                       "step (no lag); px stays on the device until read (LazyParticles), so the timing excludes the 12 B/particle "
+                       "px copy the reference's return value implies"}
         del pf
     else:
         sync_all()
@@ -521,54 +702,54 @@ def run_b200(args, wl):
             counts[0] += 1
             st = f.stats()
         dt = time.perf_counter() - t0
-        import ctypes as C
-
-        e2e = {"value": float(n) * T * ke * world / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": 16 * L * T,
+        e2e = {"value": float(n) * T * ke / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": 16 * L * T,
                "d2h_bytes_per_step": C.sizeof(mcl.mcl_stats) * T, "steps": ke, "api": "Filter.step(z_host) + Filter.stats()"}
-    sharded = None
-    if world > 1 and not args.no_sharded:
-        del filters, main_run
-        torch.cuda.empty_cache()
-        c3 = WORKLOADS["c3"]
-        sharded = measure_sharded(mcl, torch, dist, dev, c3["n"], c3["L"], args.likelihood, 8, 3)
+    del filters, main_run
+    torch.cuda.empty_cache()
+
+    extras = {}
     large = None
-    if world == 1 and args.workload == "c1" and not args.no_large:
-        # the per-GPU share of the metric's target configuration (1B particles x 64 landmarks over 8 GPUs): the
-        # same kernels at a size where launch and tail latencies no longer dominate
-        del filters, main_run
-        torch.cuda.empty_cache()
+    if args.workload == "c1" and not args.no_extras:
+        # the per-GPU share of the metric's target configuration (1B particles x 64 landmarks over 8 GPUs): the same
+        # kernels at a size where launch and tail latencies no longer dominate
         c3 = WORKLOADS["c3"]
-        lr = timed_run(c3, 12, 3, 0.1)
-        large = {"workload": c3["desc"], "value": lr["value"], "unit": "particle-steps/s", "ms_per_step": lr["ms"] / 12,
-                 "steps": 12, "ess_over_n": lr["ess"], "roofline": lr["roofline"]}
-        del lr
-        torch.cuda.empty_cache()
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    cpu = cpu_baseline(wl) if world == 1 and not args.no_cpu else None
+        lr = timed_run(c3, 12, 3, 0.1, args.likelihood, min_seconds=0.1)
+        large = extra_line(c3, lr, 12)
+        if args.likelihood == "moment":
+            # the GENERAL likelihood -- every particle against every landmark (particle_filter.py:185-192) -- on the
+            # same two shapes; the headline runs its exact O(1)-per-particle moment form
+            for key, k_ in (("c1", 40), ("c3", 6)):
+                w_ = WORKLOADS[key]
+                lr = timed_run(w_, k_, 3, 0.1, "pair", min_seconds=0.1)
+                extras[f"pair_{key}"] = dict(extra_line(w_, lr, k_), likelihood="pair", pair_loop=pair_loop(w_, lr, "pair"))
+            c2 = WORKLOADS["c2"]
+            lr = timed_run(c2, 12, 3, 0.1, "moment", min_seconds=0.1)
+            extras["c2"] = extra_line(c2, lr, 12)
+            if HAVE_RB32:
+                c4 = WORKLOADS["c4"]
+                lr = timed_run(c4, 3, 3, 0.0, "rb32", min_seconds=0.05)
+                extras["c4_rb_all_landmarks"] = dict(extra_line(c4, lr, 3), likelihood="rb32", pair_loop=pair_loop(c4, lr, "rb32"))
+    cpu = cpu_baseline(wl, procs=1) if not args.no_cpu else None
     line = {"metric": "particle-steps/s (predict+weight+resample)", "value": value, "unit": "particle-steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 state / f64 likelihood / u64 scan", "data": "synthetic",
             "config": {"workload": wl["desc"], "particles": n, "landmarks": L, "trials": T, "likelihood": args.likelihood,
+                       "same_algorithm_as_reference_arm": args.likelihood != "moment",
+                       "algorithm_note": ("the moment likelihood is an exact algebraic identity of the per-pair sum (SURVEY 7), O(1) per "
+                                          "particle; the reference arm scores every (particle, landmark) pair -- the like-for-like GPU "
+                                          "number is extras.pair_c1") if args.likelihood == "moment" else "per-pair likelihood on both arms",
                        "noise": "philox4x32-10 on device", "resampling": "forced every step",
                        "ess_over_n": ess_frac,
                        "l2": f"rotating {replicas} independent filter replicas ({replicas * state_bytes >> 20} MiB > 126 MiB L2)",
-                       "parallelism": "single GPU" if world == 1 else f"{world} ranks, one independent filter each (no data-path collective)"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "large_filter": large, "sharded_filter": sharded,
+                       "timing": f"median of {n_blocks_main} blocks of {K} steps (CUDA events), {timed_s_main:.3f} s timed",
+                       "parallelism": "single GPU"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "large_filter": large, "extras": extras,
             "gpu_launches": int(launches), "clocks": clocks}
-    if args.likelihood in ("pair", "rb_fan"):
-        # the likelihood-bound configurations (C4): what the pair loop sustains.  rb_fan scores only the landmarks
-        # the fan sensor detected (NaN rows of the observation are skipped); pair scores all L in fp64.
-        seen = float(np.mean([np.isfinite(c[..., 0]).sum(axis=-1).mean() for c in zcyc_host])) if args.likelihood == "rb_fan" else float(L)
-        k_ms = roofline["kernel_ms"]["k_step"]
-        line["pair_loop"] = {"landmarks_scored_per_step": seen, "pairs_per_s": n * T * seen / (k_ms * 1e-3),
-                             "arithmetic": "fp32 + MUFU (rcp, sqrt), branch-free atan2" if args.likelihood == "rb_fan" else "fp64, 8 operations per pair",
-                             "bound": "FP32/SFU issue" if args.likelihood == "rb_fan" else "FP64 pipe"}
+    if args.likelihood in PAIR_LOOPS:
+        seen = seen_main if args.likelihood == "rb_fan" else float(L)
+        line["pair_loop"] = {"landmarks_scored_per_step": seen, "pairs_per_s": n * T * seen / (roofline["kernel_ms"]["k_step"] * 1e-3),
+                             **PAIR_LOOPS[args.likelihood]}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():
@@ -578,11 +759,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
-    ap.add_argument("--likelihood", default="moment", choices=["pair", "moment", "rb_fan"])
+    ap.add_argument("--likelihood", default="moment", choices=["pair", "moment", "rb", "rb32", "rb_fan"])
+    ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"], help="N > 1: exchange of the sharded filter")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra workloads of the default line")
     ap.add_argument("--n", type=int, default=0, help="override the particle count of the workload (experiments)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the particle-sharded C3 measurement")
-    ap.add_argument("--no-large", action="store_true", help="N = 1, c1: skip the extra C3-shard measurement")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.n:

@@ -205,6 +205,10 @@ int mcl_get_ancestors(mcl_filter *h, uint32_t *anc_host, void *stream);
  * mcl_launch_count: kernels launched through this handle since creation. */
 int mcl_profile(mcl_filter *h, int enable);
 int mcl_profile_read(mcl_filter *h, double *ms3_host);
+/* The same for the last mcl_shard_step_peer(..., MCL_STAGE_ALL): ms[0] totals pass + totals exchange, ms[1] expansion
+ * + "done" exchange (both include the wait for the slowest peer), ms[2] per-step scalars, ms[3] k_step, ms[4]
+ * statistics exchange. */
+int mcl_profile_read_peer(mcl_filter *h, double *ms5_host);
 uint64_t mcl_launch_count(const mcl_filter *h);
 /* Debug aid (needs a library built with -DMCL_TIMELINE, else MCL_ERR_STATE): the first call (stamps_host may be NULL) arms a per-CTA phase timeline of k_step; later calls
  * copy [n_ctas][12] global-timer nanosecond stamps of the most recent step (synchronises the device;

@@ -136,6 +136,7 @@ PROTOTYPES = {
     "mcl_get_ancestors": (C.c_int, [_vp, _vp, _vp]),
     "mcl_profile": (C.c_int, [_vp, C.c_int]),
     "mcl_profile_read": (C.c_int, [_vp, _P(C.c_double)]),
+    "mcl_profile_read_peer": (C.c_int, [_vp, _P(C.c_double)]),
     "mcl_launch_count": (C.c_uint64, [_vp]),
     "mcl_debug_timeline": (C.c_int, [_vp, _vp, C.c_int64, _P(C.c_int32)]),
     "mcl_shard_total": (C.c_int, [_vp, _vp, _vp]),

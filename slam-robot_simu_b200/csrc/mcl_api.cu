@@ -133,7 +133,7 @@ struct mcl_filter {
     std::string err;
     uint64_t launches = 0;
     bool profiling = false;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // 0..3 mcl_step*, 0..4 + 5 the peer step
     unsigned long long *dbg = nullptr;  // optional k_step phase timeline (mcl_debug_timeline)
     // pinned staging ring of the per-step host inputs (z, ofs): cudaMemcpyAsync from pageable memory may wait for
     // the stream, which would put a host synchronisation into every step
@@ -1064,6 +1064,21 @@ int mcl_profile_read(mcl_filter *h, double *ms3_host) {
     return MCL_OK;
 }
 
+int mcl_profile_read_peer(mcl_filter *h, double *ms5_host) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    if (ms5_host == nullptr) return fail(h, MCL_ERR_ARG, "ms5_host is NULL");
+    if (!h->profiling || h->ev[0] == nullptr) return fail(h, MCL_ERR_STATE, "mcl_profile(h, 1) has not been called");
+    int rc = use_device(h);
+    if (rc != MCL_OK) return rc;
+    MCL_CUDA(h, cudaEventSynchronize(h->ev[5]));
+    for (int k = 0; k < 5; ++k) {
+        float ms = 0.f;
+        MCL_CUDA(h, cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1]));
+        ms5_host[k] = ms;
+    }
+    return MCL_OK;
+}
+
 uint64_t mcl_launch_count(const mcl_filter *h) { return h ? h->launches : 0; }
 
 int mcl_debug_timeline(mcl_filter *h, uint64_t *stamps_host, int64_t capacity, int32_t *n_ctas) {
@@ -1428,6 +1443,8 @@ int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_h
         if (h->stats_dirty) return fail(h, MCL_ERR_STATE, "statistics were not exchanged: mcl_shard_sync_peer first");
         h->xchg_epoch += 1;
     }
+    const bool prof = h->profiling && stages == MCL_STAGE_ALL;
+    if (prof) MCL_CUDA(h, cudaEventRecord(h->ev[0], st));
     if (may_resample && A) {
         // first pass over the weights under the GLOBAL map: tile prefixes inside contiguous segments + segment totals
         const int blocks_max = std::min(kMaxSegments, h->sm_count * 8);
@@ -1438,7 +1455,7 @@ int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_h
         MCL_LAUNCH_CHECK(h, "k_shard_total");
         h->desc_stale = true;
     }
-    if (may_resample && (A || B)) {
+    if (A || B) {  // (also when the host forbids resampling: the kernel then only records that in the plan)
         XchgParams x;
         fill_xchg(h, x, flags, (A ? kXchgPush : 0) | (B ? kXchgWait : 0));
         x.seg = h->seg;
@@ -1448,6 +1465,7 @@ int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_h
         k_xchg_total<<<1, 1024, 0, st>>>(x);
         MCL_LAUNCH_CHECK(h, "k_xchg_total");
     }
+    if (prof) MCL_CUDA(h, cudaEventRecord(h->ev[1], st));
     if (may_resample && B) {
         // second pass: global slot numbers, every tile starting from segment prefix + tile prefix (no look-back);
         // own slots -> ancestors, off-rank slots -> poses into the owner's staging
@@ -1474,6 +1492,7 @@ int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_h
         k_xchg_done<<<1, 32, 0, st>>>(x);
         MCL_LAUNCH_CHECK(h, "k_xchg_done");
     }
+    if (prof) MCL_CUDA(h, cudaEventRecord(h->ev[2], st));
     if (Cc) {
         rc = stage_inputs(h, z_host, nullptr, st);
         if (rc != MCL_OK) return rc;
@@ -1496,8 +1515,10 @@ int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_h
         win.x = reinterpret_cast<const float *>(h->peer_region + pr.off_rx);
         win.y = reinterpret_cast<const float *>(h->peer_region + pr.off_ry);
         win.th = reinterpret_cast<const float *>(h->peer_region + pr.off_rth);
+        if (prof) MCL_CUDA(h, cudaEventRecord(h->ev[3], st));
         rc = launch_step(h, noise_dev, flags, false, st, &win, h->plan);
         if (rc != MCL_OK) return rc;
+        if (prof) MCL_CUDA(h, cudaEventRecord(h->ev[4], st));
         h->cur ^= 1;
         h->step += 1;
     }
@@ -1505,6 +1526,7 @@ int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_h
         rc = launch_xchg_stats(h, (Cc ? kXchgPush : 0) | (D ? kXchgWait : 0), st);
         if (rc != MCL_OK) return rc;
     }
+    if (prof) MCL_CUDA(h, cudaEventRecord(h->ev[5], st));
     return MCL_OK;
 }
 

@@ -298,6 +298,12 @@ class Filter:
         self._check(self.lib.mcl_profile_read(self._h, ms), "mcl_profile_read")
         return ms[0], ms[1], ms[2]
 
+    def profile_read_peer(self):
+        """(totals + exchange, expansion + exchange, scalars, k_step, statistics exchange) ms of the last peer step."""
+        ms = (C.c_double * 5)()
+        self._check(self.lib.mcl_profile_read_peer(self._h, ms), "mcl_profile_read_peer")
+        return tuple(ms)
+
     def debug_timeline(self):
         """Arms (first call) / reads the k_step phase timeline: (n_ctas, 8) uint64 nanosecond stamps."""
         n = C.c_int32(0)
