@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmcl_b200.so")
+# MCL_LIB selects an experimental build of the SAME sources (tools/, kernel tuning); the default is the product library
+LIB_PATH = os.environ.get("MCL_LIB") or os.path.join(HERE, "libmcl_b200.so")
 
 MCL_ABI_VERSION = 3
 

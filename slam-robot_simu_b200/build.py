@@ -48,13 +48,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
     extra = ["-DMCL_TIMELINE"] if os.environ.get("MCL_TIMELINE") == "1" else []  # phase stamps for tools/timeline.py
-    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    extra += os.environ.get("MCL_NVCC_EXTRA", "").split()  # experiments: e.g. -DMCL_SCAN_CTAS_PER_SM=5
+    out = os.environ.get("MCL_LIB_OUT", LIB)               # ... built beside the product library, never over it
+    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed building libmcl_b200.so:\n" + proc.stderr[-4000:])
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

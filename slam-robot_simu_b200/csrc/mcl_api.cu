@@ -341,7 +341,9 @@ int launch_step_scan(mcl_filter *h, const double *z_dev, const double *ofs_dev, 
     // that derives the per-step scalars
     // (one filter: one CTA per tile, the hardware scheduler keeps the look-back pipeline full; many trials:
     // a trial's few tiles share persistent CTAs so the per-CTA prologue is paid once)
-    const int tile_ctas = !full ? 0 : (h->lay.T == 1 ? h->lay.tpt : std::min(h->lay.tpt, std::max(1, h->sm_count * 4 / h->lay.T)));
+    static const int persist_single = [] { const char *e = std::getenv("MCL_SCAN_PERSISTENT"); return e ? std::atoi(e) : 0; }();
+    const int tile_ctas = !full ? 0 : ((h->lay.T == 1 && persist_single <= 0) ? h->lay.tpt
+                                       : std::min(h->lay.tpt, std::max(1, h->sm_count * std::max(persist_single, 4) / h->lay.T)));
     sp.persistent = (tile_ctas < h->lay.tpt) ? 1 : 0;
     dim3 grid(tile_ctas + (h->stats_dirty ? 2 : 1), h->lay.T);
     h->stats_dirty = false;
@@ -368,7 +370,7 @@ int launch_shard_scan(mcl_filter *h, ScanParams &sp, int mode, cudaStream_t st) 
         // tiles are independent once their prefixes are known: persistent CTAs (tickets) pay the kernel prologue once
         // per CTA instead of once per tile (expand 0.55 -> 0.50 ms at 125 M particles)
         sp.persistent = 1;
-        grid.x = std::min(h->lay.tpt, h->sm_count * 4);
+        grid.x = std::min(h->lay.tpt, h->sm_count * MCL_SCAN_CTAS_PER_SM);
     }
     k_scan<kScanExpand><<<grid, kScanThreads, 0, st>>>(sp);
     MCL_LAUNCH_CHECK(h, "k_scan");
@@ -1482,7 +1484,7 @@ int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_h
         sp.seg_prefix = h->seg;
         sp.tiles_per_seg = h->tiles_per_seg;
         sp.persistent = 1;
-        dim3 grid(std::min(h->lay.tpt, h->sm_count * 4), 1);
+        dim3 grid(std::min(h->lay.tpt, h->sm_count * MCL_SCAN_CTAS_PER_SM), 1);
         k_scan<kScanExpand><<<grid, kScanThreads, 0, st>>>(sp);
         MCL_LAUNCH_CHECK(h, "k_scan");
     }

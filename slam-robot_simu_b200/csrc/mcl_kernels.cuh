@@ -636,6 +636,9 @@ struct ScanParams {
     uint32_t xflags;            // host flags of the step (MCL_FORCE_RESAMPLE / MCL_NO_RESAMPLE)
 };
 
+#ifndef MCL_SCAN_CTAS_PER_SM
+#define MCL_SCAN_CTAS_PER_SM 4
+#endif
 constexpr int kDirectTiles = 1024;  // tiles that sum all predecessors' aggregates directly (2M particles)
 constexpr int kScanAncestors = 0;  // write the ancestor of every slot
 constexpr int kScanExpand = 2;     // write the resampled pose of every slot (sender side of the sharded filter)
@@ -675,7 +678,7 @@ __device__ __forceinline__ void expand_store(const ScanParams &p, uint32_t *anc,
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant__ ScanParams p) {
+__global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(const __grid_constant__ ScanParams p) {
     const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kScanThreads / 32;
     __shared__ ScanShared s_sc;
@@ -684,6 +687,9 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     __shared__ uint32_t s_slot[2];
     __shared__ __align__(16) uint32_t s_mark[kScanTile];  // also the reduction scratch of prep_block
     __shared__ uint32_t s_wmax[NW];
+    __shared__ __align__(16) uint32_t s_edge[NW][2 * kScanItems];  // parked partial chunks of the warp-local fill
+    __shared__ uint32_t s_edge_slot[NW][2];
+    if (lane < 2) s_edge_slot[warp][lane] = 0xffffffffu;
 
     // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as every CTA of
     // this grid has started; nothing is read or written before the previous kernel has completed.
@@ -706,7 +712,10 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     // One tile per CTA (single filters): tiles are numbered by blockIdx.x.  CTAs are dispatched in that order, so a
     // tile's predecessors are always running (the assumption of every single-pass scan) and no ticket round trip
     // precedes the first load.  Persistent CTAs (trial batches) take tickets.
-    const bool ordered = !p.persistent;
+    // (tiles whose prefixes are known -- after a totals pass -- do not depend on each other at all: a persistent
+    //  CTA then strides over them statically, no ticket)
+    const bool static_tiles = p.tile_prefix != nullptr && p.persistent;
+    const bool ordered = !p.persistent || static_tiles;
     // When the statistics still live in the CTA partials, tile 0 (certainly running) merges (max, sum, sum^2)
     // and publishes what every tile needs -- weight map, resample gate, comb offset -- as two aligned 16-byte
     // words tagged with this launch's epoch; the others poll them (one round trip) -- 500 CTAs each reading
@@ -799,7 +808,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     // The descriptors the NEXT scan launch starts from are cleared whether or not this trial resamples: a launch
     // that skipped the clear would leave the previous resampling's aggregates / prefixes in the buffer the launch
     // after it looks back through (tiles past the direct range accept any non-zero status at once).
-    if (p.desc_next != nullptr) {
+    if (p.desc_next != nullptr && static_cast<int>(blockIdx.x) * kScanThreads < p.tpt) {
         const int n_tile_ctas = static_cast<int>(gridDim.x) - (p.do_prep ? (p.n_partials > 0 ? 2 : 1) : 0);
         unsigned long long *dn = p.desc_next + static_cast<long long>(t) * p.tpt;
         for (long long i = static_cast<long long>(blockIdx.x) * kScanThreads + tid; i < p.tpt;
@@ -811,8 +820,11 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     const float *lw = p.lw + static_cast<long long>(t) * p.ld;
     // Persistent over tiles: a CTA keeps taking tickets, so the prologue above is paid once per CTA.
     __shared__ unsigned int s_next[2];  // two slots by iteration parity: one barrier per tile is enough
+    // (requesting the next tile's weights a tile ahead -- cp.async into a double buffer -- was measured: no gain for
+    //  the expansion, and its 16 KB of shared memory cost the look-back scan 6 %)
+    const int n_tile_ctas_s = static_cast<int>(gridDim.x) - (p.do_prep ? (p.n_partials > 0 ? 2 : 1) : 0);
     int it = 0;
-    for (long long tile = s_sc.tile; tile < p.tpt; tile = s_next[it++ & 1]) {
+    for (long long tile = s_sc.tile; tile < p.tpt; tile = static_tiles ? tile + n_tile_ctas_s : static_cast<long long>(s_next[it & 1]), ++it) {
     const long long j0 = tile * kScanTile + static_cast<long long>(tid) * kScanItems;
 
     // ---- load + quantise (8 consecutive items per thread, two 16-byte loads) ----
@@ -926,29 +938,39 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
             __syncthreads();
         } else
         while (true) {
+            // one round = the 256 descriptors before `look`, nearest first (tid 0).  Two barriers per round: the
+            // poll (every descriptor of the window has at least its aggregate) and the exchange of the warp results.
             const long long idx = look - tid;
             unsigned long long d = kDescPrefix;  // tiles before the first one: an empty prefix
             if (idx >= 0) d = *reinterpret_cast<volatile unsigned long long *>(&desc[idx]);
             while (!__syncthreads_and((d >> 62) != 0ull)) {
                 if ((d >> 62) == 0ull) d = *reinterpret_cast<volatile unsigned long long *>(&desc[idx]);
             }
+            // per warp: the nearest descriptor that is already an inclusive prefix ends the sum
             const unsigned int is_prefix = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
-            if (lane == 0) s_first[warp] = is_prefix ? (warp * 32 + __ffs(is_prefix) - 1) : 0x7fffffff;
+            const int fp = is_prefix ? (__ffs(is_prefix) - 1) : 32;
+            const unsigned long long val = (lane <= fp && idx >= 0) ? (d & kDescValueMask) : 0ull;
+            // the values are below 2^53 (the weights sum to 2^52): two 32-bit hardware reductions instead of a
+            // five-step 64-bit shuffle tree
+            const unsigned int lo = __reduce_add_sync(0xffffffffu, static_cast<unsigned int>(val) & 0x7ffffffu);
+            const unsigned int hi = __reduce_add_sync(0xffffffffu, static_cast<unsigned int>(val >> 27));
+            if (lane == 0) {
+                s_warp[warp] = (static_cast<unsigned long long>(hi) << 27) + lo;
+                s_first[warp] = (fp < 32) ? 1 : 0;
+            }
             __syncthreads();
-            int first = 0x7fffffff;  // nearest predecessor (smallest tid) that already holds a prefix
+            bool found = false;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) first = min(first, s_first[w]);
-            unsigned long long contrib = (tid <= first && idx >= 0) ? (d & kDescValueMask) : 0ull;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-            if (lane == 0) s_warp[warp] = contrib;
-            __syncthreads();
-#pragma unroll
-            for (int w = 0; w < NW; ++w) excl += s_warp[w];
-            __syncthreads();
-            if (first != 0x7fffffff) break;
+            for (int w = 0; w < NW; ++w) {
+                if (!found) {
+                    excl += s_warp[w];
+                    found = s_first[w] != 0;
+                }
+            }
+            if (found) break;  // (the poll barrier of the next round orders the reuse of s_warp / s_first)
             look -= kScanThreads;
         }
+        __syncthreads();  // s_warp is reused by the next tile's block scan
         // tiles of the direct range keep their aggregate (later direct tiles sum aggregates); the LAST direct
         // tile and everything after it publish inclusive prefixes for the classic look-back
         if (tid == 0 && tile >= kDirectTiles) atomicExch(&desc[tile], kDescPrefix | (excl + tile_total));
@@ -956,7 +978,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
     if (tid == 0 && p.total != nullptr && tile == p.tpt - 1) p.total[t] = excl + tile_total;
     // The next ticket is taken only now: a ticket held by a CTA that has not started the tile would stall
     // every later tile's look-back.  Its round trip overlaps the ancestor phase below.
-    if (tid == 0) s_next[it & 1] = p.persistent ? atomicAdd(&p.tickets[t * 4 + 0], 1u) : 0xffffffffu;
+    if (tid == 0) s_next[it & 1] = (p.persistent && !static_tiles) ? atomicAdd(&p.tickets[t * 4 + 0], 1u) : 0xffffffffu;
     dbg_stamp(p.dbg, 3);
     // ---- slot range of every source: u32 counts, non-owners carry rel = 2^31 (never inside a window) ----
     const double nd = static_cast<double>(p.n_global);
@@ -990,7 +1012,9 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
         const int k_last = (k_last64 >= 0 && k_last64 < kScanItems) ? static_cast<int>(k_last64) : -1;
         const int n_valid = static_cast<int>(min(static_cast<long long>(kScanItems), max(0ll, p.n - j0)));
         double Kd = Kd0;
-        const double fs = count_le_fast(Kd, cf, p.delta, ofs);
+        // the filter's very first source owns the slots from 0 on: with ofs == 0 the tooth u_0 = 0 is "<= K" for
+        // K = 0, and the reference walk (strict >, particle_filter.py:219) leaves slot 0 with particle 0
+        const double fs = (p.j_global_base + j0 == 0) ? 0.0 : count_le_fast(Kd, cf, p.delta, ofs);
         double c = fs;
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) {
@@ -1007,138 +1031,229 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
         first_slot = static_cast<uint32_t>(static_cast<long long>(fs));
         cur = static_cast<uint32_t>(static_cast<long long>(c));
     }
-    // tile slot range [S0, S1): S0 from the first thread, S1 from the last thread holding sources
+    // ---- ancestors ----
+    // Common case: every WARP fills the slots of its own 256 sources by itself -- marks, max-scan and stores inside
+    // a 1 KB window of shared memory that only this warp touches, ordered by __syncwarp: no block barrier at all.
+    // A warp's slot range is [first_slot of lane 0, cur of lane 31); slot `first_slot` of any thread is owned by the
+    // first source at or after it that owns slots at all, so every slot of the range has a mark at or before it
+    // inside the warp (or is covered by the carry of the previous pass).  Marks hold the source index itself;
+    // 0 doubles as "empty", which is right because only the very first source can be 0 and it owns whatever
+    // precedes the first other mark.  Tiles whose sources own far more slots than sources (collapsed weights: one
+    // particle owning up to every slot) keep the block-cooperative fill below.
+    const uint32_t anc_lo = (MODE == kScanAncestors) ? 0u : static_cast<uint32_t>(p.own_lo);
+    uint32_t *anc = p.anc + static_cast<long long>(t) * p.ld;
     const long long n_in_tile = min(static_cast<long long>(kScanTile), p.n - tile * kScanTile);
     const int last_tid = static_cast<int>((n_in_tile - 1) / kScanItems);
-    if (tid == 0) s_slot[0] = first_slot;
-    if (tid == last_tid) s_slot[1] = cur;
-    __syncthreads();
-    const uint32_t S0 = s_slot[0], S1 = s_slot[1];
-    // the ancestor array is written with 32-byte stores: the windows start where (slot - first slot of anc[]) is a
-    // multiple of 8 (anc[] starts at slot 0, or at own_lo in the sharded expansion)
-    const uint32_t anc_lo = (MODE == kScanAncestors) ? 0u : static_cast<uint32_t>(p.own_lo);
-    const uint32_t mis = (S0 - anc_lo) & 7u;
-    const bool aligned = mis <= S0;
-    const uint32_t W0 = aligned ? S0 - mis : S0;
-    const uint32_t span = (S1 > S0) ? S1 - W0 : 0u;
-    const uint32_t my_off = first_slot - W0;  // threads with sources: >= 0
-
-    dbg_stamp(p.dbg, 4);
-    uint32_t *anc = p.anc + static_cast<long long>(t) * p.ld;
-    uint32_t carry = 0;  // source (local index + 1) that owns the slot just before the window
-    for (uint32_t cb = 0; cb < span; cb += kScanTile) {
-        // window of kScanTile slots starting at W0 + cb
-        // registers -> anc[] directly when the whole window belongs to this handle's ancestor array (always, unsharded)
-        const bool reg_store = (MODE == kScanAncestors) ||
-                               (aligned && static_cast<long long>(W0) + cb >= p.own_lo &&
-                                static_cast<long long>(W0) + cb + kScanTile <= p.own_hi);
-        if (cb > 0u && span > 4u * kScanTile) {
-            // Degenerate weights: one source owns many windows.  A window in which no source starts is a
-            // constant fill with the carried owner -- one barrier and one store per thread instead of a scan.
-            bool starts = false;
-            const uint32_t wofs = my_off - cb;
+    const bool big = static_cast<double>(tile_total) * cf.a1 > 3.0 * kScanTile;  // CTA-uniform
+    if (!big) {
+        uint32_t *wm = s_mark + warp * (32 * kScanItems);
+        // (the range ends with the last lane that HOLDS sources: padding lanes of the filter's last tile sit at the
+        //  final cumulative weight, which may fall short of the slots the last particle was given)
+        const int last_lane = min(31, last_tid - warp * 32);
+        const uint32_t wf = __shfl_sync(0xffffffffu, first_slot, 0);
+        const uint32_t we = (last_lane >= 0) ? __shfl_sync(0xffffffffu, cur, max(last_lane, 0)) : wf;
+        const uint32_t mis = (wf - anc_lo) & 7u;   // 32-byte stores: windows start where (slot - anc_lo) is a multiple of 8
+        const bool aligned = mis <= wf;
+        const uint32_t Wb = aligned ? wf - mis : wf;
+        const uint32_t span = (we > wf) ? we - Wb : 0u;
+        const uint32_t my_off = first_slot - Wb;
+        const uint32_t jsrc0 = static_cast<uint32_t>(tile * kScanTile) + static_cast<uint32_t>(tid * kScanItems);
+        uint32_t carry = 0u;
+        for (uint32_t cb = 0; cb < span; cb += 32 * kScanItems) {
+            if (cb > 0u) {  // (the first window was cleared before the block scan)
+                *reinterpret_cast<uint4 *>(&wm[lane * kScanItems]) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4 *>(&wm[lane * kScanItems + 4]) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            __syncwarp();
+            if (cur != first_slot) {
+                const uint32_t wofs = my_off - cb;  // modulo 2^32 (n_global < 2^31: no aliasing)
 #pragma unroll
-            for (int k = 0; k < kScanItems; ++k) starts = starts || (wofs + rel[k] < static_cast<uint32_t>(kScanTile));
-            if (!__syncthreads_or(starts)) {
-                const uint32_t j = static_cast<uint32_t>(tile * kScanTile) - 1u + carry;
-                if (reg_store) {
-                    const uint32_t slot0 = W0 + cb + static_cast<uint32_t>(tid * kScanItems);
-                    if (slot0 >= S0 && slot0 + kScanItems <= S1) {
-                        asm volatile("st.global.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(anc + (slot0 - anc_lo)), "r"(j) : "memory");
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < kScanItems; ++k)
-                            if (slot0 + k >= S0 && slot0 + k < S1) anc[slot0 + k - anc_lo] = j;
-                    }
-                } else {
-                    const int lim = static_cast<int>(min(static_cast<uint32_t>(kScanTile), span - cb));
-#pragma unroll
-                    for (int k = 0; k < kScanItems; ++k) {
-                        const int pos = k * kScanThreads + tid;
-                        const long long slot = static_cast<long long>(W0) + cb + pos;
-                        if (pos < lim && slot >= S0) expand_store(p, anc, slot, j);
-                    }
+                for (int k = 0; k < kScanItems; ++k) {
+                    const uint32_t pos = wofs + rel[k];
+                    if (pos < static_cast<uint32_t>(32 * kScanItems)) wm[pos] = jsrc0 + k;
                 }
-                continue;
             }
-        }
-        if (cb > 0u) {  // (the first window was cleared before the block scan)
-            *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(0u, 0u, 0u, 0u);
-            __syncthreads();
-        }
-        if (cur != first_slot) {
-            // slot positions relative to the window, modulo 2^32 (n_global < 2^31: no aliasing)
-            const uint32_t wofs = my_off - cb;
-            const uint32_t id0 = static_cast<uint32_t>(tid * kScanItems + 1);
-#pragma unroll
-            for (int k = 0; k < kScanItems; ++k) {
-                const uint32_t pos = wofs + rel[k];
-                if (pos < static_cast<uint32_t>(kScanTile)) s_mark[pos] = id0 + k;
+            __syncwarp();
+            uint32_t v[kScanItems];
+            {
+                const uint4 a = *reinterpret_cast<const uint4 *>(&wm[lane * kScanItems]);
+                const uint4 b = *reinterpret_cast<const uint4 *>(&wm[lane * kScanItems + 4]);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
             }
-        }
-        __syncthreads();
-        // inclusive max-scan over the window, 8 consecutive entries per thread
-        uint32_t v[kScanItems];
-        {
-            const uint4 a = *reinterpret_cast<const uint4 *>(&s_mark[tid * kScanItems]);
-            const uint4 b = *reinterpret_cast<const uint4 *>(&s_mark[tid * kScanItems + 4]);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        }
 #pragma unroll
-        for (int k = 1; k < kScanItems; ++k) v[k] = max(v[k], v[k - 1]);
-        uint32_t run = v[kScanItems - 1];
+            for (int k = 1; k < kScanItems; ++k) v[k] = max(v[k], v[k - 1]);
+            uint32_t run = v[kScanItems - 1];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, run, o);
-            if (lane >= o) run = max(run, n);
-        }
-        if (lane == 31) s_wmax[warp] = run;
-        uint32_t before = __shfl_up_sync(0xffffffffu, run, 1);
-        if (lane == 0) before = 0u;
-        __syncthreads();
-        uint32_t wbefore = carry, wall = carry;
+            for (int o = 1; o < 32; o <<= 1) run = max(run, __shfl_up_sync(0xffffffffu, run, o));  // (lanes < o get their own value)
+            uint32_t before = __shfl_up_sync(0xffffffffu, run, 1);
+            before = (lane == 0) ? carry : max(before, carry);
+            carry = max(carry, __shfl_sync(0xffffffffu, run, 31));
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            const uint32_t m = s_wmax[w];
-            if (w < warp) wbefore = max(wbefore, m);
-            wall = max(wall, m);
-        }
-        before = max(before, wbefore);
-        carry = wall;
-        const uint32_t jbase = static_cast<uint32_t>(tile * kScanTile) - 1u;
-        if (reg_store) {
-            // slots of this handle's own ancestor array (unsharded: all of them; anc holds ld >= n slots): the
-            // stores go straight from registers
-#pragma unroll
-            for (int k = 0; k < kScanItems; ++k) v[k] = jbase + max(v[k], before);
-            const uint32_t slot0 = W0 + cb + static_cast<uint32_t>(tid * kScanItems);
-            if (slot0 >= S0 && slot0 + kScanItems <= S1) {
-                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(anc + (slot0 - anc_lo)), "r"(v[0]),
-                             "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                             : "memory");
+            for (int k = 0; k < kScanItems; ++k) v[k] = max(v[k], before);
+            const uint32_t slot0 = Wb + cb + static_cast<uint32_t>(lane * kScanItems);
+            const bool reg_store = (MODE == kScanAncestors) ||
+                                   (aligned && static_cast<long long>(Wb) + cb >= p.own_lo &&
+                                    static_cast<long long>(Wb) + cb + 32 * kScanItems <= p.own_hi);
+            if (reg_store) {
+                if (slot0 >= wf && slot0 + kScanItems <= we) {
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(anc + (slot0 - anc_lo)), "r"(v[0]),
+                                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                                 : "memory");
+                } else if (slot0 + kScanItems > wf && slot0 < we) {
+                    // The (at most two) chunks the warp's range only partly covers -- the one holding its first slot
+                    // and the one holding its last -- are parked; sixteen lanes store them after the loop.  Scalar
+                    // stores right here would make the whole warp issue them for the sake of two lanes, in every pass.
+                    const int half = (slot0 < wf) ? 0 : 1;
+                    uint32_t *sc = s_edge[warp] + half * kScanItems;
+                    *reinterpret_cast<uint4 *>(sc) = make_uint4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<uint4 *>(sc + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+                    s_edge_slot[warp][half] = slot0;
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < kScanItems; ++k)
-                    if (slot0 + k >= S0 && slot0 + k < S1) anc[slot0 + k - anc_lo] = v[k];
+                    if (slot0 + k >= wf && slot0 + k < we) expand_store(p, anc, static_cast<long long>(slot0) + k, v[k]);
             }
-            // no barrier here: the next window's zeroing of s_mark follows every thread's reads above
-        } else {
-#pragma unroll
-            for (int k = 0; k < kScanItems; ++k) v[k] = max(v[k], before);
-            *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(v[4], v[5], v[6], v[7]);
-            __syncthreads();
-            // coalesced stores
-            const int lim = static_cast<int>(min(static_cast<uint32_t>(kScanTile), span - cb));
-#pragma unroll
-            for (int k = 0; k < kScanItems; ++k) {
-                const int pos = k * kScanThreads + tid;
-                const long long slot = static_cast<long long>(W0) + cb + pos;
-                if (pos < lim && slot >= S0) expand_store(p, anc, slot, jbase + s_mark[pos]);
+        }
+        __syncwarp();
+        if (lane < 2 * kScanItems) {
+            const uint32_t e0 = s_edge_slot[warp][lane >> 3];
+            const uint32_t slot = e0 + static_cast<uint32_t>(lane & 7);
+            if (e0 != 0xffffffffu && slot >= wf && slot < we) anc[slot - anc_lo] = s_edge[warp][lane];
+        }
+        __syncwarp();
+        if (lane < 2) s_edge_slot[warp][lane] = 0xffffffffu;  // re-armed for the next tile of a persistent CTA
+    } else {
+        // tile slot range [S0, S1): S0 from the first thread, S1 from the last thread holding sources
+        if (tid == 0) s_slot[0] = first_slot;
+        if (tid == last_tid) s_slot[1] = cur;
+        __syncthreads();
+        const uint32_t S0 = s_slot[0], S1 = s_slot[1];
+        // the ancestor array is written with 32-byte stores: the windows start where (slot - first slot of anc[]) is a
+        // multiple of 8 (anc[] starts at slot 0, or at own_lo in the sharded expansion)
+        const uint32_t mis = (S0 - anc_lo) & 7u;
+        const bool aligned = mis <= S0;
+        const uint32_t W0 = aligned ? S0 - mis : S0;
+        const uint32_t span = (S1 > S0) ? S1 - W0 : 0u;
+        const uint32_t my_off = first_slot - W0;  // threads with sources: >= 0
+
+        dbg_stamp(p.dbg, 4);
+        uint32_t carry = 0;  // source (local index + 1) that owns the slot just before the window
+        for (uint32_t cb = 0; cb < span; cb += kScanTile) {
+            // window of kScanTile slots starting at W0 + cb
+            // registers -> anc[] directly when the whole window belongs to this handle's ancestor array (always, unsharded)
+            const bool reg_store = (MODE == kScanAncestors) ||
+                                   (aligned && static_cast<long long>(W0) + cb >= p.own_lo &&
+                                    static_cast<long long>(W0) + cb + kScanTile <= p.own_hi);
+            if (cb > 0u && span > 4u * kScanTile) {
+                // Degenerate weights: one source owns many windows.  A window in which no source starts is a
+                // constant fill with the carried owner -- one barrier and one store per thread instead of a scan.
+                bool starts = false;
+                const uint32_t wofs = my_off - cb;
+    #pragma unroll
+                for (int k = 0; k < kScanItems; ++k) starts = starts || (wofs + rel[k] < static_cast<uint32_t>(kScanTile));
+                if (!__syncthreads_or(starts)) {
+                    const uint32_t j = static_cast<uint32_t>(tile * kScanTile) - 1u + carry;
+                    if (reg_store) {
+                        const uint32_t slot0 = W0 + cb + static_cast<uint32_t>(tid * kScanItems);
+                        if (slot0 >= S0 && slot0 + kScanItems <= S1) {
+                            asm volatile("st.global.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(anc + (slot0 - anc_lo)), "r"(j) : "memory");
+                        } else {
+    #pragma unroll
+                            for (int k = 0; k < kScanItems; ++k)
+                                if (slot0 + k >= S0 && slot0 + k < S1) anc[slot0 + k - anc_lo] = j;
+                        }
+                    } else {
+                        const int lim = static_cast<int>(min(static_cast<uint32_t>(kScanTile), span - cb));
+    #pragma unroll
+                        for (int k = 0; k < kScanItems; ++k) {
+                            const int pos = k * kScanThreads + tid;
+                            const long long slot = static_cast<long long>(W0) + cb + pos;
+                            if (pos < lim && slot >= S0) expand_store(p, anc, slot, j);
+                        }
+                    }
+                    continue;
+                }
+            }
+            if (cb > 0u) {  // (the first window was cleared before the block scan)
+                *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(0u, 0u, 0u, 0u);
+                __syncthreads();
+            }
+            if (cur != first_slot) {
+                // slot positions relative to the window, modulo 2^32 (n_global < 2^31: no aliasing)
+                const uint32_t wofs = my_off - cb;
+                const uint32_t id0 = static_cast<uint32_t>(tid * kScanItems + 1);
+    #pragma unroll
+                for (int k = 0; k < kScanItems; ++k) {
+                    const uint32_t pos = wofs + rel[k];
+                    if (pos < static_cast<uint32_t>(kScanTile)) s_mark[pos] = id0 + k;
+                }
             }
             __syncthreads();
+            // inclusive max-scan over the window, 8 consecutive entries per thread
+            uint32_t v[kScanItems];
+            {
+                const uint4 a = *reinterpret_cast<const uint4 *>(&s_mark[tid * kScanItems]);
+                const uint4 b = *reinterpret_cast<const uint4 *>(&s_mark[tid * kScanItems + 4]);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            }
+    #pragma unroll
+            for (int k = 1; k < kScanItems; ++k) v[k] = max(v[k], v[k - 1]);
+            uint32_t run = v[kScanItems - 1];
+    #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, run, o);
+                if (lane >= o) run = max(run, n);
+            }
+            if (lane == 31) s_wmax[warp] = run;
+            uint32_t before = __shfl_up_sync(0xffffffffu, run, 1);
+            if (lane == 0) before = 0u;
+            __syncthreads();
+            uint32_t wbefore = carry, wall = carry;
+    #pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const uint32_t m = s_wmax[w];
+                if (w < warp) wbefore = max(wbefore, m);
+                wall = max(wall, m);
+            }
+            before = max(before, wbefore);
+            carry = wall;
+            const uint32_t jbase = static_cast<uint32_t>(tile * kScanTile) - 1u;
+            if (reg_store) {
+                // slots of this handle's own ancestor array (unsharded: all of them; anc holds ld >= n slots): the
+                // stores go straight from registers
+    #pragma unroll
+                for (int k = 0; k < kScanItems; ++k) v[k] = jbase + max(v[k], before);
+                const uint32_t slot0 = W0 + cb + static_cast<uint32_t>(tid * kScanItems);
+                if (slot0 >= S0 && slot0 + kScanItems <= S1) {
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(anc + (slot0 - anc_lo)), "r"(v[0]),
+                                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                                 : "memory");
+                } else {
+    #pragma unroll
+                    for (int k = 0; k < kScanItems; ++k)
+                        if (slot0 + k >= S0 && slot0 + k < S1) anc[slot0 + k - anc_lo] = v[k];
+                }
+                // no barrier here: the next window's zeroing of s_mark follows every thread's reads above
+            } else {
+    #pragma unroll
+                for (int k = 0; k < kScanItems; ++k) v[k] = max(v[k], before);
+                *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(v[4], v[5], v[6], v[7]);
+                __syncthreads();
+                // coalesced stores
+                const int lim = static_cast<int>(min(static_cast<uint32_t>(kScanTile), span - cb));
+    #pragma unroll
+                for (int k = 0; k < kScanItems; ++k) {
+                    const int pos = k * kScanThreads + tid;
+                    const long long slot = static_cast<long long>(W0) + cb + pos;
+                    if (pos < lim && slot >= S0) expand_store(p, anc, slot, jbase + s_mark[pos]);
+                }
+                __syncthreads();
+            }
         }
     }
     __syncthreads();  // s_next (written at the top of this iteration) and the scratch are settled

@@ -189,6 +189,32 @@ def test_resampling_indices_bit_exact(mcl, n, kind):
     assert f.stats()[0].ess == pytest.approx(n)
 
 
+@pytest.mark.parametrize("n", [1000, 5000, 70001])
+@pytest.mark.parametrize("first", ["normal", "zero"])
+def test_resampling_with_a_zero_comb_offset(mcl, n, first):
+    """rand() may return exactly 0: the tooth u_0 = 0 then sits ON the lower end of particle 0's cumulative weight, and
+    the reference walk (strict >, :219) gives slot 0 to particle 0 -- even when that particle's weight is 0."""
+    rng = np.random.RandomState(n)
+    lw = rng.normal(0, 1.5, n)
+    if first == "zero":
+        lw[0] = -np.inf
+    lw = (lw - lw[np.isfinite(lw)].max()).astype(np.float32)
+    pos = rng.normal(0, 1, (3, n)).astype(np.float32)
+    f = mcl.Filter(n_particles=n, landmarks=[[0.0, 0.0]])
+    f.set_particles(pos[0], pos[1], pos[2], lw)
+    q = f.qweights()[0]
+    f.resample(ofs=0.0, force=True)
+    anc = f.ancestors()[0].astype(np.int64)
+    wq = O.dequantize_weights(q)
+    np.testing.assert_array_equal(anc, O.resample_indices(wq, 0.0, clamp=True))
+    assert anc[0] == 0
+    if n <= 5000:
+        try:
+            np.testing.assert_array_equal(anc, O.resample_indices_literal(wq, 0.0))
+        except IndexError:
+            pass  # the reference walk ran off the end of pw_cum (SURVEY.md section 5); ours clamps
+
+
 def test_scan_descriptors_survive_a_skipped_resampling(mcl):
     """More than 1024 scan tiles (look-back through prefixes), device ESS gate: resample -> gate holds -> resample.
     The launch whose gate held must still clear the descriptor buffer the third launch scans with."""
