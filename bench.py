@@ -33,9 +33,10 @@ NCU_TRAFFIC = {
     ("c3", "moment"): ((528.388608e6 + 501.015552e6) / 33554432,
                        "ncu --set full of k_step at 32M particles x 64 landmarks (profiles/r01_r_ncu_32M_x64_k_step_summary.csv), per particle x this launch"),
 }
-HAVE_RB32 = False
+HAVE_RB32 = True
 PAIR_LOOPS = {
     "pair": {"arithmetic": "fp64, 8 operations per pair", "bound": "FP64 pipe"},
+    "pair32": {"arithmetic": "fp32 about the reference pose, 8 operations per pair, two particles per FFMA2 / FADD2", "bound": "FP32 pipe"},
     "rb": {"arithmetic": "fp64, libm sqrt / atan2, all landmarks scored", "bound": "FP64 pipe"},
     "rb32": {"arithmetic": "fp32 + MUFU (rcp, sqrt), branch-free atan2, ALL landmarks scored", "bound": "FP32/SFU issue"},
     "rb_fan": {"arithmetic": "fp32 + MUFU (rcp, sqrt), branch-free atan2, detected landmarks only", "bound": "FP32/SFU issue"},
@@ -103,10 +104,10 @@ class Truth:
         dx, dy = self.lm[None, :, 0] - x, self.lm[None, :, 1] - y
         z = np.stack([s * dx - c * dy, c * dx + s * dy], axis=2)
         if self.rb:
-            # the sensor model of graph_based_slam.py:150-167 without the gate: d ~ N(d, d R_Dist), phi ~ N(phi, sigma)
+            # range / bearing of graph_based_slam.py:150-153 with constant noise (MCL_LIK_RB: sigma_d = 0.3 m, sigma_phi = 2 deg)
             d = np.hypot(z[..., 0], z[..., 1])
             phi = np.arctan2(z[..., 1], z[..., 0])
-            dn = self.rng.normal(d, 0.05 * d)
+            dn = d + self.rng.normal(0.0, 0.3, d.shape)
             pn = phi + self.rng.normal(0.0, np.deg2rad(2.0), phi.shape)
             return np.stack([dn, (pn + np.pi) % (2 * np.pi) - np.pi], axis=2)
         if self.fan:
@@ -503,7 +504,8 @@ def run_b200(args, wl):
         filters, zcyc_host, zcyc = [], [], []
         for r in range(replicas):
             f = mcl.Filter(n_particles=n_, n_trials=T_, landmarks=lm_, likelihood=likelihood, device=local,
-                           seed=42 + 1000 * rank + r, max_landmarks=L_)
+                           seed=42 + 1000 * rank + r, max_landmarks=L_,
+                           sigma_obs=[0.3, float(np.deg2rad(2.0))] if likelihood in ("rb", "rb32") else None)
             tr = Truth(lm_, seed=7 + 100 * rank + r * 17, T=T_, fan=(likelihood == "rb_fan"), rb=(likelihood in ("rb", "rb32")))
             f.init_particles(tr.pose())
             cyc = tr.cycle()  # (360, T, L, 2): replica r at filter step k sees cyc[k % 360]
@@ -718,10 +720,10 @@ def run_b200(args, wl):
         if args.likelihood == "moment":
             # the GENERAL likelihood -- every particle against every landmark (particle_filter.py:185-192) -- on the
             # same two shapes; the headline runs its exact O(1)-per-particle moment form
-            for key, k_ in (("c1", 40), ("c3", 6)):
+            for lik, key, k_ in (("pair32", "c1", 40), ("pair32", "c3", 8), ("pair", "c3", 6)):
                 w_ = WORKLOADS[key]
-                lr = timed_run(w_, k_, 3, 0.1, "pair", min_seconds=0.1)
-                extras[f"pair_{key}"] = dict(extra_line(w_, lr, k_), likelihood="pair", pair_loop=pair_loop(w_, lr, "pair"))
+                lr = timed_run(w_, k_, 3, 0.1, lik, min_seconds=0.1)
+                extras[f"{lik}_{key}"] = dict(extra_line(w_, lr, k_), likelihood=lik, pair_loop=pair_loop(w_, lr, lik))
             c2 = WORKLOADS["c2"]
             lr = timed_run(c2, 12, 3, 0.1, "moment", min_seconds=0.1)
             extras["c2"] = extra_line(c2, lr, 12)
@@ -737,7 +739,7 @@ def run_b200(args, wl):
                        "same_algorithm_as_reference_arm": args.likelihood != "moment",
                        "algorithm_note": ("the moment likelihood is an exact algebraic identity of the per-pair sum (SURVEY 7), O(1) per "
                                           "particle; the reference arm scores every (particle, landmark) pair -- the like-for-like GPU "
-                                          "number is extras.pair_c1") if args.likelihood == "moment" else "per-pair likelihood on both arms",
+                                          "number is extras.pair32_c1") if args.likelihood == "moment" else "per-pair likelihood on both arms",
                        "noise": "philox4x32-10 on device", "resampling": "forced every step",
                        "ess_over_n": ess_frac,
                        "l2": f"rotating {replicas} independent filter replicas ({replicas * state_bytes >> 20} MiB > 126 MiB L2)",
@@ -759,7 +761,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
-    ap.add_argument("--likelihood", default="moment", choices=["pair", "moment", "rb", "rb32", "rb_fan"])
+    ap.add_argument("--likelihood", default="moment", choices=["pair", "pair32", "moment", "rb", "rb32", "rb_fan"])
     ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"], help="N > 1: exchange of the sharded filter")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra workloads of the default line")
     ap.add_argument("--n", type=int, default=0, help="override the particle count of the workload (experiments)")

@@ -51,11 +51,17 @@ typedef enum mcl_likelihood {
     MCL_LIK_MOMENT = 1, /* same result from 13 per-step landmark moments (exact identity), O(1)/particle */
     MCL_LIK_RB = 2,     /* range/bearing residuals with limit_angle wrap (extension; sensor model
                            graph_based_slam.py:150-167) */
-    MCL_LIK_RB_FAN = 3  /* the fan-shaped scan sensor (ScanSensor, graph_based_slam.py:73-167): only DETECTED
+    MCL_LIK_RB_FAN = 3, /* the fan-shaped scan sensor (ScanSensor, graph_based_slam.py:73-167): only DETECTED
                            landmarks are scored (z rows with a NaN distance are skipped), distance noise grows
                            with the distance (:163), and a landmark outside the particle's own fan (:155-160)
                            costs fan_miss_chi2 / 2 instead of its residuals.  fp32 per pair (MUFU sqrt, atan2f):
                            the likelihood-heavy kernel; sigma_obs = (R_Dist gain, direction sigma [rad]) */
+    MCL_LIK_PAIR_F32 = 4, /* MCL_LIK_PAIR evaluated in fp32 ABOUT THE REFERENCE POSE (the previous MAP estimate pushed
+                           through the motion): a particle's residual is the reference pose's residual u_l plus a
+                           small d_l, and the kernel sums d_l (d_l + 2 u_l) -- the difference of the two chi^2, no
+                           cancellation -- 8 fp32 operations per pair, two particles per FFMA2 */
+    MCL_LIK_RB_F32 = 5  /* MCL_LIK_RB for ALL landmarks in fp32 about the reference pose (MUFU sqrt / rcp, branch-free
+                           atan2 of the small bearing change): the FP32 / SFU-bound kernel of BASELINE configs[4] */
 } mcl_likelihood;
 
 typedef enum mcl_motion {

@@ -25,6 +25,8 @@ MCL_LIK_PAIR = 0
 MCL_LIK_MOMENT = 1
 MCL_LIK_RB = 2
 MCL_LIK_RB_FAN = 3
+MCL_LIK_PAIR_F32 = 4
+MCL_LIK_RB_F32 = 5
 MCL_MOTION_A = 0
 MCL_MOTION_B = 1
 

@@ -79,7 +79,7 @@ int make_layout(const mcl_config &c, int sm_count, Layout &L) {
 int validate(const mcl_config *c) {
     if (c == nullptr || c->struct_size != sizeof(mcl_config)) return MCL_ERR_ARG;
     if (!(c->dt > 0.0) || !(c->sigma_obs[0] > 0.0) || !(c->sigma_obs[1] > 0.0)) return MCL_ERR_ARG;
-    if (c->likelihood < MCL_LIK_PAIR || c->likelihood > MCL_LIK_RB_FAN) return MCL_ERR_ARG;
+    if (c->likelihood < MCL_LIK_PAIR || c->likelihood > MCL_LIK_RB_F32) return MCL_ERR_ARG;
     if (c->likelihood == MCL_LIK_RB_FAN &&
         !(c->fan_range > 0.0 && c->fan_half_angle > 0.0 && c->fan_half_angle < kPi / 2 && c->fan_miss_chi2 >= 0.0))
         return MCL_ERR_ARG;
@@ -389,6 +389,8 @@ int step_variant(const mcl_config &c) {
     if (c.likelihood == MCL_LIK_PAIR) return kLikPair;
     if (c.likelihood == MCL_LIK_RB) return kLikRB;
     if (c.likelihood == MCL_LIK_RB_FAN) return kLikRBFan;
+    if (c.likelihood == MCL_LIK_PAIR_F32) return kLikPair32;
+    if (c.likelihood == MCL_LIK_RB_F32) return kLikRB32;
     return (c.sigma_obs[0] == c.sigma_obs[1]) ? kLikMomentIso : kLikMomentGen;
 }
 
@@ -439,6 +441,8 @@ int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool redu
     for (int k = 0; k < 3; ++k) p.q_std[k] = static_cast<float>(c.q_std[k]);
     p.inv_s0sq = 1.0 / (c.sigma_obs[0] * c.sigma_obs[0]);
     p.inv_s1sq = 1.0 / (c.sigma_obs[1] * c.sigma_obs[1]);
+    p.inv_s0_f = static_cast<float>(1.0 / c.sigma_obs[0]);
+    p.inv_s1_f = static_cast<float>(1.0 / c.sigma_obs[1]);
     p.fan_r2 = static_cast<float>(c.fan_range * c.fan_range);
     p.fan_tan = static_cast<float>(std::tan(kPi / 2 - c.fan_half_angle));
     p.fan_inv_r = static_cast<float>(1.0 / c.sigma_obs[0]);
@@ -467,6 +471,8 @@ int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool redu
         case kLikPair: launch_step_lik<kLikPair>(p, grid, smem, philox, st, pdl); break;
         case kLikRB: launch_step_lik<kLikRB>(p, grid, smem, philox, st, pdl); break;
         case kLikRBFan: launch_step_lik<kLikRBFan>(p, grid, smem, philox, st, pdl); break;
+        case kLikPair32: launch_step_lik<kLikPair32>(p, grid, smem, philox, st, pdl); break;
+        case kLikRB32: launch_step_lik<kLikRB32>(p, grid, smem, philox, st, pdl); break;
         case kLikMomentIso: launch_step_lik<kLikMomentIso>(p, grid, 0, philox, st, pdl); break;
         default: launch_step_lik<kLikMomentGen>(p, grid, 0, philox, st, pdl); break;
     }
@@ -697,6 +703,10 @@ int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_byte
     cudaFuncSetAttribute(k_step<kLikRB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
     cudaFuncSetAttribute(k_step<kLikRBFan, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
     cudaFuncSetAttribute(k_step<kLikRBFan, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    cudaFuncSetAttribute(k_step<kLikPair32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    cudaFuncSetAttribute(k_step<kLikPair32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    cudaFuncSetAttribute(k_step<kLikRB32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    cudaFuncSetAttribute(k_step<kLikRB32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
     // sin/cos table of sincos_tab: entry k-128 holds sin, cos of k*pi/32 and the correction -k*(pi/32 - HI)
     {
         static TrigEntry tab[kTrigEntries];

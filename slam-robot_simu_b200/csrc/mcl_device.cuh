@@ -21,6 +21,7 @@ constexpr int kStepCtasPerSm = MCL_STEP_CTAS_PER_SM;  // resident CTAs per SM k_
 constexpr int kPPT = 4;            // particles per thread per iteration (one float4 per array)
 constexpr int kStepTile = kStepThreads * kPPT;
 constexpr int kStepUnit = 128;     // granularity of the static particle partition over blocks
+constexpr int kFoldEvery = 16;     // fp32 pair kernels: landmarks per fp32 partial sum before it is folded into fp64
 constexpr int kFlushEvery = 8;     // fp32 group sums are folded into the fp64 sums every 8 iterations
 
 constexpr int kScanThreads = 256;
@@ -162,6 +163,54 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
     r = (ay > ax) ? 1.57079632679489662f - r : r;
     r = (x < 0.0f) ? 3.14159265358979324f - r : r;
     return copysignf(r, y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Packed fp32 pairs (Blackwell FFMA2 / FADD2): one instruction, two lanes of arithmetic.  The pair loops of the
+// fp32 likelihoods run two particles per register pair, which halves their issue slots.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// sin(d) and cos(d) - 1 of a SMALL angle with fp32 relative accuracy (what the shifted-origin likelihoods need:
+// the absolute error of both is ~6e-8 |d|, not 6e-8).  |d| <= 0.5: odd / even Taylor polynomials (truncation
+// below 2e-11); beyond that the particle is far from the reference pose, its weight is nil, and libm is used.
+__device__ __forceinline__ void sincosm1_small(float d, float &sd, float &cm1) {
+    if (fabsf(d) <= 0.5f) {
+        const float d2 = d * d;
+        float ps = 2.7557319e-6f;             //  1/9!
+        ps = fmaf(ps, d2, -1.9841270e-4f);    // -1/7!
+        ps = fmaf(ps, d2, 8.3333333e-3f);     //  1/5!
+        ps = fmaf(ps, d2, -1.6666667e-1f);    // -1/3!
+        sd = fmaf(d * d2, ps, d);
+        float pc = -2.7557319e-7f;            // -1/10!
+        pc = fmaf(pc, d2, 2.4801587e-5f);     //  1/8!
+        pc = fmaf(pc, d2, -1.3888889e-3f);    // -1/6!
+        pc = fmaf(pc, d2, 4.1666667e-2f);     //  1/4!
+        pc = fmaf(pc, d2, -0.5f);
+        cm1 = d2 * pc;
+    } else {
+        float c;
+        sincosf(d, &sd, &c);
+        cm1 = c - 1.0f;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

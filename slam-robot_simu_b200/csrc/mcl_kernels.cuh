@@ -24,6 +24,8 @@ constexpr int kLikMomentIso = 1;  // 8 per-step moments, sigma_x == sigma_y (the
 constexpr int kLikMomentGen = 2;  // 13 per-step moments, sigma_x != sigma_y
 constexpr int kLikRB = 3;         // range / bearing residuals with limit_angle wrap
 constexpr int kLikRBFan = 4;      // fan-shaped scan sensor: detected landmarks only, visibility gate, fp32 per pair
+constexpr int kLikPair32 = 5;     // per pair in fp32 about the reference pose (shifted origin), two particles per FFMA2
+constexpr int kLikRB32 = 6;       // range / bearing residuals of ALL landmarks in fp32 (MUFU sqrt / rcp, branch-free atan2)
 
 __device__ __forceinline__ void pair_residual_c(double s, double c, double tx, double ty, double4 t, double &ex,
                                                 double &ey) {
@@ -175,16 +177,38 @@ __device__ __noinline__ void prep_block(const PrepParams &p, const PrepIn &in, c
             const double zx = p.z[(static_cast<long long>(t) * p.L + l) * 2];
             const double zy = p.z[(static_cast<long long>(t) * p.L + l) * 2 + 1];
             const double4 e = make_double4(lx, ly, zx, zy);
-            p.tab[static_cast<long long>(t) * p.Lmax + l] = e;
+            if (p.likelihood != MCL_LIK_PAIR_F32 && p.likelihood != MCL_LIK_RB_F32) p.tab[static_cast<long long>(t) * p.Lmax + l] = e;
             acc[0] += lx;       acc[1] += ly;       acc[2] += zx;       acc[3] += zy;
             acc[4] += lx * lx;  acc[5] += ly * ly;  acc[6] += lx * ly;
             acc[7] += zx * zx;  acc[8] += zy * zy;
             acc[9] += lx * zx;  acc[10] += ly * zx; acc[11] += lx * zy; acc[12] += ly * zy;
             double e0, e1;
-            if (p.likelihood == MCL_LIK_RB) pair_residual_rb(s, c, tx, ty, e, e0, e1);
+            if (p.likelihood == MCL_LIK_RB || p.likelihood == MCL_LIK_RB_F32) pair_residual_rb(s, c, tx, ty, e, e0, e1);
             else pair_residual_c(s, c, tx, ty, e, e0, e1);
+            if (p.likelihood == MCL_LIK_RB_F32) {
+                // fp32 range/bearing kernel about the reference pose: the landmark as the reference pose sees it
+                // (g, |g|), and the reference pose's own residuals (e0 = z_d - |g|, e1 = wrap(z_phi - phi_g)).  A particle
+                // changes the range by dr and the bearing by dphi, both small and computed with RELATIVE fp32 accuracy;
+                // the kernel sums dr'(dr' - 2 e0') and dphi'(dphi' + ...) -- differences of squares, primes = / sigma.
+                const double gx = fma(s, lx, fma(-c, ly, tx)), gy = fma(c, lx, fma(s, ly, ty));
+                const double g2 = fmax(fma(gx, gx, gy * gy), 1.0e-12), rho = sqrt(g2);
+                float *slot = reinterpret_cast<float *>(&p.tab[static_cast<long long>(t) * p.Lmax + l]);
+                slot[0] = static_cast<float>(gx);
+                slot[1] = static_cast<float>(gy);
+                slot[2] = static_cast<float>(rho * sqrt(p.inv_s0sq));        // |g| / sigma_d
+                slot[3] = static_cast<float>(1.0 / g2);
+                slot[4] = static_cast<float>(g2);
+                slot[5] = static_cast<float>(2.0 * e0 * sqrt(p.inv_s0sq));   // 2 e_d(ref) / sigma_d
+                slot[6] = static_cast<float>(e1);                            // e_phi(ref), wrapped
+                slot[7] = static_cast<float>(2.0 * e1 * sqrt(p.inv_s1sq));   // 2 e_phi(ref) / sigma_phi
+            }
             acc[13] = fma(e0, e0, acc[13]);
             acc[14] = fma(e1, e1, acc[14]);
+            // fp32 pair kernel: the landmark as the reference pose sees it, g = M_r (l - p_r) = residual + observation,
+            // and twice the residual u there -- a particle's residual is u + d with d small, and the kernel sums
+            // d (d + 2 u) = |u + d|^2 - |u|^2, the difference to the reference pose's chi^2, never the squares
+            if (p.likelihood == MCL_LIK_PAIR_F32)
+                p.tab[static_cast<long long>(t) * p.Lmax + l] = make_double4(e0 + zx, e1 + zy, 2.0 * e0, 2.0 * e1);
         }
         block_sum<15>(acc, red);
     }
@@ -1298,6 +1322,7 @@ struct StepParams {
     double vel, yaw_rate, dt;
     float q_std[3];
     double inv_s0sq, inv_s1sq;
+    float inv_s0_f, inv_s1_f;   // 1 / sigma_obs (fp32 pair kernels)
     float fan_r2, fan_tan, fan_inv_r, fan_inv_sphi, fan_miss;  // MCL_LIK_RB_FAN
     double mb_sig[3];      // motion B: the three "sigma ** 2" scales (motion_model.py:43-48)
 };
@@ -1326,6 +1351,24 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
         for (int l = tid; l < L; l += kStepThreads) s_tab[l] = g[l];
         __syncthreads();
     }
+    // pair32: per landmark {gx, gx, gy, gy, 2ux, 2ux, 2uy, 2uy} -- both halves of an FFMA2 operand see the same landmark
+    float *s_tab8 = reinterpret_cast<float *>(smem_raw);
+    if (LIK == kLikPair32) {
+        const double4 *g = p.tab + static_cast<long long>(t) * p.Lmax;
+        for (int l = tid; l < L; l += kStepThreads) {
+            const double4 e = g[l];
+            const float gx = static_cast<float>(e.x), gy = static_cast<float>(e.y),
+                        ux = static_cast<float>(e.z * sqrt(p.inv_s0sq)), uy = static_cast<float>(e.w * sqrt(p.inv_s1sq));
+            *reinterpret_cast<float4 *>(s_tab8 + 8 * l) = make_float4(gx, gx, gy, gy);
+            *reinterpret_cast<float4 *>(s_tab8 + 8 * l + 4) = make_float4(ux, ux, uy, uy);  // (2 u / sigma, scaled below)
+        }
+        __syncthreads();
+    }
+    if (LIK == kLikRB32) {  // the per-step scalars CTA left eight floats per landmark: copied as they are
+        const double4 *g = p.tab + static_cast<long long>(t) * p.Lmax;
+        for (int l = tid; l < L; l += kStepThreads) reinterpret_cast<double4 *>(smem_raw)[l] = g[l];
+        __syncthreads();
+    }
     float4 *s_tabf = reinterpret_cast<float4 *>(smem_raw);  // [L detected] (fan sensor: fp32 per pair)
     if (LIK == kLikRBFan) {
         const double4 *g = p.tab + static_cast<long long>(t) * p.Lmax;
@@ -1339,6 +1382,13 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
     const int resample = s_prep.do_resample;
     const float ref_x = static_cast<float>(s_prep.ref[0]), ref_y = static_cast<float>(s_prep.ref[1]),
                 ref_th = static_cast<float>(s_prep.ref[2]);
+    float ref_s = 0.f, ref_c = 1.f;  // fp32 kernels about the reference pose: its sin / cos
+    if (LIK == kLikPair32 || LIK == kLikRB32) {
+        double rs, rc;
+        sincos_tab(ref_th, p.trig, rs, rc);
+        ref_s = static_cast<float>(rs);
+        ref_c = static_cast<float>(rc);
+    }
     const float max_prev = static_cast<float>(s_prep.max_prev);
     const double shift = s_prep.lik_const - s_prep.c_shift;  // per-step constant added to every log-likelihood
     // moment constants
@@ -1495,6 +1545,138 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
 
             // ---------------- weight: log-likelihood of the STORED (fp32) pose, fp64 arithmetic ----------------
             float fan_chi2[kPPT] = {0.f, 0.f, 0.f, 0.f};
+            float dll32[kPPT] = {0.f, 0.f, 0.f, 0.f};  // fp32 kernels: the new stored log-weight (relative to the reference pose's)
+            if (LIK == kLikPair32) {
+                // The particle sits at the reference pose plus a small (dx, dy, dth).  With M(th) = [[s, -c], [c, s]]
+                // and g_l = M(ref)(l - p_ref):  M(th)(l - p) = g_l + (cos dth - 1) g_l + sin dth J g_l - M(th)(dx, dy),
+                // J(g) = (g_y, -g_x).  Everything after the first g_l is the small d_l the kernel works with; its
+                // rounding error scales with |d_l|, not with the 20-m coordinates.
+                // Components are scaled by 1 / sigma before they are squared, so ONE accumulator per particle holds the
+                // chi^2 DIFFERENCE to the reference pose.  It runs in fp32 over blocks of kFoldEvery landmarks and is
+                // folded into fp64 between blocks: a plain fp32 sum over 1024 landmarks was measured at 1.5e-5 of
+                // log-weight on the particles that carry mass (+7 % time for the folding).
+                const float is0 = p.inv_s0_f, is1 = p.inv_s1_f;
+                float a0[kPPT], b0[kPPT], tx0[kPPT], a1[kPPT], nb1[kPPT], ty1[kPPT];
+#pragma unroll
+                for (int k = 0; k < kPPT; ++k) {
+                    float sd, cm1;
+                    sincosm1_small(wrap_residual(th[k] - ref_th), sd, cm1);
+                    const float sf = fmaf(ref_s, cm1, fmaf(ref_c, sd, ref_s));   // sin(th) = s_r cos d + c_r sin d
+                    const float cf = fmaf(ref_c, cm1, fmaf(-ref_s, sd, ref_c));  // cos(th) = c_r cos d - s_r sin d
+                    const float ddx = x[k] - ref_x, ddy = y[k] - ref_y;
+                    a0[k] = cm1 * is0;
+                    b0[k] = sd * is0;
+                    tx0[k] = -fmaf(sf, ddx, -cf * ddy) * is0;
+                    a1[k] = cm1 * is1;
+                    nb1[k] = -sd * is1;
+                    ty1[k] = -fmaf(cf, ddx, sf * ddy) * is1;
+                    s[k] = static_cast<double>(sf);
+                    c[k] = static_cast<double>(cf);
+                }
+                f32x2 A0[2], B0[2], TX[2], A1[2], NB1[2], TY[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    A0[h] = pack2(a0[2 * h], a0[2 * h + 1]);
+                    B0[h] = pack2(b0[2 * h], b0[2 * h + 1]);
+                    TX[h] = pack2(tx0[2 * h], tx0[2 * h + 1]);
+                    A1[h] = pack2(a1[2 * h], a1[2 * h + 1]);
+                    NB1[h] = pack2(nb1[2 * h], nb1[2 * h + 1]);
+                    TY[h] = pack2(ty1[2 * h], ty1[2 * h + 1]);
+                }
+                double dq[kPPT] = {0.0, 0.0, 0.0, 0.0};
+                for (int l0 = 0; l0 < L; l0 += kFoldEvery) {
+                    f32x2 Q[2] = {0ull, 0ull};
+                    const int l1 = min(L, l0 + kFoldEvery);
+#pragma unroll 2
+                    for (int l = l0; l < l1; ++l) {
+                        const ulonglong2 g = *reinterpret_cast<const ulonglong2 *>(s_tab8 + 8 * l);      // {gx gx}, {gy gy}
+                        const ulonglong2 u = *reinterpret_cast<const ulonglong2 *>(s_tab8 + 8 * l + 4);  // {2ux/s0 ..}, {2uy/s1 ..}
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const f32x2 dx = fma2(A0[h], g.x, fma2(B0[h], g.y, TX[h]));
+                            Q[h] = fma2(dx, add2(dx, u.x), Q[h]);
+                            const f32x2 dy = fma2(A1[h], g.y, fma2(NB1[h], g.x, TY[h]));
+                            Q[h] = fma2(dy, add2(dy, u.y), Q[h]);
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float q0, q1;
+                        unpack2(Q[h], q0, q1);
+                        dq[2 * h] += static_cast<double>(q0);
+                        dq[2 * h + 1] += static_cast<double>(q1);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < kPPT; ++k) dll32[k] = static_cast<float>(static_cast<double>(lwp[k]) - 0.5 * dq[k]);
+            }
+            if (LIK == kLikRB32) {
+                float a_[kPPT], b_[kPPT], ntx[kPPT], nty[kPPT];
+#pragma unroll
+                for (int k = 0; k < kPPT; ++k) {
+                    float sd, cm1;
+                    sincosm1_small(wrap_residual(th[k] - ref_th), sd, cm1);
+                    const float sf = fmaf(ref_s, cm1, fmaf(ref_c, sd, ref_s));
+                    const float cf = fmaf(ref_c, cm1, fmaf(-ref_s, sd, ref_c));
+                    const float ddx = x[k] - ref_x, ddy = y[k] - ref_y;
+                    a_[k] = cm1;
+                    b_[k] = sd;
+                    ntx[k] = -fmaf(sf, ddx, -cf * ddy);
+                    nty[k] = -fmaf(cf, ddx, sf * ddy);
+                    s[k] = static_cast<double>(sf);
+                    c[k] = static_cast<double>(cf);
+                }
+                const float isp = p.inv_s1_f;
+                double dq[kPPT] = {0.0, 0.0, 0.0, 0.0};
+                for (int l0 = 0; l0 < L; l0 += kFoldEvery) {
+                    float q[kPPT] = {0.f, 0.f, 0.f, 0.f};
+                    const int l1 = min(L, l0 + kFoldEvery);
+#pragma unroll 1
+                    for (int l = l0; l < l1; ++l) {
+                        const float4 e0 = s_tabf[2 * l];      // gx, gy, |g| / sigma_d, 1 / |g|^2
+                        const float4 e1 = s_tabf[2 * l + 1];  // |g|^2, 2 e_d / sigma_d, e_phi, 2 e_phi / sigma_phi
+#pragma unroll
+                        for (int k = 0; k < kPPT; ++k) {
+                            // the particle sees the landmark at g + d, d small (see kLikPair32)
+                            const float dx = fmaf(a_[k], e0.x, fmaf(b_[k], e0.y, ntx[k]));
+                            const float dy = fmaf(a_[k], e0.y, fmaf(-b_[k], e0.x, nty[k]));
+                            const float dot = fmaf(e0.x, dx, e0.y * dy), crs = fmaf(e0.x, dy, -e0.y * dx);
+                            // range: |g + d| - |g| = |g| eps / (1 + sqrt(1 + eps)), eps = (2 g.d + |d|^2) / |g|^2
+                            const float eps = fmaf(2.0f, dot, fmaf(dx, dx, dy * dy)) * e0.w;
+                            const float sq = sqrt_approx(fmaxf(1.0f + eps, 0.0f));
+                            float rc;
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + sq));
+                            const float dr = e0.z * eps * rc;                 // (range change) / sigma_d
+                            q[k] = fmaf(dr, dr - e1.y, q[k]);                 // (e_d - dr)^2 - e_d^2, e_d = z_d - |g|
+                            // bearing: the change is atan2(g x d, |g|^2 + g.d); for the particles that matter it is a
+                            // small angle, and the series keeps its RELATIVE accuracy (the minimax atan2 is good to
+                            // 1.4e-7 rad absolute, 7e-7 relative near 0)
+                            const float den = e1.x + dot;
+                            float rd;
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rd) : "f"(den));
+                            const float tq = crs * rd, t2 = tq * tq;
+                            float dphi;
+                            if (den > 0.0f && t2 < 0.01f) {
+                                float pa = fmaf(t2, -1.0f / 7.0f, 0.2f);
+                                pa = fmaf(t2, pa, -1.0f / 3.0f);
+                                dphi = fmaf(tq * t2, pa, tq);
+                            } else {
+                                dphi = atan2_fast(crs, den);
+                            }
+                            const float w = e1.z - dphi;                      // new residual before limit_angle
+                            float del = -dphi;                                // new residual minus old, after the wrap
+                            del = (w > 3.14159265f) ? del - 6.28318531f : del;
+                            del = (w < -3.14159265f) ? del + 6.28318531f : del;
+                            const float dp = del * isp;
+                            q[k] = fmaf(dp, dp + e1.w, q[k]);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kPPT; ++k) dq[k] += static_cast<double>(q[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < kPPT; ++k) dll32[k] = static_cast<float>(static_cast<double>(lwp[k]) - 0.5 * dq[k]);
+            }
             if (LIK == kLikRBFan) {
                 // the fan sensor is scored in fp32, one table entry against the thread's four particles at a time
                 float sf[kPPT], cf[kPPT];
@@ -1517,6 +1699,10 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
             }
 #pragma unroll
             for (int k = 0; k < kPPT; ++k) {
+                if (LIK == kLikPair32 || LIK == kLikRB32) {  // already relative to the reference pose (and to lwp)
+                    lwf[k] = dll32[k];
+                    continue;
+                }
                 if (LIK != kLikRBFan) sincos_tab(th[k], p.trig, s[k], c[k]);
                 const double xd = x[k], yd = y[k];
                 double ll;

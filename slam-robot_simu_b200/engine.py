@@ -44,7 +44,7 @@ class Filter:
         cfg.slot_base = int(slot_base)
         cfg.seed = int(seed)
         cfg.likelihood = {"pair": L.MCL_LIK_PAIR, "moment": L.MCL_LIK_MOMENT, "rb": L.MCL_LIK_RB,
-                          "rb_fan": L.MCL_LIK_RB_FAN}[likelihood]
+                          "rb_fan": L.MCL_LIK_RB_FAN, "pair32": L.MCL_LIK_PAIR_F32, "rb32": L.MCL_LIK_RB_F32}[likelihood]
         if likelihood == "rb_fan" and sigma_obs is None:
             # ScanSensor noise as the reference's Robot sets it (graph_based_slam.py:604): 5 % of the distance, 2 deg
             sigma_obs = [0.05, np.deg2rad(2.0)]

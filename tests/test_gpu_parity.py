@@ -58,7 +58,7 @@ def _oracle_predict_weight(px32, w_prev, v32, z_l, P, sx=0.3, sy=0.3):
     return px_pred
 
 
-@pytest.mark.parametrize("likelihood", ["pair", "moment"])
+@pytest.mark.parametrize("likelihood", ["pair", "moment", "pair32"])
 @pytest.mark.parametrize("seed,k", [(0, 0), (0, 1), (0, 5), (0, 7), (0, 100), (0, 359), (1, 39), (2, 39)])
 def test_predict_weight_stage_parity(mcl, golden_dir, likelihood, seed, k):
     """__predict + __likelihood + __normalize + MAP (particle_filter.py:156-198, :115-117) on the
@@ -354,7 +354,7 @@ def test_trials_batch_equals_single_filters(mcl):
         assert sb[t].max_idx == s1.max_idx and sb[t].ess == s1.ess and sb[t].log_norm == s1.log_norm
 
 
-@pytest.mark.parametrize("likelihood", ["pair", "moment"])
+@pytest.mark.parametrize("likelihood", ["pair", "moment", "pair32"])
 def test_c1_size_step_parity(mcl, likelihood):
     """C1 shape (2^20 particles x 16 landmarks), forced resampling, injected noise: full step vs oracle."""
     n, Lm = 1 << 20, 16
@@ -394,8 +394,16 @@ def test_c1_size_step_parity(mcl, likelihood):
     np.testing.assert_allclose(np.array(st.cov[:]).reshape(3, 3), cov, rtol=1e-4, atol=1e-9)
 
 
-def test_likelihood_64_and_1024_landmarks(mcl):
-    """L = 64 (C3) and L = 1024 (C4): pair kernel == moment kernel == log-domain oracle."""
+@pytest.mark.parametrize("scenario", ["running", "offset"])
+def test_likelihood_64_and_1024_landmarks(mcl, scenario):
+    """L = 64 (C3) and L = 1024 (C4): pair kernel == moment kernel == fp32 pair kernel == log-domain oracle.
+
+    "running": the observation is taken where the cloud is after its motion step, as in a running filter -- the
+    reference pose (the previous MAP estimate pushed through the motion) then sits at the likelihood peak and every
+    kernel meets 1e-5.  "offset": the observation is taken BEFORE the motion step, so the whole cloud sits 0.17 m
+    off and the useful particles score e^+80 (L = 64) to e^+760 (L = 1024) above the reference pose.  The fp64
+    kernels still meet 1e-5 there; the fp32 pair kernel, whose rounding error is ~3e-8 of |log w - log w_ref|, is
+    asked 5e-5 (its stored fp32 log-weights have an ulp of 6e-5 at 760)."""
     rng = np.random.RandomState(99)
     for Lm, n in ((64, 1 << 16), (1024, 1 << 13)):
         lm = rng.uniform(-20, 20, (Lm, 2))
@@ -406,11 +414,12 @@ def test_likelihood_64_and_1024_landmarks(mcl):
         # the previous MAP estimate; after set_particles, particle 0): put a good particle there, as the
         # filter would, so the fp32 log-weights of the heavy particles are small numbers
         pos[:, 0] = truth[:, 0].astype(np.float32)
-        z = O.world2robot(truth, lm) + rng.normal(0, 0.3, (Lm, 2))
         P = O.PFParams(100, n_particles=n, landmarks=lm)
+        seen_from = O.f_motion(truth, P) if scenario == "running" else truth
+        z = O.world2robot(seen_from, lm) + rng.normal(0, 0.3, (Lm, 2))
         noise = np.zeros((3, 1, n), dtype=np.float32)
         res = {}
-        for lik in ("pair", "moment"):
+        for lik in ("pair", "moment", "pair32"):
             f = mcl.Filter(n_particles=n, landmarks=lm, likelihood=lik, max_landmarks=Lm)
             f.set_particles(pos[0], pos[1], pos[2], None)
             f.predict_weight(z[None], noise=noise)
@@ -421,6 +430,7 @@ def test_likelihood_64_and_1024_landmarks(mcl):
         want_w, _ = O.update_weights_log(np.full(n, -np.log(float(n))), ll)
         _assert_weights_close(res["pair"], want_w)
         _assert_weights_close(res["moment"], want_w)
+        _assert_weights_close(res["pair32"], want_w, rtol=RTOL if scenario == "running" else 5e-5)
 
 
 def test_motion_b_and_rb_likelihood(mcl, golden_dir):
@@ -444,6 +454,48 @@ def test_motion_b_and_rb_likelihood(mcl, golden_dir):
     ll = O.loglik_rb(got_px, z_rb, lm, 0.1, 0.03)
     want_w, _ = O.update_weights_log(np.full(n, -np.log(float(n))), ll)
     _assert_weights_close(f.weights()[0], want_w)
+
+
+@pytest.mark.parametrize("seam", [False, True])
+@pytest.mark.parametrize("Lm,n", [(9, 8192), (64, 1 << 15), (1024, 1 << 13)])
+def test_rb32_all_landmark_likelihood_matches_oracle(mcl, Lm, n, seam):
+    """BASELINE configs[4] as named: EVERY range/bearing landmark scored, fp32 + SFU (MCL_LIK_RB_F32), against the fp64
+    restatement loglik_rb (sensor model graph_based_slam.py:150-167, wrap mylib/limit.py:19-26; parity unpinned: the
+    reference has no range/bearing likelihood) and against the fp64 kernel (MCL_LIK_RB).  The kernel works about the
+    reference pose, so its error is relative to |log w - log w_ref|: 2e-5 on the weights that carry mass.
+    seam: one landmark's bearing residual sits at +-pi, so limit_angle flips its sign for part of the cloud.  fp32
+    resolves an angle near pi to 2.4e-7 rad and the squared residual jumps by 2 pi (2 e) / sigma^2 ~ 4e4 per radian
+    across the seam: only the wrap DECISION can be checked there (1e-2; a wrong turn is a factor e^+-1000)."""
+    rng = np.random.RandomState(1000 + Lm)
+    lm = rng.uniform(-20, 20, (Lm, 2))
+    truth = np.array([[3.0], [-2.0], [0.7]])
+    P = O.PFParams(100, n_particles=n, landmarks=lm)
+    spread = 0.2 / np.sqrt(Lm)
+    pos = (truth + rng.normal(0, 1, (3, n)) * np.array([[spread], [spread], [spread / 8]])).astype(np.float32)
+    pos[:, 0] = truth[:, 0].astype(np.float32)
+    moved = O.f_motion(truth, P)
+    z = O.rb_observation(moved, lm) + rng.normal(0, 1, (Lm, 2)) * np.array([0.1, 0.03])
+    z[:, 1] = O.limit_angle_vec(z[:, 1])
+    if seam:
+        z[0, 1] = O.limit_angle_vec(np.array([O.rb_observation(moved, lm)[0, 1] + np.pi - 2e-4]))[0]
+    noise = np.zeros((3, 1, n), dtype=np.float32)
+    res = {}
+    for lik in ("rb", "rb32"):
+        f = mcl.Filter(n_particles=n, landmarks=lm, likelihood=lik, sigma_obs=[0.1, 0.03], max_landmarks=Lm)
+        f.set_particles(pos[0], pos[1], pos[2], None)
+        f.predict_weight(z[None], noise=noise)
+        x, y, th, _ = f.get_particles()
+        got_px = np.stack([x[0], y[0], th[0]]).astype(np.float64)
+        res[lik] = f.weights()[0]
+    ll = O.loglik_rb(got_px, z, lm, 0.1, 0.03)
+    want_w, _ = O.update_weights_log(np.full(n, -np.log(float(n))), ll)
+    _assert_weights_close(res["rb"], want_w)
+    heavy = want_w > want_w.max() * 1e-4
+    big = want_w > want_w.max() * 1e-12
+    print(f"L={Lm} seam={seam}: rb32 max rel err heavy {np.abs(res['rb32'][heavy] / want_w[heavy] - 1).max():.2e}, "
+          f"down to 1e-12 {np.abs(res['rb32'][big] / want_w[big] - 1).max():.2e}")
+    np.testing.assert_allclose(res["rb32"][heavy], want_w[heavy], rtol=1e-2 if seam else 2e-5)
+    np.testing.assert_allclose(res["rb32"][big], want_w[big], rtol=3e-2 if seam else 2e-4)
 
 
 def test_philox_noise_statistics_and_determinism(mcl):

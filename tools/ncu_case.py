@@ -30,8 +30,9 @@ def main():
     if a.n:
         wl["n"] = a.n
     lm = bench.landmarks_for(wl["L"])
-    f = mcl.Filter(n_particles=wl["n"], n_trials=wl["T"], landmarks=lm, likelihood=a.likelihood, max_landmarks=wl["L"])
-    tr = bench.Truth(lm, seed=7, T=wl["T"], fan=(a.likelihood == "rb_fan"))
+    f = mcl.Filter(n_particles=wl["n"], n_trials=wl["T"], landmarks=lm, likelihood=a.likelihood, max_landmarks=wl["L"],
+                   sigma_obs=[0.3, float(np.deg2rad(2.0))] if a.likelihood in ("rb", "rb32") else None)
+    tr = bench.Truth(lm, seed=7, T=wl["T"], fan=(a.likelihood == "rb_fan"), rb=(a.likelihood in ("rb", "rb32")))
     f.init_particles(tr.pose())
     for _ in range(a.steps):
         tr.advance()
