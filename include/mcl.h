@@ -100,6 +100,12 @@ typedef struct mcl_config {
     double fan_range;       /* scan range [m] (SCN_SENS_RANGE_m = 15)                      */
     double fan_half_angle;  /* half opening angle of the fan [rad] (SCN_SENS_ANGLE_rps = 80 deg) */
     double fan_miss_chi2;   /* chi^2 charged for a detected landmark outside the particle's fan */
+    int32_t underflow_rule; /* 1 (default): mirror particle_filter.py:234-237 -- when every pw * bn would underflow to 0
+                               in the reference's fp64 product the weights are reset to 1/NP (mcl_stats.underflow);
+                               0: pure log-domain weights (never reset unless every stored log-weight is -inf / NaN).
+                               With hundreds of landmarks the reference underflows on any un-resampled second step
+                               (SURVEY.md section 0.1): long runs on such maps want 0. */
+    int32_t reserved0;
 } mcl_config;
 
 /* Per-trial scalars of one step; the reference returns max_idx/max_val/x_est from main_pf
@@ -123,7 +129,13 @@ typedef struct mcl_stats {
     int32_t step;      /* number of mcl_step/mcl_predict_weight calls so far                */
     int32_t derived;   /* 1 once log_norm, max_weight, mean and cov have been derived from the sums:
                           the kernels write only the sums; mcl_get_stats derives the rest on the host */
-    int32_t reserved;
+    int32_t underflow; /* 1: the reference's degenerate-weight rule fired (particle_filter.py:234-237): every product
+                          pw * bn underflowed to 0 in fp64 (or every stored log-weight is -inf / NaN), the sum is 0,
+                          the quotient NaN, and the weights were reset to 1/NP.  ess = NP, max_idx = 0, est = particle
+                          0, max_weight = 1/NP; the stored log-weights are to be read as all-equal (the next step,
+                          the resampler and mcl_get_weights do so); mean / cov keep the log-domain weights. */
+    double abs_shift;  /* log of the reference's UN-normalised weight pw * bn minus the stored log-weight (what the
+                          underflow test adds to max_logw); 1e300 when no likelihood step defines it */
 } mcl_stats;
 
 int mcl_abi_version(void);

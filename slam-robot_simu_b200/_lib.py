@@ -67,6 +67,8 @@ class mcl_config(C.Structure):
         ("fan_range", C.c_double),
         ("fan_half_angle", C.c_double),
         ("fan_miss_chi2", C.c_double),
+        ("underflow_rule", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 
@@ -87,7 +89,8 @@ class mcl_stats(C.Structure):
         ("resampled", C.c_int32),
         ("step", C.c_int32),
         ("derived", C.c_int32),
-        ("reserved", C.c_int32),
+        ("underflow", C.c_int32),
+        ("abs_shift", C.c_double),
     ]
 
 

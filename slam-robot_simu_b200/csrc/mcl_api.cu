@@ -264,6 +264,8 @@ void fill_prep(mcl_filter *h, PrepParams &p, const double *z_dev, const double *
     p.r_dist = c.sigma_obs[0];
     p.dir_sigma = c.sigma_obs[1];
     p.inv_n = h->delta;
+    p.n_global = static_cast<double>(c.n_global);
+    p.underflow_rule = c.underflow_rule;
     p.seed = c.seed;
     p.step = h->step;
 }
@@ -305,6 +307,8 @@ int ensure_stats(mcl_filter *h, cudaStream_t st) {
     m.stats = h->stats;
     m.cur = h->state[h->cur];
     m.ld = h->lay.ld;
+    m.n_global = static_cast<double>(h->cfg.n_global);
+    m.apply_rule = (h->cfg.n_global == h->cfg.n_particles) ? 1 : 0;  // a shard leaves the rule to the merge of all shards
     launch_pdl(k_merge, dim3(h->lay.T), dim3(kStepThreads), 0, st, pdl_enabled() && !h->profiling, m);
     MCL_LAUNCH_CHECK(h, "k_merge");
     h->stats_dirty = false;
@@ -597,6 +601,7 @@ int mcl_config_default(mcl_config *cfg, double period_ms) {
     cfg->fan_range = 15.0;              // graph_based_slam.py:901
     cfg->fan_half_angle = 80.0 * deg;   // :902
     cfg->fan_miss_chi2 = 18.0;          // two 3-sigma residuals
+    cfg->underflow_rule = 1;            // particle_filter.py:234-237
     return MCL_OK;
 }
 
@@ -1255,6 +1260,7 @@ int mcl_shard_merge(mcl_filter *h, const mcl_stats *records_dev, int n_shards, v
     mp.G = n_shards;
     mp.m = h->cfg.n_particles;
     mp.out = h->stats;
+    mp.apply_rule = 0;  // (host-driven path: the records do not carry particle 0's pose)
     k_shard_merge<<<1, 32, 0, S(stream)>>>(mp);
     MCL_LAUNCH_CHECK(h, "k_shard_merge");
     h->tile_prefix_valid = false;
@@ -1316,10 +1322,10 @@ void fill_xchg(mcl_filter *h, XchgParams &x, uint32_t flags, int mode) {
 int launch_xchg_stats(mcl_filter *h, int mode, cudaStream_t st) {
     XchgParams x;
     fill_xchg(h, x, 0u, mode);
+    x.cur = h->state[h->cur];
     if ((mode & kXchgPush) && h->stats_dirty) {
         x.partials = h->partials;
         x.n_partials = h->lay.bpt;
-        x.cur = h->state[h->cur];
         h->stats_dirty = false;
     }
     k_xchg_stats<<<1, kStepThreads, 0, st>>>(x);

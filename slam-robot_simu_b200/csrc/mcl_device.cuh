@@ -46,7 +46,19 @@ struct PrepOut {
     float wq_scale;
     int32_t do_resample;
     int32_t L;
+    double abs_shift;      // log(pw * bn of the reference, un-normalised) - stored log-weight, for THIS step's weights
+    int32_t uniform;       // the stored weights underflowed in the reference's arithmetic: read them as all-equal
+    int32_t pad;
 };
+
+// particle_filter.py:234-237: pw_update / sum is NaN when every product pw * bn underflowed to 0 in fp64, and NaN
+// weights are replaced by 1/NP.  A product vanishes below half the smallest denormal, 2^-1075.
+constexpr double kLogUnderflow = -745.1332191019412;
+constexpr double kNoAbsShift = 1.0e300;  // no likelihood step defines the absolute scale (set_particles, RB models)
+__host__ __device__ inline bool weights_underflowed(double max_logw, double sum_w, double abs_shift) {
+    // (written so that NaN anywhere counts as underflow: the reference's isnan() test catches exactly that)
+    return !(sum_w > 0.0 && sum_w < 1.0e300 && max_logw + abs_shift >= kLogUnderflow);
+}
 
 // ---------------------------------------------------------------------------------------------
 // The transcendental part of mcl_stats from its raw sums: log-normaliser, weight of the MAP particle,

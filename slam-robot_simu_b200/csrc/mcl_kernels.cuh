@@ -84,6 +84,8 @@ struct PrepParams {
     int likelihood;
     double ess_threshold, vdt, wdt, inv_s0sq, inv_s1sq, lik_const, inv_n;
     double fan_range, fan_tan, fan_miss, r_dist, dir_sigma;  // MCL_LIK_RB_FAN
+    double n_global;        // particles of the whole filter (the uniform reset of particle_filter.py:234-237)
+    int underflow_rule;     // mcl_config::underflow_rule
     uint64_t seed;
     uint32_t step;
 };
@@ -109,6 +111,7 @@ struct PrepIn {
     double est[3];     // MAP pose of the previous step
     double max_logw;   // maximum and sum of the stored weights (weight map)
     double sum_w;
+    int uniform;       // the stored weights underflowed (reference arithmetic): all-equal, sum_w = n_global
 };
 __device__ __noinline__ void prep_block(const PrepParams &p, const PrepIn &in, const TrigEntry *trig, int t,
                                         int do_resample, double ofs, double *red) {
@@ -221,6 +224,11 @@ __device__ __noinline__ void prep_block(const PrepParams &p, const PrepIn &in, c
         po->ref[1] = ry;
         po->ref[2] = rth;
         po->max_prev = in.max_logw;
+        po->uniform = in.uniform;
+        // absolute scale of the weights this step will store: log(pw_prev) = stored - log(sum) (or -log NP after a
+        // resampling or a uniform reset), log(bn) = log-likelihood; the stored value is relative to c_shift
+        const bool cartesian = p.likelihood == MCL_LIK_PAIR || p.likelihood == MCL_LIK_MOMENT || p.likelihood == MCL_LIK_PAIR_F32;
+        po->abs_shift = (p.z != nullptr && cartesian && p.underflow_rule) ? po->c_shift - log(do_resample ? p.n_global : in.sum_w) : kNoAbsShift;
         po->lik_const = p.lik_const;
         const WeightMap wm = make_weight_map(in.max_logw, in.sum_w);
         po->wq_m = wm.m;
@@ -389,7 +397,19 @@ struct MergeScratch {  // shared memory of one merge (256 threads)
 };
 
 // (max, sum w, sum w^2) over the nb partial records of trial t; all 256 threads, result in every thread
-__device__ __noinline__ void merge_light(const double *pp, int nb, MergeScratch &sc, float &M, double &s1, double &s2) {
+__device__ __noinline__ void merge_light_raw(const double *pp, int nb, MergeScratch &sc, float &M, double &s1, double &s2);
+// ... with the reference's underflow rule applied: `uf` and the uniform (0, N, N) when it fired
+__device__ __forceinline__ void merge_light(const double *pp, int nb, MergeScratch &sc, float &M, double &s1, double &s2,
+                                            double abs_shift, double n_global, int &uf) {
+    merge_light_raw(pp, nb, sc, M, s1, s2);
+    uf = weights_underflowed(static_cast<double>(M), s1, abs_shift) ? 1 : 0;
+    if (uf) {
+        M = 0.0f;
+        s1 = n_global;
+        s2 = n_global;
+    }
+}
+__device__ __noinline__ void merge_light_raw(const double *pp, int nb, MergeScratch &sc, float &M, double &s1, double &s2) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float mx = -3.4028234e38f;
     double a1 = 0.0, a2 = 0.0;
@@ -489,7 +509,7 @@ __device__ __noinline__ void merge_best(const double *pp, int nb, MergeScratch &
 // instruction cache (once per step on one SM), hence small: rolled loops, no libm -- log-normaliser, mean and
 // covariance are derived from the sums where they are consumed (derive_stats).
 __device__ __noinline__ void merge_full(const double *pp, int nb, mcl_stats *st, const float *ex, const float *ey,
-                                        const float *eth, unsigned long long *dbg) {
+                                        const float *eth, unsigned long long *dbg, double n_global, bool apply_rule) {
     constexpr int NW = kStepThreads / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ double s_part[NW][kPart];
@@ -569,9 +589,17 @@ __device__ __noinline__ void merge_full(const double *pp, int nb, mcl_stats *st,
         for (int w = 1; w < NW; ++w)
             if (s_bk[w] > bk || (s_bk[w] == bk && s_bi[w] < bj)) { bk = s_bk[w]; bj = s_bi[w]; }
         const double s1 = s_part[0][1], s2 = s_part[0][2];
-        st->max_logw = static_cast<double>(MM);
-        st->ess = s1 * s1 / s2;  // 1 / sum (w/s1)^2, particle_filter.py:210
-        st->raw[11] = static_cast<double>(float_from_order_key(bk));  // stored log-weight of the MAP particle
+        // particle_filter.py:234-237 (a shard of a sharded filter leaves the decision to the merge of all shards)
+        const bool uf = apply_rule && weights_underflowed(static_cast<double>(MM), s1, st->abs_shift);
+        if (uf) {
+            bj = 0u;  // np.argmax of all-equal weights (:116)
+            st->sum_w = n_global;
+            st->sum_w2 = n_global;
+        }
+        st->underflow = uf ? 1 : 0;
+        st->max_logw = uf ? 0.0 : static_cast<double>(MM);
+        st->ess = uf ? n_global : s1 * s1 / s2;  // 1 / sum (w/s1)^2, particle_filter.py:210
+        st->raw[11] = uf ? 0.0 : static_cast<double>(float_from_order_key(bk));  // stored log-weight of the MAP particle
         st->max_idx = bj;
         st->est[0] = __ldcg(ex + bj);
         st->est[1] = __ldcg(ey + bj);
@@ -588,13 +616,15 @@ struct MergeParams {
     mcl_stats *stats;
     StateView cur;
     long long ld;
+    double n_global;
+    int apply_rule;
 };
 __global__ void __launch_bounds__(kStepThreads) k_merge(const MergeParams p) {
     cudaGridDependencySynchronize();  // launched programmatically behind k_step: its launch latency is hidden
     const int t = blockIdx.x;
     const long long off = static_cast<long long>(t) * p.ld;
     merge_full(p.partials + static_cast<long long>(t) * p.bpt * kPart, p.bpt, p.stats + t, p.cur.x + off, p.cur.y + off,
-               p.cur.th + off, nullptr);
+               p.cur.th + off, nullptr, p.n_global, p.apply_rule != 0);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -677,6 +707,7 @@ struct ScanShared {
     double ofs;
     float wq_m, wq_scale;
     int resample;
+    int uniform;  // the stored weights underflowed in the reference's arithmetic (particle_filter.py:234-237): all-equal
     unsigned int tile;
 };
 
@@ -729,7 +760,8 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
     const long long soff = static_cast<long long>(t) * p.ld;
     const double *pp = p.partials + static_cast<long long>(t) * p.n_partials * kPart;
     if (stats_cta) {
-        merge_full(pp, p.n_partials, p.stats + t, p.cur.x + soff, p.cur.y + soff, p.cur.th + soff, nullptr);
+        merge_full(pp, p.n_partials, p.stats + t, p.cur.x + soff, p.cur.y + soff, p.cur.th + soff, nullptr, p.prep.n_global,
+                   p.n_global == p.n);
         return;
     }
     const mcl_stats *stp = p.stats + t;
@@ -763,6 +795,7 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
             s_sc.wq_m = __uint_as_float(a.x);
             s_sc.wq_scale = __uint_as_float(a.y);
             s_sc.resample = static_cast<int>(a.z);
+            s_sc.uniform = static_cast<int>(b.w);
             s_sc.ofs = __hiloint2double(static_cast<int>(b.y), static_cast<int>(b.x));
         }
     }
@@ -771,10 +804,12 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
     double st_max = 0.0, st_sum = 1.0;
     if (merger || p.n_partials == 0) {  // CTA-uniform: this CTA derives the scalars itself
         double st_ess;
+        int st_uniform;
         if (merger) {
             float M;
             double s1, s2;
-            merge_light(pp, p.n_partials, s_merge, M, s1, s2);
+            // (a shard of a sharded filter never merges here: its statistics exchange has set n_partials = 0)
+            merge_light(pp, p.n_partials, s_merge, M, s1, s2, stp->abs_shift, p.prep.n_global, st_uniform);
             st_max = static_cast<double>(M);
             st_sum = s1;
             st_ess = s1 * s1 / s2;
@@ -782,6 +817,7 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
             st_max = stp->max_logw;
             st_sum = stp->sum_w;
             st_ess = stp->ess;
+            st_uniform = stp->underflow;
         }
         if (tid == 0) {
             const bool planned = p.plan != nullptr;
@@ -790,12 +826,14 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
             const WeightMap w0 = make_weight_map(st_max, st_sum);
             const double o = planned ? p.plan->ofs : (p.use_override ? p.ofs_override : (rs ? comb_offset(p.prep, t) : 0.0));
             s_sc.resample = rs;
+            s_sc.uniform = st_uniform;
             s_sc.wq_m = w0.m;
             s_sc.wq_scale = w0.scale;
             s_sc.ofs = o;
             if (merger && !prep_cta) {
                 const uint4 va = make_uint4(__float_as_uint(w0.m), __float_as_uint(w0.scale), static_cast<unsigned int>(rs), p.epoch);
-                const uint4 vb = make_uint4(static_cast<unsigned int>(__double2loint(o)), static_cast<unsigned int>(__double2hiint(o)), p.epoch, 0u);
+                const uint4 vb = make_uint4(static_cast<unsigned int>(__double2loint(o)), static_cast<unsigned int>(__double2hiint(o)), p.epoch,
+                                            static_cast<unsigned int>(st_uniform));
                 asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(pub), "r"(va.x), "r"(va.y), "r"(va.z), "r"(va.w) : "memory");
                 asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(pub + 1), "r"(vb.x), "r"(vb.y), "r"(vb.z), "r"(vb.w) : "memory");
             }
@@ -803,6 +841,7 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
         __syncthreads();
     }
     const int resample = s_sc.resample;
+    const int uniform = s_sc.uniform;
     const double ofs = s_sc.ofs;
     WeightMap wm;
     wm.m = s_sc.wq_m;
@@ -813,10 +852,12 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
         PrepIn in;
         in.max_logw = st_max;
         in.sum_w = st_sum;
+        in.uniform = uniform;
         if (p.n_partials > 0) {
             float bv;
             uint32_t bi;
             merge_best(pp, p.n_partials, s_merge, bv, bi);
+            if (uniform) bi = 0u;  // np.argmax of all-equal weights (:116)
             in.est[0] = p.cur.x[soff + bi];
             in.est[1] = p.cur.y[soff + bi];
             in.est[2] = p.cur.th[soff + bi];
@@ -855,8 +896,9 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
     double qd[kScanItems];  // integer-valued: rint(w * 2^52)
     if (j0 < p.n) {
         // the state arrays are padded to a multiple of 128 elements, so the vector loads stay in bounds
-        const float4 a = *reinterpret_cast<const float4 *>(lw + j0);
-        const float4 b = *reinterpret_cast<const float4 *>(lw + j0 + 4);
+        float4 a = *reinterpret_cast<const float4 *>(lw + j0);
+        float4 b = *reinterpret_cast<const float4 *>(lw + j0 + 4);
+        if (uniform) a = b = make_float4(0.f, 0.f, 0.f, 0.f);  // CTA-uniform: weights reset to 1/NP (:234-237)
         const float v[kScanItems] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         if (j0 + kScanItems <= p.n) {
 #pragma unroll
@@ -1465,6 +1507,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
                 th[0] = vt.x; th[1] = vt.y; th[2] = vt.z; th[3] = vt.w;
                 // weights stay relative to their maximum: pw * bn (:194) in logs, minus a per-step constant
                 lwp[0] = vw.x - max_prev; lwp[1] = vw.y - max_prev; lwp[2] = vw.z - max_prev; lwp[3] = vw.w - max_prev;
+                if (s_prep.uniform) lwp[0] = lwp[1] = lwp[2] = lwp[3] = 0.0f;  // weights were reset to 1/NP (:234-237)
             }
 
             // ---------------- motion noise (unit normals; Motion A scales them by sqrt(diag Q)) ----------------
@@ -1786,6 +1829,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
         st->ref[2] = s_prep.ref[2];
         st->resampled = resample;
         st->step = static_cast<int>(p.step + 1u);
+        st->abs_shift = s_prep.abs_shift;
         p.tickets[t * 4 + 0] = 0u;
     }
     partial_write(ws, p.partials + (static_cast<long long>(t) * p.bpt + blockIdx.x) * kPart, p.dbg);
@@ -1840,6 +1884,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_reduce(const StepParams p, 
         st->ref[0] = ref_x;
         st->ref[1] = ref_y;
         st->ref[2] = ref_th;
+        st->abs_shift = kNoAbsShift;  // weights set by the caller: relative only, no likelihood step behind them
         p.tickets[t * 4 + 0] = 0u;
     }
     partial_write(ws, p.partials + (static_cast<long long>(t) * p.bpt + blockIdx.x) * kPart, nullptr);
@@ -1889,6 +1934,8 @@ __global__ void __launch_bounds__(256) k_gather(const GatherParams p) {
             st->sum_w2 = p.n_global;
             st->raw[11] = 0.0;
             st->derived = 0;
+            st->underflow = 0;  // the log-weights were physically reset
+            st->abs_shift = kNoAbsShift;
         }
     }
 }
@@ -1977,6 +2024,7 @@ __global__ void k_init_stats(mcl_stats *stats, const double *pose, double n_glob
     z.ess = n_global;
     z.max_idx = 0;
     z.sum_w = n_global; z.sum_w2 = n_global; z.max_logw = 0.0;
+    z.abs_shift = kNoAbsShift;
     for (int k = 0; k < 3; ++k) { z.est[k] = pose[3 * t + k]; z.mean[k] = pose[3 * t + k]; z.ref[k] = pose[3 * t + k]; }
     stats[t] = z;
 }
@@ -2007,6 +2055,7 @@ struct ShardMergeParams {
     int G;
     long long m;           // particles per shard: global index of shard g's particle i is g * m + i
     mcl_stats *out;        // this handle's statistics block (becomes the global one)
+    int apply_rule;        // device-driven exchange: the records carry particle 0's pose, the underflow rule can be applied
 };
 __device__ __noinline__ void shard_merge_records(const ShardMergeParams p, bool derive) {
     double M = p.rec[0].max_logw;
@@ -2044,7 +2093,7 @@ __device__ __noinline__ void shard_merge_records(const ShardMergeParams p, bool 
         }
     }
     const mcl_stats &b = p.rec[bg];
-    mcl_stats o = p.rec[0];  // ref, resampled, step: identical on every shard
+    mcl_stats o = p.rec[0];  // ref, resampled, step, abs_shift: identical on every shard
     o.max_logw = M;
     o.sum_w = s1;
     o.sum_w2 = s2;
@@ -2053,6 +2102,20 @@ __device__ __noinline__ void shard_merge_records(const ShardMergeParams p, bool 
     o.raw[11] = bv;
     o.max_idx = static_cast<uint32_t>(static_cast<long long>(bg) * p.m + b.max_idx);
     for (int c = 0; c < 3; ++c) o.est[c] = b.est[c];
+    o.underflow = 0;
+    if (p.apply_rule && weights_underflowed(M, s1, o.abs_shift)) {
+        // particle_filter.py:234-237 on the GLOBAL weights: reset to 1/NP; arg-max = the first particle, whose pose
+        // shard 0 left in its record's (otherwise host-derived) mean
+        const double ng = static_cast<double>(p.m) * p.G;
+        o.underflow = 1;
+        o.max_logw = 0.0;
+        o.sum_w = ng;
+        o.sum_w2 = ng;
+        o.ess = ng;
+        o.raw[11] = 0.0;
+        o.max_idx = 0;
+        for (int c = 0; c < 3; ++c) o.est[c] = p.rec[0].mean[c];
+    }
     o.derived = 0;
     if (derive) derive_stats(o);  // (libm, once per step on one thread: the device-driven step leaves it to the host)
     *p.out = o;
@@ -2103,7 +2166,11 @@ __global__ void __launch_bounds__(kStepThreads) k_xchg_stats(const XchgParams p)
     static_assert(sizeof(mcl_stats) % sizeof(unsigned long long) == 0, "mcl_stats is copied in 8-byte words");
     if (p.mode & kXchgPush) {
         if (p.n_partials > 0)
-            merge_full(p.partials, p.n_partials, p.stats, p.cur.x, p.cur.y, p.cur.th, nullptr);
+            merge_full(p.partials, p.n_partials, p.stats, p.cur.x, p.cur.y, p.cur.th, nullptr, 0.0, false);
+        if (tid < 3 && p.cur.x != nullptr) {  // this shard's first particle: the MAP pose of a filter reset to 1/NP
+            const float *a = (tid == 0) ? p.cur.x : (tid == 1 ? p.cur.y : p.cur.th);
+            p.stats->mean[tid] = static_cast<double>(a[0]);
+        }
         __syncthreads();
         const unsigned long long *src = reinterpret_cast<const unsigned long long *>(p.stats);
         for (int i = tid; i < pv.G * kWords; i += blockDim.x) {
@@ -2126,6 +2193,7 @@ __global__ void __launch_bounds__(kStepThreads) k_xchg_stats(const XchgParams p)
             mp.G = pv.G;
             mp.m = pv.m;
             mp.out = p.stats;
+            mp.apply_rule = 1;
             shard_merge_records(mp, false);
             p.plan->gate = (p.stats->ess < p.ess_threshold) ? 1 : 0;  // particle_filter.py:211, on the GLOBAL ESS
         }
@@ -2241,6 +2309,7 @@ __global__ void __launch_bounds__(kScanThreads) k_shard_total(const float *lw, l
     if (tid == 0) s_wm = make_weight_map(stats[0].max_logw, stats[0].sum_w);
     __syncthreads();
     const WeightMap wm = s_wm;
+    const bool uniform = stats[0].underflow != 0;  // (global statistics: every shard takes the same branch)
     unsigned long long run = 0ull;  // thread 0: weight of the segment's tiles so far
     const long long t0 = static_cast<long long>(blockIdx.x) * tiles_per_seg;
     const long long t1 = min(static_cast<long long>(tpt), t0 + tiles_per_seg);
@@ -2249,8 +2318,9 @@ __global__ void __launch_bounds__(kScanThreads) k_shard_total(const float *lw, l
         const long long j0 = tile * kScanTile + static_cast<long long>(tid) * kScanItems;
         unsigned long long acc = 0ull;
         if (j0 < n) {  // the state arrays are padded to a multiple of 128 elements: the vector loads stay in bounds
-            const float4 a = *reinterpret_cast<const float4 *>(lw + j0);
-            const float4 b = *reinterpret_cast<const float4 *>(lw + j0 + 4);
+            float4 a = *reinterpret_cast<const float4 *>(lw + j0);
+            float4 b = *reinterpret_cast<const float4 *>(lw + j0 + 4);
+            if (uniform) a = b = make_float4(0.f, 0.f, 0.f, 0.f);
             const float v[kScanItems] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int k = 0; k < kScanItems; ++k)
@@ -2299,7 +2369,7 @@ __global__ void k_export_weights(const float *lw, const mcl_stats *stats, double
     const WeightMap wm = make_weight_map(stats[t].max_logw, stats[t].sum_w);
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const float v = lw[t * ld + i];
+        const float v = stats[t].underflow ? 0.0f : lw[t * ld + i];  // reset to 1/NP (:234-237)
         if (w) w[t * n + i] = static_cast<double>(weight_scaled(v, wm)) * kInvTwo52;
         if (q) q[t * n + i] = quantize_weight(v, wm);
     }

@@ -33,7 +33,7 @@ class Filter:
     def __init__(self, n_particles=1000, n_trials=1, period_ms=100.0, landmarks=None, likelihood="pair",
                  motion="a", device=0, seed=42, ess_threshold=None, q_std=None, sigma_obs=None,
                  max_landmarks=None, n_global=None, slot_base=0, motion_b_alpha=None, vel=None, yaw_rate=None,
-                 dt=None, fan_range=None, fan_half_angle=None, fan_miss_chi2=None):
+                 dt=None, fan_range=None, fan_half_angle=None, fan_miss_chi2=None, underflow_rule=True):
         torch = _torch()
         self.lib = L.load()
         cfg = default_config(period_ms)
@@ -51,6 +51,7 @@ class Filter:
         for name, val in (("fan_range", fan_range), ("fan_half_angle", fan_half_angle), ("fan_miss_chi2", fan_miss_chi2)):
             if val is not None:
                 setattr(cfg, name, float(val))
+        cfg.underflow_rule = 1 if underflow_rule else 0  # particle_filter.py:234-237 (NaN weights -> 1/NP)
         cfg.motion = {"a": L.MCL_MOTION_A, "b": L.MCL_MOTION_B}[motion]
         # ESS_TH = NP / 100 (particle_filter.py:33)
         cfg.ess_threshold = float(ess_threshold) if ess_threshold is not None else cfg.n_global / 100.0
@@ -383,7 +384,7 @@ def stats_to_dict(s: L.mcl_stats):
     return dict(log_norm=s.log_norm, ess=s.ess, max_weight=s.max_weight, max_idx=int(s.max_idx),
                 est=np.array(s.est[:]), mean=np.array(s.mean[:]), cov=np.array(s.cov[:]).reshape(3, 3),
                 sum_w=s.sum_w, sum_w2=s.sum_w2, max_logw=s.max_logw, raw=np.array(s.raw[:]), ref=np.array(s.ref[:]),
-                resampled=int(s.resampled), step=int(s.step))
+                resampled=int(s.resampled), step=int(s.step), underflow=int(s.underflow))
 
 
 def log_uniform(n_global):

@@ -418,19 +418,33 @@ def test_likelihood_64_and_1024_landmarks(mcl, scenario):
         seen_from = O.f_motion(truth, P) if scenario == "running" else truth
         z = O.world2robot(seen_from, lm) + rng.normal(0, 0.3, (Lm, 2))
         noise = np.zeros((3, 1, n), dtype=np.float32)
-        res = {}
+        res, mirrored, flags = {}, {}, {}
         for lik in ("pair", "moment", "pair32"):
-            f = mcl.Filter(n_particles=n, landmarks=lm, likelihood=lik, max_landmarks=Lm)
-            f.set_particles(pos[0], pos[1], pos[2], None)
-            f.predict_weight(z[None], noise=noise)
-            x, y, th, _ = f.get_particles()
-            got_px = np.stack([x[0], y[0], th[0]]).astype(np.float64)
-            res[lik] = f.weights()[0]
+            for rule in (False, True):
+                f = mcl.Filter(n_particles=n, landmarks=lm, likelihood=lik, max_landmarks=Lm, underflow_rule=rule)
+                f.set_particles(pos[0], pos[1], pos[2], None)
+                f.predict_weight(z[None], noise=noise)
+                x, y, th, _ = f.get_particles()
+                got_px = np.stack([x[0], y[0], th[0]]).astype(np.float64)
+                (mirrored if rule else res)[lik] = f.weights()[0]
+                flags[lik, rule] = f.stats()[0].underflow
+        # pure log-domain weights (underflow_rule = 0) against the log-domain oracle
         ll = O.loglik_cartesian(got_px, z, lm, 0.3, 0.3)
         want_w, _ = O.update_weights_log(np.full(n, -np.log(float(n))), ll)
         _assert_weights_close(res["pair"], want_w)
         _assert_weights_close(res["moment"], want_w)
         _assert_weights_close(res["pair32"], want_w, rtol=RTOL if scenario == "running" else 5e-5)
+        # the default mirrors the reference's fp64 PRODUCT (:192-196, :234-237): with 1024 landmarks 0.17 m off, every
+        # product of pdfs underflows, the reference's weights are NaN -> 1/NP, and so are the engine's
+        lit_w = O.normalize(np.full(n, 1.0 / n) * O.likelihood_product(got_px, z, lm, 0.3, 0.3), 1.0 / n)
+        ref_uniform = bool(np.all(lit_w == 1.0 / n))
+        assert ref_uniform == (scenario == "offset" and Lm == 1024)
+        for lik in ("pair", "moment", "pair32"):
+            assert flags[lik, False] == 0 and flags[lik, True] == int(ref_uniform)
+            if ref_uniform:
+                np.testing.assert_allclose(mirrored[lik], 1.0 / n, rtol=1e-6)
+            else:
+                np.testing.assert_array_equal(mirrored[lik], res[lik])
 
 
 def test_motion_b_and_rb_likelihood(mcl, golden_dir):
@@ -741,7 +755,9 @@ def test_single_and_maximum_landmark_counts(mcl):
         z = O.world2robot(truth, lm) + rng.normal(0, 0.3, (Lm, 2))
         out = {}
         for lik in ("pair", "moment"):
-            f = mcl.Filter(n_particles=n, landmarks=lm, likelihood=lik, max_landmarks=max(Lm, 8))
+            # (4096 landmarks seen 0.17 m off: the reference's fp64 product of pdfs is 0 for every particle and its
+            #  weights reset to 1/NP -- test_likelihood_64_and_1024_landmarks covers that; here the log-domain weights)
+            f = mcl.Filter(n_particles=n, landmarks=lm, likelihood=lik, max_landmarks=max(Lm, 8), underflow_rule=False)
             f.set_particles(pos[0], pos[1], pos[2], None)
             f.predict_weight(z[None], noise=np.zeros((3, 1, n), dtype=np.float32))
             x, y, th, _ = f.get_particles()
@@ -1108,3 +1124,97 @@ def test_peer_sharded_philox_run_with_device_gate(mcl):
         assert all(f.shard_plan().resampled == r1 for f in sf.shards)
         fired += r1
     assert 0 < fired < 14  # the gate both fired and held
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's degenerate-weight rule (particle_filter.py:234-237)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("likelihood", ["pair", "moment", "pair32"])
+def test_underflow_resets_the_weights_like_the_reference(mcl, golden_dir, likelihood):
+    """Golden run of the unmodified reference with the robot teleported 40 m away for steps 4 and 5: every pw * bn
+    underflows, the reference's weights become NaN and are reset to 1/NP (max_idx 0, max_val 1/NP).  The engine's
+    log-domain weights never underflow, so it detects the event (largest log(pw * bn) < log 2^-1075) and mirrors the
+    reset.  Stage by stage on the reference's arrays, then free-running through 3 -> 7 with the state carried over."""
+    g = np.load(os.path.join(golden_dir, "pf_underflow.npz"))
+    P = O.PFParams(100)
+    n = P.NP
+
+    def check(f, k, got_px, w_prev):
+        st = f.stats()[0]
+        got_w = f.weights()[0]
+        if k in (4, 5):
+            assert st.underflow == 1 and st.max_idx == 0 == int(g[f"s{k}_max_idx"])
+            np.testing.assert_allclose(got_w, 1.0 / n, rtol=1e-6)
+            assert np.all(g[f"s{k}_pw"] == 1.0 / n)
+            assert st.max_weight == pytest.approx(1.0 / n, rel=1e-12) and st.ess == pytest.approx(n)
+            np.testing.assert_array_equal(np.array(st.est[:]), got_px[:, 0])
+        else:
+            assert st.underflow == 0
+            ll = O.loglik_cartesian(got_px, g[f"s{k}_z_l"], P.LM, 0.3, 0.3)
+            with np.errstate(divide="ignore"):
+                want_w, _ = O.update_weights_log(np.log(w_prev), ll)
+            _assert_weights_close(got_w, want_w)
+            assert st.max_idx == int(np.argmax(want_w))
+        return got_w
+
+    # stage by stage: every step starts from the reference's own arrays
+    for k in range(int(g["n_steps"])):
+        px0 = g[f"s{k}_px_before"].astype(np.float32)
+        lw0 = _logw32(g[f"s{k}_pw_before"])
+        f = mcl.Filter(n_particles=n, landmarks=P.LM, likelihood=likelihood)
+        f.set_particles(px0[0], px0[1], px0[2], lw0)
+        f.predict_weight(g[f"s{k}_z_l"][None], noise=g[f"s{k}_v"].astype(np.float32)[:, None, :])
+        x, y, th, _ = f.get_particles()
+        got_w = check(f, k, np.stack([x[0], y[0], th[0]]).astype(np.float64), _weights_from_logw32(lw0))
+        if k not in (4, 5):
+            _assert_weights_close(got_w, g[f"s{k}_pw"], rtol=2e-3)  # the reference's fp64 poses: fp32 rounding of the inputs
+
+    # free-running: the uniform reset must carry into the next step's weights (pw_before = 1/NP) and into the ESS gate
+    px0 = g["s3_px_before"].astype(np.float32)
+    f = mcl.Filter(n_particles=n, landmarks=P.LM, likelihood=likelihood)
+    f.set_particles(px0[0], px0[1], px0[2], _logw32(g["s3_pw_before"]))
+    w_prev = _weights_from_logw32(_logw32(g["s3_pw_before"]))
+    for k in range(3, 8):
+        f.step(g[f"s{k}_z_l"][None], ofs=0.5 / n, noise=g[f"s{k}_v"].astype(np.float32)[:, None, :])  # device ESS gate
+        st = f.stats()[0]
+        assert st.resampled == 0  # as in the reference run: ESS = NP after a reset
+        x, y, th, _ = f.get_particles()
+        w_prev = check(f, k, np.stack([x[0], y[0], th[0]]).astype(np.float64), w_prev)
+
+
+@pytest.mark.gpu
+def test_underflow_rule_in_the_sharded_filter(mcl):
+    """The same rule on the GLOBAL weights of a device-driven sharded filter: every shard reports the reset, the
+    arg-max is global particle 0, and the forced resampling that follows treats the weights as all-equal -- particles
+    stay bit-identical to the unsharded filter's."""
+    n, G = 1 << 14, 4
+    P = O.PFParams(100)
+    bench = importlib.import_module("bench")
+    truth = bench.Truth(P.LM, seed=9)
+    far = bench.Truth(P.LM, seed=9)
+    far.x = far.x + np.array([[40.0, 40.0, 0.0]])
+    sf = mcl.LocalShardedFilter(n, P.LM, G, likelihood="pair", seed=5)
+    sf.init_particles(truth.pose()[0])
+    ref = mcl.Filter(n_particles=n, landmarks=P.LM, likelihood="pair", seed=5)
+    ref.init_particles(truth.pose()[0])
+    for k, (src, force) in enumerate([(truth, False), (far, False), (far, True), (truth, True), (truth, False)]):
+        truth.advance()
+        far.advance()
+        z = src.observe()
+        if k > 0:
+            ref.restore_stats(sf.shards[0].stats()[0], k)
+        g = sf.step(z, force_resample=force, no_resample=not force)
+        ref.step(z, force_resample=force, no_resample=not force)
+        s1 = ref.stats()[0]
+        assert g["underflow"] == s1.underflow == (1 if src is far else 0)
+        assert all(f.stats()[0].underflow == s1.underflow for f in sf.shards)
+        assert g["max_idx"] == s1.max_idx and g["ess"] == pytest.approx(s1.ess, rel=1e-6)
+        if src is far:
+            assert g["max_idx"] == 0 and g["ess"] == pytest.approx(n)
+            np.testing.assert_allclose(np.concatenate([f.weights()[0] for f in sf.shards]), 1.0 / n, rtol=1e-6)
+        x1, y1, t1, l1 = ref.get_particles()
+        xs, ys, ts, ls = sf.particles()
+        np.testing.assert_array_equal(xs, x1[0])
+        np.testing.assert_array_equal(ts, t1[0])
+        np.testing.assert_array_equal(ls, l1[0])
