@@ -34,6 +34,12 @@ NCU_TRAFFIC = {
                        "ncu --set full of k_step at 32M particles x 64 landmarks (profiles/r01_r_ncu_32M_x64_k_step_summary.csv), per particle x this launch"),
 }
 HAVE_RB32 = True
+# The LITERAL reference class (unmodified /root/reference/particle_filter.py behind oracle/mpl_stub.py, its per-particle
+# Python loop :185-192) at its own default size.  /root/reference does not exist on the GPU box, so this is a constant
+# measured in the authoring container (Intel Xeon, 1 core, 60 steps after 5 warm-up steps), not a live measurement.
+REFERENCE_LITERAL_C0 = {"value": 3.03e4, "unit": "particle-steps/s", "ms_per_step": 33.0, "config": "1000 particles x 5 landmarks",
+                        "where": "authoring container, 1 core of an Intel Xeon; NOT measured on the GPU box (the reference's sources "
+                                 "do not travel there)", "kind": "reference (literal class), recorded constant"}
 PAIR_LOOPS = {
     "pair": {"arithmetic": "fp64, 8 operations per pair", "bound": "FP64 pipe"},
     "pair32": {"arithmetic": "fp32 about the reference pose, 8 operations per pair, two particles per FFMA2 / FADD2", "bound": "FP32 pipe"},
@@ -290,7 +296,8 @@ def cpu_baseline(wl, budget_s=12.0, procs=1):
         times.append(step())
     close()
     t = float(np.median(times))
-    return {"value": n_sample / t, "unit": "particle-steps/s", "cores": procs, "kind": "port",
+    return {"literal_reference_c0": REFERENCE_LITERAL_C0,
+            "value": n_sample / t, "unit": "particle-steps/s", "cores": procs, "kind": "port",
             "sample": f"{len(times)} steps of {n_sample} particles x {wl['L']} landmarks (numpy fp64 oracle, "
                       f"{procs} process{'es' if procs > 1 else ''}), median {t * 1e3:.1f} ms/step"}
 
@@ -731,7 +738,7 @@ def run_b200(args, wl):
                 c4 = WORKLOADS["c4"]
                 lr = timed_run(c4, 3, 3, 0.0, "rb32", min_seconds=0.05)
                 extras["c4_rb_all_landmarks"] = dict(extra_line(c4, lr, 3), likelihood="rb32", pair_loop=pair_loop(c4, lr, "rb32"))
-    cpu = cpu_baseline(wl, procs=1) if not args.no_cpu else None
+    cpu = cpu_baseline(wl, procs=max(1, min(32, os.cpu_count() or 1))) if not args.no_cpu else None
     line = {"metric": "particle-steps/s (predict+weight+resample)", "value": value, "unit": "particle-steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 state / f64 likelihood / u64 scan", "data": "synthetic",

@@ -193,6 +193,13 @@ int mcl_step(mcl_filter *h, const double *z_host, const double *ofs_host, const 
 int mcl_step_dev(mcl_filter *h, const double *z_dev, const double *ofs_dev, const float *noise_dev, uint32_t flags,
                  void *stream);
 
+/* mcl_step followed by mcl_get_stats_begin in ONE crossing of the ABI: the observation is staged through a pinned
+ * ring (no host synchronisation), the two kernels and the statistics merge are enqueued, and the read-back of the
+ * [n_trials] mcl_stats is started.  Collect it with mcl_get_stats_end -- the host is free in between (the drop-in
+ * ParticleFilter.main_pf simulates the next frame's observation there). */
+int mcl_step_async(mcl_filter *h, const double *z_host, const double *ofs_host, const float *noise_dev, uint32_t flags,
+                   void *stream);
+
 /* Recompute mean/cov with the exact two-pass definition (wrap about the circular mean). */
 int mcl_pose_moments(mcl_filter *h, void *stream);
 

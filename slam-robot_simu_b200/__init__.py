@@ -13,6 +13,7 @@ from .engine import Filter, default_config, stats_to_dict  # noqa: E402
 from .particle_filter import ParticleFilter, LazyParticles  # noqa: E402
 from .sharded import LocalShardedFilter, ShardedParticleFilter  # noqa: E402
 from .scan_sensor import ScanSensor  # noqa: E402
+from .trajectory import TrajectoryLog  # noqa: E402
 
-__all__ = ["Filter", "ParticleFilter", "LazyParticles", "ShardedParticleFilter", "LocalShardedFilter", "ScanSensor", "MclError", "mcl_config", "mcl_stats", "default_config",
+__all__ = ["Filter", "ParticleFilter", "LazyParticles", "ShardedParticleFilter", "LocalShardedFilter", "ScanSensor", "TrajectoryLog", "MclError", "mcl_config", "mcl_stats", "default_config",
            "stats_to_dict"]

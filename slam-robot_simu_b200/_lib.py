@@ -130,6 +130,7 @@ PROTOTYPES = {
     "mcl_resample": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
     "mcl_predict_weight": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp]),
     "mcl_step": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, _vp]),
+    "mcl_step_async": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, _vp]),
     "mcl_step_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, _vp]),
     "mcl_pose_moments": (C.c_int, [_vp, _vp]),
     "mcl_get_stats": (C.c_int, [_vp, _P(mcl_stats), _vp]),

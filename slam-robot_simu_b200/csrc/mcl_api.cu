@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -927,6 +928,13 @@ int mcl_step_dev(mcl_filter *h, const double *z_dev, const double *ofs_dev, cons
     return step_impl(h, z_dev, ofs_dev, noise_dev, flags, S(stream));
 }
 
+int mcl_step_async(mcl_filter *h, const double *z_host, const double *ofs_host, const float *noise_dev, uint32_t flags,
+                   void *stream) {
+    int rc = mcl_step(h, z_host, ofs_host, noise_dev, flags, stream);
+    if (rc != MCL_OK) return rc;
+    return mcl_get_stats_begin(h, stream);
+}
+
 int mcl_pose_moments(mcl_filter *h, void *stream) {
     if (h == nullptr) return MCL_ERR_ARG;
     int rc = use_device(h);
@@ -1244,6 +1252,13 @@ int mcl_restore(mcl_filter *h, const mcl_stats *stats_host, uint32_t step, void 
     h->stats_from_particle0 = false;
     h->stats_dirty = false;
     h->tile_prefix_valid = false;
+    if (h->plan != nullptr) {
+        // a shard of a device-driven sharded filter: the resampling gate of the next step lives on the device
+        // (the statistics installed here are the GLOBAL ones of the filter that was saved)
+        const int32_t gate = (stats_host[0].ess < h->cfg.ess_threshold) ? 1 : 0;
+        MCL_CUDA(h, cudaMemcpy(reinterpret_cast<unsigned char *>(h->plan) + offsetof(mcl_shard_plan, gate), &gate, sizeof gate,
+                               cudaMemcpyHostToDevice));
+    }
     return MCL_OK;
 }
 

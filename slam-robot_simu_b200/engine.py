@@ -237,6 +237,23 @@ class Filter:
         self._check(self.lib.mcl_step(self._h, zz.ctypes.data, None if o is None else o.ctypes.data, self._noise_ptr(noise),
                                       flags, self._stream()), "mcl_step")
 
+    def step_async(self, z, ofs=None, noise=None, force_resample=False, no_resample=False):
+        """step() + stats_begin() in one crossing of the C ABI (mcl_step_async); collect with stats_end().
+        `z` must already be a C-contiguous float64 array of (T, L, 2) elements -- no conversion on this path."""
+        flags = self._flags(noise, force_resample, no_resample)
+        if ofs is None and not no_resample:
+            flags |= L.MCL_PHILOX_NOISE
+        o = None if ofs is None else (C.c_double * self.T)(*([float(ofs)] * self.T if np.isscalar(ofs) else [float(v) for v in ofs]))
+        self._check(self.lib.mcl_step_async(self._h, z.ctypes.data, o, self._noise_ptr(noise), flags, self._stream_cached()),
+                    "mcl_step_async")
+
+    def _stream_cached(self):
+        """The CUDA stream handle of the first call (a step every ~50 us cannot afford torch.cuda.current_stream())."""
+        s = getattr(self, "_stream_handle", None)
+        if s is None:
+            s = self._stream_handle = self._stream()
+        return s
+
     def step_dev(self, z_dev, ofs_dev=None, noise=None, force_resample=False, no_resample=False):
         """Same with z (T,L,2) / ofs (T,) fp64 CUDA tensors: no host traffic, graph-capturable."""
         flags = self._flags(noise, force_resample, no_resample)

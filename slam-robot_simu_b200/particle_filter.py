@@ -68,7 +68,7 @@ class ParticleFilter:
     """ParticleFilter(period_ms) -- particle_filter.py:21.  Keyword extras select the larger configs."""
 
     def __init__(self, period_ms, *, n_particles=1000, landmarks=None, noise="numpy", likelihood="pair",
-                 lazy_px=False, force_resample=False, device=0, seed=42, ess_div=100.0):
+                 lazy_px=False, force_resample=False, device=0, seed=42, ess_div=100.0, trajectory=None):
         if noise not in ("numpy", "philox"):
             raise ValueError("noise must be 'numpy' (reference RNG stream) or 'philox' (on-device)")
         self.__DT_s = period_ms / 1000  # :30
@@ -111,6 +111,7 @@ class ParticleFilter:
         self.__ess = float(self.__NP)  # 1 / sum((1/NP)^2)
         self.__ahead = None
         self.last_stats = None
+        self.trajectory = trajectory  # a TrajectoryLog (or None): every main_pf() is recorded into it
 
     @staticmethod
     def __mvn_factor(cov):
@@ -167,8 +168,9 @@ class ParticleFilter:
             noise = np.ascontiguousarray(v, dtype=np.float32)[:, None, :]
         z_l = z_ahead if z_ahead is not None else self.__observation(self.__x_true)  # :110
 
-        flt.step(z_l[None], ofs=ofs, noise=noise, force_resample=do_resample, no_resample=not do_resample)
-        flt.stats_begin()  # merge + device-to-host copy of the statistics block, enqueued behind the step
+        # one crossing of the C ABI: stage z_l, enqueue k_scan + k_step + the statistics merge, start the read-back
+        flt.step_async(np.ascontiguousarray(z_l, dtype=np.float64), ofs=ofs, noise=noise, force_resample=do_resample,
+                       no_resample=not do_resample)
         if self.__noise == "philox":
             # The kernels are in flight: simulate the NEXT frame's ground truth and observation now (:100, :110 of
             # the next call).  Neither depends on the filter, and with on-device noise the observation draw is the
@@ -185,6 +187,8 @@ class ParticleFilter:
         else:
             x, y, th, _ = flt.get_particles(want_logw=False)
             px = np.stack([x[0], y[0], th[0]]).astype(np.float64)
+        if self.trajectory is not None:
+            self.trajectory.record(self.__x_true, x_est, st.max_idx, st.max_weight, st, px)
         return self.__LM, self.__x_true, x_est, px, self.__Q, int(st.max_idx), float(st.max_weight)
 
     # -- extension a-14: weighted mean and covariance that feed mylib/error_ellipse.py:39-55 ------

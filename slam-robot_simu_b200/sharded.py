@@ -496,6 +496,33 @@ class ShardedParticleFilter:
         x, y, th, lw = self.flt.get_particles(device=device)
         return x[0], y[0], th[0], lw[0]
 
+    # -- checkpoint: one file per rank -------------------------------------------------------------
+    def save(self, prefix):
+        """Every rank writes `<prefix>.rank<g>.npz`: its shard (Filter.save: particles, log-weights, the GLOBAL
+        statistics block its handle holds, step counter, config).  Call on all ranks, between steps."""
+        self.drain()
+        self.flt.save(f"{prefix}.rank{self.rank}.npz")
+
+    def restore(self, prefix):
+        """Load the shard written by save() into this (already constructed and connected) filter: the particles, the
+        global statistics and the step counter.  The filter then continues bit-identically to the one that was saved."""
+        with np.load(f"{prefix}.rank{self.rank}.npz") as z:
+            cfg = self._L.mcl_config.from_buffer_copy(z["config"].tobytes())
+            if (cfg.n_global, cfg.slot_base, cfg.n_particles) != (self.n_global, self.rank * self.m, self.m):
+                raise ValueError(f"{prefix}: checkpoint of another sharding ({cfg.n_global} particles, base {cfg.slot_base})")
+            self.flt.set_particles(z["x"], z["y"], z["yaw"], z["logw"], skip_stats=True)
+            st = self._L.mcl_stats.from_buffer_copy(z["stats"].tobytes())
+            self.flt.restore_stats(st, int(z["step"]))
+            self.step_count = int(z["step"])
+        self.global_stats = self._stats_to_dict(self.flt.stats()[0])
+        self._pending = 0
+        self._spec = None
+        if self.transport == "nccl":
+            self._enqueue_totals()
+            self.torch.cuda.current_stream().synchronize()
+            self._totals = [int(v) for v in self._totals_host.tolist()]
+        return self.global_stats
+
 
 class LocalShardedFilter:
     """The same sharded filter driven by ONE process: shard g is a Filter on devices[g] (several GPUs of the box,
@@ -546,6 +573,17 @@ class LocalShardedFilter:
 
     def stats(self, shard=0):
         return self._stats_to_dict(self.shards[shard].stats()[0])
+
+    def save(self, prefix):
+        """One file per shard, `<prefix>.rank<g>.npz` (the layout ShardedParticleFilter.save writes)."""
+        for g, f in enumerate(self.shards):
+            f.save(f"{prefix}.rank{g}.npz")
+
+    def restore(self, prefix):
+        for g, f in enumerate(self.shards):
+            with np.load(f"{prefix}.rank{g}.npz") as z:
+                f.set_particles(z["x"], z["y"], z["yaw"], z["logw"], skip_stats=True)
+                f.restore_stats(self._L.mcl_stats.from_buffer_copy(z["stats"].tobytes()), int(z["step"]))
 
     def particles(self):
         parts = [f.get_particles() for f in self.shards]

@@ -1218,3 +1218,57 @@ def test_underflow_rule_in_the_sharded_filter(mcl):
         np.testing.assert_array_equal(xs, x1[0])
         np.testing.assert_array_equal(ts, t1[0])
         np.testing.assert_array_equal(ls, l1[0])
+
+
+@pytest.mark.gpu
+def test_sharded_checkpoint_restores_a_bit_identical_filter(mcl, tmp_path):
+    """SURVEY 8(f)-4 for the sharded filter: one file per shard; the restored filter (fresh handles, fresh peer
+    mappings) continues exactly like the saved one -- device gate, Philox counters and weight map included."""
+    n, G, Lm = 1 << 16, 4, 16
+    bench = importlib.import_module("bench")
+    lm = bench.landmarks_for(Lm)
+    truth = bench.Truth(lm, seed=21)
+    a = mcl.LocalShardedFilter(n, lm, G, likelihood="moment", seed=77)
+    a.init_particles(truth.pose()[0])
+    zs = []
+    for _ in range(10):
+        truth.advance()
+        zs.append(truth.observe())
+    for k in range(4):
+        a.step(zs[k])
+    a.save(str(tmp_path / "ck"))
+    want = []
+    for k in range(4, 10):
+        a.step(zs[k])
+        want.append((a.particles(), a.stats()))
+    b = mcl.LocalShardedFilter(n, lm, G, likelihood="moment", seed=77)
+    b.restore(str(tmp_path / "ck"))
+    fired = 0
+    for k in range(4, 10):
+        b.step(zs[k])
+        (xa, ya, ta, la), sa = want[k - 4]
+        xb, yb, tb, lb = b.particles()
+        np.testing.assert_array_equal(xb, xa)
+        np.testing.assert_array_equal(tb, ta)
+        np.testing.assert_array_equal(lb, la)
+        sb = b.stats()
+        assert (sb["ess"], sb["max_idx"], sb["resampled"], sb["step"]) == (sa["ess"], sa["max_idx"], sa["resampled"], sa["step"])
+        fired += sb["resampled"]
+    assert fired > 0  # the restored gate was exercised
+
+
+@pytest.mark.gpu
+def test_trajectory_log_round_trip(mcl, tmp_path):
+    """the on-disk trajectory / particle dump holds what main_pf() returned, step by step."""
+    np.random.seed(0)
+    log = mcl.TrajectoryLog(particles_every=2, max_particles=256)
+    pf = mcl.ParticleFilter(100, trajectory=log)
+    outs = [pf.main_pf() for _ in range(5)]
+    log.save(str(tmp_path / "run.npz"))
+    d = mcl.TrajectoryLog.load(str(tmp_path / "run.npz"))
+    assert len(log) == 5 and list(d["step"]) == [1, 2, 3, 4, 5] and sorted(d["clouds"]) == [0, 2, 4]
+    for k, (LM, x_true, x_est, px, Q, idx, val) in enumerate(outs):
+        np.testing.assert_array_equal(d["x_true"][k], x_true[:, 0])
+        np.testing.assert_array_equal(d["x_est"][k], x_est[:, 0])
+        assert d["max_idx"][k] == idx and d["max_weight"][k] == val
+    assert d["clouds"][4].shape == (3, 334) and np.all(np.linalg.eigvalsh(d["cov"][4][0:2, 0:2]) > 0)

@@ -191,3 +191,74 @@ def test_bench_fan_observations_follow_the_sensor_gate():
         d = np.hypot(p[vis, 0], p[vis, 1])
         assert np.all(np.abs(z[t, vis, 0] / d - 1.0) < 0.3)  # 5 % distance noise
         assert np.all(np.abs(O.limit_angle_vec(z[t, vis, 1] - np.arctan2(p[vis, 1], p[vis, 0]))) < 0.25)  # 2 deg noise
+
+
+def test_reference_animate_consumes_the_dropin_frames(pkg):
+    """INTEGRATION.md promises "one changed import": the reference's own animate() (particle_filter.py:248-328), imported
+    UNMODIFIED behind oracle/mpl_stub.py with a recording pyplot, is driven frame by frame with what the drop-in class
+    returned on a B200 (tests/golden/dropin_frames.npz, recorded by tools/record_dropin_frames.py; the reference's
+    sources and a GPU never share a machine here).  px arrives as the drop-in's LazyParticles, as it does for large
+    filters.  The same frames are checked against the reference's own seeded run (tests/golden/pf_seed0.npz)."""
+    ref_root = os.environ.get("MCL_REFERENCE", "/root/reference")
+    frames_path = os.path.join(ROOT, "tests", "golden", "dropin_frames.npz")
+    if not os.path.isdir(ref_root):
+        pytest.skip("the reference's sources are not on this machine")
+    if not os.path.exists(frames_path):
+        pytest.skip("tests/golden/dropin_frames.npz has not been recorded yet")
+    from oracle import mpl_stub
+
+    mpl_stub.install()
+    sys.path.insert(0, ref_root)
+    try:
+        import particle_filter as ref_pf  # the reference module, unmodified
+    finally:
+        sys.path.remove(ref_root)
+
+    log = []
+
+    class Ax:
+        def __getattr__(self, name):
+            def call(*a, **k):
+                log.append((name, a, k))
+            return call
+
+    class Plt(Ax):
+        def subplot2grid(self, *a, **k):
+            return Ax()
+
+    ref_pf.plt = Plt()
+    fr = np.load(frames_path)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "pf_seed0.npz"))
+
+    class FakeEngine:  # what LazyParticles asks of a Filter
+        def __init__(self, px):
+            self.n, self._px = px.shape[1], px.astype(np.float32)
+
+        def get_particles(self, want_logw=True):
+            return [self._px[0][None], self._px[1][None], self._px[2][None], None]
+
+    class Replay:
+        def __init__(self):
+            self.i = 0
+
+        def main_pf(self):
+            i = self.i
+            self.i += 1
+            px = pkg.LazyParticles(FakeEngine(fr[f"f{i}_px"]))
+            return (fr[f"f{i}_LM"], fr[f"f{i}_x_true"], fr[f"f{i}_x_est"], px, fr[f"f{i}_Q"], int(fr[f"f{i}_idx"]), float(fr[f"f{i}_val"]))
+
+    replay = Replay()
+    for i in range(int(fr["n_frames"])):
+        log.clear()
+        ref_pf.animate(i, replay, 100)
+        names = [c[0] for c in log]
+        assert names.count("scatter") == 8 and names.count("quiver") == 3 and "annotate" in names and "set_xlim" in names
+        cloud = [c for c in log if c[0] == "scatter" and c[2].get("c") == "cyan"]
+        np.testing.assert_allclose(cloud[0][1][0], fr[f"f{i}_px"][0], rtol=1e-6)  # every particle was handed to the plot
+        txt = [c for c in log if c[0] == "annotate"][0][1][0]
+        assert f"[Index]:{int(fr[f'f{i}_idx'])}" in txt
+        # the drop-in's frame against the reference's own seeded run: same RNG stream, same truth, same MAP particle
+        np.testing.assert_allclose(fr[f"f{i}_x_true"][:, 0], gold["x_true"][i], rtol=0, atol=1e-12)
+        assert int(fr[f"f{i}_idx"]) == int(gold["max_idx"][i])
+        np.testing.assert_allclose(fr[f"f{i}_x_est"][:, 0], gold["x_est"][i], rtol=1e-5, atol=1e-5)
+        assert float(fr[f"f{i}_val"]) == pytest.approx(float(gold["max_val"][i]), rel=2e-3)
