@@ -469,6 +469,83 @@ __device__ __noinline__ void merge_light_raw(const double *pp, int nb, MergeScra
     }
 }
 
+// (max, sum w, sum w^2) AND the arg-max in one pass over the records: the scalars CTA of k_scan needs both, and k_step
+// cannot start before that CTA is done -- a second pass over the (cold) records cost it ~2 us at C1
+__device__ __noinline__ void merge_light_best(const double *pp, int nb, MergeScratch &sc, float &M, double &s1, double &s2,
+                                              float &best_v, uint32_t &best_i) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float mx = -3.4028234e38f;
+    double a1 = 0.0, a2 = 0.0;
+    uint32_t bk = 0u, bi = 0xffffffffu;
+    constexpr int kB = 2;
+    for (int b0 = tid; b0 < nb; b0 += 256 * kB) {
+        double m4[kB], p4[kB], q4[kB], v4[kB], i4[kB];
+#pragma unroll
+        for (int u = 0; u < kB; ++u) {  // clamped rows, masked below: the loads are independent
+            const double *r = pp + min(b0 + u * 256, nb - 1) * kPart;
+            m4[u] = __ldcg(r);
+            p4[u] = __ldcg(r + 1);
+            q4[u] = __ldcg(r + 2);
+            v4[u] = __ldcg(r + 14);
+            i4[u] = __ldcg(r + 15);
+        }
+#pragma unroll
+        for (int u = 0; u < kB; ++u) {
+            if (b0 + u * 256 < nb) {
+                const float mb = static_cast<float>(m4[u]);
+                if (mb > mx) {
+                    const float r = ex2_approx((mx - mb) * kLog2e);
+                    a1 *= static_cast<double>(r);
+                    a2 *= static_cast<double>(r * r);
+                    mx = mb;
+                }
+                const float r = ex2_approx((mb - mx) * kLog2e);
+                a1 = fma(p4[u], static_cast<double>(r), a1);
+                a2 = fma(q4[u], static_cast<double>(r * r), a2);
+                const uint32_t k = float_order_key(static_cast<float>(v4[u]));
+                const uint32_t i = static_cast<uint32_t>(i4[u]);
+                if (k > bk || (k == bk && i < bi)) { bk = k; bi = i; }
+            }
+        }
+    }
+    float wm = mx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+    {
+        const float r = ex2_approx((mx - wm) * kLog2e);
+        a1 *= static_cast<double>(r);
+        a2 *= static_cast<double>(r * r);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    const uint32_t wk = __reduce_max_sync(0xffffffffu, bk);
+    const uint32_t wi = __reduce_min_sync(0xffffffffu, (bk == wk) ? bi : 0xffffffffu);
+    __syncthreads();  // the scratch may still be in use by a previous merge
+    if (lane == 0) { sc.m[warp] = wm; sc.a[warp] = a1; sc.b[warp] = a2; sc.k[warp] = wk; sc.i[warp] = wi; }
+    __syncthreads();
+    M = sc.m[0];
+    bk = sc.k[0];
+    bi = sc.i[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+        M = fmaxf(M, sc.m[w]);
+        if (sc.k[w] > bk || (sc.k[w] == bk && sc.i[w] < bi)) { bk = sc.k[w]; bi = sc.i[w]; }
+    }
+    s1 = 0.0;
+    s2 = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const float r = ex2_approx((sc.m[w] - M) * kLog2e);
+        s1 = fma(sc.a[w], static_cast<double>(r), s1);
+        s2 = fma(sc.b[w], static_cast<double>(r * r), s2);
+    }
+    best_v = float_from_order_key(bk);
+    best_i = bi;
+}
+
 // arg-max over the records: stored log-weight of the MAP particle and its index (smallest index on ties)
 __device__ __noinline__ void merge_best(const double *pp, int nb, MergeScratch &sc, float &best_v, uint32_t &best_i) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -802,6 +879,8 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
     __syncthreads();
     const bool merger = p.n_partials > 0 && (prep_cta || s_sc.tile == 0u);
     double st_max = 0.0, st_sum = 1.0;
+    float pre_bv = 0.f;
+    uint32_t pre_bi = 0u;
     if (merger || p.n_partials == 0) {  // CTA-uniform: this CTA derives the scalars itself
         double st_ess;
         int st_uniform;
@@ -809,7 +888,16 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
             float M;
             double s1, s2;
             // (a shard of a sharded filter never merges here: its statistics exchange has set n_partials = 0)
-            merge_light(pp, p.n_partials, s_merge, M, s1, s2, stp->abs_shift, p.prep.n_global, st_uniform);
+            if (prep_cta) {  // the scalars CTA also needs the arg-max: one pass over the records for both
+                merge_light_best(pp, p.n_partials, s_merge, M, s1, s2, pre_bv, pre_bi);
+                st_uniform = weights_underflowed(static_cast<double>(M), s1, stp->abs_shift) ? 1 : 0;
+                if (st_uniform) {
+                    M = 0.0f;
+                    s1 = s2 = p.prep.n_global;
+                }
+            } else {
+                merge_light(pp, p.n_partials, s_merge, M, s1, s2, stp->abs_shift, p.prep.n_global, st_uniform);
+            }
             st_max = static_cast<double>(M);
             st_sum = s1;
             st_ess = s1 * s1 / s2;
@@ -854,9 +942,7 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
         in.sum_w = st_sum;
         in.uniform = uniform;
         if (p.n_partials > 0) {
-            float bv;
-            uint32_t bi;
-            merge_best(pp, p.n_partials, s_merge, bv, bi);
+            uint32_t bi = pre_bi;
             if (uniform) bi = 0u;  // np.argmax of all-equal weights (:116)
             in.est[0] = p.cur.x[soff + bi];
             in.est[1] = p.cur.y[soff + bi];

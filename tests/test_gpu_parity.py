@@ -37,18 +37,17 @@ def _weights_from_logw32(lw32):
     return w / w.sum()
 
 
-def _assert_weights_close(got, want, rtol=RTOL):
-    """1e-5 relative on every weight that carries mass (down to 1e-4 of the largest: more than 99.99% of
-    the total).  The engine stores log-weights in fp32, so a weight e^-k below the largest carries a
-    relative error of about k * 1e-7: 1e-4 is asked down to 1e-12 of the largest, and an absolute floor
-    below that (those weights are under the resolution of the resampler's 2^-52 grid)."""
+def _assert_weights_close(got, want, rtol=RTOL, rtol_tail=None):
+    """north_star's 1e-5 relative on every weight down to 1e-12 of the largest (measured at C1, tools/parity_margins.py:
+    1e-6 on the weights above 1e-4 of the largest, 2.8e-6 down to 1e-12, 6.3e-6 down to 1e-20 -- the fp32 storage of
+    the log-weights costs ~1e-7 per unit of log-weight).  The fp32 pair kernels pass `rtol_tail` for the weights
+    between 1e-12 and 1e-4 of the largest.  Below 1e-12 of the largest a weight is under the resolution of the
+    resampler's 2^-52 grid and the MUFU path eventually flushes it to zero: absolute floor."""
     got, want = np.asarray(got).reshape(-1), np.asarray(want).reshape(-1)
     heavy = want > want.max() * 1e-4
     np.testing.assert_allclose(got[heavy], want[heavy], rtol=rtol)
     big = want > want.max() * 1e-12
-    np.testing.assert_allclose(got[big], want[big], rtol=max(rtol, 1e-4))
-    # below 2^-53 a weight is under the resolution of the resampler's fixed-point grid and the fp32
-    # MUFU path flushes it to zero well before that matters
+    np.testing.assert_allclose(got[big], want[big], rtol=rtol if rtol_tail is None else rtol_tail)
     np.testing.assert_allclose(got[~big], want[~big], rtol=1e-3, atol=1e-25)
 
 
@@ -87,7 +86,7 @@ def test_predict_weight_stage_parity(mcl, golden_dir, likelihood, seed, k):
     with np.errstate(divide="ignore"):
         want_w, _ = O.update_weights_log(np.log(w_prev), ll)
     got_w = f.weights()[0]
-    _assert_weights_close(got_w, want_w)
+    _assert_weights_close(got_w, want_w, rtol_tail=3e-5 if likelihood == "pair32" else None)
     assert abs(got_w.sum() - 1.0) < 1e-6
     st = f.stats()[0]
     assert st.ess == pytest.approx(O.ess(want_w), rel=RTOL)
@@ -293,7 +292,8 @@ def test_yaw_seam_mean(mcl):
     mean, cov = O.weighted_moments(np.stack([x, y, th]).astype(np.float64), _weights_from_logw32(lw))
     st = f.stats()[0]
     assert abs(O.limit_angle(st.mean[2] - mean[2])) < 1e-6
-    np.testing.assert_allclose(np.array(st.cov[:]).reshape(3, 3), cov, rtol=1e-4, atol=1e-7)
+    scale = np.sqrt(np.outer(np.diag(cov), np.diag(cov)))  # (the cross terms are ~0: absolute floor relative to the variances)
+    np.testing.assert_allclose(np.array(st.cov[:]).reshape(3, 3), cov, rtol=RTOL, atol=RTOL * scale.min())
 
 
 def test_dropin_seeded_trajectory(mcl, golden_dir):
@@ -384,14 +384,15 @@ def test_c1_size_step_parity(mcl, likelihood):
     ll = O.loglik_cartesian(got_px, z1, lm, 0.3, 0.3)
     want_w, logz = O.update_weights_log(np.full(n, -np.log(float(n))), ll)
     got_w = f.weights()[0]
-    _assert_weights_close(got_w, want_w)
+    _assert_weights_close(got_w, want_w, rtol_tail=3e-5 if likelihood == "pair32" else None)
     st = f.stats()[0]
     assert st.ess == pytest.approx(O.ess(want_w), rel=RTOL)
     mi = int(np.argmax(want_w))
     assert st.max_idx == mi or want_w[st.max_idx] >= want_w[mi] * (1 - RTOL)
     mean, cov = O.weighted_moments(got_px, want_w)
     np.testing.assert_allclose(np.array(st.mean[:]), mean, rtol=RTOL, atol=1e-6)
-    np.testing.assert_allclose(np.array(st.cov[:]).reshape(3, 3), cov, rtol=1e-4, atol=1e-9)
+    # the FUSED single-pass covariance (fp32 group sums folded into fp64, about the reference pose): measured 1.2e-6
+    np.testing.assert_allclose(np.array(st.cov[:]).reshape(3, 3), cov, rtol=RTOL, atol=1e-9)
 
 
 @pytest.mark.parametrize("scenario", ["running", "offset"])
@@ -401,9 +402,9 @@ def test_likelihood_64_and_1024_landmarks(mcl, scenario):
     "running": the observation is taken where the cloud is after its motion step, as in a running filter -- the
     reference pose (the previous MAP estimate pushed through the motion) then sits at the likelihood peak and every
     kernel meets 1e-5.  "offset": the observation is taken BEFORE the motion step, so the whole cloud sits 0.17 m
-    off and the useful particles score e^+80 (L = 64) to e^+760 (L = 1024) above the reference pose.  The fp64
-    kernels still meet 1e-5 there; the fp32 pair kernel, whose rounding error is ~3e-8 of |log w - log w_ref|, is
-    asked 5e-5 (its stored fp32 log-weights have an ulp of 6e-5 at 760)."""
+    off and the useful particles score e^+80 (L = 64) to e^+760 (L = 1024) above the reference pose.  Log-weights are
+    STORED in fp32 relative to the reference pose, and an fp32 ulp at 760 is 6e-5: outside the regime the relative
+    storage is designed for, every kernel is asked 5e-5 / 1e-4 instead of 1e-5."""
     rng = np.random.RandomState(99)
     for Lm, n in ((64, 1 << 16), (1024, 1 << 13)):
         lm = rng.uniform(-20, 20, (Lm, 2))
@@ -431,9 +432,13 @@ def test_likelihood_64_and_1024_landmarks(mcl, scenario):
         # pure log-domain weights (underflow_rule = 0) against the log-domain oracle
         ll = O.loglik_cartesian(got_px, z, lm, 0.3, 0.3)
         want_w, _ = O.update_weights_log(np.full(n, -np.log(float(n))), ll)
-        _assert_weights_close(res["pair"], want_w)
-        _assert_weights_close(res["moment"], want_w)
-        _assert_weights_close(res["pair32"], want_w, rtol=RTOL if scenario == "running" else 5e-5)
+        if scenario == "running":
+            _assert_weights_close(res["pair"], want_w)
+            _assert_weights_close(res["moment"], want_w)
+            _assert_weights_close(res["pair32"], want_w, rtol_tail=3e-5)
+        else:  # stored fp32 log-weights of +80 / +760: half an ulp is 4e-6 / 3e-5, for every kernel
+            for lik in ("pair", "moment", "pair32"):
+                _assert_weights_close(res[lik], want_w, rtol=5e-5, rtol_tail=1e-4)
         # the default mirrors the reference's fp64 PRODUCT (:192-196, :234-237): with 1024 landmarks 0.17 m off, every
         # product of pdfs underflows, the reference's weights are NaN -> 1/NP, and so are the engine's
         lit_w = O.normalize(np.full(n, 1.0 / n) * O.likelihood_product(got_px, z, lm, 0.3, 0.3), 1.0 / n)
@@ -1154,7 +1159,7 @@ def test_underflow_resets_the_weights_like_the_reference(mcl, golden_dir, likeli
             ll = O.loglik_cartesian(got_px, g[f"s{k}_z_l"], P.LM, 0.3, 0.3)
             with np.errstate(divide="ignore"):
                 want_w, _ = O.update_weights_log(np.log(w_prev), ll)
-            _assert_weights_close(got_w, want_w)
+            _assert_weights_close(got_w, want_w, rtol_tail=3e-5 if likelihood == "pair32" else None)
             assert st.max_idx == int(np.argmax(want_w))
         return got_w
 
