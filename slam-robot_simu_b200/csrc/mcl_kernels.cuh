@@ -1545,17 +1545,33 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
     const uint32_t first = static_cast<uint32_t>(min(first64, static_cast<unsigned long long>(p.n)));
     const uint32_t last = static_cast<uint32_t>(min(first64 + p.per, static_cast<unsigned long long>(p.n)));
 
-    int since_flush = 0;
-    for (uint32_t wbase = first + (tid - lane) * kPPT; wbase < last; wbase += kStepTile) {
+    // The gather is two dependent trips to memory -- ancestors, then the poses they point to -- and 6 warps per
+    // scheduler do not cover both (ncu: 22 % of the stall samples sat on these two loads).  Each thread therefore
+    // requests the ancestors of its NEXT iteration (one 16-byte cp.async into a slot only it reads back) while it works
+    // on the current one: no registers held across the iteration, one trip left exposed (k_step -3.5 % at 125 M).
+    __shared__ __align__(16) uint4 s_anc[2][kStepThreads];
+    auto request_anc = [&](uint32_t b, int buf) {
+        if (resample && b < last) {
+            const unsigned int dst = static_cast<unsigned int>(__cvta_generic_to_shared(&s_anc[buf][tid]));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(anc + b) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    request_anc(first + tid * kPPT, 0);
+    int since_flush = 0, itn = 0;
+    for (uint32_t wbase = first + (tid - lane) * kPPT; wbase < last; wbase += kStepTile, ++itn) {
         const uint32_t base = wbase + lane * kPPT;
         const bool active = base < last;  // false only in the last, partial unit of the trial
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const uint4 a4_pre = s_anc[itn & 1][tid];
+        request_anc(base + kStepTile, (itn + 1) & 1);
         float x[kPPT], y[kPPT], th[kPPT], lwp[kPPT] = {0.f, 0.f, 0.f, 0.f};
         float lwf[kPPT] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         double s[kPPT], c[kPPT];
         if (active) {
             // ---------------- load (gather through the ancestors when this step resamples) ----------------
             if (resample) {
-                const uint4 a4 = *reinterpret_cast<const uint4 *>(anc + base);
+                const uint4 a4 = a4_pre;
                 const uint32_t a[kPPT] = {a4.x, a4.y, a4.z, a4.w};
                 const uint32_t win_lo = s_win[0], win_hi = s_win[1];
                 if (base >= win_lo && base + kPPT <= win_hi) {
