@@ -524,6 +524,12 @@ int step_impl(mcl_filter *h, const double *z_dev, const double *ofs_dev, const f
 
 int stage_inputs(mcl_filter *h, const double *z_host, const double *ofs_host, cudaStream_t st) {
     if (z_host == nullptr && ofs_host == nullptr) return MCL_OK;
+    if (ofs_host != nullptr) {
+        // rand() * NP_RECIP (particle_filter.py:214) lies in [0, 1/N); the slot arithmetic relies on it
+        for (int t = 0; t < h->lay.T; ++t)
+            if (!(ofs_host[t] >= 0.0 && ofs_host[t] < h->delta))
+                return fail(h, MCL_ERR_ARG, "comb offset outside [0, 1/N): pass rand() * (1 / n_global)");
+    }
     const size_t zb = static_cast<size_t>(h->lay.T) * h->L * 2 * sizeof(double);
     const size_t ob = static_cast<size_t>(h->lay.T) * sizeof(double);
     const size_t need = static_cast<size_t>(h->lay.T) * h->lay.Lmax * 2 * sizeof(double) + ob;
@@ -1467,6 +1473,8 @@ int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_h
     if ((stages & MCL_STAGE_C) && z_host == nullptr) return fail(h, MCL_ERR_ARG, "z_host is NULL");
     if ((stages & MCL_STAGE_C) && noise_dev == nullptr && !(flags & MCL_PHILOX_NOISE))
         return fail(h, MCL_ERR_ARG, "noise_dev is NULL and MCL_PHILOX_NOISE is not set");
+    if (ofs_host != nullptr && !(ofs_host[0] >= 0.0 && ofs_host[0] < h->delta))
+        return fail(h, MCL_ERR_ARG, "comb offset outside [0, 1/N): pass rand() * (1 / n_global)");
     rc = use_device(h);
     if (rc != MCL_OK) return rc;
     cudaStream_t st = S(stream);

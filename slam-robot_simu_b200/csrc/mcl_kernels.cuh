@@ -819,9 +819,6 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
     __shared__ uint32_t s_slot[2];
     __shared__ __align__(16) uint32_t s_mark[kScanTile];  // also the reduction scratch of prep_block
     __shared__ uint32_t s_wmax[NW];
-    __shared__ __align__(16) uint32_t s_edge[NW][2 * kScanItems];  // parked partial chunks of the warp-local fill
-    __shared__ uint32_t s_edge_slot[NW][2];
-    if (lane < 2) s_edge_slot[warp][lane] = 0xffffffffu;
 
     // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as every CTA of
     // this grid has started; nothing is read or written before the previous kernel has completed.
@@ -974,6 +971,7 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
     // (requesting the next tile's weights a tile ahead -- cp.async into a double buffer -- was measured: no gain for
     //  the expansion, and its 16 KB of shared memory cost the look-back scan 6 %)
     const int n_tile_ctas_s = static_cast<int>(gridDim.x) - (p.do_prep ? (p.n_partials > 0 ? 2 : 1) : 0);
+    unsigned long long solo_prefix = 0ull;
     int it = 0;
     for (long long tile = s_sc.tile; tile < p.tpt; tile = static_tiles ? tile + n_tile_ctas_s : static_cast<long long>(s_next[it & 1]), ++it) {
     const long long j0 = tile * kScanTile + static_cast<long long>(tid) * kScanItems;
@@ -1031,8 +1029,14 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
     // tiles of the direct range also raise a bit in ready[tile / 32] once their aggregate is visible
     unsigned int *rdy = p.ready + t * (kDirectTiles / 32);
     const bool have_prefix = (MODE == kScanExpand) && p.tile_prefix != nullptr;
+    // A trial whose tiles are ALL taken by this one persistent CTA (trial batches: thousands of small filters) needs
+    // no descriptors and no look-back: the tickets come in order, so the prefix is simply carried in a register.
+    const bool solo = p.persistent && !static_tiles && n_tile_ctas_s == 1;
     if (have_prefix) {
         excl = __ldg(p.seg_prefix + tile / p.tiles_per_seg) + __ldg(p.tile_prefix + tile);
+    } else if (solo) {
+        excl = solo_prefix;
+        solo_prefix += tile_total;
     } else if (tile == 0) {
         if (tid == 0) {
             atomicExch(&desc[0], kDescAggregate | tile_total);  // == its prefix; see the direct range
@@ -1089,40 +1093,33 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
             for (int w = 0; w < NW; ++w) excl += s_warp[w];
             __syncthreads();
         } else
+        // (measured and dropped: a round with two barriers instead of four, the 64-bit shuffle tree replaced by two
+        //  hardware REDUX on 27-bit halves -- 15 % fewer look-back instructions, 0.5 % SLOWER: the scan is bound by
+        //  the latency of its dependent steps, not by instruction issue)
         while (true) {
-            // one round = the 256 descriptors before `look`, nearest first (tid 0).  Two barriers per round: the
-            // poll (every descriptor of the window has at least its aggregate) and the exchange of the warp results.
             const long long idx = look - tid;
             unsigned long long d = kDescPrefix;  // tiles before the first one: an empty prefix
             if (idx >= 0) d = *reinterpret_cast<volatile unsigned long long *>(&desc[idx]);
             while (!__syncthreads_and((d >> 62) != 0ull)) {
                 if ((d >> 62) == 0ull) d = *reinterpret_cast<volatile unsigned long long *>(&desc[idx]);
             }
-            // per warp: the nearest descriptor that is already an inclusive prefix ends the sum
             const unsigned int is_prefix = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
-            const int fp = is_prefix ? (__ffs(is_prefix) - 1) : 32;
-            const unsigned long long val = (lane <= fp && idx >= 0) ? (d & kDescValueMask) : 0ull;
-            // the values are below 2^53 (the weights sum to 2^52): two 32-bit hardware reductions instead of a
-            // five-step 64-bit shuffle tree
-            const unsigned int lo = __reduce_add_sync(0xffffffffu, static_cast<unsigned int>(val) & 0x7ffffffu);
-            const unsigned int hi = __reduce_add_sync(0xffffffffu, static_cast<unsigned int>(val >> 27));
-            if (lane == 0) {
-                s_warp[warp] = (static_cast<unsigned long long>(hi) << 27) + lo;
-                s_first[warp] = (fp < 32) ? 1 : 0;
-            }
+            if (lane == 0) s_first[warp] = is_prefix ? (warp * 32 + __ffs(is_prefix) - 1) : 0x7fffffff;
             __syncthreads();
-            bool found = false;
+            int first = 0x7fffffff;  // nearest predecessor (smallest tid) that already holds a prefix
 #pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                if (!found) {
-                    excl += s_warp[w];
-                    found = s_first[w] != 0;
-                }
-            }
-            if (found) break;  // (the poll barrier of the next round orders the reuse of s_warp / s_first)
+            for (int w = 0; w < NW; ++w) first = min(first, s_first[w]);
+            unsigned long long contrib = (tid <= first && idx >= 0) ? (d & kDescValueMask) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+            if (lane == 0) s_warp[warp] = contrib;
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < NW; ++w) excl += s_warp[w];
+            __syncthreads();
+            if (first != 0x7fffffff) break;
             look -= kScanThreads;
         }
-        __syncthreads();  // s_warp is reused by the next tile's block scan
         // tiles of the direct range keep their aggregate (later direct tiles sum aggregates); the LAST direct
         // tile and everything after it publish inclusive prefixes for the classic look-back
         if (tid == 0 && tile >= kDirectTiles) atomicExch(&desc[tile], kDescPrefix | (excl + tile_total));
@@ -1252,15 +1249,14 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
                     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(anc + (slot0 - anc_lo)), "r"(v[0]),
                                  "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                                  : "memory");
-                } else if (slot0 + kScanItems > wf && slot0 < we) {
-                    // The (at most two) chunks the warp's range only partly covers -- the one holding its first slot
-                    // and the one holding its last -- are parked; sixteen lanes store them after the loop.  Scalar
-                    // stores right here would make the whole warp issue them for the sake of two lanes, in every pass.
-                    const int half = (slot0 < wf) ? 0 : 1;
-                    uint32_t *sc = s_edge[warp] + half * kScanItems;
-                    *reinterpret_cast<uint4 *>(sc) = make_uint4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<uint4 *>(sc + 4) = make_uint4(v[4], v[5], v[6], v[7]);
-                    s_edge_slot[warp][half] = slot0;
+                }
+                // (parking the two partial chunks of a warp in shared memory and storing them once, after the loop, by
+                //  sixteen lanes removed ~6 thread-instructions per particle and made the kernel 6 % SLOWER: one more
+                //  dependent shared-memory round trip at the end of every tile)
+                else {
+#pragma unroll
+                    for (int k = 0; k < kScanItems; ++k)
+                        if (slot0 + k >= wf && slot0 + k < we) anc[slot0 + k - anc_lo] = v[k];
                 }
             } else {
 #pragma unroll
@@ -1268,14 +1264,6 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
                     if (slot0 + k >= wf && slot0 + k < we) expand_store(p, anc, static_cast<long long>(slot0) + k, v[k]);
             }
         }
-        __syncwarp();
-        if (lane < 2 * kScanItems) {
-            const uint32_t e0 = s_edge_slot[warp][lane >> 3];
-            const uint32_t slot = e0 + static_cast<uint32_t>(lane & 7);
-            if (e0 != 0xffffffffu && slot >= wf && slot < we) anc[slot - anc_lo] = s_edge[warp][lane];
-        }
-        __syncwarp();
-        if (lane < 2) s_edge_slot[warp][lane] = 0xffffffffu;  // re-armed for the next tile of a persistent CTA
     } else {
         // tile slot range [S0, S1): S0 from the first thread, S1 from the last thread holding sources
         if (tid == 0) s_slot[0] = first_slot;

@@ -774,6 +774,10 @@ def test_single_and_maximum_landmark_counts(mcl):
         _assert_weights_close(out["moment"], want_w)
     with pytest.raises(mcl.MclError):
         mcl.Filter(n_particles=16, max_landmarks=4097)
+    f = mcl.Filter(n_particles=64, landmarks=[[0.0, 0.0]])
+    f.init_particles([0.0, 0.0, 0.0])
+    with pytest.raises(mcl.MclError):  # the comb offset is rand() * NP_RECIP (:214): [0, 1/N)
+        f.resample(ofs=1.5 / 64, force=True)
 
 
 def test_anisotropic_observation_noise(mcl):
@@ -1277,3 +1281,37 @@ def test_trajectory_log_round_trip(mcl, tmp_path):
         np.testing.assert_array_equal(d["x_est"][k], x_est[:, 0])
         assert d["max_idx"][k] == idx and d["max_weight"][k] == val
     assert d["clouds"][4].shape == (3, 334) and np.all(np.linalg.eigvalsh(d["cov"][4][0:2, 0:2]) > 0)
+
+
+@pytest.mark.gpu
+def test_slots_past_the_final_cumulative_weight_are_bounded(mcl):
+    """The one intentional divergence: the integer weights sum to 2^52 (1 +- 6e-8) because the
+    scale 2^52 / sum is an fp32 number, and when they fall short the comb teeth past the total go to the LAST particle
+    (the reference's walk would raise IndexError there).  At 2^27 particles that is at most N 2^-23 = 16 slots, and
+    exactly the number the shortfall of the integer total predicts."""
+    import torch
+
+    n = 1 << 27
+    g = torch.Generator(device="cuda").manual_seed(5)
+    lw = torch.randn(n, generator=g, device="cuda", dtype=torch.float32) * 1.5
+    zero = torch.zeros(n, device="cuda", dtype=torch.float32)
+    f = mcl.Filter(n_particles=n, landmarks=[[0.0, 0.0]])
+    f.set_particles(zero, zero, zero, lw)
+    for trial in range(6):
+        if trial:  # another spread -> another sum, another rounding of the fp32 scale (the total lands on either side of 2^52)
+            f.set_particles(zero, zero, zero, lw * (1.0 + 0.21 * trial))
+        q = f.qweights()[0]
+        total = int(q.sum(dtype=np.uint64))
+        ofs = (0.11 + 0.13 * trial) / n  # rand() * NP_RECIP: in [0, 1/N)
+        f.resample(ofs=ofs, force=True)
+        anc = f.ancestors()[0]
+        assert np.all(np.diff(anc.astype(np.int64)) >= 0)
+        # teeth u_i = i / N + ofs beyond total * 2^-52 have no owner in the reference: count them from the integers
+        short = (1 << 52) - total
+        tail = int((anc == n - 1).sum())
+        fair = q[-1] * n / float(1 << 52)  # the last particle's own share of the comb
+        dumped = tail - fair
+        assert dumped <= n * 2.0 ** -23 + 2, (trial, tail, fair, short)
+        # tooth i is unowned when i / N + ofs > total 2^-52: about N short 2^-52 - N ofs of them (ofs N < 1)
+        assert abs(dumped - max(0.0, short * n / float(1 << 52) - ofs * n)) <= 2.0, (trial, dumped, short)
+        print(f"trial {trial}: total - 2^52 = {-short}, slots of the last particle {tail} (its share {fair:.2f}), dumped {dumped:.2f}")
