@@ -30,8 +30,13 @@ BYTES_K_SCAN = 8           # k_scan: log-weight 4 B in, ancestor 4 B out
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_step launch, per particle, from `ncu --set full` captures of the
 # workload named by the key (tools/ncu_case.py; summaries under profiles/).  Workloads without a capture report null.
 NCU_TRAFFIC = {
-    ("c3", "moment"): ((528.388608e6 + 501.015552e6) / 33554432,
-                       "ncu --set full of k_step at 32M particles x 64 landmarks (profiles/r01_r_ncu_32M_x64_k_step_summary.csv), per particle x this launch"),
+    ("c1", "moment"): ((16.838912e6 + 0.014080e6) / 1048576,
+                       "ncu --set full of k_step at C1 itself, 2^20 x 16 (profiles/r02_e_ncu_c1_k_scan_k_step_summary.csv): 16.8 MB read; the "
+                       "16.8 MB written stay in the 126 MB L2 (write-back) -- ncu replays start cache-cold, as the rotated replicas do"),
+    ("c3", "moment"): ((520.255744e6 + 499.668480e6) / 33554432,
+                       "ncu --set full of k_step at 32M particles x 64 landmarks (profiles/r02_d_ncu_32M_x64_k_step_moment_summary.csv), per particle x this launch"),
+    ("c3", "pair32"): ((521.427968e6 + 505.885952e6) / 33554432,
+                       "ncu --set full of k_step<pair32> at 32M particles x 64 landmarks (profiles/r02_c_ncu_32M_x64_k_step_pair32_summary.csv), per particle x this launch"),
 }
 HAVE_RB32 = True
 # The LITERAL reference class (unmodified /root/reference/particle_filter.py behind oracle/mpl_stub.py, its per-particle
