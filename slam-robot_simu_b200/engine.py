@@ -130,6 +130,11 @@ class Filter:
     def _check(self, status, where):
         L.check(status, where, self._h)
 
+    _version = 0  # bumped by every call that changes the particles (LazyParticles refuses to serve an older state)
+
+    def _changed(self):
+        self._version += 1
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self.lib.mcl_destroy(self._h)
@@ -159,6 +164,7 @@ class Filter:
         """px = repmat(x_true, 1, NP), pw = 1/NP (particle_filter.py:81-84); pose (3,) or (T,3)."""
         p = np.ascontiguousarray(np.broadcast_to(np.asarray(pose, dtype=np.float64).reshape(-1, 3), (self.T, 3)))
         self._check(self.lib.mcl_init_particles(self._h, p.ctypes.data, self._stream()), "mcl_init_particles")
+        self._changed()
 
     def set_particles(self, x, y, yaw, logw=None, skip_stats=False):
         """Arrays (T,n)/(n,) -- numpy (host) or torch CUDA tensors (device), fp32."""
@@ -175,6 +181,7 @@ class Filter:
                 raise ValueError("particle arrays must hold n_trials * n_particles elements")
         mode = (1 if on_dev else 0) | (2 if skip_stats else 0)
         self._check(self.lib.mcl_set_particles(self._h, *ptrs, mode, self._stream()), "mcl_set_particles")
+        self._changed()
         self._keep = arrs  # device sources must outlive the async copies
 
     def get_particles(self, want_logw=True, device=False):
@@ -220,12 +227,14 @@ class Filter:
         flags = (L.MCL_FORCE_RESAMPLE if force else 0) | (L.MCL_PHILOX_NOISE if ofs is None else 0)
         o = None if ofs is None else self._f64(np.broadcast_to(np.asarray(ofs, dtype=np.float64).reshape(-1), (self.T,)), (self.T,))
         self._check(self.lib.mcl_resample(self._h, None if o is None else o.ctypes.data, flags, self._stream()), "mcl_resample")
+        self._changed()
 
     def predict_weight(self, z, noise=None):
         """__predict + __likelihood + __normalize + MAP estimate (particle_filter.py:156-198, :115-117)."""
         zz = self._f64(z, (self.T, self.n_landmarks, 2))
         self._check(self.lib.mcl_predict_weight(self._h, zz.ctypes.data, self._noise_ptr(noise), self._flags(noise, False, True),
                                                 self._stream()), "mcl_predict_weight")
+        self._changed()
 
     def step(self, z, ofs=None, noise=None, force_resample=False, no_resample=False):
         """main_pf minus the ground-truth line (particle_filter.py:104-117)."""
@@ -236,6 +245,7 @@ class Filter:
             flags |= L.MCL_PHILOX_NOISE
         self._check(self.lib.mcl_step(self._h, zz.ctypes.data, None if o is None else o.ctypes.data, self._noise_ptr(noise),
                                       flags, self._stream()), "mcl_step")
+        self._changed()
 
     def step_async(self, z, ofs=None, noise=None, force_resample=False, no_resample=False):
         """step() + stats_begin() in one crossing of the C ABI (mcl_step_async); collect with stats_end().
@@ -246,6 +256,7 @@ class Filter:
         o = None if ofs is None else (C.c_double * self.T)(*([float(ofs)] * self.T if np.isscalar(ofs) else [float(v) for v in ofs]))
         self._check(self.lib.mcl_step_async(self._h, z.ctypes.data, o, self._noise_ptr(noise), flags, self._stream_cached()),
                     "mcl_step_async")
+        self._changed()
 
     def _stream_cached(self):
         """The CUDA stream handle of the first call (a step every ~50 us cannot afford torch.cuda.current_stream())."""
@@ -262,6 +273,7 @@ class Filter:
         self._check(self.lib.mcl_step_dev(self._h, C.c_void_p(z_dev.data_ptr()),
                                           None if ofs_dev is None else C.c_void_p(ofs_dev.data_ptr()),
                                           self._noise_ptr(noise), flags, self._stream()), "mcl_step_dev")
+        self._changed()
 
     def pose_moments(self):
         self._check(self.lib.mcl_pose_moments(self._h, self._stream()), "mcl_pose_moments")
@@ -353,6 +365,7 @@ class Filter:
         self._check(self.lib.mcl_shard_step(self._h, zz.ctypes.data, self._noise_ptr(noise), ptr(recv_x), ptr(recv_y),
                                             ptr(recv_yaw), int(n_prefix), int(n_suffix), self._flags(noise, False, False),
                                             self._stream()), "mcl_shard_step")
+        self._changed()
 
     def shard_merge(self, records, n_shards):
         """records: CUDA uint8 tensor holding the n_shards allgathered mcl_stats blocks."""
@@ -383,6 +396,7 @@ class Filter:
         self._check(self.lib.mcl_shard_step_peer(self._h, zz.ctypes.data, o, self._noise_ptr(noise),
                                                  self._flags(noise, force_resample, no_resample), int(stages), self._stream()),
                     "mcl_shard_step_peer")
+        self._changed()
 
     def sync_peer(self, stages=L.MCL_STAGE_C | L.MCL_STAGE_D):
         self._check(self.lib.mcl_shard_sync_peer(self._h, int(stages), self._stream()), "mcl_shard_sync_peer")

@@ -46,9 +46,14 @@ class LazyParticles:
         self._cache = None
         self.shape = (3, flt.n)
         self.dtype = np.dtype(np.float64)
+        # The reference returns the array of THIS step; a lazy view can only serve it while the filter has not moved on.
+        self._stamp = getattr(flt, "_version", None)
 
     def _fetch(self):
         if self._cache is None:
+            if self._stamp is not None and getattr(self._flt, "_version", None) != self._stamp:
+                raise RuntimeError("px of an earlier main_pf() read after the filter advanced: read it (np.asarray(px)) "
+                                   "before the next step, or construct ParticleFilter(..., lazy_px=False)")
             x, y, th, _ = self._flt.get_particles(want_logw=False)
             self._cache = np.stack([x[0], y[0], th[0]]).astype(np.float64)
         return self._cache
