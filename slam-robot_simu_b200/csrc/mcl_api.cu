@@ -347,12 +347,17 @@ int launch_step_scan(mcl_filter *h, const double *z_dev, const double *ofs_dev, 
     // (one filter: one CTA per tile, the hardware scheduler keeps the look-back pipeline full; many trials:
     // a trial's few tiles share persistent CTAs so the per-CTA prologue is paid once)
     static const int persist_single = [] { const char *e = std::getenv("MCL_SCAN_PERSISTENT"); return e ? std::atoi(e) : 0; }();
+    // geometry: all tiles in one wave of 4 per SM (a filter of up to ~1.2 M particles) -> 256 threads x 8 sources; beyond that the
+    // scan is bound by per-tile latency at a fixed number of resident tiles -> 128 threads x 16, eight tiles per SM
+    const bool wide = static_cast<long long>(h->lay.T) * h->lay.tpt > static_cast<long long>(h->sm_count) * scan_ctas_per_sm(8);
+    const int per_sm = wide ? scan_ctas_per_sm(16) : scan_ctas_per_sm(8);
     const int tile_ctas = !full ? 0 : ((h->lay.T == 1 && persist_single <= 0) ? h->lay.tpt
-                                       : std::min(h->lay.tpt, std::max(1, h->sm_count * std::max(persist_single, 4) / h->lay.T)));
+                                       : std::min(h->lay.tpt, std::max(1, h->sm_count * std::max(persist_single, per_sm) / h->lay.T)));
     sp.persistent = (tile_ctas < h->lay.tpt) ? 1 : 0;
     dim3 grid(tile_ctas + (h->stats_dirty ? 2 : 1), h->lay.T);
     h->stats_dirty = false;
-    launch_pdl(k_scan<kScanAncestors>, grid, dim3(kScanThreads), 0, st, pdl_enabled() && !h->profiling, sp);
+    if (wide) launch_pdl(k_scan<kScanAncestors, 16>, grid, dim3(kScanTile / 16), 0, st, pdl_enabled() && !h->profiling, sp);
+    else launch_pdl(k_scan<kScanAncestors, 8>, grid, dim3(kScanTile / 8), 0, st, pdl_enabled() && !h->profiling, sp);
     MCL_LAUNCH_CHECK(h, "k_scan");
     return MCL_OK;
 }
@@ -375,9 +380,9 @@ int launch_shard_scan(mcl_filter *h, ScanParams &sp, int mode, cudaStream_t st) 
         // tiles are independent once their prefixes are known: persistent CTAs (tickets) pay the kernel prologue once
         // per CTA instead of once per tile (expand 0.55 -> 0.50 ms at 125 M particles)
         sp.persistent = 1;
-        grid.x = std::min(h->lay.tpt, h->sm_count * MCL_SCAN_CTAS_PER_SM);
+        grid.x = std::min(h->lay.tpt, h->sm_count * scan_ctas_per_sm(16));
     }
-    k_scan<kScanExpand><<<grid, kScanThreads, 0, st>>>(sp);
+    k_scan<kScanExpand, 16><<<grid, kScanTile / 16, 0, st>>>(sp);
     MCL_LAUNCH_CHECK(h, "k_scan");
     k_reset_scan<<<(h->lay.tpt + 255) / 256, 256, 0, st>>>(sp.desc, sp.ready, h->tickets, h->lay.tpt);
     MCL_LAUNCH_CHECK(h, "k_reset_scan");
@@ -1523,8 +1528,8 @@ int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_h
         sp.seg_prefix = h->seg;
         sp.tiles_per_seg = h->tiles_per_seg;
         sp.persistent = 1;
-        dim3 grid(std::min(h->lay.tpt, h->sm_count * MCL_SCAN_CTAS_PER_SM), 1);
-        k_scan<kScanExpand><<<grid, kScanThreads, 0, st>>>(sp);
+        dim3 grid(std::min(h->lay.tpt, h->sm_count * scan_ctas_per_sm(16)), 1);
+        k_scan<kScanExpand, 16><<<grid, kScanTile / 16, 0, st>>>(sp);
         MCL_LAUNCH_CHECK(h, "k_scan");
     }
     if (may_resample && (B || Cc)) {
@@ -1546,7 +1551,7 @@ int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_h
             sp.trig = h->trig;
             sp.plan = h->plan;
             sp.xflags = flags;
-            launch_pdl(k_scan<kScanAncestors>, dim3(1, 1), dim3(kScanThreads), 0, st, false, sp);
+            launch_pdl(k_scan<kScanAncestors, 8>, dim3(1, 1), dim3(kScanTile / 8), 0, st, false, sp);
             MCL_LAUNCH_CHECK(h, "k_scan");
         }
         StepWindow win;

@@ -24,9 +24,13 @@ constexpr int kStepUnit = 128;     // granularity of the static particle partiti
 constexpr int kFoldEvery = 16;     // fp32 pair kernels: landmarks per fp32 partial sum before it is folded into fp64
 constexpr int kFlushEvery = 8;     // fp32 group sums are folded into the fp64 sums every 8 iterations
 
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
+// The scan is bound by the latency of a tile's dependent steps, not by issue or bytes: what
+// raises its throughput is more tiles in flight per SM.  128 threads x 16 sources keep the tile at 2048 particles
+// and let EIGHT tiles reside on an SM (64 registers x 128 threads each) instead of four.
+constexpr int kScanThreads = 128;
+constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr int kScanWin = 32 * kScanItems;  // slots one warp fills per window of its private shared-memory strip
 
 // partial-reduction record (doubles)
 //  0 m   1 s1   2 s2   3 dx 4 dy 5 dth 6 sin 7 cos 8 xx 9 xy 10 yy 11 xth 12 yth 13 thth

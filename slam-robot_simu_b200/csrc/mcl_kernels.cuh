@@ -410,22 +410,22 @@ __device__ __forceinline__ void merge_light(const double *pp, int nb, MergeScrat
     }
 }
 __device__ __noinline__ void merge_light_raw(const double *pp, int nb, MergeScratch &sc, float &M, double &s1, double &s2) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = static_cast<int>(blockDim.x) >> 5;
     float mx = -3.4028234e38f;
     double a1 = 0.0, a2 = 0.0;
     constexpr int kB = 4;
-    for (int b0 = tid; b0 < nb; b0 += 256 * kB) {
+    for (int b0 = tid; b0 < nb; b0 += static_cast<int>(blockDim.x) * kB) {
         double m4[kB], p4[kB], q4[kB];
 #pragma unroll
         for (int u = 0; u < kB; ++u) {  // clamped rows, masked below: the 12 loads are independent
-            const double *r = pp + min(b0 + u * 256, nb - 1) * kPart;
+            const double *r = pp + min(b0 + u * static_cast<int>(blockDim.x), nb - 1) * kPart;
             m4[u] = __ldcg(r);
             p4[u] = __ldcg(r + 1);
             q4[u] = __ldcg(r + 2);
         }
 #pragma unroll
         for (int u = 0; u < kB; ++u) {
-            if (b0 + u * 256 < nb) {
+            if (b0 + u * static_cast<int>(blockDim.x) < nb) {
                 const float mb = static_cast<float>(m4[u]);
                 if (mb > mx) {
                     const float r = ex2_approx((mx - mb) * kLog2e);
@@ -457,12 +457,10 @@ __device__ __noinline__ void merge_light_raw(const double *pp, int nb, MergeScra
     if (lane == 0) { sc.m[warp] = wm; sc.a[warp] = a1; sc.b[warp] = a2; }
     __syncthreads();
     M = sc.m[0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) M = fmaxf(M, sc.m[w]);
+    for (int w = 1; w < nw; ++w) M = fmaxf(M, sc.m[w]);
     s1 = 0.0;
     s2 = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < nw; ++w) {
         const float r = ex2_approx((sc.m[w] - M) * kLog2e);
         s1 = fma(sc.a[w], static_cast<double>(r), s1);
         s2 = fma(sc.b[w], static_cast<double>(r * r), s2);
@@ -473,16 +471,16 @@ __device__ __noinline__ void merge_light_raw(const double *pp, int nb, MergeScra
 // cannot start before that CTA is done -- a second pass over the (cold) records cost it ~2 us at C1
 __device__ __noinline__ void merge_light_best(const double *pp, int nb, MergeScratch &sc, float &M, double &s1, double &s2,
                                               float &best_v, uint32_t &best_i) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = static_cast<int>(blockDim.x) >> 5;
     float mx = -3.4028234e38f;
     double a1 = 0.0, a2 = 0.0;
     uint32_t bk = 0u, bi = 0xffffffffu;
     constexpr int kB = 2;
-    for (int b0 = tid; b0 < nb; b0 += 256 * kB) {
+    for (int b0 = tid; b0 < nb; b0 += static_cast<int>(blockDim.x) * kB) {
         double m4[kB], p4[kB], q4[kB], v4[kB], i4[kB];
 #pragma unroll
         for (int u = 0; u < kB; ++u) {  // clamped rows, masked below: the loads are independent
-            const double *r = pp + min(b0 + u * 256, nb - 1) * kPart;
+            const double *r = pp + min(b0 + u * static_cast<int>(blockDim.x), nb - 1) * kPart;
             m4[u] = __ldcg(r);
             p4[u] = __ldcg(r + 1);
             q4[u] = __ldcg(r + 2);
@@ -491,7 +489,7 @@ __device__ __noinline__ void merge_light_best(const double *pp, int nb, MergeScr
         }
 #pragma unroll
         for (int u = 0; u < kB; ++u) {
-            if (b0 + u * 256 < nb) {
+            if (b0 + u * static_cast<int>(blockDim.x) < nb) {
                 const float mb = static_cast<float>(m4[u]);
                 if (mb > mx) {
                     const float r = ex2_approx((mx - mb) * kLog2e);
@@ -529,15 +527,13 @@ __device__ __noinline__ void merge_light_best(const double *pp, int nb, MergeScr
     M = sc.m[0];
     bk = sc.k[0];
     bi = sc.i[0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) {
+    for (int w = 1; w < nw; ++w) {
         M = fmaxf(M, sc.m[w]);
         if (sc.k[w] > bk || (sc.k[w] == bk && sc.i[w] < bi)) { bk = sc.k[w]; bi = sc.i[w]; }
     }
     s1 = 0.0;
     s2 = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < nw; ++w) {
         const float r = ex2_approx((sc.m[w] - M) * kLog2e);
         s1 = fma(sc.a[w], static_cast<double>(r), s1);
         s2 = fma(sc.b[w], static_cast<double>(r * r), s2);
@@ -548,20 +544,20 @@ __device__ __noinline__ void merge_light_best(const double *pp, int nb, MergeScr
 
 // arg-max over the records: stored log-weight of the MAP particle and its index (smallest index on ties)
 __device__ __noinline__ void merge_best(const double *pp, int nb, MergeScratch &sc, float &best_v, uint32_t &best_i) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = static_cast<int>(blockDim.x) >> 5;
     uint32_t bk = 0u, bi = 0xffffffffu;
     constexpr int kB = 4;
-    for (int b0 = tid; b0 < nb; b0 += 256 * kB) {
+    for (int b0 = tid; b0 < nb; b0 += static_cast<int>(blockDim.x) * kB) {
         double v4[kB], i4[kB];
 #pragma unroll
         for (int u = 0; u < kB; ++u) {
-            const double *r = pp + min(b0 + u * 256, nb - 1) * kPart;
+            const double *r = pp + min(b0 + u * static_cast<int>(blockDim.x), nb - 1) * kPart;
             v4[u] = __ldcg(r + 14);
             i4[u] = __ldcg(r + 15);
         }
 #pragma unroll
         for (int u = 0; u < kB; ++u) {
-            if (b0 + u * 256 < nb) {
+            if (b0 + u * static_cast<int>(blockDim.x) < nb) {
                 const uint32_t k = float_order_key(static_cast<float>(v4[u]));
                 const uint32_t i = static_cast<uint32_t>(i4[u]);
                 if (k > bk || (k == bk && i < bi)) { bk = k; bi = i; }
@@ -575,8 +571,7 @@ __device__ __noinline__ void merge_best(const double *pp, int nb, MergeScratch &
     __syncthreads();
     bk = sc.k[0];
     bi = sc.i[0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w)
+    for (int w = 1; w < nw; ++w)
         if (sc.k[w] > bk || (sc.k[w] == bk && sc.i[w] < bi)) { bk = sc.k[w]; bi = sc.i[w]; }
     best_v = float_from_order_key(bk);
     best_i = bi;
@@ -588,12 +583,12 @@ __device__ __noinline__ void merge_best(const double *pp, int nb, MergeScratch &
 __device__ __noinline__ void merge_full(const double *pp, int nb, mcl_stats *st, const float *ex, const float *ey,
                                         const float *eth, unsigned long long *dbg, double n_global, bool apply_rule) {
     constexpr int NW = kStepThreads / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = static_cast<int>(blockDim.x) >> 5;
     __shared__ double s_part[NW][kPart];
     __shared__ float s_mx[NW];
     __shared__ uint32_t s_bk[NW], s_bi[NW];
     const int col = tid & (kPart - 1), row0 = tid >> 4;  // 16 threads read one 128-byte record
-    constexpr int kRows = kStepThreads / kPart;
+    const int kRows = static_cast<int>(blockDim.x) / kPart;  // 16 threads read one 128-byte record
     dbg_stamp(dbg, 7);
     // pass 1: the global maximum of the partial maxima (loads in explicit batches: one L2 round trip each)
     constexpr int kBatch = 8;
@@ -610,8 +605,7 @@ __device__ __noinline__ void merge_full(const double *pp, int nb, mcl_stats *st,
     if (lane == 0) s_mx[warp] = mx;
     __syncthreads();
     float MM = s_mx[0];
-#pragma unroll
-    for (int w = 1; w < NW; ++w) MM = fmaxf(MM, s_mx[w]);
+    for (int w = 1; w < nw; ++w) MM = fmaxf(MM, s_mx[w]);
     dbg_stamp(dbg, 8);
     // pass 2: column `col` of every record, rescaled to MM (columns 1..13 are sums; column 2 carries squares)
     double acc = 0.0;
@@ -651,8 +645,7 @@ __device__ __noinline__ void merge_full(const double *pp, int nb, mcl_stats *st,
     __syncthreads();
     if (tid >= 1 && tid <= kNumSums) {  // thread c sums column c over the warps
         double tot = 0.0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) tot += s_part[w][tid];
+        for (int w = 0; w < nw; ++w) tot += s_part[w][tid];
         if (tid == 1) st->sum_w = tot;
         else if (tid == 2) st->sum_w2 = tot;
         else st->raw[tid - 3] = tot;  // dx dy dth sin cos xx xy yy xth yth thth
@@ -662,8 +655,7 @@ __device__ __noinline__ void merge_full(const double *pp, int nb, mcl_stats *st,
     dbg_stamp(dbg, 10);
     if (tid == 0) {
         uint32_t bk = s_bk[0], bj = s_bi[0];
-#pragma unroll
-        for (int w = 1; w < NW; ++w)
+        for (int w = 1; w < nw; ++w)
             if (s_bk[w] > bk || (s_bk[w] == bk && s_bi[w] < bj)) { bk = s_bk[w]; bj = s_bi[w]; }
         const double s1 = s_part[0][1], s2 = s_part[0][2];
         // particle_filter.py:234-237 (a shard of a sharded filter leaves the decision to the merge of all shards)
@@ -767,9 +759,6 @@ struct ScanParams {
     uint32_t xflags;            // host flags of the step (MCL_FORCE_RESAMPLE / MCL_NO_RESAMPLE)
 };
 
-#ifndef MCL_SCAN_CTAS_PER_SM
-#define MCL_SCAN_CTAS_PER_SM 4
-#endif
 constexpr int kDirectTiles = 1024;  // tiles that sum all predecessors' aggregates directly (2M particles)
 constexpr int kScanAncestors = 0;  // write the ancestor of every slot
 constexpr int kScanExpand = 2;     // write the resampled pose of every slot (sender side of the sharded filter)
@@ -809,8 +798,14 @@ __device__ __forceinline__ void expand_store(const ScanParams &p, uint32_t *anc,
     }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(const __grid_constant__ ScanParams p) {
+// ITEMS sources per thread, 2048 / ITEMS threads per tile.  16: eight tiles resident per SM -- the geometry of large
+// scans, which are bound by the latency of a tile at a fixed number of resident tiles (0.64 -> 0.49 ms at 125 M).
+// 8: four tiles of 256 threads -- shorter per-tile latency, better while all tiles of a filter fit in ONE wave (C1).
+constexpr int scan_ctas_per_sm(int items) { return items == 16 ? 8 : 4; }
+template <int MODE, int ITEMS>
+__global__ void __launch_bounds__(kScanTile / ITEMS, scan_ctas_per_sm(ITEMS)) k_scan(const __grid_constant__ ScanParams p) {
+    // (the names of the namespace-scope defaults, re-bound to this instantiation's geometry)
+    constexpr int kScanItems = ITEMS, kScanThreads = kScanTile / ITEMS, kScanWin = 32 * ITEMS;
     const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kScanThreads / 32;
     __shared__ ScanShared s_sc;
@@ -975,31 +970,37 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
     for (long long tile = s_sc.tile; tile < p.tpt; tile = static_cast<long long>(s_next[it & 1]), ++it) {
     const long long j0 = tile * kScanTile + static_cast<long long>(tid) * kScanItems;
 
-    // ---- load + quantise (8 consecutive items per thread, two 16-byte loads) ----
-    double qd[kScanItems];  // integer-valued: rint(w * 2^52)
+    // ---- load + quantise (16 consecutive items per thread, four 16-byte loads) ----
+    // The integers rint(w 2^52) are kept as fp32 (exact: rintf of an fp32 value) -- 16 registers instead of 32 --
+    // and widened where they are summed.
+    float qf[kScanItems];
     if (j0 < p.n) {
         // the state arrays are padded to a multiple of 128 elements, so the vector loads stay in bounds
-        float4 a = *reinterpret_cast<const float4 *>(lw + j0);
-        float4 b = *reinterpret_cast<const float4 *>(lw + j0 + 4);
-        if (uniform) a = b = make_float4(0.f, 0.f, 0.f, 0.f);  // CTA-uniform: weights reset to 1/NP (:234-237)
-        const float v[kScanItems] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float v[kScanItems];
+#pragma unroll
+        for (int c = 0; c < kScanItems / 4; ++c) {
+            float4 a = *reinterpret_cast<const float4 *>(lw + j0 + 4 * c);
+            if (uniform) a = make_float4(0.f, 0.f, 0.f, 0.f);  // CTA-uniform: weights reset to 1/NP (:234-237)
+            v[4 * c] = a.x; v[4 * c + 1] = a.y; v[4 * c + 2] = a.z; v[4 * c + 3] = a.w;
+        }
         if (j0 + kScanItems <= p.n) {
 #pragma unroll
-            for (int k = 0; k < kScanItems; ++k) qd[k] = quantize_weight_d(v[k], wm);
+            for (int k = 0; k < kScanItems; ++k) qf[k] = rintf(weight_scaled(v[k], wm));
         } else {
 #pragma unroll
-            for (int k = 0; k < kScanItems; ++k) qd[k] = (j0 + k < p.n) ? quantize_weight_d(v[k], wm) : 0.0;
+            for (int k = 0; k < kScanItems; ++k) qf[k] = (j0 + k < p.n) ? rintf(weight_scaled(v[k], wm)) : 0.0f;
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < kScanItems; ++k) qd[k] = 0.0;
+        for (int k = 0; k < kScanItems; ++k) qf[k] = 0.0f;
     }
     // the first mark window is cleared here, off the critical path: the barriers of the block scan order it
-    *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(0u, 0u, 0u, 0u);  // the thread's own 32 bytes
-    *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int c = 0; c < kScanItems / 4; ++c)  // the thread's own 64 bytes (= its lane's strip of the warp's window)
+        *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4 * c]) = make_uint4(0u, 0u, 0u, 0u);
     double tsum_d = 0.0;  // sums of integers below 2^53 are exact in fp64
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) tsum_d += qd[k];
+    for (int k = 0; k < kScanItems; ++k) tsum_d += static_cast<double>(qf[k]);
     const unsigned long long tsum = static_cast<unsigned long long>(tsum_d);
 
     // ---- block exclusive scan of the thread sums ----
@@ -1096,19 +1097,26 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
         //  hardware REDUX on 27-bit halves -- 15 % fewer look-back instructions, 0.5 % SLOWER: the scan is bound by
         //  the latency of its dependent steps, not by instruction issue)
         while (true) {
-            const long long idx = look - tid;
-            unsigned long long d = kDescPrefix;  // tiles before the first one: an empty prefix
-            if (idx >= 0) d = *reinterpret_cast<volatile unsigned long long *>(&desc[idx]);
-            while (!__syncthreads_and((d >> 62) != 0ull)) {
-                if ((d >> 62) == 0ull) d = *reinterpret_cast<volatile unsigned long long *>(&desc[idx]);
+            // one round = the 256 descriptors before `look`, two per thread: position tid (nearest first) and tid + 128
+            const long long idx0 = look - tid, idx1 = look - kScanThreads - tid;
+            unsigned long long d0 = kDescPrefix, d1 = kDescPrefix;  // tiles before the first one: an empty prefix
+            if (idx0 >= 0) d0 = *reinterpret_cast<volatile unsigned long long *>(&desc[idx0]);
+            if (idx1 >= 0) d1 = *reinterpret_cast<volatile unsigned long long *>(&desc[idx1]);
+            while (!__syncthreads_and((d0 >> 62) != 0ull && (d1 >> 62) != 0ull)) {
+                if ((d0 >> 62) == 0ull) d0 = *reinterpret_cast<volatile unsigned long long *>(&desc[idx0]);
+                if ((d1 >> 62) == 0ull) d1 = *reinterpret_cast<volatile unsigned long long *>(&desc[idx1]);
             }
-            const unsigned int is_prefix = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
-            if (lane == 0) s_first[warp] = is_prefix ? (warp * 32 + __ffs(is_prefix) - 1) : 0x7fffffff;
+            const unsigned int pre0 = __ballot_sync(0xffffffffu, (d0 >> 62) == 2ull);
+            const unsigned int pre1 = __ballot_sync(0xffffffffu, (d1 >> 62) == 2ull);
+            if (lane == 0)
+                s_first[warp] = pre0 ? (warp * 32 + __ffs(pre0) - 1)
+                                     : (pre1 ? (kScanThreads + warp * 32 + __ffs(pre1) - 1) : 0x7fffffff);
             __syncthreads();
-            int first = 0x7fffffff;  // nearest predecessor (smallest tid) that already holds a prefix
+            int first = 0x7fffffff;  // nearest predecessor (smallest position) that already holds a prefix
 #pragma unroll
             for (int w = 0; w < NW; ++w) first = min(first, s_first[w]);
-            unsigned long long contrib = (tid <= first && idx >= 0) ? (d & kDescValueMask) : 0ull;
+            unsigned long long contrib = ((tid <= first && idx0 >= 0) ? (d0 & kDescValueMask) : 0ull) +
+                                         ((tid + kScanThreads <= first && idx1 >= 0) ? (d1 & kDescValueMask) : 0ull);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
             if (lane == 0) s_warp[warp] = contrib;
@@ -1117,7 +1125,7 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
             for (int w = 0; w < NW; ++w) excl += s_warp[w];
             __syncthreads();
             if (first != 0x7fffffff) break;
-            look -= kScanThreads;
+            look -= 2 * kScanThreads;
         }
         // tiles of the direct range keep their aggregate (later direct tiles sum aggregates); the LAST direct
         // tile and everything after it publish inclusive prefixes for the classic look-back
@@ -1145,7 +1153,7 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
         cur = first_slot;
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) {
-            Kd += qd[k];
+            Kd += static_cast<double>(qf[k]);
             const uint32_t end = count_le_bits(Kd, cf.a1, a0m, ok);
             rel[k] = (end != cur) ? cur - first_slot : 0x80000000u;
             cur = end;
@@ -1166,7 +1174,7 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
         double c = fs;
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) {
-            Kd += qd[k];
+            Kd += static_cast<double>(qf[k]);
             double end = count_le_fast(Kd, cf, p.delta, ofs);
             if (k == k_last) end = nd;
             if (k < n_valid && end > c) {
@@ -1180,21 +1188,42 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
         cur = static_cast<uint32_t>(static_cast<long long>(c));
     }
     // ---- ancestors ----
-    // Common case: every WARP fills the slots of its own 256 sources by itself -- marks, max-scan and stores inside
-    // a 1 KB window of shared memory that only this warp touches, ordered by __syncwarp: no block barrier at all.
-    // A warp's slot range is [first_slot of lane 0, cur of lane 31); slot `first_slot` of any thread is owned by the
-    // first source at or after it that owns slots at all, so every slot of the range has a mark at or before it
-    // inside the warp (or is covered by the carry of the previous pass).  Marks hold the source index itself;
-    // 0 doubles as "empty", which is right because only the very first source can be 0 and it owns whatever
-    // precedes the first other mark.  Tiles whose sources own far more slots than sources (collapsed weights: one
-    // particle owning up to every slot) keep the block-cooperative fill below.
+    // Common case: every WARP fills the slots of its own 512 sources by itself -- marks, max-scan and stores inside
+    // a 2 KB strip of shared memory that only this warp touches, ordered by __syncwarp: no block barrier at all.
+    // A warp's slot range is [first_slot of lane 0, cur of its last lane holding sources); slot `first_slot` of any
+    // thread is owned by the first source at or after it that owns slots at all, so every slot of the range has a
+    // mark at or before it inside the warp (or is covered by the carry of the previous pass).  Marks hold the source
+    // index itself; 0 doubles as "empty", which is right because only the very first source can be 0 and it owns
+    // whatever precedes the first other mark.  Tiles whose sources own far more slots than sources (collapsed
+    // weights: one particle owning up to every slot) keep the block-cooperative fill below.
     const uint32_t anc_lo = (MODE == kScanAncestors) ? 0u : static_cast<uint32_t>(p.own_lo);
     uint32_t *anc = p.anc + static_cast<long long>(t) * p.ld;
     const long long n_in_tile = min(static_cast<long long>(kScanTile), p.n - tile * kScanTile);
     const int last_tid = static_cast<int>((n_in_tile - 1) / kScanItems);
+    // eight consecutive slots from registers: one 32-byte store when the chunk lies inside [lo, hi) and in this
+    // handle's ancestor array, else slot by slot (the two partial chunks of a range; off-rank slots of an expansion)
+    auto store8 = [&](uint32_t slot0, const uint32_t (&v)[8], uint32_t lo, uint32_t hi, bool reg_store) {
+        if (reg_store) {
+            if (slot0 >= lo && slot0 + 8u <= hi) {
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(anc + (slot0 - anc_lo)), "r"(v[0]),
+                             "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                             : "memory");
+            } else {
+                // (parking the partial chunks in shared memory and storing them once per warp was measured 6 % SLOWER:
+                //  one more dependent shared-memory round trip at the end of every tile)
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (slot0 + k >= lo && slot0 + k < hi) anc[slot0 + k - anc_lo] = v[k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (slot0 + k >= lo && slot0 + k < hi) expand_store(p, anc, static_cast<long long>(slot0) + k, v[k]);
+        }
+    };
     const bool big = static_cast<double>(tile_total) * cf.a1 > 3.0 * kScanTile;  // CTA-uniform
     if (!big) {
-        uint32_t *wm = s_mark + warp * (32 * kScanItems);
+        uint32_t *wm = s_mark + warp * kScanWin;
         // (the range ends with the last lane that HOLDS sources: padding lanes of the filter's last tile sit at the
         //  final cumulative weight, which may fall short of the slots the last particle was given)
         const int last_lane = min(31, last_tid - warp * 32);
@@ -1207,10 +1236,11 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
         const uint32_t my_off = first_slot - Wb;
         const uint32_t jsrc0 = static_cast<uint32_t>(tile * kScanTile) + static_cast<uint32_t>(tid * kScanItems);
         uint32_t carry = 0u;
-        for (uint32_t cb = 0; cb < span; cb += 32 * kScanItems) {
+        for (uint32_t cb = 0; cb < span; cb += kScanWin) {
             if (cb > 0u) {  // (the first window was cleared before the block scan)
-                *reinterpret_cast<uint4 *>(&wm[lane * kScanItems]) = make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<uint4 *>(&wm[lane * kScanItems + 4]) = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int c = 0; c < kScanItems / 4; ++c)
+                    *reinterpret_cast<uint4 *>(&wm[lane * kScanItems + 4 * c]) = make_uint4(0u, 0u, 0u, 0u);
             }
             __syncwarp();
             if (cur != first_slot) {
@@ -1218,49 +1248,35 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
 #pragma unroll
                 for (int k = 0; k < kScanItems; ++k) {
                     const uint32_t pos = wofs + rel[k];
-                    if (pos < static_cast<uint32_t>(32 * kScanItems)) wm[pos] = jsrc0 + k;
+                    if (pos < static_cast<uint32_t>(kScanWin)) wm[pos] = jsrc0 + k;
                 }
             }
             __syncwarp();
-            uint32_t v[kScanItems];
-            {
-                const uint4 a = *reinterpret_cast<const uint4 *>(&wm[lane * kScanItems]);
-                const uint4 b = *reinterpret_cast<const uint4 *>(&wm[lane * kScanItems + 4]);
-                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-                v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-            }
-#pragma unroll
-            for (int k = 1; k < kScanItems; ++k) v[k] = max(v[k], v[k - 1]);
-            uint32_t run = v[kScanItems - 1];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) run = max(run, __shfl_up_sync(0xffffffffu, run, o));  // (lanes < o get their own value)
-            uint32_t before = __shfl_up_sync(0xffffffffu, run, 1);
-            before = (lane == 0) ? carry : max(before, carry);
-            carry = max(carry, __shfl_sync(0xffffffffu, run, 31));
-#pragma unroll
-            for (int k = 0; k < kScanItems; ++k) v[k] = max(v[k], before);
-            const uint32_t slot0 = Wb + cb + static_cast<uint32_t>(lane * kScanItems);
             const bool reg_store = (MODE == kScanAncestors) ||
                                    (aligned && static_cast<long long>(Wb) + cb >= p.own_lo &&
-                                    static_cast<long long>(Wb) + cb + 32 * kScanItems <= p.own_hi);
-            if (reg_store) {
-                if (slot0 >= wf && slot0 + kScanItems <= we) {
-                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(anc + (slot0 - anc_lo)), "r"(v[0]),
-                                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                                 : "memory");
-                }
-                // (parking the two partial chunks of a warp in shared memory and storing them once, after the loop, by
-                //  sixteen lanes removed ~6 thread-instructions per particle and made the kernel 6 % SLOWER: one more
-                //  dependent shared-memory round trip at the end of every tile)
-                else {
+                                    static_cast<long long>(Wb) + cb + kScanWin <= p.own_hi);
+            // the window in chunks of 256 slots: eight consecutive slots per lane and chunk
 #pragma unroll
-                    for (int k = 0; k < kScanItems; ++k)
-                        if (slot0 + k >= wf && slot0 + k < we) anc[slot0 + k - anc_lo] = v[k];
+            for (int half = 0; half < kScanWin / 256; ++half) {
+                if (cb + half * 256u >= span) break;  // warp-uniform
+                uint32_t v[8];
+                {
+                    const uint4 a = *reinterpret_cast<const uint4 *>(&wm[half * 256 + lane * 8]);
+                    const uint4 b = *reinterpret_cast<const uint4 *>(&wm[half * 256 + lane * 8 + 4]);
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
                 }
-            } else {
 #pragma unroll
-                for (int k = 0; k < kScanItems; ++k)
-                    if (slot0 + k >= wf && slot0 + k < we) expand_store(p, anc, static_cast<long long>(slot0) + k, v[k]);
+                for (int k = 1; k < 8; ++k) v[k] = max(v[k], v[k - 1]);
+                uint32_t run = v[7];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) run = max(run, __shfl_up_sync(0xffffffffu, run, o));  // (lanes < o get their own value)
+                uint32_t before = __shfl_up_sync(0xffffffffu, run, 1);
+                before = (lane == 0) ? carry : max(before, carry);
+                carry = max(carry, __shfl_sync(0xffffffffu, run, 31));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = max(v[k], before);
+                store8(Wb + cb + static_cast<uint32_t>(half * 256 + lane * 8), v, wf, we, reg_store);
             }
         }
     } else {
@@ -1278,34 +1294,31 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
         const uint32_t my_off = first_slot - W0;  // threads with sources: >= 0
 
         dbg_stamp(p.dbg, 4);
-        uint32_t carry = 0;  // source (local index + 1) that owns the slot just before the window
+        uint32_t carry = 0;  // source (tile-local index + 1) that owns the slot just before the window
+        const uint32_t jbase = static_cast<uint32_t>(tile * kScanTile) - 1u;
         for (uint32_t cb = 0; cb < span; cb += kScanTile) {
-            // window of kScanTile slots starting at W0 + cb
+            // window of kScanTile slots starting at W0 + cb; every thread handles kScanItems consecutive slots of it
             // registers -> anc[] directly when the whole window belongs to this handle's ancestor array (always, unsharded)
             const bool reg_store = (MODE == kScanAncestors) ||
                                    (aligned && static_cast<long long>(W0) + cb >= p.own_lo &&
                                     static_cast<long long>(W0) + cb + kScanTile <= p.own_hi);
+            const uint32_t slot0 = W0 + cb + static_cast<uint32_t>(tid * kScanItems);
             if (cb > 0u && span > 4u * kScanTile) {
                 // Degenerate weights: one source owns many windows.  A window in which no source starts is a
-                // constant fill with the carried owner -- one barrier and one store per thread instead of a scan.
+                // constant fill with the carried owner -- one barrier and two stores per thread instead of a scan.
                 bool starts = false;
                 const uint32_t wofs = my_off - cb;
-    #pragma unroll
+#pragma unroll
                 for (int k = 0; k < kScanItems; ++k) starts = starts || (wofs + rel[k] < static_cast<uint32_t>(kScanTile));
                 if (!__syncthreads_or(starts)) {
-                    const uint32_t j = static_cast<uint32_t>(tile * kScanTile) - 1u + carry;
+                    const uint32_t j = jbase + carry;
                     if (reg_store) {
-                        const uint32_t slot0 = W0 + cb + static_cast<uint32_t>(tid * kScanItems);
-                        if (slot0 >= S0 && slot0 + kScanItems <= S1) {
-                            asm volatile("st.global.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(anc + (slot0 - anc_lo)), "r"(j) : "memory");
-                        } else {
-    #pragma unroll
-                            for (int k = 0; k < kScanItems; ++k)
-                                if (slot0 + k >= S0 && slot0 + k < S1) anc[slot0 + k - anc_lo] = j;
-                        }
+                        const uint32_t c8[8] = {j, j, j, j, j, j, j, j};
+                        store8(slot0, c8, S0, S1, true);
+                        store8(slot0 + 8u, c8, S0, S1, true);
                     } else {
                         const int lim = static_cast<int>(min(static_cast<uint32_t>(kScanTile), span - cb));
-    #pragma unroll
+#pragma unroll
                         for (int k = 0; k < kScanItems; ++k) {
                             const int pos = k * kScanThreads + tid;
                             const long long slot = static_cast<long long>(W0) + cb + pos;
@@ -1316,43 +1329,38 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
                 }
             }
             if (cb > 0u) {  // (the first window was cleared before the block scan)
-                *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int c = 0; c < kScanItems / 4; ++c)
+                    *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4 * c]) = make_uint4(0u, 0u, 0u, 0u);
                 __syncthreads();
             }
             if (cur != first_slot) {
                 // slot positions relative to the window, modulo 2^32 (n_global < 2^31: no aliasing)
                 const uint32_t wofs = my_off - cb;
                 const uint32_t id0 = static_cast<uint32_t>(tid * kScanItems + 1);
-    #pragma unroll
+#pragma unroll
                 for (int k = 0; k < kScanItems; ++k) {
                     const uint32_t pos = wofs + rel[k];
                     if (pos < static_cast<uint32_t>(kScanTile)) s_mark[pos] = id0 + k;
                 }
             }
             __syncthreads();
-            // inclusive max-scan over the window, 8 consecutive entries per thread
-            uint32_t v[kScanItems];
-            {
-                const uint4 a = *reinterpret_cast<const uint4 *>(&s_mark[tid * kScanItems]);
-                const uint4 b = *reinterpret_cast<const uint4 *>(&s_mark[tid * kScanItems + 4]);
-                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-                v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            // inclusive max-scan over the window: first the maximum of the thread's own 16 entries ...
+            uint32_t tmax = 0u;
+#pragma unroll
+            for (int c = 0; c < kScanItems / 4; ++c) {
+                const uint4 a = *reinterpret_cast<const uint4 *>(&s_mark[tid * kScanItems + 4 * c]);
+                tmax = max(max(tmax, max(a.x, a.y)), max(a.z, a.w));
             }
-    #pragma unroll
-            for (int k = 1; k < kScanItems; ++k) v[k] = max(v[k], v[k - 1]);
-            uint32_t run = v[kScanItems - 1];
-    #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t n = __shfl_up_sync(0xffffffffu, run, o);
-                if (lane >= o) run = max(run, n);
-            }
+            uint32_t run = tmax;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) run = max(run, __shfl_up_sync(0xffffffffu, run, o));
             if (lane == 31) s_wmax[warp] = run;
             uint32_t before = __shfl_up_sync(0xffffffffu, run, 1);
             if (lane == 0) before = 0u;
             __syncthreads();
             uint32_t wbefore = carry, wall = carry;
-    #pragma unroll
+#pragma unroll
             for (int w = 0; w < NW; ++w) {
                 const uint32_t m = s_wmax[w];
                 if (w < warp) wbefore = max(wbefore, m);
@@ -1360,39 +1368,44 @@ __global__ void __launch_bounds__(kScanThreads, MCL_SCAN_CTAS_PER_SM) k_scan(con
             }
             before = max(before, wbefore);
             carry = wall;
-            const uint32_t jbase = static_cast<uint32_t>(tile * kScanTile) - 1u;
-            if (reg_store) {
-                // slots of this handle's own ancestor array (unsharded: all of them; anc holds ld >= n slots): the
-                // stores go straight from registers
-    #pragma unroll
-                for (int k = 0; k < kScanItems; ++k) v[k] = jbase + max(v[k], before);
-                const uint32_t slot0 = W0 + cb + static_cast<uint32_t>(tid * kScanItems);
-                if (slot0 >= S0 && slot0 + kScanItems <= S1) {
-                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(anc + (slot0 - anc_lo)), "r"(v[0]),
-                                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                                 : "memory");
-                } else {
-    #pragma unroll
-                    for (int k = 0; k < kScanItems; ++k)
-                        if (slot0 + k >= S0 && slot0 + k < S1) anc[slot0 + k - anc_lo] = v[k];
+            // ... then the entries again, eight at a time, with the running maximum carried along
+            uint32_t running = before;
+#pragma unroll
+            for (int g = 0; g < kScanItems / 8; ++g) {
+                uint32_t v[8];
+                {
+                    const uint4 a = *reinterpret_cast<const uint4 *>(&s_mark[tid * kScanItems + 8 * g]);
+                    const uint4 b = *reinterpret_cast<const uint4 *>(&s_mark[tid * kScanItems + 8 * g + 4]);
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
                 }
-                // no barrier here: the next window's zeroing of s_mark follows every thread's reads above
-            } else {
-    #pragma unroll
-                for (int k = 0; k < kScanItems; ++k) v[k] = max(v[k], before);
-                *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems]) = make_uint4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 4]) = make_uint4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    running = max(running, v[k]);
+                    v[k] = running;
+                }
+                if (reg_store) {
+                    // slots of this handle's own ancestor array (unsharded: all of them): straight from registers
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] += jbase;
+                    store8(slot0 + 8u * g, v, S0, S1, true);
+                } else {
+                    *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 8 * g]) = make_uint4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<uint4 *>(&s_mark[tid * kScanItems + 8 * g + 4]) = make_uint4(v[4], v[5], v[6], v[7]);
+                }
+            }
+            if (!reg_store) {
                 __syncthreads();
                 // coalesced stores
                 const int lim = static_cast<int>(min(static_cast<uint32_t>(kScanTile), span - cb));
-    #pragma unroll
+#pragma unroll
                 for (int k = 0; k < kScanItems; ++k) {
                     const int pos = k * kScanThreads + tid;
                     const long long slot = static_cast<long long>(W0) + cb + pos;
                     if (pos < lim && slot >= S0) expand_store(p, anc, slot, jbase + s_mark[pos]);
                 }
-                __syncthreads();
             }
+            __syncthreads();  // every read of the window is done before the next one is cleared
         }
     }
     __syncthreads();  // s_next (written at the top of this iteration) and the scratch are settled
@@ -2407,13 +2420,15 @@ __global__ void __launch_bounds__(kScanThreads) k_shard_total(const float *lw, l
         const long long j0 = tile * kScanTile + static_cast<long long>(tid) * kScanItems;
         unsigned long long acc = 0ull;
         if (j0 < n) {  // the state arrays are padded to a multiple of 128 elements: the vector loads stay in bounds
-            float4 a = *reinterpret_cast<const float4 *>(lw + j0);
-            float4 b = *reinterpret_cast<const float4 *>(lw + j0 + 4);
-            if (uniform) a = b = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float v[kScanItems] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int k = 0; k < kScanItems; ++k)
-                if (j0 + k < n) acc += quantize_weight(v[k], wm);
+            for (int c = 0; c < kScanItems / 4; ++c) {
+                float4 a = *reinterpret_cast<const float4 *>(lw + j0 + 4 * c);
+                if (uniform) a = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (j0 + 4 * c + k < n) acc += quantize_weight(v[k], wm);
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
