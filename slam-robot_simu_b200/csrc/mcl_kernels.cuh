@@ -153,7 +153,8 @@ __device__ __noinline__ void prep_block(const PrepParams &p, const PrepIn &in, c
             if (lane == 0) s_cnt[warp] = __popc(b);
             __syncthreads();
             int pos = base, tot = 0;
-            for (int w = 0; w < nw; ++w) {
+        #pragma unroll
+    for (int w = 0; w < nw; ++w) {
                 if (w < warp) pos += s_cnt[w];
                 tot += s_cnt[w];
             }
@@ -331,7 +332,7 @@ __device__ __forceinline__ float float_from_order_key(uint32_t k) {
 // in partials[] and exits -- no fence, no ticket, no "last CTA".  The records are merged where they are
 // consumed, each consumer reading only the columns it needs:
 //   merge_light  (max, sum w, sum w^2)  every tile CTA of the next k_scan: weight map + ESS gate
-//   merge_best   (arg-max)              the scalars CTA of k_scan: MAP pose -> reference pose
+//   merge_light_best (+ arg-max)        the scalars CTA of k_scan: MAP pose -> reference pose
 //   merge_full   (all 14 columns)       the statistics CTA of k_scan, or k_merge on demand: mcl_stats
 // All merges run the same code on the same records in the same order: every CTA derives bit-identical values.
 // -------------------------------------------------------------------------------------------------
@@ -397,11 +398,13 @@ struct MergeScratch {  // shared memory of one merge (256 threads)
 };
 
 // (max, sum w, sum w^2) over the nb partial records of trial t; all 256 threads, result in every thread
+template <int NT>
 __device__ __noinline__ void merge_light_raw(const double *pp, int nb, MergeScratch &sc, float &M, double &s1, double &s2);
 // ... with the reference's underflow rule applied: `uf` and the uniform (0, N, N) when it fired
+template <int NT>
 __device__ __forceinline__ void merge_light(const double *pp, int nb, MergeScratch &sc, float &M, double &s1, double &s2,
                                             double abs_shift, double n_global, int &uf) {
-    merge_light_raw(pp, nb, sc, M, s1, s2);
+    merge_light_raw<NT>(pp, nb, sc, M, s1, s2);
     uf = weights_underflowed(static_cast<double>(M), s1, abs_shift) ? 1 : 0;
     if (uf) {
         M = 0.0f;
@@ -409,23 +412,25 @@ __device__ __forceinline__ void merge_light(const double *pp, int nb, MergeScrat
         s2 = n_global;
     }
 }
+template <int NT>
 __device__ __noinline__ void merge_light_raw(const double *pp, int nb, MergeScratch &sc, float &M, double &s1, double &s2) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = static_cast<int>(blockDim.x) >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nw = NT / 32;
     float mx = -3.4028234e38f;
     double a1 = 0.0, a2 = 0.0;
     constexpr int kB = 4;
-    for (int b0 = tid; b0 < nb; b0 += static_cast<int>(blockDim.x) * kB) {
+    for (int b0 = tid; b0 < nb; b0 += NT * kB) {
         double m4[kB], p4[kB], q4[kB];
 #pragma unroll
         for (int u = 0; u < kB; ++u) {  // clamped rows, masked below: the 12 loads are independent
-            const double *r = pp + min(b0 + u * static_cast<int>(blockDim.x), nb - 1) * kPart;
+            const double *r = pp + min(b0 + u * NT, nb - 1) * kPart;
             m4[u] = __ldcg(r);
             p4[u] = __ldcg(r + 1);
             q4[u] = __ldcg(r + 2);
         }
 #pragma unroll
         for (int u = 0; u < kB; ++u) {
-            if (b0 + u * static_cast<int>(blockDim.x) < nb) {
+            if (b0 + u * NT < nb) {
                 const float mb = static_cast<float>(m4[u]);
                 if (mb > mx) {
                     const float r = ex2_approx((mx - mb) * kLog2e);
@@ -457,9 +462,11 @@ __device__ __noinline__ void merge_light_raw(const double *pp, int nb, MergeScra
     if (lane == 0) { sc.m[warp] = wm; sc.a[warp] = a1; sc.b[warp] = a2; }
     __syncthreads();
     M = sc.m[0];
+#pragma unroll
     for (int w = 1; w < nw; ++w) M = fmaxf(M, sc.m[w]);
     s1 = 0.0;
     s2 = 0.0;
+#pragma unroll
     for (int w = 0; w < nw; ++w) {
         const float r = ex2_approx((sc.m[w] - M) * kLog2e);
         s1 = fma(sc.a[w], static_cast<double>(r), s1);
@@ -469,18 +476,20 @@ __device__ __noinline__ void merge_light_raw(const double *pp, int nb, MergeScra
 
 // (max, sum w, sum w^2) AND the arg-max in one pass over the records: the scalars CTA of k_scan needs both, and k_step
 // cannot start before that CTA is done -- a second pass over the (cold) records cost it ~2 us at C1
+template <int NT>
 __device__ __noinline__ void merge_light_best(const double *pp, int nb, MergeScratch &sc, float &M, double &s1, double &s2,
                                               float &best_v, uint32_t &best_i) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = static_cast<int>(blockDim.x) >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nw = NT / 32;
     float mx = -3.4028234e38f;
     double a1 = 0.0, a2 = 0.0;
     uint32_t bk = 0u, bi = 0xffffffffu;
     constexpr int kB = 2;
-    for (int b0 = tid; b0 < nb; b0 += static_cast<int>(blockDim.x) * kB) {
+    for (int b0 = tid; b0 < nb; b0 += NT * kB) {
         double m4[kB], p4[kB], q4[kB], v4[kB], i4[kB];
 #pragma unroll
         for (int u = 0; u < kB; ++u) {  // clamped rows, masked below: the loads are independent
-            const double *r = pp + min(b0 + u * static_cast<int>(blockDim.x), nb - 1) * kPart;
+            const double *r = pp + min(b0 + u * NT, nb - 1) * kPart;
             m4[u] = __ldcg(r);
             p4[u] = __ldcg(r + 1);
             q4[u] = __ldcg(r + 2);
@@ -489,7 +498,7 @@ __device__ __noinline__ void merge_light_best(const double *pp, int nb, MergeScr
         }
 #pragma unroll
         for (int u = 0; u < kB; ++u) {
-            if (b0 + u * static_cast<int>(blockDim.x) < nb) {
+            if (b0 + u * NT < nb) {
                 const float mb = static_cast<float>(m4[u]);
                 if (mb > mx) {
                     const float r = ex2_approx((mx - mb) * kLog2e);
@@ -527,12 +536,14 @@ __device__ __noinline__ void merge_light_best(const double *pp, int nb, MergeScr
     M = sc.m[0];
     bk = sc.k[0];
     bi = sc.i[0];
+#pragma unroll
     for (int w = 1; w < nw; ++w) {
         M = fmaxf(M, sc.m[w]);
         if (sc.k[w] > bk || (sc.k[w] == bk && sc.i[w] < bi)) { bk = sc.k[w]; bi = sc.i[w]; }
     }
     s1 = 0.0;
     s2 = 0.0;
+#pragma unroll
     for (int w = 0; w < nw; ++w) {
         const float r = ex2_approx((sc.m[w] - M) * kLog2e);
         s1 = fma(sc.a[w], static_cast<double>(r), s1);
@@ -542,53 +553,20 @@ __device__ __noinline__ void merge_light_best(const double *pp, int nb, MergeScr
     best_i = bi;
 }
 
-// arg-max over the records: stored log-weight of the MAP particle and its index (smallest index on ties)
-__device__ __noinline__ void merge_best(const double *pp, int nb, MergeScratch &sc, float &best_v, uint32_t &best_i) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = static_cast<int>(blockDim.x) >> 5;
-    uint32_t bk = 0u, bi = 0xffffffffu;
-    constexpr int kB = 4;
-    for (int b0 = tid; b0 < nb; b0 += static_cast<int>(blockDim.x) * kB) {
-        double v4[kB], i4[kB];
-#pragma unroll
-        for (int u = 0; u < kB; ++u) {
-            const double *r = pp + min(b0 + u * static_cast<int>(blockDim.x), nb - 1) * kPart;
-            v4[u] = __ldcg(r + 14);
-            i4[u] = __ldcg(r + 15);
-        }
-#pragma unroll
-        for (int u = 0; u < kB; ++u) {
-            if (b0 + u * static_cast<int>(blockDim.x) < nb) {
-                const uint32_t k = float_order_key(static_cast<float>(v4[u]));
-                const uint32_t i = static_cast<uint32_t>(i4[u]);
-                if (k > bk || (k == bk && i < bi)) { bk = k; bi = i; }
-            }
-        }
-    }
-    const uint32_t wk = __reduce_max_sync(0xffffffffu, bk);
-    const uint32_t wi = __reduce_min_sync(0xffffffffu, (bk == wk) ? bi : 0xffffffffu);
-    __syncthreads();
-    if (lane == 0) { sc.k[warp] = wk; sc.i[warp] = wi; }
-    __syncthreads();
-    bk = sc.k[0];
-    bi = sc.i[0];
-    for (int w = 1; w < nw; ++w)
-        if (sc.k[w] > bk || (sc.k[w] == bk && sc.i[w] < bi)) { bk = sc.k[w]; bi = sc.i[w]; }
-    best_v = float_from_order_key(bk);
-    best_i = bi;
-}
-
 // All columns -> mcl_stats (sums, ESS, MAP index and pose).  One 256-thread CTA per trial; runs with a cold
 // instruction cache (once per step on one SM), hence small: rolled loops, no libm -- log-normaliser, mean and
 // covariance are derived from the sums where they are consumed (derive_stats).
+template <int NT>
 __device__ __noinline__ void merge_full(const double *pp, int nb, mcl_stats *st, const float *ex, const float *ey,
                                         const float *eth, unsigned long long *dbg, double n_global, bool apply_rule) {
     constexpr int NW = kStepThreads / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = static_cast<int>(blockDim.x) >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nw = NT / 32;
     __shared__ double s_part[NW][kPart];
     __shared__ float s_mx[NW];
     __shared__ uint32_t s_bk[NW], s_bi[NW];
     const int col = tid & (kPart - 1), row0 = tid >> 4;  // 16 threads read one 128-byte record
-    const int kRows = static_cast<int>(blockDim.x) / kPart;  // 16 threads read one 128-byte record
+    constexpr int kRows = NT / kPart;  // 16 threads read one 128-byte record
     dbg_stamp(dbg, 7);
     // pass 1: the global maximum of the partial maxima (loads in explicit batches: one L2 round trip each)
     constexpr int kBatch = 8;
@@ -605,6 +583,7 @@ __device__ __noinline__ void merge_full(const double *pp, int nb, mcl_stats *st,
     if (lane == 0) s_mx[warp] = mx;
     __syncthreads();
     float MM = s_mx[0];
+#pragma unroll
     for (int w = 1; w < nw; ++w) MM = fmaxf(MM, s_mx[w]);
     dbg_stamp(dbg, 8);
     // pass 2: column `col` of every record, rescaled to MM (columns 1..13 are sums; column 2 carries squares)
@@ -645,7 +624,8 @@ __device__ __noinline__ void merge_full(const double *pp, int nb, mcl_stats *st,
     __syncthreads();
     if (tid >= 1 && tid <= kNumSums) {  // thread c sums column c over the warps
         double tot = 0.0;
-        for (int w = 0; w < nw; ++w) tot += s_part[w][tid];
+    #pragma unroll
+    for (int w = 0; w < nw; ++w) tot += s_part[w][tid];
         if (tid == 1) st->sum_w = tot;
         else if (tid == 2) st->sum_w2 = tot;
         else st->raw[tid - 3] = tot;  // dx dy dth sin cos xx xy yy xth yth thth
@@ -655,7 +635,8 @@ __device__ __noinline__ void merge_full(const double *pp, int nb, mcl_stats *st,
     dbg_stamp(dbg, 10);
     if (tid == 0) {
         uint32_t bk = s_bk[0], bj = s_bi[0];
-        for (int w = 1; w < nw; ++w)
+    #pragma unroll
+    for (int w = 1; w < nw; ++w)
             if (s_bk[w] > bk || (s_bk[w] == bk && s_bi[w] < bj)) { bk = s_bk[w]; bj = s_bi[w]; }
         const double s1 = s_part[0][1], s2 = s_part[0][2];
         // particle_filter.py:234-237 (a shard of a sharded filter leaves the decision to the merge of all shards)
@@ -692,7 +673,7 @@ __global__ void __launch_bounds__(kStepThreads) k_merge(const MergeParams p) {
     cudaGridDependencySynchronize();  // launched programmatically behind k_step: its launch latency is hidden
     const int t = blockIdx.x;
     const long long off = static_cast<long long>(t) * p.ld;
-    merge_full(p.partials + static_cast<long long>(t) * p.bpt * kPart, p.bpt, p.stats + t, p.cur.x + off, p.cur.y + off,
+    merge_full<kStepThreads>(p.partials + static_cast<long long>(t) * p.bpt * kPart, p.bpt, p.stats + t, p.cur.x + off, p.cur.y + off,
                p.cur.th + off, nullptr, p.n_global, p.apply_rule != 0);
 }
 
@@ -829,7 +810,7 @@ __global__ void __launch_bounds__(kScanTile / ITEMS, scan_ctas_per_sm(ITEMS)) k_
     const long long soff = static_cast<long long>(t) * p.ld;
     const double *pp = p.partials + static_cast<long long>(t) * p.n_partials * kPart;
     if (stats_cta) {
-        merge_full(pp, p.n_partials, p.stats + t, p.cur.x + soff, p.cur.y + soff, p.cur.th + soff, nullptr, p.prep.n_global,
+        merge_full<kScanThreads>(pp, p.n_partials, p.stats + t, p.cur.x + soff, p.cur.y + soff, p.cur.th + soff, nullptr, p.prep.n_global,
                    p.n_global == p.n);
         return;
     }
@@ -880,14 +861,14 @@ __global__ void __launch_bounds__(kScanTile / ITEMS, scan_ctas_per_sm(ITEMS)) k_
             double s1, s2;
             // (a shard of a sharded filter never merges here: its statistics exchange has set n_partials = 0)
             if (prep_cta) {  // the scalars CTA also needs the arg-max: one pass over the records for both
-                merge_light_best(pp, p.n_partials, s_merge, M, s1, s2, pre_bv, pre_bi);
+                merge_light_best<kScanThreads>(pp, p.n_partials, s_merge, M, s1, s2, pre_bv, pre_bi);
                 st_uniform = weights_underflowed(static_cast<double>(M), s1, stp->abs_shift) ? 1 : 0;
                 if (st_uniform) {
                     M = 0.0f;
                     s1 = s2 = p.prep.n_global;
                 }
             } else {
-                merge_light(pp, p.n_partials, s_merge, M, s1, s2, stp->abs_shift, p.prep.n_global, st_uniform);
+                merge_light<kScanThreads>(pp, p.n_partials, s_merge, M, s1, s2, stp->abs_shift, p.prep.n_global, st_uniform);
             }
             st_max = static_cast<double>(M);
             st_sum = s1;
@@ -2268,7 +2249,7 @@ __global__ void __launch_bounds__(kStepThreads) k_xchg_stats(const XchgParams p)
     static_assert(sizeof(mcl_stats) % sizeof(unsigned long long) == 0, "mcl_stats is copied in 8-byte words");
     if (p.mode & kXchgPush) {
         if (p.n_partials > 0)
-            merge_full(p.partials, p.n_partials, p.stats, p.cur.x, p.cur.y, p.cur.th, nullptr, 0.0, false);
+            merge_full<kStepThreads>(p.partials, p.n_partials, p.stats, p.cur.x, p.cur.y, p.cur.th, nullptr, 0.0, false);
         if (tid < 3 && p.cur.x != nullptr) {  // this shard's first particle: the MAP pose of a filter reset to 1/NP
             const float *a = (tid == 0) ? p.cur.x : (tid == 1 ? p.cur.y : p.cur.th);
             p.stats->mean[tid] = static_cast<double>(a[0]);
