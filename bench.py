@@ -459,7 +459,7 @@ def measure_sharded(mcl, torch, dist, dev, n_per_gpu, L, likelihood, steps, warm
         sf.drain()
         sf.flt.profile(False)
         acc /= 8
-        kern = {"totals_pass+exchange": acc[0], "expansion+exchange": acc[1], "scalars": acc[2], "k_step": acc[3], "statistics_exchange": acc[4]}
+        kern = {"totals_pass+exchange": acc[0], "scalars+expansion+exchange": acc[1], "unused": acc[2], "k_step": acc[3], "statistics_exchange": acc[4]}
         pl = sf.plan()
         moved = int(sf.m - (pl.win_hi - pl.win_lo))
     mv = torch.tensor([float(moved or 0)], device=dev, dtype=torch.float64)

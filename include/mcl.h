@@ -230,9 +230,9 @@ int mcl_get_ancestors(mcl_filter *h, uint32_t *anc_host, void *stream);
  * mcl_launch_count: kernels launched through this handle since creation. */
 int mcl_profile(mcl_filter *h, int enable);
 int mcl_profile_read(mcl_filter *h, double *ms3_host);
-/* The same for the last mcl_shard_step_peer(..., MCL_STAGE_ALL): ms[0] totals pass + totals exchange, ms[1] expansion
- * + "done" exchange (both include the wait for the slowest peer), ms[2] per-step scalars, ms[3] k_step, ms[4]
- * statistics exchange. */
+/* The same for the last mcl_shard_step_peer(..., MCL_STAGE_ALL): ms[0] totals pass + totals exchange, ms[1] per-step
+ * scalars and expansion (side by side) + "done" exchange (both include the wait for the slowest peer), ms[2] = 0
+ * (historic: the scalars used to run here), ms[3] k_step, ms[4] statistics exchange. */
 int mcl_profile_read_peer(mcl_filter *h, double *ms5_host);
 uint64_t mcl_launch_count(const mcl_filter *h);
 /* Debug aid (needs a library built with -DMCL_TIMELINE, else MCL_ERR_STATE): the first call (stamps_host may be NULL) arms a per-CTA phase timeline of k_step; later calls
@@ -306,8 +306,8 @@ int mcl_shard_step(mcl_filter *h, const double *z_host, const float *noise_dev, 
 #define MCL_IPC_HANDLE_BYTES 64
 #define MCL_MAX_SHARDS 16
 #define MCL_STAGE_A 1u /* integer weight totals; push them                                   */
-#define MCL_STAGE_B 2u /* wait for the totals; plan; expansion; push "done"                  */
-#define MCL_STAGE_C 4u /* wait for "done"; predict + weight; push the statistics record      */
+#define MCL_STAGE_B 2u /* wait for the totals; plan; per-step scalars (needs z_host) beside the expansion; push "done" */
+#define MCL_STAGE_C 4u /* wait for "done"; predict + weight (needs noise_dev or Philox); push the statistics record */
 #define MCL_STAGE_D 8u /* wait for the records; merge; resampling gate of the next step      */
 #define MCL_STAGE_ALL 15u
 

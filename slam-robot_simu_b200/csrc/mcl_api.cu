@@ -1475,7 +1475,7 @@ int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_h
     if ((stages & MCL_STAGE_ALL) == 0 || (stages & ~MCL_STAGE_ALL) != 0) return fail(h, MCL_ERR_ARG, "bad stages");
     if (h->L <= 0) return fail(h, MCL_ERR_STATE, "mcl_set_landmarks has not been called");
     if (!h->have_particles) return fail(h, MCL_ERR_STATE, "particles are not initialised");
-    if ((stages & MCL_STAGE_C) && z_host == nullptr) return fail(h, MCL_ERR_ARG, "z_host is NULL");
+    if ((stages & (MCL_STAGE_B | MCL_STAGE_C)) && z_host == nullptr) return fail(h, MCL_ERR_ARG, "z_host is NULL");
     if ((stages & MCL_STAGE_C) && noise_dev == nullptr && !(flags & MCL_PHILOX_NOISE))
         return fail(h, MCL_ERR_ARG, "noise_dev is NULL and MCL_PHILOX_NOISE is not set");
     if (ofs_host != nullptr && !(ofs_host[0] >= 0.0 && ofs_host[0] < h->delta))
@@ -1512,6 +1512,21 @@ int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_h
         MCL_LAUNCH_CHECK(h, "k_xchg_total");
     }
     if (prof) MCL_CUDA(h, cudaEventRecord(h->ev[1], st));
+    if (B) {
+        // per-step scalars (one CTA; the gate comes from the plan).  They depend on the statistics and the plan only,
+        // so they are enqueued BEFORE the expansion, which is launched programmatically behind them and runs beside them.
+        rc = stage_inputs(h, z_host, nullptr, st);
+        if (rc != MCL_OK) return rc;
+        ScanParams sp;
+        fill_scan(h, sp);
+        fill_prep(h, sp.prep, h->z, nullptr, flags);
+        sp.do_prep = 1;
+        sp.trig = h->trig;
+        sp.plan = h->plan;
+        sp.xflags = flags;
+        launch_pdl(k_scan<kScanAncestors, 8>, dim3(1, 1), dim3(kScanTile / 8), 0, st, false, sp);
+        MCL_LAUNCH_CHECK(h, "k_scan");
+    }
     if (may_resample && B) {
         // second pass: global slot numbers, every tile starting from segment prefix + tile prefix (no look-back);
         // own slots -> ancestors, off-rank slots -> poses into the owner's staging
@@ -1528,8 +1543,9 @@ int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_h
         sp.seg_prefix = h->seg;
         sp.tiles_per_seg = h->tiles_per_seg;
         sp.persistent = 1;
+        sp.no_dep_sync = 1;
         dim3 grid(std::min(h->lay.tpt, h->sm_count * scan_ctas_per_sm(16)), 1);
-        k_scan<kScanExpand, 16><<<grid, kScanTile / 16, 0, st>>>(sp);
+        launch_pdl(k_scan<kScanExpand, 16>, grid, dim3(kScanTile / 16), 0, st, pdl_enabled(), sp);
         MCL_LAUNCH_CHECK(h, "k_scan");
     }
     if (may_resample && (B || Cc)) {
@@ -1540,20 +1556,6 @@ int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_h
     }
     if (prof) MCL_CUDA(h, cudaEventRecord(h->ev[2], st));
     if (Cc) {
-        rc = stage_inputs(h, z_host, nullptr, st);
-        if (rc != MCL_OK) return rc;
-        // per-step scalars; the gate comes from the plan
-        {
-            ScanParams sp;
-            fill_scan(h, sp);
-            fill_prep(h, sp.prep, h->z, nullptr, flags);
-            sp.do_prep = 1;
-            sp.trig = h->trig;
-            sp.plan = h->plan;
-            sp.xflags = flags;
-            launch_pdl(k_scan<kScanAncestors, 8>, dim3(1, 1), dim3(kScanTile / 8), 0, st, false, sp);
-            MCL_LAUNCH_CHECK(h, "k_scan");
-        }
         StepWindow win;
         win.lo = 0u;
         win.hi = static_cast<uint32_t>(h->lay.n);

@@ -738,6 +738,7 @@ struct ScanParams {
     const ShardPlan *plan;
     const PeerView *pv;
     uint32_t xflags;            // host flags of the step (MCL_FORCE_RESAMPLE / MCL_NO_RESAMPLE)
+    int no_dep_sync;            // launched programmatically behind a kernel whose results it does not need
 };
 
 constexpr int kDirectTiles = 1024;  // tiles that sum all predecessors' aggregates directly (2M particles)
@@ -799,7 +800,9 @@ __global__ void __launch_bounds__(kScanTile / ITEMS, scan_ctas_per_sm(ITEMS)) k_
     // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as every CTA of
     // this grid has started; nothing is read or written before the previous kernel has completed.
     cudaTriggerProgrammaticLaunchCompletion();
-    cudaGridDependencySynchronize();
+    // (the expansion of the device-driven sharded step is launched programmatically behind the per-step scalars
+    //  kernel, on which it does not depend: it runs beside it)
+    if (!p.no_dep_sync) cudaGridDependencySynchronize();
     // per-step scalars are the job of one extra CTA per trial: they are only needed by k_step, and their
     // once-per-step code (cold instruction cache) must not delay a tile that every later tile waits for
     dbg_stamp(p.dbg, 0);

@@ -329,7 +329,7 @@ class Filter:
         return ms[0], ms[1], ms[2]
 
     def profile_read_peer(self):
-        """(totals + exchange, expansion + exchange, scalars, k_step, statistics exchange) ms of the last peer step."""
+        """(totals + exchange, scalars + expansion + exchange, 0, k_step, statistics exchange) ms of the last peer step."""
         ms = (C.c_double * 5)()
         self._check(self.lib.mcl_profile_read_peer(self._h, ms), "mcl_profile_read_peer")
         return tuple(ms)

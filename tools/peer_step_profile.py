@@ -48,7 +48,7 @@ def main():
         f.step_peer(cyc[(25 + a.steps + k) % 360], force_resample=True)
         acc += np.array(f.profile_read_peer())
     acc /= a.steps
-    names = ["totals pass + exchange", "expansion + exchange", "scalars", "k_step", "statistics exchange"]
+    names = ["totals pass + exchange", "scalars + expansion + exchange", "(unused)", "k_step", "statistics exchange"]
     for nm, v in zip(names, acc):
         print(f"  {nm:26s} {v * 1e3:9.1f} us")
     f.profile(False)
