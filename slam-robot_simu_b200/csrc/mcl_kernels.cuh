@@ -783,7 +783,10 @@ __device__ __forceinline__ void expand_store(const ScanParams &p, uint32_t *anc,
 // ITEMS sources per thread, 2048 / ITEMS threads per tile.  16: eight tiles resident per SM -- the geometry of large
 // scans, which are bound by the latency of a tile at a fixed number of resident tiles (0.64 -> 0.49 ms at 125 M).
 // 8: four tiles of 256 threads -- shorter per-tile latency, better while all tiles of a filter fit in ONE wave (C1).
-constexpr int scan_ctas_per_sm(int items) { return items == 16 ? 8 : 4; }
+#ifndef MCL_SCAN16_CTAS
+#define MCL_SCAN16_CTAS 8
+#endif
+constexpr int scan_ctas_per_sm(int items) { return items == 16 ? MCL_SCAN16_CTAS : 4; }
 template <int MODE, int ITEMS>
 __global__ void __launch_bounds__(kScanTile / ITEMS, scan_ctas_per_sm(ITEMS)) k_scan(const __grid_constant__ ScanParams p) {
     // (the names of the namespace-scope defaults, re-bound to this instantiation's geometry)
@@ -2399,14 +2402,25 @@ __global__ void __launch_bounds__(kScanThreads) k_shard_total(const float *lw, l
     unsigned long long run = 0ull;  // thread 0: weight of the segment's tiles so far
     const long long t0 = static_cast<long long>(blockIdx.x) * tiles_per_seg;
     const long long t1 = min(static_cast<long long>(tpt), t0 + tiles_per_seg);
+    // The loads of the NEXT tile are issued before the current one is reduced: a tile is 64 bytes per thread, and with
+    // one tile in flight per CTA the pass ran at 3.9 TB/s, bound by the load -> reduce -> barrier chain of each tile.
+    float4 cur4[kScanItems / 4], nxt4[kScanItems / 4];
+    auto load_tile = [&](long long tile, float4 (&dst)[kScanItems / 4]) {
+        const long long j0 = tile * kScanTile + static_cast<long long>(tid) * kScanItems;
+#pragma unroll
+        for (int c = 0; c < kScanItems / 4; ++c)  // the state arrays are padded to a multiple of 128 elements: in bounds
+            dst[c] = (tile < t1 && j0 < n) ? *reinterpret_cast<const float4 *>(lw + j0 + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    load_tile(t0, cur4);
     int par = 0;
     for (long long tile = t0; tile < t1; ++tile, par ^= 1) {
+        load_tile(tile + 1, nxt4);
         const long long j0 = tile * kScanTile + static_cast<long long>(tid) * kScanItems;
         unsigned long long acc = 0ull;
-        if (j0 < n) {  // the state arrays are padded to a multiple of 128 elements: the vector loads stay in bounds
+        if (j0 < n) {
 #pragma unroll
             for (int c = 0; c < kScanItems / 4; ++c) {
-                float4 a = *reinterpret_cast<const float4 *>(lw + j0 + 4 * c);
+                float4 a = cur4[c];
                 if (uniform) a = make_float4(0.f, 0.f, 0.f, 0.f);
                 const float v[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
@@ -2425,6 +2439,8 @@ __global__ void __launch_bounds__(kScanThreads) k_shard_total(const float *lw, l
             tile_prefix[tile] = run;
             run += s;
         }
+#pragma unroll
+        for (int c = 0; c < kScanItems / 4; ++c) cur4[c] = nxt4[c];
     }
     if (tid == 0) {
         seg_total[blockIdx.x] = run;
