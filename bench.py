@@ -432,17 +432,22 @@ def measure_sharded(mcl, torch, dist, dev, n_per_gpu, L, likelihood, steps, warm
     sampler = ClockSampler(dev.index)
     launches0 = sf.flt.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_blocks)]
-    t0 = time.perf_counter()
     for e0, e1 in evs:
         e0.record()
         run(steps)
         e1.record()
-    _read_clocks(sampler)
+    _read_clocks(sampler)  # (the GPU is still working through the queue; NVML queries take milliseconds)
+    g = sf.drain()
+    torch.cuda.synchronize()
+    launches = (sf.flt.launch_count() - launches0) // n_blocks  # per block of `steps` steps, as `steps` is reported
+    # end to end: the same number of steps again, by the host clock alone (no NVML query inside the region)
+    dist.barrier()
+    t0 = time.perf_counter()
+    run(steps * n_blocks)
     g = sf.drain()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     dist.barrier()
-    launches = sf.flt.launch_count() - launches0
     block_ms = float(np.median([e0.elapsed_time(e1) for e0, e1 in evs]))
     t = torch.tensor([block_ms, wall], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
