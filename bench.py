@@ -618,12 +618,16 @@ def run_b200(args, wl):
 
     def extra_line(w_, lr, K_):
         return {"workload": w_["desc"], "value": lr["value"], "unit": "particle-steps/s", "ms_per_step": lr["ms"] / K_,
-                "steps": K_, "blocks": lr["blocks"], "ess_over_n": lr["ess"], "roofline": lr["roofline"]}
+                "steps": K_, "blocks": lr["blocks"], "ess_over_n": lr["ess"], "roofline": lr["roofline"], "clocks": lr["clocks"]}
 
-    def pair_loop(w_, lr, likelihood):
+    def pair_loop(w_, lr, likelihood, K_):
+        # pairs_per_s: from k_step timed alone (CUDA events around single launches, the GPU idle in between: burst
+        # clocks); pairs_per_s_sustained: from the back-to-back timed steps (a likelihood-bound kernel on the whole chip
+        # runs into the power cap -- see this entry's `clocks`)
         k_ms = lr["roofline"]["kernel_ms"]["k_step"]
         seen = lr["landmarks_seen"] if likelihood == "rb_fan" else float(w_["L"])
-        return {"landmarks_scored_per_step": seen, "pairs_per_s": w_["n"] * w_["T"] * seen / (k_ms * 1e-3), **PAIR_LOOPS[likelihood]}
+        return {"landmarks_scored_per_step": seen, "pairs_per_s": w_["n"] * w_["T"] * seen / (k_ms * 1e-3),
+                "pairs_per_s_sustained": w_["n"] * w_["T"] * seen / (lr["ms"] / K_ * 1e-3), **PAIR_LOOPS[likelihood]}
 
     # ------------------------------------------------------------------------------------------------------
     # N > 1: the headline is ONE filter sharded over the N GPUs (BASELINE.json configs[3]); extras: one independent
@@ -697,7 +701,7 @@ def run_b200(args, wl):
                                 lazy_px=True, force_resample=True, device=local, seed=4242 + rank)
         for _ in range(max(W, 20)):
             pf.main_pf()
-        ke = int(min(20000, max(K, 0.25 / 60e-6)))
+        ke = int(min(20000, max(K, 0.25 / max(60e-6, 1.7 * ms / K * 1e-3))))  # about 0.25 s of calls
         sync_all()
         t0 = time.perf_counter()
         for _ in range(ke):
@@ -740,14 +744,14 @@ def run_b200(args, wl):
             for lik, key, k_ in (("pair32", "c1", 40), ("pair32", "c3", 8), ("pair", "c3", 6)):
                 w_ = WORKLOADS[key]
                 lr = timed_run(w_, k_, 3, 0.1, lik, min_seconds=0.1)
-                extras[f"{lik}_{key}"] = dict(extra_line(w_, lr, k_), likelihood=lik, pair_loop=pair_loop(w_, lr, lik))
+                extras[f"{lik}_{key}"] = dict(extra_line(w_, lr, k_), likelihood=lik, pair_loop=pair_loop(w_, lr, lik, k_))
             c2 = WORKLOADS["c2"]
             lr = timed_run(c2, 12, 3, 0.1, "moment", min_seconds=0.1)
             extras["c2"] = extra_line(c2, lr, 12)
             if HAVE_RB32:
                 c4 = WORKLOADS["c4"]
                 lr = timed_run(c4, 4, 3, 0.0, "rb32", min_seconds=0.4)  # (33 ms per step: three blocks of four)
-                extras["c4_rb_all_landmarks"] = dict(extra_line(c4, lr, 4), likelihood="rb32", pair_loop=pair_loop(c4, lr, "rb32"))
+                extras["c4_rb_all_landmarks"] = dict(extra_line(c4, lr, 4), likelihood="rb32", pair_loop=pair_loop(c4, lr, "rb32", 4))
     cpu = cpu_baseline(wl, procs=max(1, min(32, os.cpu_count() or 1))) if not args.no_cpu else None
     line = {"metric": "particle-steps/s (predict+weight+resample)", "value": value, "unit": "particle-steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",

@@ -225,6 +225,14 @@ bool pdl_enabled() {
     }();
     return on;
 }
+// Programmatic launch hides ~3 us of launch latency per kernel: worth 10 % of a 32 us step at C1, nothing at 125 M
+// particles, and at C4 (16.8 M x 1024 landmarks, k_step 33 ms) it was measured to COST 14 ms per step: the dependent
+// k_step CTAs become resident early and sit on the registers the scan's remaining tiles need.  Small steps only.
+bool pdl_for(const mcl_filter *h);
+
+bool pdl_for(const mcl_filter *h) {
+    return pdl_enabled() && !h->profiling && static_cast<long long>(h->lay.T) * h->lay.n <= (1ll << 23);
+}
 
 template <typename P>
 void launch_pdl(void (*kernel)(P), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, const P &params) {
@@ -310,7 +318,7 @@ int ensure_stats(mcl_filter *h, cudaStream_t st) {
     m.ld = h->lay.ld;
     m.n_global = static_cast<double>(h->cfg.n_global);
     m.apply_rule = (h->cfg.n_global == h->cfg.n_particles) ? 1 : 0;  // a shard leaves the rule to the merge of all shards
-    launch_pdl(k_merge, dim3(h->lay.T), dim3(kStepThreads), 0, st, pdl_enabled() && !h->profiling, m);
+    launch_pdl(k_merge, dim3(h->lay.T), dim3(kStepThreads), 0, st, pdl_for(h), m);
     MCL_LAUNCH_CHECK(h, "k_merge");
     h->stats_dirty = false;
     return MCL_OK;
@@ -356,8 +364,8 @@ int launch_step_scan(mcl_filter *h, const double *z_dev, const double *ofs_dev, 
     sp.persistent = (tile_ctas < h->lay.tpt) ? 1 : 0;
     dim3 grid(tile_ctas + (h->stats_dirty ? 2 : 1), h->lay.T);
     h->stats_dirty = false;
-    if (wide) launch_pdl(k_scan<kScanAncestors, 16>, grid, dim3(kScanTile / 16), 0, st, pdl_enabled() && !h->profiling, sp);
-    else launch_pdl(k_scan<kScanAncestors, 8>, grid, dim3(kScanTile / 8), 0, st, pdl_enabled() && !h->profiling, sp);
+    if (wide) launch_pdl(k_scan<kScanAncestors, 16>, grid, dim3(kScanTile / 16), 0, st, pdl_for(h), sp);
+    else launch_pdl(k_scan<kScanAncestors, 8>, grid, dim3(kScanTile / 8), 0, st, pdl_for(h), sp);
     MCL_LAUNCH_CHECK(h, "k_scan");
     return MCL_OK;
 }
@@ -475,7 +483,7 @@ int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool redu
         return MCL_OK;
     }
     const bool philox = (noise_dev == nullptr);
-    const bool pdl = pdl_enabled() && !h->profiling;
+    const bool pdl = pdl_for(h);
     const size_t smem = static_cast<size_t>(h->L) * sizeof(double4);
     switch (step_variant(c)) {
         case kLikPair: launch_step_lik<kLikPair>(p, grid, smem, philox, st, pdl); break;
