@@ -484,7 +484,8 @@ int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool redu
     }
     const bool philox = (noise_dev == nullptr);
     const bool pdl = pdl_for(h);
-    const size_t smem = static_cast<size_t>(h->L) * sizeof(double4);
+    // shared-memory landmark table: 32 bytes per landmark; the fp32 range/bearing kernel stages every value twice (64)
+    const size_t smem = static_cast<size_t>(h->L) * sizeof(double4) * (c.likelihood == MCL_LIK_RB_F32 ? 2 : 1);
     switch (step_variant(c)) {
         case kLikPair: launch_step_lik<kLikPair>(p, grid, smem, philox, st, pdl); break;
         case kLikRB: launch_step_lik<kLikRB>(p, grid, smem, philox, st, pdl); break;
@@ -793,6 +794,8 @@ int mcl_set_landmarks(mcl_filter *h, const double *lm_xy_host, int32_t n_landmar
     if (h == nullptr) return MCL_ERR_ARG;
     if (lm_xy_host == nullptr || n_landmarks < 1 || n_landmarks > h->lay.Lmax)
         return fail(h, MCL_ERR_ARG, "landmark table is NULL or larger than max_landmarks");
+    if (h->cfg.likelihood == MCL_LIK_RB_F32 && n_landmarks > 2048)
+        return fail(h, MCL_ERR_ARG, "MCL_LIK_RB_F32 stages 64 bytes per landmark in shared memory: at most 2048 landmarks");
     int rc = use_device(h);
     if (rc != MCL_OK) return rc;
     MCL_CUDA(h, cudaMemcpyAsync(h->lm, lm_xy_host, static_cast<size_t>(n_landmarks) * 2 * sizeof(double),

@@ -199,6 +199,16 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
     f32x2 r;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));

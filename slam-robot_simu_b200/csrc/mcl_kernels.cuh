@@ -193,18 +193,18 @@ __device__ __noinline__ void prep_block(const PrepParams &p, const PrepIn &in, c
                 // fp32 range/bearing kernel about the reference pose: the landmark as the reference pose sees it
                 // (g, |g|), and the reference pose's own residuals (e0 = z_d - |g|, e1 = wrap(z_phi - phi_g)).  A particle
                 // changes the range by dr and the bearing by dphi, both small and computed with RELATIVE fp32 accuracy;
-                // the kernel sums dr'(dr' - 2 e0') and dphi'(dphi' + ...) -- differences of squares, primes = / sigma.
+                // the kernel sums dr'(dr' - 2 e0') and dphi (dphi - 2 e1) -- differences of squares, primes = / sigma.
                 const double gx = fma(s, lx, fma(-c, ly, tx)), gy = fma(c, lx, fma(s, ly, ty));
                 const double g2 = fmax(fma(gx, gx, gy * gy), 1.0e-12), rho = sqrt(g2);
                 float *slot = reinterpret_cast<float *>(&p.tab[static_cast<long long>(t) * p.Lmax + l]);
                 slot[0] = static_cast<float>(gx);
                 slot[1] = static_cast<float>(gy);
                 slot[2] = static_cast<float>(rho * sqrt(p.inv_s0sq));        // |g| / sigma_d
-                slot[3] = static_cast<float>(1.0 / g2);
+                slot[3] = static_cast<float>(2.0 / g2);
                 slot[4] = static_cast<float>(g2);
                 slot[5] = static_cast<float>(2.0 * e0 * sqrt(p.inv_s0sq));   // 2 e_d(ref) / sigma_d
                 slot[6] = static_cast<float>(e1);                            // e_phi(ref), wrapped
-                slot[7] = static_cast<float>(2.0 * e1 * sqrt(p.inv_s1sq));   // 2 e_phi(ref) / sigma_phi
+                slot[7] = static_cast<float>(2.0 * e1);                      // 2 e_phi(ref); 1 / sigma_phi^2 where the sums are folded
             }
             acc[13] = fma(e0, e0, acc[13]);
             acc[14] = fma(e1, e1, acc[14]);
@@ -1479,9 +1479,18 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
         }
         __syncthreads();
     }
-    if (LIK == kLikRB32) {  // the per-step scalars CTA left eight floats per landmark: copied as they are
-        const double4 *g = p.tab + static_cast<long long>(t) * p.Lmax;
-        for (int l = tid; l < L; l += kStepThreads) reinterpret_cast<double4 *>(smem_raw)[l] = g[l];
+    if (LIK == kLikRB32) {
+        // the per-step scalars CTA left eight floats per landmark; staged with every value twice, so that both halves
+        // of an FFMA2 operand (two particles) see the same landmark: 64 bytes per landmark
+        const float4 *g = reinterpret_cast<const float4 *>(p.tab + static_cast<long long>(t) * p.Lmax);
+        float4 *d = reinterpret_cast<float4 *>(smem_raw);
+        for (int l = tid; l < L; l += kStepThreads) {
+            const float4 a = g[2 * l], b = g[2 * l + 1];
+            d[4 * l] = make_float4(a.x, a.x, a.y, a.y);
+            d[4 * l + 1] = make_float4(a.z, a.z, a.w, a.w);
+            d[4 * l + 2] = make_float4(b.x, b.x, b.y, b.y);
+            d[4 * l + 3] = make_float4(b.z, b.z, b.w, b.w);
+        }
         __syncthreads();
     }
     float4 *s_tabf = reinterpret_cast<float4 *>(smem_raw);  // [L detected] (fan sensor: fp32 per pair)
@@ -1743,7 +1752,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
                 for (int k = 0; k < kPPT; ++k) dll32[k] = static_cast<float>(static_cast<double>(lwp[k]) - 0.5 * dq[k]);
             }
             if (LIK == kLikRB32) {
-                float a_[kPPT], b_[kPPT], ntx[kPPT], nty[kPPT];
+                float c1_[kPPT], b_[kPPT], ntx[kPPT], nty[kPPT];
 #pragma unroll
                 for (int k = 0; k < kPPT; ++k) {
                     float sd, cm1;
@@ -1751,60 +1760,99 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
                     const float sf = fmaf(ref_s, cm1, fmaf(ref_c, sd, ref_s));
                     const float cf = fmaf(ref_c, cm1, fmaf(-ref_s, sd, ref_c));
                     const float ddx = x[k] - ref_x, ddy = y[k] - ref_y;
-                    a_[k] = cm1;
+                    c1_[k] = 1.0f + cm1;
                     b_[k] = sd;
                     ntx[k] = -fmaf(sf, ddx, -cf * ddy);
                     nty[k] = -fmaf(cf, ddx, sf * ddy);
                     s[k] = static_cast<double>(sf);
                     c[k] = static_cast<double>(cf);
                 }
-                const float isp = p.inv_s1_f;
+                // The particle sees the landmark at R g + T: the reference pose's view g turned by the yaw difference
+                // delta (R = [[cos, sin], [-sin, cos]]) and shifted by T = -M(theta)(dx, dy).  With u = g.T, v = g x T:
+                //   |R g + T|^2 - |g|^2 = |T|^2 + 2 (cos delta u - sin delta v)   (the turn changes no norm: no cancellation)
+                //   g . (R g + T) = cos delta |g|^2 + u,   g x (R g + T) = -sin delta |g|^2 + v
+                // Two particles per register pair (FFMA2 / FMUL2 / FADD2): 23 packed instructions, 3 MUFU and the clamp per
+                // TWO pairs on the main path; limit_angle's +-2 pi turn only for a landmark whose reference residual lies
+                // within 0.11 rad of the seam (a warp-uniform test) or a particle far from the reference pose.
+                f32x2 C1[2], NB[2], TX[2], TY[2], NTX[2], T2h[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k0 = 2 * h, k1 = 2 * h + 1;
+                    C1[h] = pack2(c1_[k0], c1_[k1]);
+                    NB[h] = pack2(-b_[k0], -b_[k1]);
+                    TX[h] = pack2(ntx[k0], ntx[k1]);
+                    NTX[h] = pack2(-ntx[k0], -ntx[k1]);
+                    TY[h] = pack2(nty[k0], nty[k1]);
+                    T2h[h] = pack2(0.5f * fmaf(ntx[k0], ntx[k0], nty[k0] * nty[k0]), 0.5f * fmaf(ntx[k1], ntx[k1], nty[k1] * nty[k1]));
+                }
+                const f32x2 kOne = pack2(1.0f, 1.0f);
+                const f32x2 kC3 = pack2(-1.0f / 3.0f, -1.0f / 3.0f), kC5 = pack2(0.2f, 0.2f), kC7 = pack2(-1.0f / 7.0f, -1.0f / 7.0f);
+                const ulonglong2 *tab2 = reinterpret_cast<const ulonglong2 *>(smem_raw);
                 double dq[kPPT] = {0.0, 0.0, 0.0, 0.0};
                 for (int l0 = 0; l0 < L; l0 += kFoldEvery) {
-                    float q[kPPT] = {0.f, 0.f, 0.f, 0.f};
+                    f32x2 Qr[2] = {0ull, 0ull}, Qp[2] = {0ull, 0ull};  // range terms in sigma_d units, bearing terms in rad^2
                     const int l1 = min(L, l0 + kFoldEvery);
 #pragma unroll 1
                     for (int l = l0; l < l1; ++l) {
-                        const float4 e0 = s_tabf[2 * l];      // gx, gy, |g| / sigma_d, 1 / |g|^2
-                        const float4 e1 = s_tabf[2 * l + 1];  // |g|^2, 2 e_d / sigma_d, e_phi, 2 e_phi / sigma_phi
+                        const ulonglong2 t0 = tab2[4 * l];      // {gx gx}, {gy gy}
+                        const ulonglong2 t1 = tab2[4 * l + 1];  // {|g|/sigma_d ..}, {2/|g|^2 ..}
+                        const ulonglong2 t2q = tab2[4 * l + 2]; // {|g|^2 ..}, {2 e_d/sigma_d ..}
+                        const ulonglong2 t3 = tab2[4 * l + 3];  // {e_phi ..}, {2 e_phi ..}
+                        float ephi, ephi_;
+                        unpack2(t3.x, ephi, ephi_);
+                        const bool seam = fabsf(ephi) > 3.03f;  // |dphi| < 0.1003 on the main path: no turn possible elsewhere
 #pragma unroll
-                        for (int k = 0; k < kPPT; ++k) {
-                            // the particle sees the landmark at g + d, d small (see kLikPair32)
-                            const float dx = fmaf(a_[k], e0.x, fmaf(b_[k], e0.y, ntx[k]));
-                            const float dy = fmaf(a_[k], e0.y, fmaf(-b_[k], e0.x, nty[k]));
-                            const float dot = fmaf(e0.x, dx, e0.y * dy), crs = fmaf(e0.x, dy, -e0.y * dx);
-                            // range: |g + d| - |g| = |g| eps / (1 + sqrt(1 + eps)), eps = (2 g.d + |d|^2) / |g|^2
-                            const float eps = fmaf(2.0f, dot, fmaf(dx, dx, dy * dy)) * e0.w;
-                            const float sq = sqrt_approx(fmaxf(1.0f + eps, 0.0f));
-                            float rc;
-                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + sq));
-                            const float dr = e0.z * eps * rc;                 // (range change) / sigma_d
-                            q[k] = fmaf(dr, dr - e1.y, q[k]);                 // (e_d - dr)^2 - e_d^2, e_d = z_d - |g|
-                            // bearing: the change is atan2(g x d, |g|^2 + g.d); for the particles that matter it is a
-                            // small angle, and the series keeps its RELATIVE accuracy (the minimax atan2 is good to
-                            // 1.4e-7 rad absolute, 7e-7 relative near 0)
-                            const float den = e1.x + dot;
-                            float rd;
-                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rd) : "f"(den));
-                            const float tq = crs * rd, t2 = tq * tq;
-                            float dphi;
-                            if (den > 0.0f && t2 < 0.01f) {
-                                float pa = fmaf(t2, -1.0f / 7.0f, 0.2f);
-                                pa = fmaf(t2, pa, -1.0f / 3.0f);
-                                dphi = fmaf(tq * t2, pa, tq);
-                            } else {
-                                dphi = atan2_fast(crs, den);
+                        for (int h = 0; h < 2; ++h) {
+                            const f32x2 u = fma2(t0.x, TX[h], mul2(t0.y, TY[h]));
+                            const f32x2 v = fma2(t0.x, TY[h], mul2(t0.y, NTX[h]));
+                            const f32x2 den = fma2(C1[h], t2q.x, u);
+                            const f32x2 crs = fma2(NB[h], t2q.x, v);
+                            // range: |g| (sqrt(1 + eps) - 1) = |g| eps / (1 + sqrt(1 + eps)), eps = (|R g + T|^2 - |g|^2) / |g|^2.
+                            // (Its series in eps with this closed form as the fallback measured SLOWER, 28.8 vs 26.4 ms at C4:
+                            // some landmark is always at arm's length of some lane, so the warp pays both.  One MUFU.RCP of
+                            // the product (1 + sqrt(1 + eps)) (|g|^2 + g.d) in place of the two below: 27.7 ms.  The loop is
+                            // bound by the FP32 pipe, where a packed instruction holds two issue cycles -- not by the SFU.)
+                            const f32x2 eps = mul2(fma2(C1[h], u, fma2(NB[h], v, T2h[h])), t1.y);
+                            float o0, o1, r0, r1;
+                            unpack2(add2(kOne, eps), o0, o1);
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(1.0f + sqrt_approx(fmaxf(o0, 0.0f))));
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(1.0f + sqrt_approx(fmaxf(o1, 0.0f))));
+                            const f32x2 dr = mul2(mul2(t1.x, eps), pack2(r0, r1));
+                            Qr[h] = fma2(dr, sub2(dr, t2q.y), Qr[h]);  // (e_d - dr)^2 - e_d^2, dr = (range change) / sigma_d
+                            // bearing: the change is atan2(g x (R g + T), g . (R g + T)): a small angle for the particles that
+                            // matter, where the series keeps its RELATIVE accuracy
+                            float d0, d1;
+                            unpack2(den, d0, d1);
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+                            const f32x2 tq = mul2(crs, pack2(r0, r1)), tt = mul2(tq, tq);
+                            f32x2 dphi = fma2(mul2(tq, tt), fma2(tt, fma2(tt, kC7, kC5), kC3), tq);
+                            float q0, q1;
+                            unpack2(tt, q0, q1);
+                            const bool ok0 = d0 > 0.0f && q0 < 0.01f, ok1 = d1 > 0.0f && q1 < 0.01f;
+                            if (!(ok0 && ok1) || seam) {
+                                float c0, c1, p0, p1;
+                                unpack2(crs, c0, c1);
+                                unpack2(dphi, p0, p1);
+                                if (!ok0) p0 = atan2_fast(c0, d0);  // far from the reference pose
+                                if (!ok1) p1 = atan2_fast(c1, d1);
+                                // limit_angle (mylib/limit.py:19-26) as the +-2 pi turn of (new residual - old residual)
+                                const float w0 = ephi - p0, w1 = ephi - p1;
+                                p0 -= (w0 > 3.14159265f) ? -6.28318531f : ((w0 < -3.14159265f) ? 6.28318531f : 0.0f);
+                                p1 -= (w1 > 3.14159265f) ? -6.28318531f : ((w1 < -3.14159265f) ? 6.28318531f : 0.0f);
+                                dphi = pack2(p0, p1);
                             }
-                            const float w = e1.z - dphi;                      // new residual before limit_angle
-                            float del = -dphi;                                // new residual minus old, after the wrap
-                            del = (w > 3.14159265f) ? del - 6.28318531f : del;
-                            del = (w < -3.14159265f) ? del + 6.28318531f : del;
-                            const float dp = del * isp;
-                            q[k] = fmaf(dp, dp + e1.w, q[k]);
+                            Qp[h] = fma2(dphi, sub2(dphi, t3.y), Qp[h]);  // (e_phi - dphi)^2 - e_phi^2, in rad^2
                         }
                     }
 #pragma unroll
-                    for (int k = 0; k < kPPT; ++k) dq[k] += static_cast<double>(q[k]);
+                    for (int h = 0; h < 2; ++h) {
+                        float q0, q1, f0, f1;
+                        unpack2(Qr[h], q0, q1);
+                        unpack2(Qp[h], f0, f1);
+                        dq[2 * h] += fma(static_cast<double>(f0), p.inv_s1sq, static_cast<double>(q0));
+                        dq[2 * h + 1] += fma(static_cast<double>(f1), p.inv_s1sq, static_cast<double>(q1));
+                    }
                 }
 #pragma unroll
                 for (int k = 0; k < kPPT; ++k) dll32[k] = static_cast<float>(static_cast<double>(lwp[k]) - 0.5 * dq[k]);
