@@ -37,6 +37,8 @@ NCU_TRAFFIC = {
                        "ncu --set full of k_step at 32M particles x 64 landmarks (profiles/r02_d_ncu_32M_x64_k_step_moment_summary.csv), per particle x this launch"),
     ("c3", "pair32"): ((521.427968e6 + 505.885952e6) / 33554432,
                        "ncu --set full of k_step<pair32> at 32M particles x 64 landmarks (profiles/r02_c_ncu_32M_x64_k_step_pair32_summary.csv), per particle x this launch"),
+    ("c4", "rb32"): ((195.028992e6 + 254.922752e6) / 16777216,
+                     "ncu --set full of k_step<rb32> at C4 itself, 16.8M x 1024 (profiles/r02_h_ncu_c4_rb32_k_step_summary.csv)"),
 }
 HAVE_RB32 = True
 # The LITERAL reference class (unmodified /root/reference/particle_filter.py behind oracle/mpl_stub.py, its per-particle
@@ -49,7 +51,8 @@ PAIR_LOOPS = {
     "pair": {"arithmetic": "fp64, 8 operations per pair", "bound": "FP64 pipe"},
     "pair32": {"arithmetic": "fp32 about the reference pose, 8 operations per pair, two particles per FFMA2 / FADD2", "bound": "FP32 pipe"},
     "rb": {"arithmetic": "fp64, libm sqrt / atan2, all landmarks scored", "bound": "FP64 pipe"},
-    "rb32": {"arithmetic": "fp32 + MUFU (rcp, sqrt), branch-free atan2, ALL landmarks scored", "bound": "FP32/SFU issue"},
+    "rb32": {"arithmetic": "fp32 two particles per FFMA2/FMUL2/FADD2 + MUFU (sqrt, 2 rcp), series atan2, ALL landmarks scored",
+             "bound": "issue (FMA pipe 54 %, XU 51 %, issue slots 63 %: profiles/r02_h_ncu_c4_rb32_k_step_summary.csv)"},
     "rb_fan": {"arithmetic": "fp32 + MUFU (rcp, sqrt), branch-free atan2, detected landmarks only", "bound": "FP32/SFU issue"},
 }
 
@@ -750,7 +753,7 @@ def run_b200(args, wl):
             extras["c2"] = extra_line(c2, lr, 12)
             if HAVE_RB32:
                 c4 = WORKLOADS["c4"]
-                lr = timed_run(c4, 4, 3, 0.0, "rb32", min_seconds=0.4)  # (33 ms per step: three blocks of four)
+                lr = timed_run(c4, 4, 3, 0.0, "rb32", min_seconds=0.4)  # (25 ms per step: four blocks of four)
                 extras["c4_rb_all_landmarks"] = dict(extra_line(c4, lr, 4), likelihood="rb32", pair_loop=pair_loop(c4, lr, "rb32", 4))
     cpu = cpu_baseline(wl, procs=max(1, min(32, os.cpu_count() or 1))) if not args.no_cpu else None
     line = {"metric": "particle-steps/s (predict+weight+resample)", "value": value, "unit": "particle-steps/s",

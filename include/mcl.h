@@ -60,8 +60,10 @@ typedef enum mcl_likelihood {
                            through the motion): a particle's residual is the reference pose's residual u_l plus a
                            small d_l, and the kernel sums d_l (d_l + 2 u_l) -- the difference of the two chi^2, no
                            cancellation -- 8 fp32 operations per pair, two particles per FFMA2 */
-    MCL_LIK_RB_F32 = 5  /* MCL_LIK_RB for ALL landmarks in fp32 about the reference pose (MUFU sqrt / rcp, branch-free
-                           atan2 of the small bearing change): the FP32 / SFU-bound kernel of BASELINE configs[4] */
+    MCL_LIK_RB_F32 = 5  /* MCL_LIK_RB for ALL landmarks in fp32 about the reference pose (MUFU sqrt / rcp, series
+                           atan2 of the small bearing change, two particles per FFMA2): the FP32 / SFU-bound kernel
+                           of BASELINE configs[4].  64 bytes of shared memory per landmark: mcl_set_landmarks
+                           returns MCL_ERR_ARG beyond 2048 landmarks */
 } mcl_likelihood;
 
 typedef enum mcl_motion {

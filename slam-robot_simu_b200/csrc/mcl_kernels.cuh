@@ -1811,7 +1811,8 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
                             // (Its series in eps with this closed form as the fallback measured SLOWER, 28.8 vs 26.4 ms at C4:
                             // some landmark is always at arm's length of some lane, so the warp pays both.  One MUFU.RCP of
                             // the product (1 + sqrt(1 + eps)) (|g|^2 + g.d) in place of the two below: 27.7 ms.  The loop is
-                            // bound by the FP32 pipe, where a packed instruction holds two issue cycles -- not by the SFU.)
+                            // runs at FMA pipe 54 %, XU 51 %, issue 63 % (profiles/r02_h_ncu_c4_rb32_k_step_summary.csv): no one pipe
+                            // to relieve.  ONE fallback branch per landmark behind both halves, so that they interleave: 25.7 ms.)
                             const f32x2 eps = mul2(fma2(C1[h], u, fma2(NB[h], v, T2h[h])), t1.y);
                             float o0, o1, r0, r1;
                             unpack2(add2(kOne, eps), o0, o1);
