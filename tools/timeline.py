@@ -31,6 +31,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="c1")
     ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--rotate", type=int, default=0, help="step this many other filters between the measured steps (what bench.py "
+                    "does: data L2-cold, code L2-warm) instead of flushing the L2 with a fill (code cold as well)")
     a = ap.parse_args()
     import torch
 
@@ -47,9 +49,20 @@ def main():
     for k in range(30):
         f.step_dev(cyc[k], force_resample=True)
     f.debug_timeline()  # arm
-    n_scan = wl["T"] * ((wl["n"] + 2047) // 2048 + 2)  # the api sizes the scan region for tpt + 1 CTAs
+    n_scan = wl["T"] * ((wl["n"] + 2047) // 2048 + 2)  # the api sizes the scan region for tpt + 2 CTAs
+    others = []
+    for r in range(a.rotate):
+        g = mcl.Filter(n_particles=wl["n"], n_trials=wl["T"], landmarks=lm, likelihood="moment", max_landmarks=wl["L"], seed=100 + r)
+        g.init_particles(tr.pose())
+        others.append(g)
     for rep in range(3):
-        junk = torch.empty(64 << 20, dtype=torch.float32, device="cuda").fill_(1.0)  # flush L2
+        junk = None
+        if others:
+            for k in range(4):
+                for g in others:
+                    g.step_dev(cyc[k], force_resample=True)
+        else:
+            junk = torch.empty(64 << 20, dtype=torch.float32, device="cuda").fill_(1.0)  # flush L2
         torch.cuda.synchronize()
         f.step_dev(cyc[30 + rep], force_resample=True)
         t = f.debug_timeline().astype(np.int64)
@@ -57,6 +70,8 @@ def main():
         t0 = tc[:, 0][tc[:, 0] > 0].min()
         print(f"--- step {rep}: microseconds after the first k_scan CTA started")
         show("k_scan", tc, SCAN, t0)
+        print("    tile 0 (merges and publishes): " + "  ".join(f"{nm} {(v - t0) / 1e3:.2f}" for nm, v in zip(SCAN + ["-"], tc[0]) if v > 0))
+        print("    scalars CTA: " + "  ".join(f"{nm} {(v - t0) / 1e3:.2f}" for nm, v in zip(SCAN + ["-"], tc[-1]) if v > 0))
         show("k_step", ts, STEP, t0)
         del junk
 
