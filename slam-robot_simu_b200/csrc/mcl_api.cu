@@ -907,7 +907,7 @@ int mcl_resample(mcl_filter *h, const double *ofs_host, uint32_t flags, void *st
     g.n = h->lay.n;
     g.ld = h->lay.ld;
     g.n_global = static_cast<double>(h->cfg.n_global);
-    const int bx = static_cast<int>(std::min<long long>((h->lay.n + 255) / 256, 148 * 16));
+    const int bx = static_cast<int>(std::min<long long>((h->lay.n + 255) / 256, static_cast<long long>(h->sm_count) * 16));
     k_gather<<<dim3(bx, h->lay.T), 256, 0, st>>>(g);
     MCL_LAUNCH_CHECK(h, "k_gather");
     h->cur ^= 1;
@@ -1052,7 +1052,7 @@ static int export_weights(mcl_filter *h, double *w_host, uint64_t *q_host, void 
     const Layout &L = h->lay;
     // the idle state buffer (16 B per particle) is the staging area for the 8 B per particle export
     void *stage = h->state[h->cur ^ 1].x;
-    const int bx = static_cast<int>(std::min<long long>((L.n + 255) / 256, 148 * 16));
+    const int bx = static_cast<int>(std::min<long long>((L.n + 255) / 256, static_cast<long long>(h->sm_count) * 16));
     k_export_weights<<<dim3(bx, L.T), 256, 0, st>>>(h->state[h->cur].lw, h->stats, w_host ? static_cast<double *>(stage) : nullptr,
                                                      q_host ? static_cast<unsigned long long *>(stage) : nullptr, L.n, L.ld);
     MCL_LAUNCH_CHECK(h, "k_export_weights");
