@@ -1181,7 +1181,9 @@ __global__ void __launch_bounds__(kScanTile / ITEMS, scan_ctas_per_sm(ITEMS)) k_
     // thread is owned by the first source at or after it that owns slots at all, so every slot of the range has a
     // mark at or before it inside the warp (or is covered by the carry of the previous pass).  Marks hold the source
     // index itself; 0 doubles as "empty", which is right because only the very first source can be 0 and it owns
-    // whatever precedes the first other mark.  Tiles whose sources own far more slots than sources (collapsed
+    // whatever precedes the first other mark.  (A strip of 1024 slots per warp, so that one pass of marks nearly
+    // always suffices, was measured: k_scan 0.486 -> 0.665 ms at 125 M -- 18 KB of shared memory per CTA and the
+    // lanes' strips 128 bytes apart.)  Tiles whose sources own far more slots than sources (collapsed
     // weights: one particle owning up to every slot) keep the block-cooperative fill below.
     const uint32_t anc_lo = (MODE == kScanAncestors) ? 0u : static_cast<uint32_t>(p.own_lo);
     uint32_t *anc = p.anc + static_cast<long long>(t) * p.ld;
