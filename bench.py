@@ -714,8 +714,8 @@ def run_b200(args, wl):
         e2e = {"value": float(n) * ke / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": 16 * L,
                "d2h_bytes_per_step": C.sizeof(mcl.mcl_stats), "steps": ke, "ms_per_step": dt / ke * 1e3,
                "api": "ParticleFilter(period_ms, noise='philox', lazy_px=True, force_resample=True).main_pf()",
-               "note": "host truth motion + observation draw, H2D of z_l, k_scan + k_step + k_merge, D2H of the mcl_stats block of THIS "
-                       "step (no lag); px stays on the device until read (LazyParticles), so the timing excludes the 12 B/particle "
+               "note": "host truth motion + observation draw, z_l read by k_scan from the pinned staging slot over PCIe (no copy operation), k_scan + k_step + k_merge, the mcl_stats block of THIS step written by k_merge into pinned host memory "
+                       "(no lag); px stays on the device until read (LazyParticles), so the timing excludes the 12 B/particle "
                        "px copy the reference's return value implies"}
         del pf
     else:

@@ -196,7 +196,8 @@ int mcl_step_dev(mcl_filter *h, const double *z_dev, const double *ofs_dev, cons
                  void *stream);
 
 /* mcl_step followed by mcl_get_stats_begin in ONE crossing of the ABI: the observation is staged through a pinned
- * ring (no host synchronisation), the two kernels and the statistics merge are enqueued, and the read-back of the
+ * ring (no host synchronisation; an observation of at most 4 KB is read by the step straight from that pinned,
+ * mapped slot -- no copy operation), the two kernels and the statistics merge are enqueued, and the read-back of the
  * [n_trials] mcl_stats is started.  Collect it with mcl_get_stats_end -- the host is free in between (the drop-in
  * ParticleFilter.main_pf simulates the next frame's observation there). */
 int mcl_step_async(mcl_filter *h, const double *z_host, const double *ofs_host, const float *noise_dev, uint32_t flags,
@@ -210,7 +211,10 @@ int mcl_pose_moments(mcl_filter *h, void *stream);
 int mcl_get_stats(mcl_filter *h, mcl_stats *out_host, void *stream);
 /* The same in two halves, so the host can work while the step runs: mcl_get_stats_begin enqueues the pending
  * merge, the copy into a pinned buffer of the handle and an event, and returns at once; mcl_get_stats_end waits
- * for that event only and fills out_host (log_norm / max_weight / mean / cov derived on the host as above). */
+ * for that event only and fills out_host (log_norm / max_weight / mean / cov derived on the host as above).
+ * A single filter (n_trials == 1) with a merge pending skips the copy: the merge kernel writes the block into the
+ * pinned, mapped buffer itself and releases a sequence number that mcl_get_stats_end polls (errors surface through
+ * the event). */
 int mcl_get_stats_begin(mcl_filter *h, void *stream);
 int mcl_get_stats_end(mcl_filter *h, mcl_stats *out_host);
 /* Device address of the [n_trials] mcl_stats block (for callers that poll asynchronously).  On the device

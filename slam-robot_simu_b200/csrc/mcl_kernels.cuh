@@ -145,8 +145,8 @@ __device__ __noinline__ void prep_block(const PrepParams &p, const PrepIn &in, c
             double zd = 0.0, zp = 0.0;
             bool seen = false;
             if (l < p.L) {
-                zd = p.z[(static_cast<long long>(t) * p.L + l) * 2];
-                zp = p.z[(static_cast<long long>(t) * p.L + l) * 2 + 1];
+                zd = __ldcv(&p.z[(static_cast<long long>(t) * p.L + l) * 2]);
+                zp = __ldcv(&p.z[(static_cast<long long>(t) * p.L + l) * 2 + 1]);
                 seen = zd > 0.0 && zd < 1.0e300 && zp == zp;  // NaN fails every comparison
             }
             const unsigned int b = __ballot_sync(0xffffffffu, seen);
@@ -178,8 +178,8 @@ __device__ __noinline__ void prep_block(const PrepParams &p, const PrepIn &in, c
         const double tx = -(s * rx - c * ry), ty = -(c * rx + s * ry);
         for (int l = tid; l < p.L; l += blockDim.x) {
             const double lx = p.lm[2 * l], ly = p.lm[2 * l + 1];
-            const double zx = p.z[(static_cast<long long>(t) * p.L + l) * 2];
-            const double zy = p.z[(static_cast<long long>(t) * p.L + l) * 2 + 1];
+            const double zx = __ldcv(&p.z[(static_cast<long long>(t) * p.L + l) * 2]);  // (z may be mapped host memory: never a cached copy)
+            const double zy = __ldcv(&p.z[(static_cast<long long>(t) * p.L + l) * 2 + 1]);
             const double4 e = make_double4(lx, ly, zx, zy);
             if (p.likelihood != MCL_LIK_PAIR_F32 && p.likelihood != MCL_LIK_RB_F32) p.tab[static_cast<long long>(t) * p.Lmax + l] = e;
             acc[0] += lx;       acc[1] += ly;       acc[2] += zx;       acc[3] += zy;
@@ -668,6 +668,11 @@ struct MergeParams {
     long long ld;
     double n_global;
     int apply_rule;
+    // single filters read back through mcl_step_async / mcl_get_stats_begin: the block also lands in pinned host memory
+    // mapped into the device (no copy-engine operation behind the kernel), then the flag takes the read-back's number
+    uint32_t *host_out;
+    unsigned int *host_flag;
+    unsigned int host_seq;
 };
 __global__ void __launch_bounds__(kStepThreads) k_merge(const MergeParams p) {
     cudaGridDependencySynchronize();  // launched programmatically behind k_step: its launch latency is hidden
@@ -675,6 +680,15 @@ __global__ void __launch_bounds__(kStepThreads) k_merge(const MergeParams p) {
     const long long off = static_cast<long long>(t) * p.ld;
     merge_full<kStepThreads>(p.partials + static_cast<long long>(t) * p.bpt * kPart, p.bpt, p.stats + t, p.cur.x + off, p.cur.y + off,
                p.cur.th + off, nullptr, p.n_global, p.apply_rule != 0);
+    if (p.host_out != nullptr) {  // (gridDim.x == 1)
+        __syncthreads();
+        constexpr int kWords = static_cast<int>(sizeof(mcl_stats) / sizeof(uint32_t));
+        static_assert(kWords <= kStepThreads && sizeof(mcl_stats) % sizeof(uint32_t) == 0, "one word per thread");
+        if (threadIdx.x < kWords) p.host_out[threadIdx.x] = __ldcg(reinterpret_cast<const uint32_t *>(p.stats) + threadIdx.x);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_sys(p.host_flag, p.host_seq);
+    }
 }
 
 // -------------------------------------------------------------------------------------------------

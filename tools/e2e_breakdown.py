@@ -34,8 +34,7 @@ def main():
             return r
         setattr(obj, name, inner)
 
-    wrap(flt, "step", "Filter.step (H2D of z + 2 launches, enqueue)")
-    wrap(flt, "stats_begin", "Filter.stats_begin (k_merge + D2H, enqueue)")
+    wrap(flt, "step_async", "Filter.step_async (stage z, 3 launches, D2H: enqueue)")
     wrap(flt, "stats_end", "Filter.stats_end (wait for the GPU + derive)")
     for _ in range(50):
         pf.main_pf()
