@@ -191,7 +191,9 @@ int mcl_predict_weight(mcl_filter *h, const double *z_host, const float *noise_d
 /* main_pf (:86-119) without the ground-truth line: resample -> predict -> weight -> estimate. */
 int mcl_step(mcl_filter *h, const double *z_host, const double *ofs_host, const float *noise_dev, uint32_t flags,
              void *stream);
-/* Same, with z and ofs already resident on the device (no host traffic, CUDA-graph friendly). */
+/* Same, with z and ofs already resident on the device: no host traffic and no synchronisation, so a run of steps can
+ * be captured in a CUDA graph (tests: test_steps_captured_in_a_cuda_graph).  A captured step carries the buffer parity
+ * and the step / Philox counters of the call that was captured: a graph stands for THOSE steps, it is not a loop body. */
 int mcl_step_dev(mcl_filter *h, const double *z_dev, const double *ofs_dev, const float *noise_dev, uint32_t flags,
                  void *stream);
 

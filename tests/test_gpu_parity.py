@@ -572,6 +572,45 @@ def test_rb32_landmark_capacity(mcl):
         f.set_landmarks(lm)
 
 
+def test_steps_captured_in_a_cuda_graph(mcl):
+    """mcl_step_dev touches no host memory and synchronises nothing: a run of steps can be captured in a CUDA graph
+    (programmatic-launch edges included) and launched as one unit.  The graph bakes in the buffer parity and the
+    step counters of the steps it holds, so it stands for THOSE steps: launched once it must leave the filter in
+    exactly the state the same calls leave it in eagerly."""
+    import torch
+    n, Lm, K = 50000, 5, 6
+    lm = np.random.default_rng(3).uniform(-15, 15, (Lm, 2))
+    rng = np.random.RandomState(8)
+    z = torch.from_numpy(rng.normal(0, 3, (K, 1, Lm, 2))).cuda()
+
+    def fresh():
+        f = mcl.Filter(n_particles=n, landmarks=lm, seed=11)
+        f.init_particles([1.0, 2.0, 0.3])
+        return f
+
+    eager = fresh()
+    for k in range(K):
+        eager.step_dev(z[k], force_resample=(k % 2 == 0))
+    want = eager.get_particles()
+    want_stats = eager.stats()[0]
+
+    graphed = fresh()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for k in range(K):
+                graphed.step_dev(z[k], force_resample=(k % 2 == 0))
+    g.replay()
+    torch.cuda.synchronize()
+    got = graphed.get_particles()
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
+    got_stats = graphed.stats()[0]
+    assert got_stats.max_idx == want_stats.max_idx and got_stats.ess == want_stats.ess
+
+
 def test_philox_noise_statistics_and_determinism(mcl):
     """Device noise cannot be bit-compared with MT19937: check moments, independence of launch
     geometry (trial batching / particle offset) and run-to-run determinism."""
