@@ -557,7 +557,14 @@ def run_b200(args, wl):
                 torch.cuda.synchronize()
         for i in range(W_):
             step_dev(i % replicas)
-        n_blocks = int(min(2000, max(1, math.ceil(min_seconds * 1e3 / (est_ms * K_)))))
+        # the step time at the loaded state sizes the timed region (the first, cold steps above overestimate it)
+        e0.record()
+        for i in range(2 * K_):
+            step_dev(i % replicas)
+        e1.record()
+        torch.cuda.synchronize()
+        est_ms = min(est_ms, max(e0.elapsed_time(e1) / (2 * K_), 1e-3))
+        n_blocks = int(min(4000, max(1, math.ceil(1.15 * min_seconds * 1e3 / (est_ms * K_)))))
         if world > 1:  # the same number of blocks on every rank
             nb = torch.tensor([n_blocks], device=dev)
             dist.all_reduce(nb, op=dist.ReduceOp.MAX)
