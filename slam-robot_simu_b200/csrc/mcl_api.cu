@@ -28,7 +28,7 @@ struct Layout {
     int T, Lmax, tpt, bpt, cov_bpt;
     uint32_t per;
     size_t off_state[2], off_anc, off_desc, off_tickets, off_partials, off_cov, off_stats, off_prep, off_tab, off_lm,
-        off_z, off_ofs, off_pose, off_total, off_trig, off_pub, off_ready, off_seg, total;
+        off_z, off_ofs, off_pose, off_total, off_trig, off_pub, off_ready, off_seg, off_reccount, total;
 };
 
 int make_layout(const mcl_config &c, int sm_count, Layout &L) {
@@ -74,6 +74,7 @@ int make_layout(const mcl_config &c, int sm_count, Layout &L) {
     L.off_ready = o;    o = align_up(o + static_cast<size_t>(2) * L.T * (kDirectTiles / 32) * sizeof(unsigned int), kAlign);
     L.off_trig = o;     o = align_up(o + static_cast<size_t>(kTrigEntries) * sizeof(TrigEntry), kAlign);
     L.off_seg = o;      o = align_up(o + static_cast<size_t>(kMaxSegments) * sizeof(unsigned long long), kAlign);
+    L.off_reccount = o; o = align_up(o + static_cast<size_t>(L.T) * sizeof(unsigned int), kAlign);
     L.total = o;
     return MCL_OK;
 }
@@ -127,6 +128,10 @@ struct mcl_filter {
     // in flight while step k + 1 is enqueued (the host then never idles the GPU waiting for statistics)
     mcl_stats *stats_pinned[2] = {nullptr, nullptr};  // mapped: [T] blocks, then the flag word of the direct landing
     cudaEvent_t stats_event[2] = {nullptr, nullptr};
+    unsigned int *rec_count = nullptr;  // [T] producer CTAs finished so far (partial_write)
+    unsigned int rec_target = 0u;       // ... and the value once every launch enqueued so far has finished
+    bool merge_follows = false;         // set around the step of mcl_step_async
+    bool partials_counted = false;      // the launch that wrote `partials` counted its CTAs (a scan may wait on the count)
     unsigned int stats_expect[2] = {0u, 0u};  // != 0: k_merge lands the block itself and sets the flag to this number
     unsigned int stats_seq = 0u;
     uint64_t stats_begun = 0, stats_ended = 0;
@@ -369,6 +374,9 @@ int launch_step_scan(mcl_filter *h, const double *z_dev, const double *ofs_dev, 
     const int tile_ctas = !full ? 0 : ((h->lay.T == 1 && persist_single <= 0) ? h->lay.tpt
                                        : std::min(h->lay.tpt, std::max(1, h->sm_count * std::max(persist_single, per_sm) / h->lay.T)));
     sp.persistent = (tile_ctas < h->lay.tpt) ? 1 : 0;
+    sp.rec_count = h->rec_count;
+    sp.rec_target = h->rec_target;
+    sp.early_merge = (h->lay.T == 1 && !wide && !sp.persistent && sp.n_partials > 0 && h->partials_counted && pdl_for(h)) ? 1 : 0;
     dim3 grid(tile_ctas + (h->stats_dirty ? 2 : 1), h->lay.T);
     h->stats_dirty = false;
     if (wide) launch_pdl(k_scan<kScanAncestors, 16>, grid, dim3(kScanTile / 16), 0, st, pdl_for(h), sp);
@@ -443,6 +451,13 @@ int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool redu
     p.tab = h->tab;
     p.trig = h->trig;
     p.partials = h->partials;
+    h->partials_counted = !h->merge_follows;
+    if (h->merge_follows) {  // mcl_step_async: k_merge is enqueued right behind this launch, no scan will poll the count
+        p.rec_count = nullptr;
+    } else {
+        p.rec_count = h->rec_count;
+        h->rec_target += static_cast<unsigned int>(h->lay.bpt);  // (every counted k_step / k_reduce launch: bpt CTAs per trial)
+    }
     p.tickets = h->tickets;
     p.stats = h->stats;
     p.dbg = h->dbg;
@@ -739,6 +754,7 @@ int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_byte
     h->total = reinterpret_cast<unsigned long long *>(h->ws + L.off_total);
     h->trig = reinterpret_cast<TrigEntry *>(h->ws + L.off_trig);
     h->seg = reinterpret_cast<unsigned long long *>(h->ws + L.off_seg);
+    h->rec_count = reinterpret_cast<unsigned int *>(h->ws + L.off_reccount);
     h->wm_pub = reinterpret_cast<uint4 *>(h->ws + L.off_pub);
     h->ready[0] = reinterpret_cast<unsigned int *>(h->ws + L.off_ready);
     h->ready[1] = h->ready[0] + static_cast<size_t>(L.T) * (kDirectTiles / 32);
@@ -776,6 +792,7 @@ int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_byte
     if (e == cudaSuccess)
         e = cudaMemset(h->ws + L.off_ready, 0, static_cast<size_t>(2) * L.T * (kDirectTiles / 32) * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_pub, 0, static_cast<size_t>(L.T) * 2 * sizeof(uint4));
+    if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_reccount, 0, static_cast<size_t>(L.T) * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_stats, 0, static_cast<size_t>(L.T) * sizeof(mcl_stats));
     if (e != cudaSuccess) {
         if (h->owns_ws) cudaFree(h->ws);
@@ -981,7 +998,10 @@ int mcl_step_dev(mcl_filter *h, const double *z_dev, const double *ofs_dev, cons
 
 int mcl_step_async(mcl_filter *h, const double *z_host, const double *ofs_host, const float *noise_dev, uint32_t flags,
                    void *stream) {
+    if (h == nullptr) return MCL_ERR_ARG;
+    h->merge_follows = true;
     int rc = mcl_step(h, z_host, ofs_host, noise_dev, flags, stream);
+    h->merge_follows = false;
     if (rc != MCL_OK) return rc;
     return mcl_get_stats_begin(h, stream);
 }

@@ -336,7 +336,11 @@ __device__ __forceinline__ float float_from_order_key(uint32_t k) {
 //   merge_full   (all 14 columns)       the statistics CTA of k_scan, or k_merge on demand: mcl_stats
 // All merges run the same code on the same records in the same order: every CTA derives bit-identical values.
 // -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void partial_write(WarpStats &ws, double *pp, unsigned long long *dbg) {
+// rec_count: the last thing a producer CTA does is count itself as finished, releasing everything it stored (its poses
+// and weights, its record, CTA 0's mcl_stats fields).  The NEXT kernel's merging CTAs (k_scan: resident 2 - 15 us early
+// under programmatic dependent launch, tools/timeline.py --back-to-back) take the count as their dependency instead of
+// the completion of the grid.
+__device__ __forceinline__ void partial_write(WarpStats &ws, double *pp, unsigned long long *dbg, unsigned int *rec_count) {
     constexpr int NW = kStepThreads / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ double s_sum[NW][kNumSums];
@@ -387,6 +391,12 @@ __device__ __forceinline__ void partial_write(WarpStats &ws, double *pp, unsigne
             pp[14] = static_cast<double>(float_from_order_key(bk));
             pp[15] = static_cast<double>(bi);
         }
+    }
+    // (barrier, then ONE releasing reduction: the release is cumulative over what the barrier ordered before it --
+    //  the semaphore idiom of CUTLASS; a fence in every thread cost the tail 0.5 us)
+    if (rec_count != nullptr) {  // (null: the statistics merge follows at once -- mcl_step_async -- and nobody polls)
+        __syncthreads();
+        if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(rec_count) : "memory");
     }
     dbg_stamp(dbg, 4);
 }
@@ -708,6 +718,9 @@ struct ScanParams {
     PrepParams prep;
     unsigned long long *dbg;    // optional phase timeline [T][tpt + 1][kDbgSlots]
     int do_prep;                // 1: the LAST block of each trial's row (an extra one) only writes PrepOut
+    int early_merge;            // one-wave scan of a single filter: the merging CTAs wait for rec_count, not for the grid
+    const unsigned int *rec_count;  // [T] producer CTAs finished so far
+    unsigned int rec_target;    // ... and the count at which the producer of the partials is done
     const TrigEntry *trig;
     const float *lw;            // [T][ld]
     mcl_stats *stats;           // [T] statistics of the stored weights (weight map, ESS, estimate)
@@ -819,16 +832,41 @@ __global__ void __launch_bounds__(kScanTile / ITEMS, scan_ctas_per_sm(ITEMS)) k_
     cudaTriggerProgrammaticLaunchCompletion();
     // (the expansion of the device-driven sharded step is launched programmatically behind the per-step scalars
     //  kernel, on which it does not depend: it runs beside it)
-    if (!p.no_dep_sync) cudaGridDependencySynchronize();
     // per-step scalars are the job of one extra CTA per trial: they are only needed by k_step, and their
     // once-per-step code (cold instruction cache) must not delay a tile that every later tile waits for
-    dbg_stamp(p.dbg, 0);
     const bool prep_cta = p.do_prep && blockIdx.x == gridDim.x - 1;
     // ... and another extra CTA merges ALL columns of the partials into mcl_stats (host read-back, k_cov)
     const bool stats_cta = p.do_prep && p.n_partials > 0 && blockIdx.x == gridDim.x - 2;
     __shared__ MergeScratch s_merge;
     const long long soff = static_cast<long long>(t) * p.ld;
     const double *pp = p.partials + static_cast<long long>(t) * p.n_partials * kPart;
+    // One-wave scan of a single filter.  Under programmatic dependent launch this grid's CTAs become resident as the
+    // producer's CTAs retire -- tile 0 some 12 us before the producer grid has completed -- and then sit in
+    // cudaGridDependencySynchronize; only after it did tile 0 start to merge the producer's records (cold: ~4 us) while
+    // every other tile waited for its publication.  For tile 0 and the scalars CTA the dependency is therefore the
+    // count of finished producer CTAs: each producer CTA releases all its stores when it counts itself, so at the
+    // target everything this kernel reads is visible and no producer CTA still reads the ancestors.  ONE thread polls
+    // (the SM is shared with producer CTAs still at work); tile 0 first runs the merge once on whatever the records
+    // hold -- result discarded -- which brings its instructions and the records' lines in.
+    const bool early_cta = p.early_merge && p.n_partials > 0 && !p.no_dep_sync && (prep_cta || (blockIdx.x == 0 && !p.persistent));
+    if (early_cta) {
+        __shared__ int s_done;
+        if (tid == 0) s_done = (ld_acquire_gpu(p.rec_count + t) == p.rec_target) ? 1 : 0;
+        __syncthreads();
+        if (!s_done) {  // (CTA-uniform) there is time to spend
+            if (!prep_cta) {
+                float m_;
+                double a_, b_;
+                merge_light_raw<kScanThreads>(pp, p.n_partials, s_merge, m_, a_, b_);
+            }
+            if (tid == 0)
+                while (ld_acquire_gpu(p.rec_count + t) != p.rec_target) __nanosleep(200);
+            __syncthreads();
+        }
+    } else if (!p.no_dep_sync) {
+        cudaGridDependencySynchronize();
+    }
+    dbg_stamp(p.dbg, 0);
     if (stats_cta) {
         merge_full<kScanThreads>(pp, p.n_partials, p.stats + t, p.cur.x + soff, p.cur.y + soff, p.cur.th + soff, nullptr, p.prep.n_global,
                    p.n_global == p.n);
@@ -1436,6 +1474,7 @@ struct StepParams {
     const double4 *tab;    // [T][Lmax]
     const TrigEntry *trig; // [kTrigEntries]
     double *partials;      // [T][bpt][kPart]
+    unsigned int *rec_count;  // [T] producer CTAs finished so far (monotonic; see partial_write)
     unsigned int *tickets; // [T][4]
     mcl_stats *stats;      // [T]
     unsigned long long *dbg;  // optional phase timeline [T][bpt][kDbgSlots]
@@ -1986,7 +2025,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
         st->abs_shift = s_prep.abs_shift;
         p.tickets[t * 4 + 0] = 0u;
     }
-    partial_write(ws, p.partials + (static_cast<long long>(t) * p.bpt + blockIdx.x) * kPart, p.dbg);
+    partial_write(ws, p.partials + (static_cast<long long>(t) * p.bpt + blockIdx.x) * kPart, p.dbg, p.rec_count ? p.rec_count + t : nullptr);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -2041,7 +2080,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) k_reduce(const StepParams p, 
         st->abs_shift = kNoAbsShift;  // weights set by the caller: relative only, no likelihood step behind them
         p.tickets[t * 4 + 0] = 0u;
     }
-    partial_write(ws, p.partials + (static_cast<long long>(t) * p.bpt + blockIdx.x) * kPart, nullptr);
+    partial_write(ws, p.partials + (static_cast<long long>(t) * p.bpt + blockIdx.x) * kPart, nullptr, p.rec_count ? p.rec_count + t : nullptr);
 }
 
 // -------------------------------------------------------------------------------------------------

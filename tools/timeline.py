@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 STEP = ["start", "scalars", "loop", "flush", "partial"]
-SCAN = ["start", "prologue", "tile-scan", "look-back", "counts", "filled", "prep-done"]
+SCAN = ["start", "prologue", "tile-scan", "look-back", "counts", "filled", "prep-done", "-", "-", "-", "-", "entry"]
 
 
 def show(title, t, names, t0):
@@ -31,6 +31,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="c1")
     ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--back-to-back", action="store_true", help="the measured step follows another step of the SAME filter "
+                    "without a synchronisation in between: shows whether k_scan's CTAs are resident before k_step has drained")
     ap.add_argument("--rotate", type=int, default=0, help="step this many other filters between the measured steps (what bench.py "
                     "does: data L2-cold, code L2-warm) instead of flushing the L2 with a fill (code cold as well)")
     a = ap.parse_args()
@@ -64,6 +66,8 @@ def main():
         else:
             junk = torch.empty(64 << 20, dtype=torch.float32, device="cuda").fill_(1.0)  # flush L2
         torch.cuda.synchronize()
+        if a.back_to_back:
+            f.step_dev(cyc[29], force_resample=True)
         f.step_dev(cyc[30 + rep], force_resample=True)
         t = f.debug_timeline().astype(np.int64)
         ts, tc = t[:-n_scan], t[-n_scan:]
