@@ -377,6 +377,7 @@ int launch_step_scan(mcl_filter *h, const double *z_dev, const double *ofs_dev, 
     sp.rec_count = h->rec_count;
     sp.rec_target = h->rec_target;
     sp.early_merge = (h->lay.T == 1 && !wide && !sp.persistent && sp.n_partials > 0 && h->partials_counted && pdl_for(h)) ? 1 : 0;
+    sp.extras_front = sp.early_merge;
     dim3 grid(tile_ctas + (h->stats_dirty ? 2 : 1), h->lay.T);
     h->stats_dirty = false;
     if (wide) launch_pdl(k_scan<kScanAncestors, 16>, grid, dim3(kScanTile / 16), 0, st, pdl_for(h), sp);

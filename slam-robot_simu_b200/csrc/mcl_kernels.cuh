@@ -719,6 +719,7 @@ struct ScanParams {
     unsigned long long *dbg;    // optional phase timeline [T][tpt + 1][kDbgSlots]
     int do_prep;                // 1: the LAST block of each trial's row (an extra one) only writes PrepOut
     int early_merge;            // one-wave scan of a single filter: the merging CTAs wait for rec_count, not for the grid
+    int extras_front;           // the extra CTAs are blocks 1.. of the row (dispatched first, resident earliest), not the last
     const unsigned int *rec_count;  // [T] producer CTAs finished so far
     unsigned int rec_target;    // ... and the count at which the producer of the partials is done
     const TrigEntry *trig;
@@ -834,9 +835,14 @@ __global__ void __launch_bounds__(kScanTile / ITEMS, scan_ctas_per_sm(ITEMS)) k_
     //  kernel, on which it does not depend: it runs beside it)
     // per-step scalars are the job of one extra CTA per trial: they are only needed by k_step, and their
     // once-per-step code (cold instruction cache) must not delay a tile that every later tile waits for
-    const bool prep_cta = p.do_prep && blockIdx.x == gridDim.x - 1;
+    // (with the early dependency below the extra CTAs are blocks 1 and 2 of the row, so that they are dispatched -- and
+    //  resident -- as early as tile 0; `lin` is a CTA's index among the tile CTAs)
+    const int n_extra_ctas = p.do_prep ? (p.n_partials > 0 ? 2 : 1) : 0;
+    const bool front = p.extras_front != 0;
+    const bool prep_cta = p.do_prep && blockIdx.x == (front ? 1u : gridDim.x - 1);
     // ... and another extra CTA merges ALL columns of the partials into mcl_stats (host read-back, k_cov)
-    const bool stats_cta = p.do_prep && p.n_partials > 0 && blockIdx.x == gridDim.x - 2;
+    const bool stats_cta = p.do_prep && p.n_partials > 0 && blockIdx.x == (front ? 2u : gridDim.x - 2);
+    const unsigned int lin = (front && blockIdx.x != 0u) ? blockIdx.x - static_cast<unsigned int>(n_extra_ctas) : blockIdx.x;
     __shared__ MergeScratch s_merge;
     const long long soff = static_cast<long long>(t) * p.ld;
     const double *pp = p.partials + static_cast<long long>(t) * p.n_partials * kPart;
@@ -854,11 +860,11 @@ __global__ void __launch_bounds__(kScanTile / ITEMS, scan_ctas_per_sm(ITEMS)) k_
         if (tid == 0) s_done = (ld_acquire_gpu(p.rec_count + t) == p.rec_target) ? 1 : 0;
         __syncthreads();
         if (!s_done) {  // (CTA-uniform) there is time to spend
-            if (!prep_cta) {
-                float m_;
-                double a_, b_;
-                merge_light_raw<kScanThreads>(pp, p.n_partials, s_merge, m_, a_, b_);
-            }
+            float m_, v_;
+            double a_, b_;
+            uint32_t i_;
+            if (prep_cta) merge_light_best<kScanThreads>(pp, p.n_partials, s_merge, m_, a_, b_, v_, i_);
+            else merge_light_raw<kScanThreads>(pp, p.n_partials, s_merge, m_, a_, b_);
             if (tid == 0)
                 while (ld_acquire_gpu(p.rec_count + t) != p.rec_target) __nanosleep(200);
             __syncthreads();
@@ -891,7 +897,7 @@ __global__ void __launch_bounds__(kScanTile / ITEMS, scan_ctas_per_sm(ITEMS)) k_
             asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(pub));
             asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(pub + 1));
         }
-        const unsigned int tk = prep_cta ? 0xffffffffu : (ordered ? blockIdx.x : atomicAdd(&p.tickets[t * 4 + 0], 1u));
+        const unsigned int tk = prep_cta ? 0xffffffffu : (ordered ? lin : atomicAdd(&p.tickets[t * 4 + 0], 1u));
         s_sc.tile = tk;
         if (may_poll && tk != 0u) {
             while (a.w != p.epoch || b.z != p.epoch) {
@@ -989,10 +995,10 @@ __global__ void __launch_bounds__(kScanTile / ITEMS, scan_ctas_per_sm(ITEMS)) k_
     // The descriptors the NEXT scan launch starts from are cleared whether or not this trial resamples: a launch
     // that skipped the clear would leave the previous resampling's aggregates / prefixes in the buffer the launch
     // after it looks back through (tiles past the direct range accept any non-zero status at once).
-    if (p.desc_next != nullptr && static_cast<int>(blockIdx.x) * kScanThreads < p.tpt) {
-        const int n_tile_ctas = static_cast<int>(gridDim.x) - (p.do_prep ? (p.n_partials > 0 ? 2 : 1) : 0);
+    if (p.desc_next != nullptr && static_cast<int>(lin) * kScanThreads < p.tpt) {
+        const int n_tile_ctas = static_cast<int>(gridDim.x) - n_extra_ctas;
         unsigned long long *dn = p.desc_next + static_cast<long long>(t) * p.tpt;
-        for (long long i = static_cast<long long>(blockIdx.x) * kScanThreads + tid; i < p.tpt;
+        for (long long i = static_cast<long long>(lin) * kScanThreads + tid; i < p.tpt;
              i += static_cast<long long>(n_tile_ctas) * kScanThreads)
             dn[i] = 0ull;
     }
@@ -1003,7 +1009,7 @@ __global__ void __launch_bounds__(kScanTile / ITEMS, scan_ctas_per_sm(ITEMS)) k_
     __shared__ unsigned int s_next[2];  // two slots by iteration parity: one barrier per tile is enough
     // (requesting the next tile's weights a tile ahead -- cp.async into a double buffer -- was measured: no gain for
     //  the expansion, and its 16 KB of shared memory cost the look-back scan 6 %)
-    const int n_tile_ctas_s = static_cast<int>(gridDim.x) - (p.do_prep ? (p.n_partials > 0 ? 2 : 1) : 0);
+    const int n_tile_ctas_s = static_cast<int>(gridDim.x) - n_extra_ctas;
     unsigned long long solo_prefix = 0ull;
     int it = 0;
     for (long long tile = s_sc.tile; tile < p.tpt; tile = static_cast<long long>(s_next[it & 1]), ++it) {

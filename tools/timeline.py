@@ -75,7 +75,9 @@ def main():
         print(f"--- step {rep}: microseconds after the first k_scan CTA started")
         show("k_scan", tc, SCAN, t0)
         print("    tile 0 (merges and publishes): " + "  ".join(f"{nm} {(v - t0) / 1e3:.2f}" for nm, v in zip(SCAN + ["-"], tc[0]) if v > 0))
-        print("    scalars CTA: " + "  ".join(f"{nm} {(v - t0) / 1e3:.2f}" for nm, v in zip(SCAN + ["-"], tc[-1]) if v > 0))
+        prep_rows = np.nonzero(tc[:, 6] > 0)[0]  # (the scalars CTA is the only one that stamps "prep-done")
+        prow = tc[prep_rows[0]] if prep_rows.size else tc[-1]
+        print("    scalars CTA: " + "  ".join(f"{nm} {(v - t0) / 1e3:.2f}" for nm, v in zip(SCAN + ["-"], prow) if v > 0))
         show("k_step", ts, STEP, t0)
         del junk
 
