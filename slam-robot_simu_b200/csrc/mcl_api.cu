@@ -28,7 +28,7 @@ struct Layout {
     int T, Lmax, tpt, bpt, cov_bpt;
     uint32_t per;
     size_t off_state[2], off_anc, off_desc, off_tickets, off_partials, off_cov, off_stats, off_prep, off_tab, off_lm,
-        off_z, off_ofs, off_pose, off_total, off_trig, off_pub, off_ready, off_seg, off_reccount, total;
+        off_z, off_ofs, off_pose, off_total, off_trig, off_pub, off_ready, off_seg, off_reccount, off_prepflag, total;
 };
 
 int make_layout(const mcl_config &c, int sm_count, Layout &L) {
@@ -75,6 +75,7 @@ int make_layout(const mcl_config &c, int sm_count, Layout &L) {
     L.off_trig = o;     o = align_up(o + static_cast<size_t>(kTrigEntries) * sizeof(TrigEntry), kAlign);
     L.off_seg = o;      o = align_up(o + static_cast<size_t>(kMaxSegments) * sizeof(unsigned long long), kAlign);
     L.off_reccount = o; o = align_up(o + static_cast<size_t>(L.T) * sizeof(unsigned int), kAlign);
+    L.off_prepflag = o; o = align_up(o + static_cast<size_t>(L.T) * sizeof(unsigned int), kAlign);
     L.total = o;
     return MCL_OK;
 }
@@ -130,6 +131,8 @@ struct mcl_filter {
     cudaEvent_t stats_event[2] = {nullptr, nullptr};
     unsigned int *rec_count = nullptr;  // [T] producer CTAs finished so far (partial_write)
     unsigned int rec_target = 0u;       // ... and the value once every launch enqueued so far has finished
+    unsigned int *prep_flag = nullptr;  // [T] epoch of the scalars (released by the scalars CTA of k_scan)
+    unsigned int prep_epoch = 0u;
     bool merge_follows = false;         // set around the step of mcl_step_async
     bool partials_counted = false;      // the launch that wrote `partials` counted its CTAs (a scan may wait on the count)
     unsigned int stats_expect[2] = {0u, 0u};  // != 0: k_merge lands the block itself and sets the flag to this number
@@ -289,6 +292,8 @@ void fill_prep(mcl_filter *h, PrepParams &p, const double *z_dev, const double *
 
 void fill_scan(mcl_filter *h, ScanParams &p) {
     p = ScanParams{};
+    p.prep_flag = h->prep_flag;
+    p.prep_epoch = h->prep_epoch;
     p.lw = h->state[h->cur].lw;
     p.stats = h->stats;
     p.desc = h->desc[h->desc_cur];
@@ -344,6 +349,8 @@ int launch_step_scan(mcl_filter *h, const double *z_dev, const double *ofs_dev, 
     fill_scan(h, sp);
     fill_prep(h, sp.prep, z_dev, ofs_dev, flags);
     sp.do_prep = 1;
+    h->prep_epoch += 1u;
+    sp.prep_epoch = h->prep_epoch;
     sp.trig = h->trig;
     sp.dbg = (h->dbg != nullptr && full) ? h->dbg + static_cast<size_t>(h->lay.T) * h->lay.bpt * kDbgSlots : nullptr;
     if (full) {
@@ -507,6 +514,9 @@ int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool redu
     }
     const bool philox = (noise_dev == nullptr);
     const bool pdl = pdl_for(h);
+    p.prep_flag = h->prep_flag;
+    p.prep_epoch = h->prep_epoch;
+    p.early_prep = (pdl && win == nullptr && plan == nullptr) ? 1 : 0;
     // shared-memory landmark table: 32 bytes per landmark; the fp32 range/bearing kernel stages every value twice (64)
     const size_t smem = static_cast<size_t>(h->L) * sizeof(double4) * (c.likelihood == MCL_LIK_RB_F32 ? 2 : 1);
     switch (step_variant(c)) {
@@ -756,6 +766,7 @@ int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_byte
     h->trig = reinterpret_cast<TrigEntry *>(h->ws + L.off_trig);
     h->seg = reinterpret_cast<unsigned long long *>(h->ws + L.off_seg);
     h->rec_count = reinterpret_cast<unsigned int *>(h->ws + L.off_reccount);
+    h->prep_flag = reinterpret_cast<unsigned int *>(h->ws + L.off_prepflag);
     h->wm_pub = reinterpret_cast<uint4 *>(h->ws + L.off_pub);
     h->ready[0] = reinterpret_cast<unsigned int *>(h->ws + L.off_ready);
     h->ready[1] = h->ready[0] + static_cast<size_t>(L.T) * (kDirectTiles / 32);
@@ -794,6 +805,7 @@ int mcl_create(const mcl_config *cfg, void *workspace_dev, size_t workspace_byte
         e = cudaMemset(h->ws + L.off_ready, 0, static_cast<size_t>(2) * L.T * (kDirectTiles / 32) * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_pub, 0, static_cast<size_t>(L.T) * 2 * sizeof(uint4));
     if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_reccount, 0, static_cast<size_t>(L.T) * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_prepflag, 0, static_cast<size_t>(L.T) * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(h->ws + L.off_stats, 0, static_cast<size_t>(L.T) * sizeof(mcl_stats));
     if (e != cudaSuccess) {
         if (h->owns_ws) cudaFree(h->ws);
@@ -1621,6 +1633,8 @@ int mcl_shard_step_peer(mcl_filter *h, const double *z_host, const double *ofs_h
         fill_scan(h, sp);
         fill_prep(h, sp.prep, h->z, nullptr, flags);
         sp.do_prep = 1;
+        h->prep_epoch += 1u;
+        sp.prep_epoch = h->prep_epoch;
         sp.trig = h->trig;
         sp.plan = h->plan;
         sp.xflags = flags;

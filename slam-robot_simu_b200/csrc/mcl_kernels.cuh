@@ -720,6 +720,8 @@ struct ScanParams {
     int do_prep;                // 1: the LAST block of each trial's row (an extra one) only writes PrepOut
     int early_merge;            // one-wave scan of a single filter: the merging CTAs wait for rec_count, not for the grid
     int extras_front;           // the extra CTAs are blocks 1.. of the row (dispatched first, resident earliest), not the last
+    unsigned int *prep_flag;    // [T] the scalars CTA releases this launch's epoch here once PrepOut and the table are written
+    unsigned int prep_epoch;
     const unsigned int *rec_count;  // [T] producer CTAs finished so far
     unsigned int rec_target;    // ... and the count at which the producer of the partials is done
     const TrigEntry *trig;
@@ -990,6 +992,10 @@ __global__ void __launch_bounds__(kScanTile / ITEMS, scan_ctas_per_sm(ITEMS)) k_
         }
         prep_block(p.prep, in, p.trig, t, resample, ofs, reinterpret_cast<double *>(s_mark));
         dbg_stamp(p.dbg, 6);
+        // k_step's CTAs (resident early under programmatic launch) read the scalars and stage the table before the
+        // rest of this grid has finished: barrier, then one release that is cumulative over the CTA's stores
+        __syncthreads();
+        if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.prep_flag + t), "r"(p.prep_epoch) : "memory");
         return;
     }
     // The descriptors the NEXT scan launch starts from are cleared whether or not this trial resamples: a launch
@@ -1481,6 +1487,9 @@ struct StepParams {
     const TrigEntry *trig; // [kTrigEntries]
     double *partials;      // [T][bpt][kPart]
     unsigned int *rec_count;  // [T] producer CTAs finished so far (monotonic; see partial_write)
+    const unsigned int *prep_flag;  // [T] epoch of the scalars in `prep` / `tab` (released by the scalars CTA of k_scan)
+    unsigned int prep_epoch;
+    int early_prep;           // read the scalars behind prep_flag, BEFORE the scan grid has completed
     unsigned int *tickets; // [T][4]
     mcl_stats *stats;      // [T]
     unsigned long long *dbg;  // optional phase timeline [T][bpt][kDbgSlots]
@@ -1512,7 +1521,15 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
     __shared__ uint32_t s_win[2];
 
     cudaTriggerProgrammaticLaunchCompletion();  // see k_scan
-    cudaGridDependencySynchronize();
+    // The per-step constants below need the scalars CTA of the scan only, the particle loop the whole scan: a CTA that
+    // is resident before the scan has drained (programmatic launch) spends that time on its 0.75 us of set-up.
+    if (p.early_prep) {
+        if (tid == 0)
+            while (ld_acquire_gpu(p.prep_flag + t) != p.prep_epoch) __nanosleep(200);
+        __syncthreads();
+    } else {
+        cudaGridDependencySynchronize();
+    }
     dbg_stamp(p.dbg, 0);
     if (tid < static_cast<int>(sizeof(PrepOut) / sizeof(double)))
         reinterpret_cast<double *>(&s_prep)[tid] = reinterpret_cast<const double *>(p.prep + t)[tid];
@@ -1614,6 +1631,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    if (p.early_prep) cudaGridDependencySynchronize();  // ancestors, and the state buffer the scan's scalars CTA read
     request_anc(first + tid * kPPT, 0);
     int since_flush = 0, itn = 0;
     for (uint32_t wbase = first + (tid - lane) * kPPT; wbase < last; wbase += kStepTile, ++itn) {
