@@ -470,6 +470,9 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// the early-dependency waits of k_scan / k_step give up after this long and use cudaGridDependencySynchronize instead
+constexpr unsigned long long kEarlyWaitNs = 5000000ull;
+__device__ __forceinline__ unsigned long long global_timer_ns();
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

@@ -867,9 +867,18 @@ __global__ void __launch_bounds__(kScanTile / ITEMS, scan_ctas_per_sm(ITEMS)) k_
             uint32_t i_;
             if (prep_cta) merge_light_best<kScanThreads>(pp, p.n_partials, s_merge, m_, a_, b_, v_, i_);
             else merge_light_raw<kScanThreads>(pp, p.n_partials, s_merge, m_, a_, b_);
-            if (tid == 0)
-                while (ld_acquire_gpu(p.rec_count + t) != p.rec_target) __nanosleep(200);
+            if (tid == 0) {
+                // (bounded: a count that never arrives falls back to the dependency every other CTA uses)
+                const unsigned long long t0 = global_timer_ns();
+                int ok = 1;
+                while (ld_acquire_gpu(p.rec_count + t) != p.rec_target) {
+                    __nanosleep(200);
+                    if (global_timer_ns() - t0 > kEarlyWaitNs) { ok = 0; break; }
+                }
+                s_done = ok;
+            }
             __syncthreads();
+            if (!s_done) cudaGridDependencySynchronize();
         }
     } else if (!p.no_dep_sync) {
         cudaGridDependencySynchronize();
@@ -1524,9 +1533,18 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) k_step(const __g
     // The per-step constants below need the scalars CTA of the scan only, the particle loop the whole scan: a CTA that
     // is resident before the scan has drained (programmatic launch) spends that time on its 0.75 us of set-up.
     if (p.early_prep) {
-        if (tid == 0)
-            while (ld_acquire_gpu(p.prep_flag + t) != p.prep_epoch) __nanosleep(200);
+        __shared__ int s_flag_ok;
+        if (tid == 0) {
+            const unsigned long long t0 = global_timer_ns();
+            int ok = 1;
+            while (ld_acquire_gpu(p.prep_flag + t) != p.prep_epoch) {
+                __nanosleep(200);
+                if (global_timer_ns() - t0 > kEarlyWaitNs) { ok = 0; break; }  // (bounded: fall back to the grid dependency)
+            }
+            s_flag_ok = ok;
+        }
         __syncthreads();
+        if (!s_flag_ok) cudaGridDependencySynchronize();
     } else {
         cudaGridDependencySynchronize();
     }
