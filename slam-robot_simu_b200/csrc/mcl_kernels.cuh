@@ -717,7 +717,7 @@ __global__ void __launch_bounds__(kStepThreads) k_merge(const MergeParams p) {
 struct ScanParams {
     PrepParams prep;
     unsigned long long *dbg;    // optional phase timeline [T][tpt + 1][kDbgSlots]
-    int do_prep;                // 1: the LAST block of each trial's row (an extra one) only writes PrepOut
+    int do_prep;                // 1: an extra block of each trial's row (the last one, or block 1: extras_front) only writes PrepOut
     int early_merge;            // one-wave scan of a single filter: the merging CTAs wait for rec_count, not for the grid
     int extras_front;           // the extra CTAs are blocks 1.. of the row (dispatched first, resident earliest), not the last
     unsigned int *prep_flag;    // [T] the scalars CTA releases this launch's epoch here once PrepOut and the table are written
