@@ -7,6 +7,9 @@
 //            merge the previous step's CTA partials into mcl_stats.
 //   k_step   [gather through the ancestors] + predict + weight + statistics; every CTA leaves one 128-byte partial
 //            record -- the records are merged where they are consumed (next k_scan, k_merge, k_xchg_stats).
+// Small steps are chained by programmatic dependent launch, and the kernels' ends overlap: a CTA that is resident
+// before its predecessor grid has drained waits for exactly what it reads -- k_scan's merging CTAs for the count of
+// finished k_step CTAs, k_step's set-up for the scalars CTA's flag -- and for the whole grid only where it must.
 // Stage / utility kernels: k_reduce (statistics only), k_gather (stand-alone resampling gather),
 // k_cov (exact two-pass covariance), k_export_weights, k_init*, k_fill, k_reset_scan.
 #pragma once
