@@ -836,6 +836,7 @@ __global__ void __launch_bounds__(kScanTile / ITEMS, scan_ctas_per_sm(ITEMS)) k_
     // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as every CTA of
     // this grid has started; nothing is read or written before the previous kernel has completed.
     cudaTriggerProgrammaticLaunchCompletion();
+    dbg_stamp(p.dbg, 11);  // entry, before any dependency is resolved (tools/timeline.py --back-to-back)
     // (the expansion of the device-driven sharded step is launched programmatically behind the per-step scalars
     //  kernel, on which it does not depend: it runs beside it)
     // per-step scalars are the job of one extra CTA per trial: they are only needed by k_step, and their
