@@ -459,8 +459,11 @@ int launch_step(mcl_filter *h, const float *noise_dev, uint32_t flags, bool redu
     p.tab = h->tab;
     p.trig = h->trig;
     p.partials = h->partials;
-    h->partials_counted = !h->merge_follows;
-    if (h->merge_follows) {  // mcl_step_async: k_merge is enqueued right behind this launch, no scan will poll the count
+    // the CTAs count themselves only when a scan may wait on the count: not when k_merge is enqueued right behind this
+    // launch (mcl_step_async), and not without programmatic launch (large filters, profiling) -- there the next kernel
+    // starts after this grid has completed anyway
+    h->partials_counted = !h->merge_follows && pdl_for(h);
+    if (!h->partials_counted) {
         p.rec_count = nullptr;
     } else {
         p.rec_count = h->rec_count;
